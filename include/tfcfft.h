@@ -1,0 +1,116 @@
+/* tfcfft.h -- C ABI of the B200-native TFC-GAN frequency-domain loss path.
+ *
+ * The reference (nudro/TFC-GAN, Python) has no FFI: the path is a set of module-level Python
+ * functions duplicated per training script.  This header is the boundary
+ * the build creates for them; every entry point names the reference code it replaces
+ * (paths relative to the reference checkout):
+ *
+ *   tfcfft_loss        TFC-GAN-FFT/TFCGAN_multigpu_patchFFT_16P.py:271-375  (FFT_Components,
+ *                      fft_components, calculate_ffts: 16-patch loss)
+ *                      TFC-GAN-FFT/TFCGAN_multigpu_patchFFT.py:498-511       (4-patch, mean)
+ *                      TFC-GAN-FFT/TFCGAN_multigpu_patchFFT_experiment.py:317-339 (4-patch, sum)
+ *                      TFC-GAN-FFT/TFCGAN_multigpu_globalFFT.py:494-499      (global)
+ *                      TFC-STN/TFCGAN_STN21_Original_NewModel3_B2A.py:461-467 (global_fourier_loss)
+ *                      TFC-GAN-FFT/Devcom_MagMSE.py:91-118                   (mse_spec, per image:
+ *                      flags LOG_MAGNITUDE|FULL_SPECTRUM|DIST_MSE|NO_PHASE, per_image != NULL)
+ *                      -- plus the backward pass the reference lacks (its loss is detached, SURVEY.md
+ *                      section 0 fact 2): d loss / d fake, written to grad_fake in the same launch.
+ *   tfcfft_grad_scale  the multiplication by grad_output that autograd performs for
+ *                      scaler.scale(loss_G).backward() (TFCGAN_multigpu_patchFFT_16P.py:607-610)
+ *
+ * Conventions: plain pointers and sizes only; every device buffer (inputs, outputs, workspace) is
+ * owned by the caller; the library allocates nothing on the device, keeps no pointer after a call
+ * returns, never synchronises the host, and enqueues all work on the caller's stream.  Return
+ * code 0 = OK, negative = tfcfft_status argument error (nothing was launched), positive =
+ * cudaError_t.  No exceptions cross this boundary and there is no CPU fallback.
+ */
+#ifndef TFCFFT_H_
+#define TFCFFT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFCFFT_VERSION 100 /* major*100 + minor */
+
+/* element type of fake / real / grad_fake */
+enum tfcfft_dtype { TFCFFT_F32 = 0, TFCFFT_F16 = 1, TFCFFT_BF16 = 2, TFCFFT_U8 = 3 };
+
+/* flags (default 0 = the reference training loss: luma, amplitude + phase, L1, half spectrum,
+ * mean over patches) */
+#define TFCFFT_CHANNELS_RGB  (1u << 0) /* one spectrum per channel instead of ITU-R 601 luma      */
+#define TFCFFT_NO_PHASE      (1u << 1) /* amplitude term only: loss = weight * amp                */
+#define TFCFFT_DIST_MSE      (1u << 2) /* squared difference instead of absolute difference       */
+#define TFCFFT_PATCH_SUM     (1u << 3) /* sum over patches (fft_loss) instead of mean             */
+#define TFCFFT_LOG_MAGNITUDE (1u << 4) /* log |F| (Devcom_MagMSE.py:105-106)                      */
+#define TFCFFT_FULL_SPECTRUM (1u << 5) /* mean over the full P x P plane (fft2) not P x (P/2+1)   */
+#define TFCFFT_QUANTIZE_U8   (1u << 6) /* reference-as-shipped input path: uint8 wrap + integer
+                                          luma (patchFFT_16P.py:300); forward only               */
+#define TFCFFT_FORCE_SPLIT   (1u << 31) /* testing: route P = 64 / 128 through the split path     */
+
+enum tfcfft_status {
+    TFCFFT_OK = 0,
+    TFCFFT_ERR_NULL = -1,        /* null descriptor / required pointer                            */
+    TFCFFT_ERR_STRUCT = -2,      /* struct_size mismatch (ABI version skew)                       */
+    TFCFFT_ERR_DTYPE = -3,
+    TFCFFT_ERR_SHAPE = -4,       /* H != W, C not in {1,3}, H % grid, patch side not in {16..512}  */
+    TFCFFT_ERR_STRIDE = -5,      /* innermost stride != 1 or outer strides not multiples of 4      */
+    TFCFFT_ERR_ALIGNMENT = -6,   /* base pointer not aligned to 4 elements                         */
+    TFCFFT_ERR_FLAGS = -7,       /* unsupported flag combination                                   */
+    TFCFFT_ERR_WORKSPACE = -8,   /* workspace null, misaligned or smaller than workspace_bytes     */
+    TFCFFT_ERR_NO_GRADIENT = -9, /* gradient requested for QUANTIZE_U8 or a uint8 input            */
+    TFCFFT_ERR_EMPTY = -10       /* N == 0                                                         */
+};
+
+typedef struct tfcfft_desc {
+    uint32_t struct_size; /* sizeof(tfcfft_desc) */
+    int32_t dtype;        /* tfcfft_dtype */
+    int32_t grid;         /* patches per side: 1 global, 2 = 4-patch, 4 = 16-patch */
+    uint32_t flags;
+    int64_t n, c, h, w;      /* NCHW */
+    int64_t fake_stride[4];  /* element strides; views such as B[:, :, 0:64, 64:128] are fine */
+    int64_t real_stride[4];
+    int64_t grad_stride[4];  /* ignored when grad_fake == NULL */
+    float weight;            /* multiplies the loss and the gradient (1/100 at patchFFT_16P.py:607) */
+    float input_scale;       /* x' = input_scale * x before the transform (ignored with QUANTIZE_U8) */
+} tfcfft_desc;
+
+int tfcfft_version(void);
+const char* tfcfft_strerror(int rc);
+
+/* Host-only argument check; tfcfft_loss performs the same check first. */
+int tfcfft_validate(const tfcfft_desc* d);
+
+/* Bytes of caller-owned device scratch tfcfft_loss needs for `d` (0 if `d` is invalid). */
+size_t tfcfft_workspace_bytes(const tfcfft_desc* d);
+
+/* Zeroes the workspace header.  Call once after allocating a workspace (and after any call that
+ * returned a CUDA error); calls leave the header zeroed for the next call.  A workspace must not be
+ * shared by calls that may run concurrently on different streams. */
+int tfcfft_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
+
+/* Loss (and, when grad_fake != NULL, d loss / d fake) in one pass over the inputs.
+ *   out        device float[4]: weight * 1/2 (amp + pha)  [weight * amp with NO_PHASE], amp, pha,
+ *              non-finite flag
+ *   per_image  device float[2*N] or NULL: per-image (amp, pha) terms; their mean over N is amp/pha
+ *   grad_fake  device buffer of d->dtype laid out by grad_stride, or NULL for forward only
+ * The reduction order is fixed: the loss is bit-stable from run to run. */
+int tfcfft_loss(const tfcfft_desc* d, const void* fake, const void* real, float* out, float* per_image,
+                void* grad_fake, void* workspace, size_t workspace_bytes, void* stream);
+
+/* dst[i] = src[i] * host_scale * (*dev_scale)   (dev_scale may be NULL; dst may equal src);
+ * numel elements of `dtype`, both 16-byte aligned. */
+int tfcfft_grad_scale(void* dst, const void* src, int32_t dtype, int64_t numel, const float* dev_scale,
+                      float host_scale, void* stream);
+
+/* Number of kernels this library has launched in this process since the last reset. */
+int64_t tfcfft_launch_count(void);
+void tfcfft_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFCFFT_H_ */

@@ -1,0 +1,112 @@
+"""Host-side check of the kernels' algebra: ``libtfcfft_emu.so`` executes the very templates the
+sm_100a kernels instantiate (index maps of the digit-reversed in-place FFT, Hermitian un-mixing, bin
+ownership, reduction layout), serially on the CPU, and must agree with the oracle.  This is test
+infrastructure, not a product fallback."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from inputs import make_gray_pairs, make_pair
+from util import L, emulate, flags_of, l2rel
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "golden_cases.json")))
+
+CASES = [
+    # side, grid, options
+    (64, 4, dict()),
+    (64, 2, dict(channels="rgb")),
+    (64, 1, dict(distance="mse", patch_reduce="sum")),
+    (128, 1, dict(use_phase=False)),
+    (128, 2, dict(spectrum="full", channels="rgb")),
+    (256, 4, dict()),
+    (256, 2, dict(distance="mse")),
+    (256, 1, dict()),
+    (256, 1, dict(channels="rgb", use_phase=False, log_magnitude=True, spectrum="full", distance="mse")),
+    (512, 1, dict()),
+    (256, 4, dict(force_split=True)),
+    (256, 2, dict(force_split=True, channels="rgb")),
+]
+
+
+@pytest.mark.parametrize("side,grid,opt", CASES, ids=[f"{s}-g{g}-{'-'.join(f'{k}={v}' for k, v in o.items()) or 'default'}" for s, g, o in CASES])
+def test_emulation_matches_r1(side, grid, opt):
+    n = 2 if side <= 256 else 1
+    fake, real = make_pair("uniform", 7, (n, 3, side, side), "float32")
+    rc, out, per, g = emulate(fake, real, grid, flags_of(**opt), weight=0.7, input_scale=3.0)
+    assert rc == 0
+    okw = {k: v for k, v in opt.items() if k != "force_split"}
+    l, a, p, gr = oracle.spectral_loss_and_grad_r1(fake, real, grid=grid, weight=0.7, input_scale=3.0, **okw)
+    assert out[0] == pytest.approx(l, rel=1e-5)
+    assert out[1] == pytest.approx(a, rel=1e-5)
+    assert out[2] == pytest.approx(p, rel=1e-5, abs=1e-12)
+    assert l2rel(g, gr) <= 1e-3
+    assert per[:, 0].mean() == pytest.approx(a, rel=1e-5)
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+def test_emulation_half_inputs(dtype):
+    fake, real = make_pair("tanh", 3, (2, 3, 128, 128), "float32")
+    tf = torch.from_numpy(fake).to(getattr(torch, dtype))
+    tr = torch.from_numpy(real).to(getattr(torch, dtype))
+    if dtype == "float16":
+        af, ar, code = tf.numpy(), tr.numpy(), L.F16
+    else:
+        af, ar, code = tf.view(torch.int16).numpy().view(np.uint16), tr.view(torch.int16).numpy().view(np.uint16), L.BF16
+    rc, out, _, g = emulate(af, ar, 2, 0, input_scale=255.0, dtype_code=code)
+    assert rc == 0
+    l, a, p, gr = oracle.spectral_loss_and_grad_r1(tf.double().numpy(), tr.double().numpy(), grid=2, input_scale=255.0)
+    assert out[0] == pytest.approx(l, rel=1e-5)
+    g32 = torch.from_numpy(g.view(np.int16)).view(torch.bfloat16).float().numpy() if dtype == "bfloat16" else g.astype(np.float32)
+    assert l2rel(g32, gr) <= (1e-2 if dtype == "bfloat16" else 2e-3)  # output rounding of the 16-bit gradient
+
+
+LOSS_CASES = [c for c in GOLD["cases"] if "loss" in c]
+
+
+@pytest.mark.parametrize("case", LOSS_CASES, ids=[c["name"] for c in LOSS_CASES])
+def test_emulation_quantised_mode_matches_reference_golden(case):
+    """QUANTIZE_U8 (reference-as-shipped input path) against what the reference's own code produced."""
+    fake, real = make_pair(case["kind"], case["seed"], (case["n"], 3, 256, 256), case["dtype"])
+    flags = flags_of(quantize=True, patch_reduce=case["patch_reduce"])
+    rc, out, _, _ = emulate(fake, real, case["grid"], flags, weight=case.get("weight", 1.0), grad=False)
+    assert rc == 0
+    assert out[0] == pytest.approx(case["loss"], rel=1e-4)
+    if "amp" in case:
+        assert out[1] == pytest.approx(case["amp"], rel=1e-4)
+        assert out[2] == pytest.approx(case["pha"], rel=1e-4)
+
+
+def test_emulation_mag_mse_metric_matches_reference_golden():
+    case = next(c for c in GOLD["cases"] if c["name"] == "mag_mse_71")
+    reals, fakes = make_gray_pairs(case["seed"], case["n"], case["side"])
+    r = np.stack(reals)[:, None]
+    f = np.stack(fakes)[:, None]
+    flags = flags_of(use_phase=False, distance="mse", log_magnitude=True, spectrum="full")
+    rc, out, per, _ = emulate(f, r, 1, flags, grad=False)
+    assert rc == 0
+    vals = per[:, 0]
+    assert not np.isfinite(vals[1])  # the constant image: log(0) -> skipped by the reference
+    np.testing.assert_allclose(vals[[0, 2, 3]], case["values"], rtol=1e-4)
+    assert out[3] == 1.0  # non-finite flag
+
+
+def test_emulation_rejects_gradient_for_quantised_inputs():
+    fake, real = make_pair("uniform", 1, (1, 3, 64, 64), "float32")
+    rc, *_ = emulate(fake, real, 1, flags_of(quantize=True), grad=True)
+    assert rc == -9
+
+
+def test_emulation_strided_views():
+    """Reference-style patch views (``B[:, :, 64:128, 64:128]``) are consumed in place."""
+    fake, real = make_pair("uniform", 4, (2, 3, 256, 256), "float32")
+    fv, rv = fake[:, :, 64:128, 64:128], real[:, :, 128:192, 0:64]
+    rc, out, _, g = emulate(fv, rv, 1, 0, grad=False)
+    assert rc == 0
+    l, *_ = oracle.spectral_loss_r1(torch.from_numpy(fv.copy()), torch.from_numpy(rv.copy()), grid=1)
+    assert out[0] == pytest.approx(float(l), rel=1e-5)

@@ -1,0 +1,61 @@
+"""Shared helpers for the tests."""
+
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+import tfc_gan_b200 as tfc
+
+L = tfc._lib
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_PATH = os.path.join(ROOT, "tfc-gan_b200", "libtfcfft_emu.so")
+
+NP_DTYPES = {"float32": L.F32, "float16": L.F16, "uint8": L.U8}
+
+
+def flags_of(channels="luma", use_phase=True, distance="l1", patch_reduce="mean", log_magnitude=False,
+             spectrum="half", quantize=False, force_split=False):
+    return tfc.SpectralConfig(channels=channels, use_phase=use_phase, distance=distance, patch_reduce=patch_reduce,
+                              log_magnitude=log_magnitude, spectrum=spectrum, quantize=quantize,
+                              force_split=force_split).flags()
+
+
+_EMU = None
+
+
+def emu_lib():
+    global _EMU
+    if _EMU is None:
+        _EMU = ctypes.CDLL(EMU_PATH)
+        _EMU.tfcfft_emulate.restype = ctypes.c_int
+        _EMU.tfcfft_emulate.argtypes = [ctypes.POINTER(L.Desc)] + [ctypes.c_void_p] * 5
+    return _EMU
+
+
+def _strides(a):
+    return [s // a.itemsize for s in a.strides]
+
+
+def emulate(fake: np.ndarray, real: np.ndarray, grid: int, flags: int, weight=1.0, input_scale=1.0, grad=True,
+            dtype_code=None):
+    """Runs the kernels' arithmetic serially on the CPU (libtfcfft_emu.so).  bf16 is passed as uint16
+    arrays with ``dtype_code=L.BF16``."""
+    n = fake.shape[0]
+    code = dtype_code if dtype_code is not None else NP_DTYPES[str(fake.dtype)]
+    out = np.zeros(4, np.float32)
+    per = np.zeros((n, 2), np.float32)
+    g = np.zeros_like(fake) if grad else None
+    d = L.make_desc(code, grid, flags, fake.shape, _strides(fake), _strides(real), _strides(g) if grad else None,
+                    weight, input_scale)
+    rc = emu_lib().tfcfft_emulate(ctypes.byref(d), fake.ctypes.data, real.ctypes.data, out.ctypes.data,
+                                  per.ctypes.data, g.ctypes.data if grad else None)
+    return rc, out, per, g
+
+
+def l2rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))

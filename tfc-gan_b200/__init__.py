@@ -1,0 +1,22 @@
+"""tfc-gan_b200 -- B200-native frequency-domain (FFT) loss path of TFC-GAN.
+
+Scope: SURVEY.md §8.  ``SpectralLoss`` / ``spectral_loss`` are the clean entry points; ``compat``
+keeps the reference's function names and positional signatures.  All arithmetic runs in the
+hand-written sm_100a kernels behind the C ABI in ``include/tfcfft.h``.
+"""
+
+from . import compat, dist  # noqa: F401
+from .functional import (  # noqa: F401
+    SpectralConfig,
+    launch_count,
+    reset_launch_count,
+    spectral_loss,
+    spectral_loss_and_grad,
+    spectral_terms_per_image,
+)
+from .modules import SpectralLoss  # noqa: F401
+
+__all__ = [
+    "SpectralConfig", "SpectralLoss", "spectral_loss", "spectral_loss_and_grad", "spectral_terms_per_image",
+    "launch_count", "reset_launch_count", "compat", "dist",
+]

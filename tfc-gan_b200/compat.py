@@ -1,0 +1,122 @@
+"""Drop-in replacements that keep the reference's call signatures.
+
+The reference has no operator API: the FFT helpers are module-level functions copy-pasted into
+every training script, reading a global ``opt``.  These functions take the same
+positional arguments and return the same kind of value, but shapes come from the tensors and the
+work runs in the fused CUDA path -- with a gradient, which the reference lacks.
+
+Two modes (``set_mode``):
+
+* ``"r1"`` (default): differentiable.  Luma with Pillow's coefficients, no uint8 quantisation,
+  ``input_scale = 255`` so magnitudes are on the reference's 8-bit scale.
+* ``"r0"``: the reference as shipped -- uint8 wrap + integer luma (``...patchFFT_16P.py:300``), forward
+  only; the result carries no gradient, exactly like the reference's detached loss.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from .functional import SpectralConfig, spectral_loss, spectral_terms_per_image
+
+_MODE = {"mode": "r1", "input_scale": 255.0}
+
+
+def set_mode(mode: str = "r1", input_scale: float = 255.0) -> None:
+    if mode not in ("r0", "r1"):
+        raise ValueError("mode must be 'r0' or 'r1'")
+    _MODE["mode"], _MODE["input_scale"] = mode, float(input_scale)
+
+
+def _cfg(grid, patch_reduce="mean", weight=1.0):
+    if _MODE["mode"] == "r0":
+        return SpectralConfig(grid=grid, patch_reduce=patch_reduce, weight=weight, quantize=True)
+    return SpectralConfig(grid=grid, patch_reduce=patch_reduce, weight=weight, input_scale=_MODE["input_scale"])
+
+
+def make_16_patches(B):
+    """``make_16_patches`` (``TFC-GAN-FFT/TFCGAN_multigpu_patchFFT_16P.py:227-253``): 16 row-major
+    views ``B1..B16`` of side ``H/4`` (B1..B4 = top row, left to right)."""
+    p = B.shape[2] // 4
+    return tuple(B[:, :, y * p:(y + 1) * p, x * p:(x + 1) * p] for y in range(4) for x in range(4))
+
+
+def make_4_patches(B):
+    """The quadrant slicing of ``TFCGAN_multigpu_patchFFT.py:468-471`` (TL, TR, BL, BR)."""
+    p = B.shape[2] // 2
+    return tuple(B[:, :, y * p:(y + 1) * p, x * p:(x + 1) * p] for y in range(2) for x in range(2))
+
+
+def _common_base(patches, g):
+    """If ``patches`` are the row-major ``g x g`` tiling views of one NCHW tensor, return it."""
+    b = patches[0]._base if patches[0]._base is not None else None
+    if b is None or b.dim() != 4:
+        return None
+    p = patches[0].shape[-1]
+    if b.shape[2] != g * p or b.shape[3] != g * p or b.shape[:2] != patches[0].shape[:2]:
+        return None
+    for i, t in enumerate(patches):
+        y, x = divmod(i, g)
+        if t._base is not b or t.shape != patches[0].shape or t.stride() != b.stride():
+            return None
+        if t.storage_offset() != b.storage_offset() + y * p * b.stride(2) + x * p * b.stride(3):
+            return None
+    return b
+
+
+def _assemble(patches, g):
+    b = _common_base(patches, g)
+    if b is not None:
+        return b
+    rows = [torch.cat(list(patches[y * g:(y + 1) * g]), dim=-1) for y in range(g)]
+    return torch.cat(rows, dim=-2)
+
+
+def calculate_ffts(*patches):
+    """``calculate_ffts(fake_B1..fake_B16, B1..B16)`` (``...patchFFT_16P.py:323-375``) -> scalar
+    ``1/2 (1/16 sum L1(A) + 1/16 sum L1(P))``.  Views of a common tensor are routed to one fused
+    launch on that tensor; separately allocated patches are concatenated first."""
+    if len(patches) != 32:
+        raise TypeError(f"calculate_ffts expects 32 tensors, got {len(patches)}")
+    fake = _assemble(patches[:16], 4)
+    real = _assemble(patches[16:], 4)
+    return spectral_loss(fake, real, config=_cfg(4))
+
+
+def fft_loss(fake_B, B1, B2, B3, B4):
+    """``fft_loss`` (``TFCGAN_multigpu_patchFFT_experiment.py:317-339``): 4-patch loss with the patch
+    terms SUMMED; the real quadrants arrive as separate tensors from the loader
+    (``datasets_temp.py:76-118``)."""
+    real = _assemble((B1, B2, B3, B4), 2)
+    return spectral_loss(fake_B, real, config=_cfg(2, "sum"))
+
+
+def patch4_fft_loss(fake_B, B1, B2, B3, B4):
+    """The inline 4-patch block of ``TFCGAN_multigpu_patchFFT.py:498-511`` (patch terms averaged)."""
+    real = _assemble((B1, B2, B3, B4), 2)
+    return spectral_loss(fake_B, real, config=_cfg(2, "mean"))
+
+
+def global_fft_loss(fake_B, real_B):
+    """The inline global block of ``TFCGAN_multigpu_globalFFT.py:494-499``."""
+    return spectral_loss(fake_B, real_B, config=_cfg(1))
+
+
+def global_fourier_loss(BR, fake_B):
+    """``global_fourier_loss(BR, fake_B)`` (``TFC-STN/TFCGAN_STN21_Original_NewModel3_B2A.py:461-467``):
+    global loss times the 0.01 lambda; note the (real, fake) argument order."""
+    return spectral_loss(fake_B, BR, config=_cfg(1, weight=0.01))
+
+
+def mse_spec(real_gray, fake_gray, metric: str = "mse"):
+    """``mse_spec`` (``TFC-GAN-FFT/Devcom_MagMSE.py:91-118``; ``metric="mae"``:
+    ``eval/Eurecom/Eurecom_MagOther.py:90-117``) on uint8 grey images given as ``[N,H,W]`` /
+    ``[N,1,H,W]`` CUDA tensors.  Returns ``(values, mean)``: per-pair scores with the pairs whose log
+    spectrum is not finite dropped (the reference's ``except: continue``), and their mean."""
+    r = real_gray if real_gray.dim() == 4 else real_gray[:, None]
+    f = fake_gray if fake_gray.dim() == 4 else fake_gray[:, None]
+    cfg = SpectralConfig(grid=1, use_phase=False, distance="mse" if metric == "mse" else "l1",
+                         log_magnitude=True, spectrum="full")
+    per = spectral_terms_per_image(f, r, config=cfg)[:, 0]
+    values = per[torch.isfinite(per)]
+    return values, values.mean()

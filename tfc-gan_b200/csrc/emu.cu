@@ -1,0 +1,113 @@
+// emu.cu -- serial CPU execution of the kernels' own arithmetic (libtfcfft_emu.so).
+//
+// TEST INFRASTRUCTURE.  This is NOT a fallback: the product package never loads it.  It exists so
+// that the index arithmetic of the in-place digit-reversed FFT passes, the Hermitian un-mixing,
+// the bin ownership rules and the reduction layout -- the parts of spectral_core.cuh that are easy
+// to get subtly wrong -- can be checked against the oracle by the `-m "not gpu"` tests in a
+// container without a GPU.  It runs the same __host__ __device__ templates the sm_100a kernels
+// instantiate, with one serial "thread" (SerialCtx) instead of a thread block.
+#include <cstdlib>
+#include <vector>
+
+#include "host_common.h"
+
+using namespace tfcfft;
+
+namespace {
+
+template <int P, typename T, bool LUMA3>
+void run_resident(Params prm) {
+    SerialCtx ctx;
+    std::vector<float2> s((size_t)P * (P + 1)), tw(P);
+    fill_twiddles<P>(ctx, tw.data());
+    for (int tile = 0; tile < prm.tiles_total; ++tile) {
+        float a = 0.f, p = 0.f;
+        tile_process<P, T, LUMA3>(ctx, prm, tile, s.data(), tw.data(), a, p);
+        prm.partials[2 * tile] = a;
+        prm.partials[2 * tile + 1] = p;
+    }
+}
+
+template <int P, typename T, bool LUMA3>
+void run_split(Params prm) {
+    if constexpr (P >= 64) {
+        using Sp = Split<P>;
+        SerialCtx ctx;
+        std::vector<float2> s((size_t)P * (2 * Sp::GS + 1) + (size_t)Sp::RS * (P + 1)), tw(P);
+        fill_twiddles<P>(ctx, tw.data());
+        for (int base = 0; base < prm.tiles_total; base += prm.chunk_tiles) {
+            prm.tile_base = base;
+            const int nt = prm.tiles_total - base < prm.chunk_tiles ? prm.tiles_total - base : prm.chunk_tiles;
+            for (int lt = 0; lt < nt; ++lt)
+                for (int sl = 0; sl < Sp::ROW_SLABS; ++sl) split_rows_fwd<P, T, LUMA3>(ctx, prm, lt, sl, s.data(), tw.data());
+            for (int lt = 0; lt < nt; ++lt)
+                for (int pr = 0; pr < Sp::PARTS; ++pr) {
+                    float a = 0.f, p = 0.f;
+                    split_cols<P>(ctx, prm, lt, pr, s.data(), tw.data(), a, p);
+                    prm.partials[2 * ((size_t)(base + lt) * Sp::PARTS + pr)] = a;
+                    prm.partials[2 * ((size_t)(base + lt) * Sp::PARTS + pr) + 1] = p;
+                }
+            if (prm.grad)
+                for (int lt = 0; lt < nt; ++lt)
+                    for (int sl = 0; sl < Sp::ROW_SLABS; ++sl) split_rows_inv<P, T, LUMA3>(ctx, prm, lt, sl, s.data(), tw.data());
+        }
+    }
+}
+
+template <int P, typename T, bool LUMA3>
+void run(const Params& prm, bool split) {
+    if (split) run_split<P, T, LUMA3>(prm);
+    else if constexpr (P <= 128) run_resident<P, T, LUMA3>(prm);
+}
+
+template <int P, typename T>
+void run_l(const Params& prm, bool split, bool luma3) {
+    if (luma3) run<P, T, true>(prm, split);
+    else run<P, T, false>(prm, split);
+}
+
+template <int P>
+void run_t(const Params& prm, bool split, bool luma3, int dtype) {
+    switch (dtype) {
+        case TFCFFT_F32: run_l<P, float>(prm, split, luma3); break;
+        case TFCFFT_F16: run_l<P, __half>(prm, split, luma3); break;
+        case TFCFFT_BF16: run_l<P, __nv_bfloat16>(prm, split, luma3); break;
+        case TFCFFT_U8: run_l<P, uint8_t>(prm, split, luma3); break;
+    }
+}
+
+}  // namespace
+
+// Same contract as tfcfft_loss, but every pointer is HOST memory and no workspace is passed in.
+extern "C" int tfcfft_emulate(const tfcfft_desc* d, const void* fake, const void* real, float* out, float* per_image,
+                              void* grad_fake) {
+    Geometry g;
+    int rc = validate_desc(d, &g);
+    if (rc) return rc;
+    if (!fake || !real || !out) return TFCFFT_ERR_NULL;
+    if ((rc = check_grad_args(d, grad_fake))) return rc;
+    if ((rc = check_alignment(d, fake, real, grad_fake))) return rc;
+    std::vector<char> ws(g.ws_bytes, 0);
+    Params prm = make_params(d, g, fake, real, grad_fake, out, per_image, ws.data());
+    switch (g.p) {
+        case 16: run_t<16>(prm, g.split, g.luma3, d->dtype); break;
+        case 32: run_t<32>(prm, g.split, g.luma3, d->dtype); break;
+        case 64: run_t<64>(prm, g.split, g.luma3, d->dtype); break;
+        case 128: run_t<128>(prm, g.split, g.luma3, d->dtype); break;
+        case 256: run_t<256>(prm, g.split, g.luma3, d->dtype); break;
+        case 512: run_t<512>(prm, g.split, g.luma3, d->dtype); break;
+    }
+    double sa = 0.0, sp = 0.0;
+    for (int img = 0; img < prm.n; ++img) {
+        double a, p;
+        image_sums(prm, img, a, p);
+        if (per_image) {
+            per_image[2 * img] = (float)(a * prm.norm * prm.n);
+            per_image[2 * img + 1] = (float)(p * prm.norm * prm.n);
+        }
+        sa += a;
+        sp += p;
+    }
+    write_outputs(prm, sa, sp);
+    return TFCFFT_OK;
+}

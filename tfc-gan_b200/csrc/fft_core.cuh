@@ -1,0 +1,225 @@
+// fft_core.cuh -- register-level DFT butterflies and in-place shared-memory FFT passes.
+//
+// Everything here is __host__ __device__ so that the exact same index arithmetic and
+// floating-point sequence can be executed serially on the CPU by the emulation library
+// (csrc/emu.cu, used by the `-m "not gpu"` tests) and by the sm_100a kernels.
+//
+// Transform convention (matches np.fft / torch.fft, which the reference calls at
+// TFC-GAN-FFT/TFCGAN_multigpu_patchFFT_16P.py:278): forward X[k] = sum_n x[n] e^{-2 pi i k n / P},
+// unnormalised; the inverse here is the unnormalised adjoint (e^{+...}, no 1/P).
+//
+// A P-point line is transformed in place by 2 or 3 decimation-in-frequency passes with
+// radices (R1, R2, R3).  The forward transform leaves the spectrum in digit-reversed
+// POSITION order; the inverse (decimation in time, passes in reverse order) consumes exactly
+// that order and returns natural order, so no reordering pass is ever needed:
+//     position q = k1*(R2*R3) + k2*R3 + k3   <->   frequency k = k1 + R1*k2 + R1*R2*k3.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <cuda_runtime.h>
+
+#define TFC_HD __host__ __device__ __forceinline__
+
+namespace tfcfft {
+
+// cos / sin of 2*pi*k/32 -- the only butterfly constants radices <= 32 need.
+constexpr float kCos32[32] = {
+    1.f, 0.98078528f, 0.923879533f, 0.831469612f, 0.707106781f, 0.555570233f, 0.382683432f, 0.195090322f,
+    0.f, -0.195090322f, -0.382683432f, -0.555570233f, -0.707106781f, -0.831469612f, -0.923879533f, -0.98078528f,
+    -1.f, -0.98078528f, -0.923879533f, -0.831469612f, -0.707106781f, -0.555570233f, -0.382683432f, -0.195090322f,
+    0.f, 0.195090322f, 0.382683432f, 0.555570233f, 0.707106781f, 0.831469612f, 0.923879533f, 0.98078528f};
+constexpr float kSin32[32] = {
+    0.f, 0.195090322f, 0.382683432f, 0.555570233f, 0.707106781f, 0.831469612f, 0.923879533f, 0.98078528f,
+    1.f, 0.98078528f, 0.923879533f, 0.831469612f, 0.707106781f, 0.555570233f, 0.382683432f, 0.195090322f,
+    0.f, -0.195090322f, -0.382683432f, -0.555570233f, -0.707106781f, -0.831469612f, -0.923879533f, -0.98078528f,
+    -1.f, -0.98078528f, -0.923879533f, -0.831469612f, -0.707106781f, -0.555570233f, -0.382683432f, -0.195090322f};
+
+TFC_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+TFC_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// a * w
+TFC_HD float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
+// a * conj(w)
+TFC_HD float2 cmulc(float2 a, float2 w) { return make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y); }
+
+// a * W_R^K with W_R = e^{-2 pi i / R} (INV: e^{+2 pi i / R}); trivial factors cost no multiplies.
+template <int R, int K, bool INV>
+TFC_HD float2 mul_w(float2 a) {
+    constexpr int k32 = (K * (32 / R)) % 32;
+    constexpr float c8 = 0.707106781186547524f;
+    if constexpr (k32 == 0) {
+        return a;
+    } else if constexpr (k32 == 8) {  // -i (fwd) / +i (inv)
+        return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+    } else if constexpr (k32 == 16) {
+        return make_float2(-a.x, -a.y);
+    } else if constexpr (k32 == 24) {
+        return INV ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+    } else if constexpr (k32 == 4) {  // (1 -+ i)/sqrt2
+        return INV ? make_float2((a.x - a.y) * c8, (a.x + a.y) * c8) : make_float2((a.x + a.y) * c8, (a.y - a.x) * c8);
+    } else if constexpr (k32 == 12) {  // (-1 -+ i)/sqrt2
+        return INV ? make_float2(-(a.x + a.y) * c8, (a.x - a.y) * c8) : make_float2((a.y - a.x) * c8, -(a.x + a.y) * c8);
+    } else {
+        constexpr float wr = kCos32[k32];
+        constexpr float wi = INV ? kSin32[k32] : -kSin32[k32];
+        return make_float2(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
+    }
+}
+
+template <int R, bool INV, int K>
+TFC_HD void dft_combine(float2* v, const float2* e, const float2* o) {
+    if constexpr (K < R / 2) {
+        const float2 t = mul_w<R, K, INV>(o[K]);
+        v[K] = cadd(e[K], t);
+        v[K + R / 2] = csub(e[K], t);
+        dft_combine<R, INV, K + 1>(v, e, o);
+    }
+}
+
+// In-register R-point DFT, natural order in and out (R in {1,2,4,8,16,32}).
+template <int R, bool INV>
+struct Dft {
+    TFC_HD static void run(float2* v) {
+        float2 e[R / 2], o[R / 2];
+#pragma unroll
+        for (int k = 0; k < R / 2; ++k) {
+            e[k] = v[2 * k];
+            o[k] = v[2 * k + 1];
+        }
+        Dft<R / 2, INV>::run(e);
+        Dft<R / 2, INV>::run(o);
+        dft_combine<R, INV, 0>(v, e, o);
+    }
+};
+template <bool INV>
+struct Dft<1, INV> {
+    TFC_HD static void run(float2*) {}
+};
+
+// Radix plan per line length.
+template <int P> struct Plan;
+template <> struct Plan<16>  { static constexpr int R1 = 4,  R2 = 4,  R3 = 1; };
+template <> struct Plan<32>  { static constexpr int R1 = 8,  R2 = 4,  R3 = 1; };
+template <> struct Plan<64>  { static constexpr int R1 = 8,  R2 = 8,  R3 = 1; };
+template <> struct Plan<128> { static constexpr int R1 = 16, R2 = 8,  R3 = 1; };
+template <> struct Plan<256> { static constexpr int R1 = 16, R2 = 16, R3 = 1; };
+template <> struct Plan<512> { static constexpr int R1 = 8,  R2 = 8,  R3 = 8; };
+
+template <int P>
+TFC_HD int freq_of_pos(int q) {
+    using Pl = Plan<P>;
+    const int k1 = q / (Pl::R2 * Pl::R3), rem = q % (Pl::R2 * Pl::R3);
+    const int k2 = rem / Pl::R3, k3 = rem % Pl::R3;
+    return k1 + Pl::R1 * k2 + Pl::R1 * Pl::R2 * k3;
+}
+template <int P>
+TFC_HD int pos_of_freq(int k) {
+    using Pl = Plan<P>;
+    const int k1 = k % Pl::R1, k2 = (k / Pl::R1) % Pl::R2, k3 = k / (Pl::R1 * Pl::R2);
+    return k1 * (Pl::R2 * Pl::R3) + k2 * Pl::R3 + k3;
+}
+// position of the frequency -k (mod P)
+template <int P>
+TFC_HD int neg_pos(int q) { return pos_of_freq<P>((P - freq_of_pos<P>(q)) & (P - 1)); }
+
+// Execution context: the kernels pass {threadIdx, blockDim, __syncthreads}; the CPU emulation
+// passes a single serial "thread".
+struct SerialCtx {
+    int tid = 0, nthreads = 1;
+    TFC_HD void sync() const {}
+};
+#ifdef __CUDACC__
+struct BlockCtx {
+    int tid, nthreads;
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+#endif
+
+// One radix-R pass over `1 << log2_lines` independent P-point lines held in memory `s`:
+// element e of line l lives at s[l*ls + e*es].  L is the current DIF block length.
+// tw[t] = e^{-2 pi i t / P}, t in [0, P).
+template <int P, int R, int L, bool INV, class Ctx>
+TFC_HD void fft_pass(const Ctx& ctx, float2* s, int es, int ls, int log2_lines, const float2* tw) {
+    constexpr int M = L / R;    // distance between butterfly legs (in elements)
+    constexpr int JT = P / R;   // butterflies per line
+    const int ntask = JT << log2_lines;
+    const int lmask = (1 << log2_lines) - 1;
+    for (int t = ctx.tid; t < ntask; t += ctx.nthreads) {
+        const int line = t & lmask, jj = t >> log2_lines;
+        const int blk = jj / M, j = jj % M;
+        float2* base = s + line * ls + (blk * L + j) * es;
+        float2 v[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = base[m * M * es];
+        if constexpr (!INV) {
+            Dft<R, false>::run(v);
+            if constexpr (M > 1) {
+#pragma unroll
+                for (int k = 1; k < R; ++k) v[k] = cmul(v[k], tw[(P / L) * j * k]);
+            }
+        } else {
+            if constexpr (M > 1) {
+#pragma unroll
+                for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], tw[(P / L) * j * k]);
+            }
+            Dft<R, true>::run(v);
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) base[k * M * es] = v[k];
+    }
+}
+
+// All passes of a batch of lines, each followed by a barrier.
+template <int P, bool INV, class Ctx>
+TFC_HD void fft_lines(const Ctx& ctx, float2* s, int es, int ls, int log2_lines, const float2* tw) {
+    using Pl = Plan<P>;
+    constexpr int L2 = P / Pl::R1, L3 = P / (Pl::R1 * Pl::R2);
+    if constexpr (!INV) {
+        fft_pass<P, Pl::R1, P, false>(ctx, s, es, ls, log2_lines, tw);
+        ctx.sync();
+        if constexpr (Pl::R2 > 1) {
+            fft_pass<P, Pl::R2, L2, false>(ctx, s, es, ls, log2_lines, tw);
+            ctx.sync();
+        }
+        if constexpr (Pl::R3 > 1) {
+            fft_pass<P, Pl::R3, L3, false>(ctx, s, es, ls, log2_lines, tw);
+            ctx.sync();
+        }
+    } else {
+        if constexpr (Pl::R3 > 1) {
+            fft_pass<P, Pl::R3, L3, true>(ctx, s, es, ls, log2_lines, tw);
+            ctx.sync();
+        }
+        if constexpr (Pl::R2 > 1) {
+            fft_pass<P, Pl::R2, L2, true>(ctx, s, es, ls, log2_lines, tw);
+            ctx.sync();
+        }
+        fft_pass<P, Pl::R1, P, true>(ctx, s, es, ls, log2_lines, tw);
+        ctx.sync();
+    }
+}
+
+// tw[t] = (cos 2 pi t / P, -sin 2 pi t / P)
+template <int P, class Ctx>
+TFC_HD void fill_twiddles(const Ctx& ctx, float2* tw) {
+    for (int t = ctx.tid; t < P; t += ctx.nthreads) {
+        float sn, cs;
+#ifdef __CUDA_ARCH__
+        sincospif(2.0f * (float)t / (float)P, &sn, &cs);
+#else
+        const double a = 2.0 * 3.14159265358979323846 * (double)t / (double)P;
+        sn = (float)sin(a);
+        cs = (float)cos(a);
+#endif
+        tw[t] = make_float2(cs, -sn);
+    }
+}
+
+constexpr __host__ __device__ int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
+
+TFC_HD int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
+}  // namespace tfcfft

@@ -1,0 +1,170 @@
+// host_common.h -- argument validation, workspace layout and Params construction shared by the
+// C-ABI library (tfcfft_api.cu) and the CPU emulation library (emu.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include "spectral_core.cuh"
+
+namespace tfcfft {
+
+constexpr size_t kWsHeader = 256;                      // ticket counter, padded
+constexpr size_t kWsChunkBytes = size_t(48) << 20;     // split path: spectrum workspace per chunk
+
+inline size_t elem_size(int dtype) {
+    switch (dtype) {
+        case TFCFFT_F32: return 4;
+        case TFCFFT_F16: case TFCFFT_BF16: return 2;
+        case TFCFFT_U8: return 1;
+        default: return 0;
+    }
+}
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Geometry {
+    int p;            // patch side
+    int cprime;       // spectra per tile position
+    bool luma3;       // 3 channels folded to luma
+    bool split;       // split path (P >= 256 or forced)
+    int parts;        // partial sums per tile
+    long long tiles_total;
+    long long chunk_tiles;
+    size_t partial_bytes, ws_bytes;
+};
+
+inline int split_parts(int p) {
+    switch (p) {
+        case 64: return Split<64>::PARTS;
+        case 128: return Split<128>::PARTS;
+        case 256: return Split<256>::PARTS;
+        case 512: return Split<512>::PARTS;
+        default: return 1;
+    }
+}
+
+inline int validate_desc(const tfcfft_desc* d, Geometry* geo) {
+    if (!d) return TFCFFT_ERR_NULL;
+    if (d->struct_size != sizeof(tfcfft_desc)) return TFCFFT_ERR_STRUCT;
+    if (elem_size(d->dtype) == 0) return TFCFFT_ERR_DTYPE;
+    if (d->n == 0) return TFCFFT_ERR_EMPTY;
+    if (d->n < 0 || d->n > (1 << 24)) return TFCFFT_ERR_SHAPE;
+    if (d->c != 1 && d->c != 3) return TFCFFT_ERR_SHAPE;
+    if (d->h != d->w || d->h <= 0 || d->grid <= 0 || d->h % d->grid) return TFCFFT_ERR_SHAPE;
+    const long long p = d->h / d->grid;
+    if (p != 16 && p != 32 && p != 64 && p != 128 && p != 256 && p != 512) return TFCFFT_ERR_SHAPE;
+    const unsigned known = TFCFFT_CHANNELS_RGB | TFCFFT_NO_PHASE | TFCFFT_DIST_MSE | TFCFFT_PATCH_SUM |
+                           TFCFFT_LOG_MAGNITUDE | TFCFFT_FULL_SPECTRUM | TFCFFT_QUANTIZE_U8 | TFCFFT_FORCE_SPLIT;
+    if (d->flags & ~known) return TFCFFT_ERR_FLAGS;
+    // the reference quantises to a single grey channel; a per-channel quantised variant does not exist
+    if ((d->flags & TFCFFT_QUANTIZE_U8) && (d->flags & TFCFFT_CHANNELS_RGB) && d->c == 3) return TFCFFT_ERR_FLAGS;
+    if ((d->flags & TFCFFT_FORCE_SPLIT) && p < 64) return TFCFFT_ERR_FLAGS;
+    for (int t = 0; t < 2; ++t) {
+        const int64_t* st = t ? d->real_stride : d->fake_stride;
+        if (st[3] != 1) return TFCFFT_ERR_STRIDE;
+        for (int i = 0; i < 3; ++i)
+            if (st[i] % 4 != 0 || st[i] < 0) return TFCFFT_ERR_STRIDE;
+    }
+    if (geo) {
+        geo->p = (int)p;
+        geo->luma3 = (d->c == 3) && !(d->flags & TFCFFT_CHANNELS_RGB);
+        geo->cprime = (d->c == 3 && !geo->luma3) ? 3 : 1;
+        geo->split = (p >= 256) || (d->flags & TFCFFT_FORCE_SPLIT);
+        geo->parts = geo->split ? split_parts((int)p) : 1;
+        geo->tiles_total = (long long)d->n * geo->cprime * d->grid * d->grid;
+        geo->partial_bytes = align_up((size_t)geo->tiles_total * geo->parts * 2 * sizeof(float), 256);
+        geo->chunk_tiles = 0;
+        size_t z = 0;
+        if (geo->split) {
+            const size_t per_tile = (size_t)p * p * sizeof(float2);
+            long long ct = (long long)(kWsChunkBytes / per_tile);
+            if (ct < 1) ct = 1;
+            if (ct > geo->tiles_total) ct = geo->tiles_total;
+            geo->chunk_tiles = ct;
+            z = (size_t)ct * per_tile;
+        }
+        geo->ws_bytes = kWsHeader + geo->partial_bytes + z;
+    }
+    return TFCFFT_OK;
+}
+
+inline int check_grad_args(const tfcfft_desc* d, const void* grad) {
+    if (!grad) return TFCFFT_OK;
+    if ((d->flags & TFCFFT_QUANTIZE_U8) || d->dtype == TFCFFT_U8) return TFCFFT_ERR_NO_GRADIENT;
+    if (d->grad_stride[3] != 1) return TFCFFT_ERR_STRIDE;
+    for (int i = 0; i < 3; ++i)
+        if (d->grad_stride[i] % 4 != 0 || d->grad_stride[i] < 0) return TFCFFT_ERR_STRIDE;
+    return TFCFFT_OK;
+}
+
+inline int check_alignment(const tfcfft_desc* d, const void* fake, const void* real, const void* grad) {
+    const uintptr_t a = 4 * elem_size(d->dtype);
+    if ((uintptr_t)fake % a || (uintptr_t)real % a || (grad && (uintptr_t)grad % a)) return TFCFFT_ERR_ALIGNMENT;
+    return TFCFFT_OK;
+}
+
+// Pillow's convert("L") coefficients as exact binary fractions (oracle/r1_differentiable.py LUMA_WEIGHTS)
+constexpr float kLuma[3] = {19595.0f / 65536.0f, 38470.0f / 65536.0f, 7471.0f / 65536.0f};
+
+inline Params make_params(const tfcfft_desc* d, const Geometry& g, const void* fake, const void* real, void* grad,
+                          float* out, float* per_image, void* ws) {
+    Params p{};
+    p.fake = fake;
+    p.real = real;
+    p.grad = grad;
+    for (int i = 0; i < 4; ++i) {
+        p.fs[i] = d->fake_stride[i];
+        p.rs[i] = d->real_stride[i];
+        p.gs[i] = grad ? d->grad_stride[i] : 0;
+    }
+    p.n = (int)d->n; p.c = (int)d->c; p.h = (int)d->h; p.w = (int)d->w;
+    p.grid = d->grid;
+    p.p = g.p;
+    p.cprime = g.cprime;
+    p.tiles_per_image = g.cprime * d->grid * d->grid;
+    p.tiles_total = (int)g.tiles_total;
+    p.flags = d->flags;
+    const float sc = (d->flags & TFCFFT_QUANTIZE_U8) ? 1.0f : d->input_scale;
+    for (int i = 0; i < 3; ++i) {
+        p.lw[i] = g.luma3 ? kLuma[i] * sc : sc;
+        p.gw[i] = p.lw[i];
+    }
+    const double kbins = (d->flags & TFCFFT_FULL_SPECTRUM) ? (double)g.p * g.p : (double)g.p * (g.p / 2 + 1);
+    const double red = (d->flags & TFCFFT_PATCH_SUM) ? (double)d->grid * d->grid : 1.0;
+    p.norm = red / ((double)d->n * g.cprime * d->grid * d->grid * kbins);
+    p.weight = d->weight;
+    if (d->flags & TFCFFT_NO_PHASE) {
+        p.sa = (float)((double)d->weight * p.norm);
+        p.sp = 0.f;
+    } else {
+        p.sa = p.sp = (float)(0.5 * (double)d->weight * p.norm);
+    }
+    char* w = reinterpret_cast<char*>(ws);
+    p.counter = reinterpret_cast<unsigned*>(w);
+    p.partials = reinterpret_cast<float*>(w + kWsHeader);
+    p.parts = g.parts;
+    p.out = out;
+    p.per_image = per_image;
+    p.zws = g.split ? reinterpret_cast<float2*>(w + kWsHeader + g.partial_bytes) : nullptr;
+    p.tile_base = 0;
+    p.chunk_tiles = (int)g.chunk_tiles;
+    return p;
+}
+
+inline const char* status_string(int rc) {
+    switch (rc) {
+        case TFCFFT_OK: return "ok";
+        case TFCFFT_ERR_NULL: return "tfcfft: null descriptor or required pointer";
+        case TFCFFT_ERR_STRUCT: return "tfcfft: descriptor struct_size mismatch (ABI version skew)";
+        case TFCFFT_ERR_DTYPE: return "tfcfft: unsupported dtype (f32, f16, bf16, u8)";
+        case TFCFFT_ERR_SHAPE: return "tfcfft: unsupported shape (need C in {1,3}, H == W, H % grid == 0, patch side in {16,32,64,128,256,512})";
+        case TFCFFT_ERR_STRIDE: return "tfcfft: unsupported strides (innermost must be 1, outer strides multiples of 4 elements)";
+        case TFCFFT_ERR_ALIGNMENT: return "tfcfft: base pointer not aligned to 4 elements";
+        case TFCFFT_ERR_FLAGS: return "tfcfft: unsupported flag combination";
+        case TFCFFT_ERR_WORKSPACE: return "tfcfft: workspace null, misaligned or too small";
+        case TFCFFT_ERR_NO_GRADIENT: return "tfcfft: no gradient exists for quantised (uint8) inputs";
+        case TFCFFT_ERR_EMPTY: return "tfcfft: empty batch (N == 0)";
+        default: return nullptr;
+    }
+}
+
+}  // namespace tfcfft

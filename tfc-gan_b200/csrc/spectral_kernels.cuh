@@ -1,0 +1,187 @@
+// spectral_kernels.cuh -- sm_100a kernels of the generic (all sizes, all modes) path.
+//
+//   resident_kernel      P <= 128: persistent CTAs, one complex tile resident in shared memory:
+//                        load+luma+pack -> row FFT -> column FFT -> loss + spectral gradient ->
+//                        inverse column FFT -> inverse row FFT -> gradient store.
+//   split_rows_fwd / split_cols / split_rows_inv
+//                        P >= 256 (tile does not fit one CTA's shared memory): the row and column
+//                        transforms run in separate launches that exchange the complex spectrum
+//                        through an L2-sized workspace chunk.
+//   grad_scale_kernel    dst = src * scale (autograd's multiplication by grad_output).
+//
+// Roofline / algorithmic bytes are documented in DESIGN.md.
+#pragma once
+#include "spectral_core.cuh"
+
+namespace tfcfft {
+
+template <int P> struct ResidentCfg {
+    static constexpr int NT = P <= 16 ? 64 : P <= 32 ? 128 : P <= 64 ? 256 : 512;
+    static constexpr size_t SMEM = ((size_t)P * (P + 1) + P) * sizeof(float2);
+};
+template <int P> struct SplitCfg {
+    static constexpr int NT = 256;
+    static constexpr size_t SMEM_ROWS = ((size_t)Split<P>::RS * (P + 1) + P) * sizeof(float2);
+    static constexpr size_t SMEM_COLS = ((size_t)P * (2 * Split<P>::GS + 1) + P) * sizeof(float2);
+};
+
+// Block sum of two floats; result valid in thread 0.  Fixed shape -> deterministic.
+__device__ __forceinline__ void block_sum2(float& a, float& b) {
+    __shared__ float red[2][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+        red[0][wid] = a;
+        red[1][wid] = b;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        a = lane < nw ? red[0][lane] : 0.f;
+        b = lane < nw ? red[1][lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, o);
+            b += __shfl_down_sync(0xffffffffu, b, o);
+        }
+    }
+    __syncthreads();
+}
+
+// Last block to arrive sums all partials in a fixed order (double) and writes the outputs;
+// the ticket counter is left at zero for the next call.
+__device__ __forceinline__ void finish(const Params& prm, unsigned total_blocks) {
+    __shared__ bool last;
+    __shared__ double dred[2][32];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(prm.counter, 1u) == total_blocks - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double a = 0.0, p = 0.0;
+    const double img_norm = prm.norm * (double)prm.n;
+    for (int img = threadIdx.x; img < prm.n; img += blockDim.x) {
+        const float* q = prm.partials + (long long)img * prm.tiles_per_image * prm.parts * 2;
+        double ia = 0.0, ip = 0.0;
+        for (int i = 0; i < prm.tiles_per_image * prm.parts; ++i) {
+            ia += (double)__ldcg(q + 2 * i);
+            ip += (double)__ldcg(q + 2 * i + 1);
+        }
+        if (prm.per_image) {
+            prm.per_image[2 * img] = (float)(ia * img_norm);
+            prm.per_image[2 * img + 1] = (float)(ip * img_norm);
+        }
+        a += ia;
+        p += ip;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        p += __shfl_down_sync(0xffffffffu, p, o);
+    }
+    if (lane == 0) {
+        dred[0][wid] = a;
+        dred[1][wid] = p;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = 0.0;
+        p = 0.0;
+        for (int w = 0; w < nw; ++w) {
+            a += dred[0][w];
+            p += dred[1][w];
+        }
+        write_outputs(prm, a, p);
+        *prm.counter = 0u;
+    }
+}
+
+template <int P, typename T, bool LUMA3>
+__global__ void __launch_bounds__(ResidentCfg<P>::NT) resident_kernel(const __grid_constant__ Params prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    float2* tw = s + P * (P + 1);
+    const BlockCtx ctx{(int)threadIdx.x, (int)blockDim.x};
+    fill_twiddles<P>(ctx, tw);
+    ctx.sync();
+    for (int tile = blockIdx.x; tile < prm.tiles_total; tile += gridDim.x) {
+        float a = 0.f, p = 0.f;
+        tile_process<P, T, LUMA3>(ctx, prm, tile, s, tw, a, p);
+        block_sum2(a, p);
+        if (threadIdx.x == 0) {
+            prm.partials[2 * tile] = a;
+            prm.partials[2 * tile + 1] = p;
+        }
+    }
+    finish(prm, gridDim.x);
+}
+
+template <int P, typename T, bool LUMA3>
+__global__ void __launch_bounds__(SplitCfg<P>::NT) split_rows_fwd_kernel(const __grid_constant__ Params prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    float2* tw = s + Split<P>::RS * (P + 1);
+    const BlockCtx ctx{(int)threadIdx.x, (int)blockDim.x};
+    fill_twiddles<P>(ctx, tw);
+    ctx.sync();
+    split_rows_fwd<P, T, LUMA3>(ctx, prm, blockIdx.x / Split<P>::ROW_SLABS, blockIdx.x % Split<P>::ROW_SLABS, s, tw);
+}
+
+template <int P>
+__global__ void __launch_bounds__(SplitCfg<P>::NT) split_cols_kernel(const __grid_constant__ Params prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    float2* tw = s + P * (2 * Split<P>::GS + 1);
+    const BlockCtx ctx{(int)threadIdx.x, (int)blockDim.x};
+    fill_twiddles<P>(ctx, tw);
+    ctx.sync();
+    const int lt = blockIdx.x / Split<P>::PARTS, pair = blockIdx.x % Split<P>::PARTS;
+    float a = 0.f, p = 0.f;
+    split_cols<P>(ctx, prm, lt, pair, s, tw, a, p);
+    block_sum2(a, p);
+    if (threadIdx.x == 0) {
+        const long long slot = (long long)(prm.tile_base + lt) * Split<P>::PARTS + pair;
+        prm.partials[2 * slot] = a;
+        prm.partials[2 * slot + 1] = p;
+    }
+    finish(prm, (unsigned)prm.tiles_total * Split<P>::PARTS);  // ticket runs across all chunks
+}
+
+template <int P, typename T, bool LUMA3>
+__global__ void __launch_bounds__(SplitCfg<P>::NT) split_rows_inv_kernel(const __grid_constant__ Params prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    float2* tw = s + Split<P>::RS * (P + 1);
+    const BlockCtx ctx{(int)threadIdx.x, (int)blockDim.x};
+    fill_twiddles<P>(ctx, tw);
+    ctx.sync();
+    split_rows_inv<P, T, LUMA3>(ctx, prm, blockIdx.x / Split<P>::ROW_SLABS, blockIdx.x % Split<P>::ROW_SLABS, s, tw);
+}
+
+// dst = src * host_scale * (*dev_scale); 16-byte vectors, grid-stride.
+template <typename T>
+__global__ void __launch_bounds__(256) grad_scale_kernel(T* __restrict__ dst, const T* __restrict__ src, long long numel,
+                                                         const float* __restrict__ dev_scale, float host_scale) {
+    const float sc = host_scale * (dev_scale ? __ldg(dev_scale) : 1.0f);
+    constexpr int V = 16 / sizeof(T);
+    const long long nvec = numel / V;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        uint4 raw = reinterpret_cast<const uint4*>(src)[i];
+        T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+        for (int k = 0; k < V; ++k) e[k] = (T)((float)e[k] * sc);
+        reinterpret_cast<uint4*>(dst)[i] = raw;
+    }
+    for (long long i = nvec * V + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride)
+        dst[i] = (T)((float)src[i] * sc);
+}
+
+}  // namespace tfcfft

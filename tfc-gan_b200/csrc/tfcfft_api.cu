@@ -1,0 +1,198 @@
+// tfcfft_api.cu -- the C-ABI entry points of libtfcfft.so (include/tfcfft.h).
+//
+// Host side only validates, builds the kernel parameter block and enqueues launches on the
+// caller's stream.  No device allocation, no host synchronisation, no fallback of any kind.
+#include <atomic>
+#include <cstdio>
+
+#include "host_common.h"
+#include "spectral_kernels.cuh"
+
+using namespace tfcfft;
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+
+struct DeviceInfo {
+    int sms = 0;
+};
+DeviceInfo device_info() {
+    // queried per call: cheap (cached by the runtime) and keeps the library free of global state
+    DeviceInfo di;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev);
+    return di;
+}
+
+#define TFC_LAUNCH_CHECK()                       \
+    do {                                         \
+        cudaError_t e__ = cudaGetLastError();    \
+        if (e__ != cudaSuccess) return (int)e__; \
+    } while (0)
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+
+template <int P, typename T, bool LUMA3>
+int launch_resident(const Params& prm, cudaStream_t st) {
+    auto kernel = resident_kernel<P, T, LUMA3>;
+    constexpr size_t smem = ResidentCfg<P>::SMEM;
+    constexpr int nt = ResidentCfg<P>::NT;
+    if (int rc = set_smem(kernel, smem)) return rc;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    const long long cap = (long long)device_info().sms * per_sm;  // persistent: one wave
+    const int grid = (int)(prm.tiles_total < cap ? prm.tiles_total : cap);
+    kernel<<<grid, nt, smem, st>>>(prm);
+    g_launches++;
+    TFC_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int P, typename T, bool LUMA3>
+int launch_split(Params prm, cudaStream_t st) {
+    if constexpr (P >= 64) {
+        using Sp = Split<P>;
+        auto k1 = split_rows_fwd_kernel<P, T, LUMA3>;
+        auto k2 = split_cols_kernel<P>;
+        auto k3 = split_rows_inv_kernel<P, T, LUMA3>;
+        if (int rc = set_smem(k1, SplitCfg<P>::SMEM_ROWS)) return rc;
+        if (int rc = set_smem(k2, SplitCfg<P>::SMEM_COLS)) return rc;
+        if (int rc = set_smem(k3, SplitCfg<P>::SMEM_ROWS)) return rc;
+        for (int base = 0; base < prm.tiles_total; base += prm.chunk_tiles) {
+            prm.tile_base = base;
+            const int nt = prm.tiles_total - base < prm.chunk_tiles ? prm.tiles_total - base : prm.chunk_tiles;
+            k1<<<nt * Sp::ROW_SLABS, SplitCfg<P>::NT, SplitCfg<P>::SMEM_ROWS, st>>>(prm);
+            g_launches++;
+            TFC_LAUNCH_CHECK();
+            k2<<<nt * Sp::PARTS, SplitCfg<P>::NT, SplitCfg<P>::SMEM_COLS, st>>>(prm);
+            g_launches++;
+            TFC_LAUNCH_CHECK();
+            if (prm.grad) {
+                k3<<<nt * Sp::ROW_SLABS, SplitCfg<P>::NT, SplitCfg<P>::SMEM_ROWS, st>>>(prm);
+                g_launches++;
+                TFC_LAUNCH_CHECK();
+            }
+        }
+        return 0;
+    } else {
+        return TFCFFT_ERR_SHAPE;
+    }
+}
+
+template <int P, typename T, bool LUMA3>
+int launch(const Params& prm, bool split, cudaStream_t st) {
+    if (split) return launch_split<P, T, LUMA3>(prm, st);
+    if constexpr (P <= 128) {
+        return launch_resident<P, T, LUMA3>(prm, st);
+    } else {
+        return TFCFFT_ERR_SHAPE;
+    }
+}
+
+template <int P, typename T>
+int launch_l(const Params& prm, bool split, bool luma3, cudaStream_t st) {
+    return luma3 ? launch<P, T, true>(prm, split, st) : launch<P, T, false>(prm, split, st);
+}
+
+template <int P>
+int launch_t(const Params& prm, bool split, bool luma3, int dtype, cudaStream_t st) {
+    switch (dtype) {
+        case TFCFFT_F32: return launch_l<P, float>(prm, split, luma3, st);
+        case TFCFFT_F16: return launch_l<P, __half>(prm, split, luma3, st);
+        case TFCFFT_BF16: return launch_l<P, __nv_bfloat16>(prm, split, luma3, st);
+        case TFCFFT_U8: return launch_l<P, uint8_t>(prm, split, luma3, st);
+    }
+    return TFCFFT_ERR_DTYPE;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tfcfft_version(void) { return TFCFFT_VERSION; }
+
+const char* tfcfft_strerror(int rc) {
+    if (rc > 0) return cudaGetErrorString((cudaError_t)rc);
+    const char* s = status_string(rc);
+    return s ? s : "tfcfft: unknown status";
+}
+
+int tfcfft_validate(const tfcfft_desc* d) { return validate_desc(d, nullptr); }
+
+size_t tfcfft_workspace_bytes(const tfcfft_desc* d) {
+    Geometry g;
+    if (validate_desc(d, &g) != TFCFFT_OK) return 0;
+    return g.ws_bytes;
+}
+
+int tfcfft_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
+    if (!workspace || workspace_bytes < kWsHeader || ((uintptr_t)workspace & 255)) return TFCFFT_ERR_WORKSPACE;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, kWsHeader, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+int tfcfft_loss(const tfcfft_desc* d, const void* fake, const void* real, float* out, float* per_image, void* grad_fake,
+                void* workspace, size_t workspace_bytes, void* stream) {
+    Geometry g;
+    int rc = validate_desc(d, &g);
+    if (rc) return rc;
+    if (!fake || !real || !out) return TFCFFT_ERR_NULL;
+    if ((rc = check_grad_args(d, grad_fake))) return rc;
+    if ((rc = check_alignment(d, fake, real, grad_fake))) return rc;
+    if (!workspace || workspace_bytes < g.ws_bytes || ((uintptr_t)workspace & 255)) return TFCFFT_ERR_WORKSPACE;
+    const Params prm = make_params(d, g, fake, real, grad_fake, out, per_image, workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (g.p) {
+        case 16: return launch_t<16>(prm, g.split, g.luma3, d->dtype, st);
+        case 32: return launch_t<32>(prm, g.split, g.luma3, d->dtype, st);
+        case 64: return launch_t<64>(prm, g.split, g.luma3, d->dtype, st);
+        case 128: return launch_t<128>(prm, g.split, g.luma3, d->dtype, st);
+        case 256: return launch_t<256>(prm, g.split, g.luma3, d->dtype, st);
+        case 512: return launch_t<512>(prm, g.split, g.luma3, d->dtype, st);
+    }
+    return TFCFFT_ERR_SHAPE;
+}
+
+int tfcfft_grad_scale(void* dst, const void* src, int32_t dtype, int64_t numel, const float* dev_scale, float host_scale,
+                      void* stream) {
+    if (!dst || !src) return TFCFFT_ERR_NULL;
+    if (numel <= 0) return numel == 0 ? 0 : TFCFFT_ERR_SHAPE;
+    if (((uintptr_t)dst & 15) || ((uintptr_t)src & 15)) return TFCFFT_ERR_ALIGNMENT;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t es = elem_size(dtype);
+    if (es == 0 || dtype == TFCFFT_U8) return TFCFFT_ERR_DTYPE;
+    const long long nvec = numel / (16 / (long long)es) + 1;
+    long long blocks = (nvec + 255) / 256;
+    const long long cap = (long long)device_info().sms * 16;
+    if (blocks > cap) blocks = cap;
+    switch (dtype) {
+        case TFCFFT_F32:
+            grad_scale_kernel<float><<<(int)blocks, 256, 0, st>>>((float*)dst, (const float*)src, numel, dev_scale, host_scale);
+            break;
+        case TFCFFT_F16:
+            grad_scale_kernel<__half><<<(int)blocks, 256, 0, st>>>((__half*)dst, (const __half*)src, numel, dev_scale, host_scale);
+            break;
+        case TFCFFT_BF16:
+            grad_scale_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)src, numel, dev_scale, host_scale);
+            break;
+    }
+    g_launches++;
+    TFC_LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t tfcfft_launch_count(void) { return g_launches.load(); }
+void tfcfft_launch_count_reset(void) { g_launches.store(0); }
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+"""``torch.autograd.Function`` over the C-ABI library: the differentiable FFT loss.
+
+Replaces, on the GPU and with a gradient, the reference's per-sample CPU detour
+``fft_components`` / ``calculate_ffts`` (``TFC-GAN-FFT/TFCGAN_multigpu_patchFFT_16P.py:271-375``),
+the 4-patch and global variants (``TFCGAN_multigpu_patchFFT.py:498-511``,
+``TFCGAN_multigpu_globalFFT.py:494-499``) and the offline ``mse_spec`` metric
+(``Devcom_MagMSE.py:91-118``).  PyTorch is used for device memory and streams only; all
+arithmetic happens in ``libtfcfft.so``.  There is no CPU or cuFFT fallback: a missing library or a
+non-CUDA tensor raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16, torch.uint8: _lib.U8}
+
+
+@dataclass(frozen=True)
+class SpectralConfig:
+    """Options of the loss (defaults = the reference training loss on luma)."""
+
+    grid: int = 4                # 1 global, 2 = 4-patch, 4 = 16-patch
+    channels: str = "luma"       # "luma" (reference: .convert("L")) | "rgb" (per channel)
+    use_phase: bool = True       # amplitude + phase (reference) or amplitude only
+    distance: str = "l1"         # "l1" (nn.L1Loss) | "mse"
+    patch_reduce: str = "mean"   # "mean" (calculate_ffts) | "sum" (fft_loss)
+    log_magnitude: bool = False  # log|F| (Devcom_MagMSE)
+    spectrum: str = "half"       # "half" rfft2 plane | "full" fft2 plane
+    weight: float = 1.0
+    input_scale: float = 1.0
+    quantize: bool = False       # reference-as-shipped uint8 wrap + integer luma; forward only
+    force_split: bool = False    # testing: route 64/128 patches through the split kernels
+
+    def flags(self) -> int:
+        if self.channels not in ("luma", "rgb"):
+            raise ValueError(f"channels must be 'luma' or 'rgb', got {self.channels!r}")
+        if self.distance not in ("l1", "mse"):
+            raise ValueError(f"distance must be 'l1' or 'mse', got {self.distance!r}")
+        if self.patch_reduce not in ("mean", "sum"):
+            raise ValueError(f"patch_reduce must be 'mean' or 'sum', got {self.patch_reduce!r}")
+        if self.spectrum not in ("half", "full"):
+            raise ValueError(f"spectrum must be 'half' or 'full', got {self.spectrum!r}")
+        f = 0
+        if self.channels == "rgb":
+            f |= _lib.CHANNELS_RGB
+        if not self.use_phase:
+            f |= _lib.NO_PHASE
+        if self.distance == "mse":
+            f |= _lib.DIST_MSE
+        if self.patch_reduce == "sum":
+            f |= _lib.PATCH_SUM
+        if self.log_magnitude:
+            f |= _lib.LOG_MAGNITUDE
+        if self.spectrum == "full":
+            f |= _lib.FULL_SPECTRUM
+        if self.quantize:
+            f |= _lib.QUANTIZE_U8
+        if self.force_split:
+            f |= _lib.FORCE_SPLIT
+        return f
+
+
+# one workspace per (device, stream): calls on different streams may overlap
+_WORKSPACES: dict = {}
+
+
+def _workspace(device: torch.device, stream_ptr: int, nbytes: int) -> torch.Tensor:
+    key = (device.index, stream_ptr)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _lib.check(_lib.load().tfcfft_workspace_init(ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream_ptr)),
+                   "tfcfft_workspace_init")
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def _acceptable(t: torch.Tensor) -> bool:
+    st = t.stride()
+    return st[3] == 1 and all(s % 4 == 0 and s >= 0 for s in st[:3]) and t.data_ptr() % (4 * t.element_size()) == 0
+
+
+def _prep(fake: torch.Tensor, real: torch.Tensor):
+    if fake.dim() != 4 or real.dim() != 4 or fake.shape != real.shape:
+        raise ValueError(f"fake and real must be 4-D NCHW tensors of the same shape, got {tuple(fake.shape)} / {tuple(real.shape)}")
+    if not (fake.is_cuda and real.is_cuda):
+        raise RuntimeError("tfcfft runs on CUDA tensors only (no CPU fallback)")
+    if fake.device != real.device:
+        raise RuntimeError("fake and real must live on the same device")
+    if fake.shape[0] == 0:
+        raise ValueError("empty batch")
+    if fake.dtype not in _DTYPES:
+        fake = fake.float()
+    if real.dtype != fake.dtype:
+        if fake.dtype == torch.uint8 or real.dtype == torch.uint8:
+            raise ValueError("uint8 inputs must both be uint8")
+        fake, real = fake.float(), real.float()
+    # views with 16-byte friendly strides (e.g. B[:, :, 0:64, 64:128]) pass straight through
+    if not _acceptable(fake):
+        fake = fake.contiguous()
+    if not _acceptable(real):
+        real = real.contiguous()
+    return fake, real
+
+
+def _launch(fake, real, cfg: SpectralConfig, want_grad: bool, want_per_image: bool):
+    lib = _lib.load()
+    dev = fake.device
+    with torch.cuda.device(dev):
+        stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        per = torch.empty((fake.shape[0], 2), dtype=torch.float32, device=dev) if want_per_image else None
+        grad = torch.empty(fake.shape, dtype=fake.dtype, device=dev) if want_grad else None
+        desc = _lib.make_desc(
+            _DTYPES[fake.dtype], cfg.grid, cfg.flags(), fake.shape, fake.stride(), real.stride(),
+            grad.stride() if want_grad else None, cfg.weight, cfg.input_scale,
+        )
+        nbytes = lib.tfcfft_workspace_bytes(ctypes.byref(desc))
+        if nbytes == 0:
+            _lib.check(lib.tfcfft_validate(ctypes.byref(desc)), "tfcfft_validate")
+        ws = _workspace(dev, stream_ptr, nbytes)
+        rc = lib.tfcfft_loss(
+            ctypes.byref(desc), fake.data_ptr(), real.data_ptr(), out.data_ptr(),
+            per.data_ptr() if want_per_image else None, grad.data_ptr() if want_grad else None,
+            ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream_ptr),
+        )
+        if rc > 0:  # a CUDA error may have left the ticket header dirty
+            _WORKSPACES.pop((dev.index, stream_ptr), None)
+        _lib.check(rc, "tfcfft_loss")
+    return out, per, grad
+
+
+class _SpectralLossFn(torch.autograd.Function):
+    """forward: loss and the unit gradient in ONE pass over fake / real (3 tensor passes of HBM
+    traffic); backward: one scaling launch by ``grad_output`` (weight x GradScaler scale)."""
+
+    @staticmethod
+    def forward(ctx, fake, real, cfg):
+        fake_p, real_p = _prep(fake.detach(), real.detach())
+        want_grad = ctx.needs_input_grad[0] and not cfg.quantize and fake_p.dtype != torch.uint8
+        out, _, grad = _launch(fake_p, real_p, cfg, want_grad, False)
+        ctx.has_grad = want_grad
+        ctx.in_dtype = fake.dtype
+        if want_grad:
+            ctx.save_for_backward(grad)
+        terms = out[1:3]
+        ctx.mark_non_differentiable(terms)
+        return out[0], terms
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_loss, _grad_terms):
+        if not ctx.has_grad:
+            return None, None, None
+        (unit,) = ctx.saved_tensors
+        lib = _lib.load()
+        dev = unit.device
+        with torch.cuda.device(dev):
+            stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+            go = grad_loss.detach().to(device=dev, dtype=torch.float32).contiguous()
+            res = torch.empty_like(unit)
+            _lib.check(
+                lib.tfcfft_grad_scale(res.data_ptr(), unit.data_ptr(), _DTYPES[unit.dtype], unit.numel(),
+                                      go.data_ptr(), 1.0, ctypes.c_void_p(stream_ptr)),
+                "tfcfft_grad_scale",
+            )
+        if res.dtype != ctx.in_dtype:
+            res = res.to(ctx.in_dtype)
+        return res, None, None
+
+
+def spectral_loss(fake, real, *, return_terms: bool = False, config: SpectralConfig | None = None, **options):
+    """Differentiable frequency-domain loss.  ``options`` are the fields of :class:`SpectralConfig`.
+
+    Returns a 0-dim fp32 CUDA tensor (``weight * 1/2 (amp + pha)``); with ``return_terms`` also a
+    detached ``[2]`` tensor ``(amp, pha)`` for logging.  Gradient flows to ``fake`` only -- ``real``
+    is data in every reference call site.
+    """
+    cfg = config if config is not None else SpectralConfig(**options)
+    loss, terms = _SpectralLossFn.apply(fake, real, cfg)
+    return (loss, terms) if return_terms else loss
+
+
+@torch.no_grad()
+def spectral_loss_and_grad(fake, real, *, config: SpectralConfig | None = None, **options):
+    """The fused hot path without autograd: ``(loss, terms, d loss / d fake)`` in one launch."""
+    cfg = config if config is not None else SpectralConfig(**options)
+    fake_p, real_p = _prep(fake, real)
+    out, _, grad = _launch(fake_p, real_p, cfg, True, False)
+    return out[0], out[1:3], grad
+
+
+@torch.no_grad()
+def spectral_terms_per_image(fake, real, *, config: SpectralConfig | None = None, **options):
+    """Forward only: ``[N, 2]`` per-image ``(amp, pha)`` terms (their mean over N is the batch term)."""
+    cfg = config if config is not None else SpectralConfig(**options)
+    fake_p, real_p = _prep(fake, real)
+    _, per, _ = _launch(fake_p, real_p, cfg, False, True)
+    return per
+
+
+def launch_count() -> int:
+    """Kernels launched by ``libtfcfft.so`` in this process since the last reset."""
+    return int(_lib.load().tfcfft_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib.load().tfcfft_launch_count_reset()

@@ -1,0 +1,40 @@
+"""``nn.Module`` front end of the FFT loss (stateless: no parameters, no buffers, so reference
+checkpoints -- ``TFC-GAN-FFT/TFCGAN_multigpu_patchFFT_16P.py:692-695`` -- are unaffected)."""
+
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .functional import SpectralConfig, spectral_loss
+
+
+class SpectralLoss(nn.Module):
+    """``SpectralLoss(grid, channels, use_phase, distance, patch_reduce, ...)(fake, real) -> scalar``.
+
+    ``grid=4`` is the 16-patch loss (``calculate_ffts``, ``...patchFFT_16P.py:323-375``), ``grid=2`` the
+    4-patch loss (``TFCGAN_multigpu_patchFFT.py:498-511``), ``grid=1`` the global loss
+    (``TFCGAN_multigpu_globalFFT.py:494-499``).  ``weight`` folds the call-site factor (``1/100`` at
+    ``...patchFFT_16P.py:607``) into the kernel.  After each call ``last_terms`` holds the detached
+    ``(amp, pha)`` terms for logging (the reference logs ``loss_FFT.item()`` every step, ``:664``).
+    """
+
+    def __init__(self, grid: int = 4, channels: str = "luma", use_phase: bool = True, distance: str = "l1",
+                 patch_reduce: str = "mean", log_magnitude: bool = False, spectrum: str = "half",
+                 weight: float = 1.0, input_scale: float = 1.0, quantize: bool = False):
+        super().__init__()
+        self.config = SpectralConfig(grid=grid, channels=channels, use_phase=use_phase, distance=distance,
+                                     patch_reduce=patch_reduce, log_magnitude=log_magnitude, spectrum=spectrum,
+                                     weight=weight, input_scale=input_scale, quantize=quantize)
+        self.config.flags()  # validate early
+        self.last_terms = None
+
+    def forward(self, fake: torch.Tensor, real: torch.Tensor) -> torch.Tensor:
+        loss, terms = spectral_loss(fake, real, config=self.config, return_terms=True)
+        self.last_terms = terms
+        return loss
+
+    def extra_repr(self) -> str:
+        c = self.config
+        return (f"grid={c.grid}, channels={c.channels!r}, use_phase={c.use_phase}, distance={c.distance!r}, "
+                f"patch_reduce={c.patch_reduce!r}, weight={c.weight}, input_scale={c.input_scale}")
