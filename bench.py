@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- FFT-loss forward+backward throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the hot path (loss + d loss / d fake) over one batch of synthetic
+fake / real images.  Default workload = BASELINE.json configs[1]: global-FFT loss, 256x256,
+batch 64 per GPU, fp32 (luma spectrum = the reference's channel handling).
+Under torchrun (N > 1) the batch dimension is sharded: every rank processes its own 64 images,
+no data-path collective (weak scaling); rank 0 prints ONE JSON line.
+
+value       images/s, inputs resident in HBM, fused tfcfft_loss launch(es) only; inputs rotate over
+            a pool of batches larger than L2 so no step sees L2-hot data.
+e2e         same metric through the public nn.Module + .backward(), inputs copied from pinned
+            host memory every step and the loss read back to the host every step.
+roofline    algorithmic bytes (3*C*H*W*4 per image) / device time of the
+            hot-path launches, against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline  the oracle's R1 (torch.fft, fp32, fwd+bwd) on this box's host cores, bounded sample.
+--impl reference  the same CPU arm as a stand-alone line (rank 0 only).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fft_loss_fwd_bwd_images_per_sec"
+UNIT = "images/s"
+
+WORKLOADS = {
+    # name: (grid, side, per-GPU batch, channels)
+    "global-fft-256-b64": dict(grid=1, side=256, batch=64, channels="luma"),      # BASELINE configs[1]
+    "patch16-fft-256-b256": dict(grid=4, side=256, batch=256, channels="luma"),   # north_star target shape
+    "patch16-fft-256-b32": dict(grid=4, side=256, batch=32, channels="luma"),     # configs[2] per-GPU shard
+    "patch4-fft-256-b256": dict(grid=2, side=256, batch=256, channels="luma"),    # configs[3]
+    "global-fft-256-b64-rgb": dict(grid=1, side=256, batch=64, channels="rgb"),
+    "patch16-fft-256-b256-rgb": dict(grid=4, side=256, batch=256, channels="rgb"),
+    "patch16-fft-512-b64": dict(grid=4, side=512, batch=64, channels="luma"),     # configs[4]
+    "global-fft-512-b32": dict(grid=1, side=512, batch=32, channels="luma"),      # configs[4]
+}
+DEFAULT_WORKLOAD = "global-fft-256-b64"
+VARIANTS = ["patch16-fft-256-b256", "patch4-fft-256-b256", "patch16-fft-256-b256-rgb", "global-fft-256-b64-rgb"]
+L2_BYTES = 126 << 20
+
+
+def bytes_per_image(side: int) -> int:
+    return 3 * 3 * side * side * 4  # read fake + read real + write grad, fp32 RGB
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_for(workload: str):
+    """DRAM bytes per step from the committed ncu --set full capture, if any (profiles/traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: NVML polling thread during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+        s = sorted(self.samples)
+        return {
+            "sm_mhz": s[len(s) // 2] if s else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(s),
+        }
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's R1 (torch.fft) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(wl, budget_s: float, steps: int | None = None, warmup: int = 1, sample_batch: int = 8):
+    """R1 fp32 fwd+bwd on `sample_batch` images of the workload, all host threads.  Returns a dict."""
+    import torch
+
+    import oracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(1234)
+    side = wl["side"]
+    fake = torch.empty(sample_batch, 3, side, side).uniform_(-1, 1, generator=g)
+    real = torch.empty(sample_batch, 3, side, side).uniform_(-1, 1, generator=g)
+
+    def step():
+        fk = fake.clone().requires_grad_(True)
+        loss, _, _ = oracle.spectral_loss_r1(fk, real, grid=wl["grid"], channels=wl["channels"], dtype=torch.float32)
+        loss.backward()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        step()
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while True:
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if steps is not None and len(times) >= steps:
+            break
+        if time.perf_counter() > t_end:  # bounded: the CPU arm never runs longer than its budget
+            break
+    total = sum(times)
+    res = {
+        "value": sample_batch * len(times) / total,
+        "unit": UNIT,
+        "cores": cores,
+        "kind": "port",
+        "sample": f"{len(times)} steps x {sample_batch} images of {side}x{side}, oracle R1 (torch.fft fp32 fwd+bwd, "
+                  f"channels={wl['channels']}, grid={wl['grid']}), torch {torch.__version__}, {cores} threads",
+        "ms_per_step": 1e3 * total / len(times),
+        "steps": len(times),
+    }
+    # the reference as shipped (R0: uint8 + PIL-style luma + numpy rfft2), forward only, one thread
+    try:
+        t0 = time.perf_counter()
+        oracle.spectral_loss_r0(fake[:4].numpy(), real[:4].numpy(), wl["grid"])
+        res["as_shipped_r0_fwd_only_images_per_s"] = 4 / (time.perf_counter() - t0)
+    except Exception:
+        pass
+    return res
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = 60.0 if args.steps_given else 20.0
+    cb = cpu_arm(wl, budget, steps=args.steps if args.steps_given else None, warmup=max(1, min(args.warmup, 3)))
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": cb["steps"],
+        "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, **{k: wl[k] for k in ("grid", "side", "channels")},
+                   "per_gpu_batch": wl["batch"], "note": "CPU arm: each step is a bounded 8-image sample of the workload"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    if "as_shipped_r0_fwd_only_images_per_s" in cb:
+        line["as_shipped_r0_fwd_only_images_per_s"] = cb["as_shipped_r0_fwd_only_images_per_s"]
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def time_kernel_path(tfc, torch, wl, steps, warmup, barrier):
+    """Device-timed fused loss+grad steps on resident inputs.  Returns (seconds, launches, pool)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    per_batch = 2 * wl["batch"] * 3 * wl["side"] ** 2 * 4
+    pool_n = max(2, -(-3 * L2_BYTES // per_batch))  # inputs in the pool >= 3x L2
+    g = torch.Generator(device=dev).manual_seed(1234 + int(os.environ.get("RANK", "0")))
+    pool = []
+    for _ in range(pool_n):
+        f = torch.empty(wl["batch"], 3, wl["side"], wl["side"], device=dev).uniform_(-1, 1, generator=g)
+        r = torch.empty_like(f).uniform_(-1, 1, generator=g)
+        pool.append((f, r))
+    cfg = tfc.SpectralConfig(grid=wl["grid"], channels=wl["channels"], weight=0.01, input_scale=255.0)
+    sink = None
+    for i in range(warmup):
+        f, r = pool[i % pool_n]
+        sink = tfc.spectral_loss_and_grad(f, r, config=cfg)
+    torch.cuda.synchronize()
+    barrier()
+    tfc.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        f, r = pool[(warmup + i) % pool_n]
+        sink = tfc.spectral_loss_and_grad(f, r, config=cfg)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    secs = e0.elapsed_time(e1) / 1e3
+    launches = tfc.launch_count()
+    assert torch.isfinite(sink[0]).item(), "non-finite loss in the timed region"
+    return secs, launches, pool_n
+
+
+def time_e2e(tfc, torch, wl, steps, warmup, barrier, dist):
+    """Public API (nn.Module + backward) with pinned-host inputs copied in and the loss read back
+    every step; H2D of step i+1 overlaps the kernels of step i on a second stream."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    shape = (wl["batch"], 3, wl["side"], wl["side"])
+    g = torch.Generator().manual_seed(99)
+    host = [(torch.empty(shape).uniform_(-1, 1, generator=g).pin_memory(),
+             torch.empty(shape).uniform_(-1, 1, generator=g).pin_memory()) for _ in range(2)]
+    dbuf = [(torch.empty(shape, device=dev), torch.empty(shape, device=dev)) for _ in range(2)]
+    mod = tfc.SpectralLoss(grid=wl["grid"], channels=wl["channels"], weight=0.01, input_scale=255.0)
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream(dev)
+
+    def issue_copy(i):
+        b = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[b])
+            dbuf[b][0].copy_(host[b][0], non_blocking=True)
+            dbuf[b][1].copy_(host[b][1], non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def compute(i):
+        b = i % 2
+        main.wait_event(ready[b])
+        fk = dbuf[b][0].detach().requires_grad_(True)
+        loss = mod(fk, dbuf[b][1])
+        loss.backward()
+        freed[b].record(main)
+        terms = mod.last_terms
+        if dist is not None:
+            terms = tfc.dist.global_mean_terms(terms, wl["batch"])  # the logged value, 2 floats over NCCL
+        return loss, terms, fk.grad
+
+    for b in range(2):
+        freed[b].record(main)
+    total = warmup + steps
+    issue_copy(0)
+    t0 = None
+    last = None
+    for i in range(total):
+        if i == warmup:
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+        if i + 1 < total:
+            issue_copy(i + 1)
+        loss, terms, grad = compute(i)
+        last = loss.item()  # device -> host read of the step's result, every step
+    torch.cuda.synchronize()
+    barrier()
+    secs = time.perf_counter() - t0
+    assert last == last, "nan loss in e2e"
+    h2d = 2 * shape[0] * shape[1] * shape[2] * shape[3] * 4
+    return secs, h2d, 4
+
+
+def run_ours(args, wl):
+    import torch
+
+    import tfc_gan_b200 as tfc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def maxr(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    secs, launches, pool_n = time_kernel_path(tfc, torch, wl, args.steps, args.warmup, barrier)
+    clocks = sampler.stop()
+    secs = maxr(secs)
+    images = world * wl["batch"] * args.steps
+    value = images / secs
+
+    e2e_steps = max(3, min(args.steps, 200))
+    e_secs, h2d, d2h = time_e2e(tfc, torch, wl, e2e_steps, max(3, min(args.warmup, 10)), barrier, dist)
+    e_secs = maxr(e_secs)
+    e2e_value = world * wl["batch"] * e2e_steps / e_secs
+
+    peak, peak_src = peaks()
+    bpi = bytes_per_image(wl["side"])
+    achieved = (wl["batch"] * args.steps * bpi / secs) / 1e9  # per GPU
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": args.workload, "grid": wl["grid"], "side": wl["side"], "channels": wl["channels"],
+            "per_gpu_batch": wl["batch"], "global_batch": world * wl["batch"], "parallelism": f"dp{world}",
+            "l2": f"inputs rotate over a pool of {pool_n} batches ({pool_n * 2 * wl['batch'] * 3 * wl['side']**2 * 4 >> 20} MiB > 126 MiB L2)",
+        },
+        "roofline": {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic_for(args.workload), "peak_source": peak_src,
+            "kernel": "all launches of one tfcfft_loss call (per-GPU)", "algorithmic_bytes_per_image": bpi,
+            "launches_per_step": launches / args.steps,
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "SpectralLoss(fake, real).backward(); loss.item()"},
+        "clocks": clocks,
+        "gpu_launches": launches,
+    }
+    if rank == 0 and world == 1 and not args.no_variants:
+        var = {}
+        for name in VARIANTS:
+            w = WORKLOADS[name]
+            s, _, _ = time_kernel_path(tfc, torch, w, max(10, args.steps // 4), 3, barrier)
+            ips = w["batch"] * max(10, args.steps // 4) / s
+            var[name] = {"value": ips, "unit": UNIT, "roofline_frac": ips * bytes_per_image(w["side"]) / 1e9 / peak}
+        line["variants"] = var
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_arm(wl, 12.0)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if "as_shipped_r0_fwd_only_images_per_s" in cb:
+            line["cpu_baseline"]["as_shipped_r0_fwd_only_images_per_s"] = cb["as_shipped_r0_fwd_only_images_per_s"]
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
+    args = ap.parse_args()
+    args.steps_given = args.steps is not None
+    if args.steps is None:
+        args.steps = 2000
+    if args.warmup is None:
+        args.warmup = 50
+    args.warmup = max(args.warmup, 3)
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()
