@@ -119,7 +119,7 @@ def test_quantised_mode_has_no_gradient_like_the_reference():
     f = cu(fake).requires_grad_(True)
     loss = tfc.spectral_loss(f, cu(real), grid=4, quantize=True)
     assert not loss.requires_grad or f.grad is None
-    assert float(loss) == pytest.approx(float(oracle.spectral_loss_r0(fake, real, 4)[0]), rel=LOSS_TOL)
+    assert loss.item() == pytest.approx(float(oracle.spectral_loss_r0(fake, real, 4)[0]), rel=LOSS_TOL)
 
 
 def test_compat_signatures():
@@ -201,17 +201,20 @@ def test_run_to_run_bit_stable():
 
 
 def test_finite_difference_directions():
+    """Directional derivatives of the smooth variant (amplitude-only, squared distance); the phase term
+    jumps by 2*pi when a bin crosses the negative real axis, so central differences do not apply to it."""
     fake, real = make_pair("tanh", 21, (1, 3, 128, 128), "float32")
     f, r = cu(fake).double(), cu(real).double()
-    _, _, g = tfc.spectral_loss_and_grad(f.float(), r.float(), grid=2, distance="mse", input_scale=4.0)
+    opt = dict(grid=2, distance="mse", use_phase=False, input_scale=4.0)
+    _, _, g = tfc.spectral_loss_and_grad(f.float(), r.float(), **opt)
     rs = np.random.RandomState(0)
-    for _ in range(8):
+    for _ in range(16):
         d = torch.from_numpy(rs.normal(size=fake.shape)).cuda()
-        eps = 1e-3
-        lp = oracle.spectral_loss_r1((f + eps * d).cpu(), r.cpu(), grid=2, distance="mse", input_scale=4.0)[0]
-        lm = oracle.spectral_loss_r1((f - eps * d).cpu(), r.cpu(), grid=2, distance="mse", input_scale=4.0)[0]
+        eps = 1e-4
+        lp = oracle.spectral_loss_r1((f + eps * d).cpu(), r.cpu(), **opt)[0]
+        lm = oracle.spectral_loss_r1((f - eps * d).cpu(), r.cpu(), **opt)[0]
         fd = float(lp - lm) / (2 * eps)
-        assert float((g.double() * d).sum()) == pytest.approx(fd, rel=2e-3)
+        assert float((g.double() * d).sum()) == pytest.approx(fd, rel=1e-3)
 
 
 # ---- properties at BASELINE.json's full sizes (no oracle needed) --------------------------------
