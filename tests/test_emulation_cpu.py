@@ -110,3 +110,16 @@ def test_emulation_strided_views():
     assert rc == 0
     l, *_ = oracle.spectral_loss_r1(torch.from_numpy(fv.copy()), torch.from_numpy(rv.copy()), grid=1)
     assert out[0] == pytest.approx(float(l), rel=1e-5)
+
+
+@pytest.mark.parametrize("opt", [dict(), dict(channels="rgb", distance="mse"), dict(use_phase=False)])
+def test_packed_pair_path_matches_generic_path(opt):
+    """The packed 64x64 tile-pair fast path and the generic resident path are two implementations of the
+    same algebra; odd tile counts exercise the duplicated last lane."""
+    fake, real = make_pair("tanh", 17, (3, 3, 64, 64), "float32")  # grid=1: 3 (luma) or 9 (rgb) tiles, odd
+    rc, o1, p1, g1 = emulate(fake, real, 1, flags_of(**opt), input_scale=255.0)
+    rc2, o2, p2, g2 = emulate(fake, real, 1, flags_of(force_generic=True, **opt), input_scale=255.0)
+    assert rc == 0 and rc2 == 0
+    np.testing.assert_allclose(o1[:3], o2[:3], rtol=2e-6)
+    np.testing.assert_allclose(p1, p2, rtol=2e-6)
+    assert l2rel(g1, g2) <= 2e-5

@@ -53,6 +53,7 @@ CASES = [
     (128, 4, dict()),
     (64, 4, dict(spectrum="full")),
     (64, 1, dict()),
+    (256, 4, dict(force_generic=True)),                 # generic resident kernel (the default is the packed pair path)
     (256, 4, dict(force_split=True)),                   # split kernels on a size the resident path also covers
     (256, 2, dict(force_split=True, channels="rgb")),
 ]
@@ -64,11 +65,31 @@ def test_loss_and_gradient_match_oracle(side, grid, opt, kind):
     n = 3 if side <= 256 else 2
     fake, real = make_pair(kind, 101, (n, 3, side, side), "float32")
     loss, terms, grad = run_cuda(fake, real, grid=grid, weight=0.01, input_scale=255.0, **opt)
-    okw = {k: v for k, v in opt.items() if k != "force_split"}
+    okw = {k: v for k, v in opt.items() if not k.startswith("force_")}
     l, a, p, g = oracle.spectral_loss_and_grad_r1(fake, real, grid=grid, weight=0.01, input_scale=255.0, **okw)
     assert loss == pytest.approx(l, rel=LOSS_TOL)
     assert terms[0] == pytest.approx(a, rel=LOSS_TOL)
     assert terms[1] == pytest.approx(p, rel=LOSS_TOL, abs=1e-12)
+    assert l2rel(grad, g) <= GRAD_TOL
+
+
+def test_phase_dominated_gradient():
+    """input_scale = 1 on [-1,1] data: |F| is small, the phase term dominates the gradient -- the hardest
+    case for the fast atan2 / rsqrt of the packed path."""
+    fake, real = make_pair("uniform", 55, (2, 3, 256, 256), "float32")
+    for opt in (dict(), dict(force_generic=True)):
+        loss, terms, grad = run_cuda(fake, real, grid=4, **opt)
+        l, a, p, g = oracle.spectral_loss_and_grad_r1(fake, real, grid=4)
+        assert loss == pytest.approx(l, rel=LOSS_TOL)
+        assert terms[1] == pytest.approx(p, rel=LOSS_TOL)
+        assert l2rel(grad, g) <= GRAD_TOL
+
+
+def test_odd_tile_count_and_single_channel():
+    fake, real = make_pair("tanh", 56, (3, 1, 64, 64), "float32")  # 3 tiles: the last pair is half empty
+    loss, terms, grad = run_cuda(fake, real, grid=1, input_scale=255.0)
+    l, a, p, g = oracle.spectral_loss_and_grad_r1(fake, real, grid=1, input_scale=255.0)
+    assert loss == pytest.approx(l, rel=LOSS_TOL)
     assert l2rel(grad, g) <= GRAD_TOL
 
 

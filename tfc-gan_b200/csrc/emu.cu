@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "host_common.h"
+#include "pair_tile.cuh"
 
 using namespace tfcfft;
 
@@ -25,6 +26,27 @@ void run_resident(Params prm) {
         tile_process<P, T, LUMA3>(ctx, prm, tile, s.data(), tw.data(), a, p);
         prm.partials[2 * tile] = a;
         prm.partials[2 * tile + 1] = p;
+    }
+}
+
+template <int P, typename T, bool LUMA3>
+void run_pair(Params prm) {
+    if constexpr (P == 64) {
+        SerialCtx ctx;
+        std::vector<float4> s((size_t)P * PairCfg<P>::LD), tw(P);
+        fill_twiddles4<P>(ctx, tw.data());
+        for (int ta = 0; ta < prm.tiles_total; ta += 2) {
+            const bool b_valid = ta + 1 < prm.tiles_total;
+            const int tb = b_valid ? ta + 1 : ta;
+            float2 a = make_float2(0.f, 0.f), p = make_float2(0.f, 0.f);
+            pair_process<P, T, LUMA3>(ctx, prm, ta, tb, b_valid, s.data(), tw.data(), a, p);
+            prm.partials[2 * ta] = a.x;
+            prm.partials[2 * ta + 1] = p.x;
+            if (b_valid) {
+                prm.partials[2 * tb] = a.y;
+                prm.partials[2 * tb + 1] = p.y;
+            }
+        }
     }
 }
 
@@ -57,6 +79,7 @@ void run_split(Params prm) {
 template <int P, typename T, bool LUMA3>
 void run(const Params& prm, bool split) {
     if (split) run_split<P, T, LUMA3>(prm);
+    else if (P == 64 && pair_supported(prm)) run_pair<P, T, LUMA3>(prm);
     else if constexpr (P <= 128) run_resident<P, T, LUMA3>(prm);
 }
 

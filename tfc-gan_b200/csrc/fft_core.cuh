@@ -41,6 +41,97 @@ TFC_HD float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.
 // a * conj(w)
 TFC_HD float2 cmulc(float2 a, float2 w) { return make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y); }
 
+// ---------------------------------------------------------------------------------------------
+// Packed pair arithmetic: one f32x2 register pair carries the SAME element of TWO independent
+// transforms (tile A in .x, tile B in .y), so every butterfly add / multiply is one FADD2 / FMUL2 /
+// FFMA2 on sm_100a -- half the issue slots of the scalar code for identical arithmetic.
+// ---------------------------------------------------------------------------------------------
+TFC_HD float2 p_add(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+TFC_HD float2 p_neg(float2 a) { return make_float2(-a.x, -a.y); }  // folds into the operand modifier
+TFC_HD float2 p_sub(float2 a, float2 b) { return p_add(a, p_neg(b)); }
+TFC_HD float2 p_mul(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    return __fmul2_rn(a, b);
+#else
+    return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+TFC_HD float2 p_fma(float2 a, float2 b, float2 c) {
+#ifdef __CUDA_ARCH__
+    return __ffma2_rn(a, b, c);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+TFC_HD float2 p_dup(float s) { return make_float2(s, s); }
+
+struct c2 {  // two complex numbers: (re.x, im.x) of transform A, (re.y, im.y) of transform B
+    float2 re, im;
+};
+TFC_HD c2 make_c2(float2 re, float2 im) {
+    c2 r;
+    r.re = re;
+    r.im = im;
+    return r;
+}
+TFC_HD c2 cadd(c2 a, c2 b) { return make_c2(p_add(a.re, b.re), p_add(a.im, b.im)); }
+TFC_HD c2 csub(c2 a, c2 b) { return make_c2(p_sub(a.re, b.re), p_sub(a.im, b.im)); }
+// twiddle tables for packed data hold (wr, wr, wi, wi) so both lanes see the same factor
+TFC_HD c2 cmul(c2 a, float4 w) {
+    const float2 wr = make_float2(w.x, w.y), wi = make_float2(w.z, w.w);
+    return make_c2(p_fma(a.re, wr, p_neg(p_mul(a.im, wi))), p_fma(a.re, wi, p_mul(a.im, wr)));
+}
+TFC_HD c2 cmulc(c2 a, float4 w) {
+    const float2 wr = make_float2(w.x, w.y), wi = make_float2(w.z, w.w);
+    return make_c2(p_fma(a.re, wr, p_mul(a.im, wi)), p_fma(a.im, wr, p_neg(p_mul(a.re, wi))));
+}
+
+template <int R, int K, bool INV>
+TFC_HD c2 mul_w(c2 a) {
+    constexpr int k32 = (K * (32 / R)) % 32;
+    constexpr float c8 = 0.707106781186547524f;
+    if constexpr (k32 == 0) {
+        return a;
+    } else if constexpr (k32 == 8) {
+        return INV ? make_c2(p_neg(a.im), a.re) : make_c2(a.im, p_neg(a.re));
+    } else if constexpr (k32 == 16) {
+        return make_c2(p_neg(a.re), p_neg(a.im));
+    } else if constexpr (k32 == 24) {
+        return INV ? make_c2(a.im, p_neg(a.re)) : make_c2(p_neg(a.im), a.re);
+    } else if constexpr (k32 == 4) {
+        return INV ? make_c2(p_mul(p_sub(a.re, a.im), p_dup(c8)), p_mul(p_add(a.re, a.im), p_dup(c8)))
+                   : make_c2(p_mul(p_add(a.re, a.im), p_dup(c8)), p_mul(p_sub(a.im, a.re), p_dup(c8)));
+    } else if constexpr (k32 == 12) {
+        return INV ? make_c2(p_mul(p_add(a.re, a.im), p_dup(-c8)), p_mul(p_sub(a.re, a.im), p_dup(c8)))
+                   : make_c2(p_mul(p_sub(a.im, a.re), p_dup(c8)), p_mul(p_add(a.re, a.im), p_dup(-c8)));
+    } else {
+        constexpr float wr = kCos32[k32];
+        constexpr float wi = INV ? kSin32[k32] : -kSin32[k32];
+        return make_c2(p_fma(a.re, p_dup(wr), p_mul(a.im, p_dup(-wi))), p_fma(a.re, p_dup(wi), p_mul(a.im, p_dup(wr))));
+    }
+}
+
+// storage element <-> arithmetic type
+template <class E> struct Cx;
+template <> struct Cx<float2> {
+    using C = float2;
+    using TW = float2;
+    TFC_HD static C ld(const float2& e) { return e; }
+    TFC_HD static float2 st(const C& c) { return c; }
+};
+template <> struct Cx<float4> {  // (reA, reB, imA, imB)
+    using C = c2;
+    using TW = float4;
+    TFC_HD static C ld(const float4& e) { return make_c2(make_float2(e.x, e.y), make_float2(e.z, e.w)); }
+    TFC_HD static float4 st(const C& c) { return make_float4(c.re.x, c.re.y, c.im.x, c.im.y); }
+};
+
 // a * W_R^K with W_R = e^{-2 pi i / R} (INV: e^{+2 pi i / R}); trivial factors cost no multiplies.
 template <int R, int K, bool INV>
 TFC_HD float2 mul_w(float2 a) {
@@ -65,10 +156,10 @@ TFC_HD float2 mul_w(float2 a) {
     }
 }
 
-template <int R, bool INV, int K>
-TFC_HD void dft_combine(float2* v, const float2* e, const float2* o) {
+template <int R, bool INV, int K, class C>
+TFC_HD void dft_combine(C* v, const C* e, const C* o) {
     if constexpr (K < R / 2) {
-        const float2 t = mul_w<R, K, INV>(o[K]);
+        const C t = mul_w<R, K, INV>(o[K]);
         v[K] = cadd(e[K], t);
         v[K + R / 2] = csub(e[K], t);
         dft_combine<R, INV, K + 1>(v, e, o);
@@ -78,8 +169,9 @@ TFC_HD void dft_combine(float2* v, const float2* e, const float2* o) {
 // In-register R-point DFT, natural order in and out (R in {1,2,4,8,16,32}).
 template <int R, bool INV>
 struct Dft {
-    TFC_HD static void run(float2* v) {
-        float2 e[R / 2], o[R / 2];
+    template <class C>
+    TFC_HD static void run(C* v) {
+        C e[R / 2], o[R / 2];
 #pragma unroll
         for (int k = 0; k < R / 2; ++k) {
             e[k] = v[2 * k];
@@ -92,7 +184,8 @@ struct Dft {
 };
 template <bool INV>
 struct Dft<1, INV> {
-    TFC_HD static void run(float2*) {}
+    template <class C>
+    TFC_HD static void run(C*) {}
 };
 
 // Radix plan per line length.
@@ -136,20 +229,23 @@ struct BlockCtx {
 
 // One radix-R pass over `1 << log2_lines` independent P-point lines held in memory `s`:
 // element e of line l lives at s[l*ls + e*es].  L is the current DIF block length.
-// tw[t] = e^{-2 pi i t / P}, t in [0, P).
-template <int P, int R, int L, bool INV, class Ctx>
-TFC_HD void fft_pass(const Ctx& ctx, float2* s, int es, int ls, int log2_lines, const float2* tw) {
+// tw[t] = e^{-2 pi i t / P}, t in [0, P)  (float2, or (wr,wr,wi,wi) float4 for packed data).
+// LINE_FAST: consecutive threads take consecutive lines (else consecutive butterflies of a line).
+template <int P, int R, int L, bool INV, bool LINE_FAST = true, class E, class Ctx>
+TFC_HD void fft_pass(const Ctx& ctx, E* s, int es, int ls, int log2_lines, const typename Cx<E>::TW* tw) {
+    using C = typename Cx<E>::C;
     constexpr int M = L / R;    // distance between butterfly legs (in elements)
     constexpr int JT = P / R;   // butterflies per line
     const int ntask = JT << log2_lines;
     const int lmask = (1 << log2_lines) - 1;
     for (int t = ctx.tid; t < ntask; t += ctx.nthreads) {
-        const int line = t & lmask, jj = t >> log2_lines;
+        const int line = LINE_FAST ? (t & lmask) : (t / JT);
+        const int jj = LINE_FAST ? (t >> log2_lines) : (t % JT);
         const int blk = jj / M, j = jj % M;
-        float2* base = s + line * ls + (blk * L + j) * es;
-        float2 v[R];
+        E* base = s + line * ls + (blk * L + j) * es;
+        C v[R];
 #pragma unroll
-        for (int m = 0; m < R; ++m) v[m] = base[m * M * es];
+        for (int m = 0; m < R; ++m) v[m] = Cx<E>::ld(base[m * M * es]);
         if constexpr (!INV) {
             Dft<R, false>::run(v);
             if constexpr (M > 1) {
@@ -164,13 +260,13 @@ TFC_HD void fft_pass(const Ctx& ctx, float2* s, int es, int ls, int log2_lines, 
             Dft<R, true>::run(v);
         }
 #pragma unroll
-        for (int k = 0; k < R; ++k) base[k * M * es] = v[k];
+        for (int k = 0; k < R; ++k) base[k * M * es] = Cx<E>::st(v[k]);
     }
 }
 
 // All passes of a batch of lines, each followed by a barrier.
-template <int P, bool INV, class Ctx>
-TFC_HD void fft_lines(const Ctx& ctx, float2* s, int es, int ls, int log2_lines, const float2* tw) {
+template <int P, bool INV, class E, class Ctx>
+TFC_HD void fft_lines(const Ctx& ctx, E* s, int es, int ls, int log2_lines, const typename Cx<E>::TW* tw) {
     using Pl = Plan<P>;
     constexpr int L2 = P / Pl::R1, L3 = P / (Pl::R1 * Pl::R2);
     if constexpr (!INV) {

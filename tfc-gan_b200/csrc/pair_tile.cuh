@@ -1,0 +1,334 @@
+// pair_tile.cuh -- the fast path for 64x64 patches (16-patch loss on 256x256, the north-star shape).
+//
+// Two tiles (A, B) are processed TOGETHER by one CTA: every shared-memory element is a float4
+// (reA, reB, imA, imB) and every arithmetic instruction of the transforms is a packed f32x2 op
+// (FADD2 / FMUL2 / FFMA2) whose two lanes belong to the two tiles.  Compared with the generic
+// resident kernel (spectral_kernels.cuh) this
+//   * halves the issue slots of all butterfly / twiddle / un-mixing arithmetic,
+//   * makes every shared-memory access a conflict-free 128-bit LDS/STS,
+//   * enumerates exactly the half-plane bins (no idle lanes in the loss pass),
+//   * runs the inverse column transforms on the 33 non-zero columns only,
+//   * replaces atan2f / sqrtf / division by MUFU approximations + a packed minimax polynomial.
+// The stage functions are __host__ __device__ so the CPU emulation (emu.cu) executes the same code.
+#pragma once
+#include "spectral_core.cuh"
+
+namespace tfcfft {
+
+template <int P>
+struct PairCfg {
+    static constexpr int NT = 256;
+    static constexpr int LD = P + 1;  // float4 row pitch, odd: row and column walks are conflict-free
+    static constexpr size_t SMEM = ((size_t)P * LD + P) * sizeof(float4);
+};
+
+// ---- MUFU-level approximations (1-2 ulp), exact libm on the host emulation -------------------
+TFC_HD float fast_rcp(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+TFC_HD float fast_rsqrt(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+TFC_HD float fast_sqrt(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+
+// atan2 of two lanes.  atan(t) = t * P7(t^2) on [0,1] (minimax, |err| < 4e-8 in exact arithmetic,
+// ~1.5e-7 evaluated in fp32); octant fix-ups per lane.  atan2(+-0, 0) = 0 and atan2(+0, x<0) = +pi as
+// NumPy / torch.
+TFC_HD float2 atan2_pair(float2 y, float2 x) {
+    const float ax0 = fabsf(x.x), ay0 = fabsf(y.x), ax1 = fabsf(x.y), ay1 = fabsf(y.y);
+    const float mx0 = fmaxf(ax0, ay0), mn0 = fminf(ax0, ay0);
+    const float mx1 = fmaxf(ax1, ay1), mn1 = fminf(ax1, ay1);
+    float2 t;
+    t.x = mx0 > 1e-30f ? mn0 * fast_rcp(mx0) : 0.f;
+    t.y = mx1 > 1e-30f ? mn1 * fast_rcp(mx1) : 0.f;
+    const float2 s = p_mul(t, t);
+    float2 p = p_dup(-4.0545672114e-03f);
+    p = p_fma(p, s, p_dup(2.1862957868e-02f));
+    p = p_fma(p, s, p_dup(-5.5912326758e-02f));
+    p = p_fma(p, s, p_dup(9.6421973272e-02f));
+    p = p_fma(p, s, p_dup(-1.3908629550e-01f));
+    p = p_fma(p, s, p_dup(1.9946565651e-01f));
+    p = p_fma(p, s, p_dup(-3.3329860784e-01f));
+    p = p_fma(p, s, p_dup(9.9999933558e-01f));
+    float2 r = p_mul(p, t);
+    constexpr float kPi = 3.14159265358979f, kHalfPi = 1.57079632679490f;
+    if (ay0 > ax0) r.x = kHalfPi - r.x;
+    if (ay1 > ax1) r.y = kHalfPi - r.y;
+    if (x.x < 0.f) r.x = kPi - r.x;
+    if (x.y < 0.f) r.y = kPi - r.y;
+    if (y.x < 0.f) r.x = -r.x;
+    if (y.y < 0.f) r.y = -r.y;
+    return r;
+}
+
+TFC_HD float sign_of(float d) {  // copysign(1, d): the sign(0) = 0 case only matters when F == 0, where the
+                                 // gradient is already zeroed through 1/|F| := 0
+#if defined(__CUDA_ARCH__)
+    return __int_as_float((__float_as_int(d) & 0x80000000) | 0x3f800000);
+#else
+    return d < 0.f ? -1.f : 1.f;
+#endif
+}
+
+// Loss terms and spectral gradient of one half-plane bin for both tiles.  zk = Z(k), zm = Z(-k).
+TFC_HD c2 bin_eval_pair(const Params& prm, bool mse, bool phase, c2 zk, c2 zm, float2& accA, float2& accP) {
+    const float2 fx = p_add(zk.re, zm.re), fy = p_sub(zk.im, zm.im);  // 2F
+    const float2 rx = p_add(zk.im, zm.im), ry = p_sub(zm.re, zk.re);  // 2R
+    const float2 fsq = p_fma(fx, fx, p_mul(fy, fy)), rsq = p_fma(rx, rx, p_mul(ry, ry));
+    float2 finv, f2, r2;
+    finv.x = fsq.x > 1e-35f ? fast_rsqrt(fsq.x) : 0.f;
+    finv.y = fsq.y > 1e-35f ? fast_rsqrt(fsq.y) : 0.f;
+    f2 = p_mul(fsq, finv);  // |2F|
+    r2.x = fast_sqrt(rsq.x);
+    r2.y = fast_sqrt(rsq.y);
+    const float2 da = p_mul(p_sub(f2, r2), p_dup(0.5f));
+    float2 ga;
+    if (mse) {
+        accA = p_fma(da, da, accA);
+        ga = p_add(da, da);
+    } else {
+        accA.x += fabsf(da.x);
+        accA.y += fabsf(da.y);
+        ga = make_float2(sign_of(da.x), sign_of(da.y));
+    }
+    const float2 ca = p_mul(p_mul(ga, finv), p_dup(prm.sa));
+    c2 g = make_c2(p_mul(ca, fx), p_mul(ca, fy));
+    if (phase) {
+        const float2 dp = p_sub(atan2_pair(fy, fx), atan2_pair(ry, rx));
+        float2 gp;
+        if (mse) {
+            accP = p_fma(dp, dp, accP);
+            gp = p_add(dp, dp);
+        } else {
+            accP.x += fabsf(dp.x);
+            accP.y += fabsf(dp.y);
+            gp = make_float2(sign_of(dp.x), sign_of(dp.y));
+        }
+        const float2 cp = p_mul(p_mul(gp, p_mul(finv, finv)), p_dup(2.f * prm.sp));
+        g.re = p_fma(p_neg(cp), fy, g.re);
+        g.im = p_fma(cp, fx, g.im);
+    }
+    return g;
+}
+
+// XOR swizzle of the freshly loaded tile: the loader's 4-pixel STS.128 bursts become conflict-free.
+TFC_HD int swz(int x) { return x ^ ((x >> 3) & 3); }
+
+// (wr, wr, wi, wi) table of e^{-2 pi i t / P}
+template <int P, class Ctx>
+TFC_HD void fill_twiddles4(const Ctx& ctx, float4* tw) {
+    for (int t = ctx.tid; t < P; t += ctx.nthreads) {
+        float sn, cs;
+#ifdef __CUDA_ARCH__
+        sincospif(2.0f * (float)t / (float)P, &sn, &cs);
+#else
+        const double a = 2.0 * 3.14159265358979323846 * (double)t / (double)P;
+        sn = (float)sin(a);
+        cs = (float)cos(a);
+#endif
+        tw[t] = make_float4(cs, cs, -sn, -sn);
+    }
+}
+
+// ---- stage 0: global -> luma -> packed tile pair ----------------------------------------------
+template <int P, typename T, bool LUMA3, class Ctx>
+TFC_HD void pair_load(const Ctx& ctx, const Params& prm, const TileCoord& ta, const TileCoord& tb, float4* s) {
+    constexpr int LD = PairCfg<P>::LD, XV = P / 4;
+    const T* fa = tile_ptr<T>(prm.fake, prm.fs, ta, P);
+    const T* ra = tile_ptr<T>(prm.real, prm.rs, ta, P);
+    const T* fb = tile_ptr<T>(prm.fake, prm.fs, tb, P);
+    const T* rb = tile_ptr<T>(prm.real, prm.rs, tb, P);
+    for (int it = ctx.tid; it < P * XV; it += ctx.nthreads) {
+        const int x = (it % XV) * 4, y = it / XV;
+        float vfa[4], vra[4], vfb[4], vrb[4];
+        load_px4<T, LUMA3>(prm, fa, prm.fs, y, x, vfa);
+        load_px4<T, LUMA3>(prm, ra, prm.rs, y, x, vra);
+        load_px4<T, LUMA3>(prm, fb, prm.fs, y, x, vfb);
+        load_px4<T, LUMA3>(prm, rb, prm.rs, y, x, vrb);
+        float4* row = s + y * LD;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) row[swz(x + i)] = make_float4(vfa[i], vfb[i], vra[i], vrb[i]);
+    }
+}
+
+// ---- stages 1+2: forward row passes.  The first works in place on the swizzled addresses (each
+// task rewrites exactly the words it read); the second owns whole groups of R2 positions, reads them
+// through the swizzle and writes plain positions, which removes the swizzle for free. ------------
+template <int P, class Ctx>
+TFC_HD void pair_rows_first(const Ctx& ctx, float4* s, const float4* tw) {
+    constexpr int R = Plan<P>::R1, M = P / R, LD = PairCfg<P>::LD;
+    for (int t = ctx.tid; t < P * M; t += ctx.nthreads) {
+        const int j = t % M, y = t / M;  // consecutive threads: consecutive columns of one row
+        float4* row = s + y * LD;
+        c2 v[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = Cx<float4>::ld(row[swz(j + m * M)]);
+        Dft<R, false>::run(v);
+#pragma unroll
+        for (int k = 1; k < R; ++k) v[k] = cmul(v[k], tw[j * k]);
+#pragma unroll
+        for (int k = 0; k < R; ++k) row[swz(j + k * M)] = Cx<float4>::st(v[k]);
+    }
+}
+
+template <int P, class Ctx>
+TFC_HD void pair_rows_second(const Ctx& ctx, float4* s) {
+    constexpr int R = Plan<P>::R2, NB = P / R, LD = PairCfg<P>::LD;
+    for (int t = ctx.tid; t < P * NB; t += ctx.nthreads) {
+        const int y = t % P, k1 = t / P;  // consecutive threads: consecutive rows (odd pitch: conflict-free)
+        float4* grp = s + y * LD + k1 * R;
+        c2 v[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = Cx<float4>::ld(s[y * LD + swz(k1 * R + j)]);
+        Dft<R, false>::run(v);
+#pragma unroll
+        for (int k = 0; k < R; ++k) grp[k] = Cx<float4>::st(v[k]);
+    }
+}
+
+// ---- loss pass over exactly the half-plane bins -------------------------------------------------
+template <int P, class Ctx>
+TFC_HD void pair_bins(const Ctx& ctx, const Params& prm, float4* s, float2& accA, float2& accP) {
+    constexpr int LD = PairCfg<P>::LD, H = P / 2;
+    const bool mse = (prm.flags & TFCFFT_DIST_MSE) != 0, phase = !(prm.flags & TFCFFT_NO_PHASE);
+    const bool want_grad = prm.grad != nullptr;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    // regular columns kx = 1 .. P/2-1: one item per bin, mirror position zeroed for the inverse rows
+    for (int it = ctx.tid; it < P * (H - 1); it += ctx.nthreads) {
+        const int qy = it % P, kx = 1 + it / P;  // consecutive threads: consecutive row positions
+        const int qx = pos_of_freq<P>(kx), qxm = pos_of_freq<P>(P - kx), qym = neg_pos<P>(qy);
+        float4* pk = s + qy * LD + qx;
+        float4* pm = s + qym * LD + qxm;
+        const c2 g = bin_eval_pair(prm, mse, phase, Cx<float4>::ld(*pk), Cx<float4>::ld(*pm), accA, accP);
+        if (want_grad) {
+            *pk = Cx<float4>::st(g);
+            *pm = zero;
+        }
+    }
+    // self-conjugate columns kx = 0 and kx = P/2: the item owns rows ky and -ky
+    for (int it = ctx.tid; it < 2 * (H + 1); it += ctx.nthreads) {
+        const int ky = it % (H + 1), qx = pos_of_freq<P>((it / (H + 1)) * H);
+        const int qy = pos_of_freq<P>(ky), qym = pos_of_freq<P>((P - ky) & (P - 1));
+        float4* pk = s + qy * LD + qx;
+        float4* pm = s + qym * LD + qx;
+        const c2 zk = Cx<float4>::ld(*pk), zm = Cx<float4>::ld(*pm);
+        const c2 g = bin_eval_pair(prm, mse, phase, zk, zm, accA, accP);
+        if (qym != qy) {
+            const c2 g2 = bin_eval_pair(prm, mse, phase, zm, zk, accA, accP);
+            if (want_grad) *pm = Cx<float4>::st(g2);
+        }
+        if (want_grad) *pk = Cx<float4>::st(g);
+    }
+}
+
+// ---- inverse column passes on the P/2+1 non-zero columns only ----------------------------------
+// column positions with kx <= P/2: {k1*R2 + k2 : k2 < R2/2} (P/2 of them) plus the Nyquist column R2/2
+template <int P, int R, int L, class Ctx>
+TFC_HD void pair_cols_inv_pass(const Ctx& ctx, float4* s, const float4* tw) {
+    constexpr int LD = PairCfg<P>::LD, R2 = Plan<P>::R2, HR = R2 / 2, M = L / R, JT = P / R;
+    constexpr int NL = P / 2 + 1;
+    for (int t = ctx.tid; t < NL * JT; t += ctx.nthreads) {
+        const int li = t % NL, jj = t / NL;
+        const int qx = li < P / 2 ? (li / HR) * R2 + (li % HR) : HR;
+        const int blk = jj / M, j = jj % M;
+        float4* base = s + (blk * L + j) * LD + qx;
+        c2 v[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = Cx<float4>::ld(base[m * M * LD]);
+        if constexpr (M > 1) {
+#pragma unroll
+            for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], tw[(P / L) * j * k]);
+        }
+        Dft<R, true>::run(v);
+#pragma unroll
+        for (int k = 0; k < R; ++k) base[k * M * LD] = Cx<float4>::st(v[k]);
+    }
+}
+
+// ---- last inverse row pass: real part -> gradient in global memory ----------------------------
+template <int P, typename T, bool LUMA3, class Ctx>
+TFC_HD void pair_rows_last(const Ctx& ctx, const Params& prm, const TileCoord& ta, const TileCoord& tb, bool b_valid,
+                           const float4* s, const float4* tw) {
+    constexpr int R = Plan<P>::R1, M = P / R, LD = PairCfg<P>::LD;
+    constexpr int NC = LUMA3 ? 3 : 1;
+    T* ga = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, ta, P));
+    T* gb = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tb, P));
+    for (int t = ctx.tid; t < P * M; t += ctx.nthreads) {
+        const int j = t % M, y = t / M;  // consecutive threads: consecutive pixels of one row
+        const float4* row = s + y * LD;
+        c2 v[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) v[k] = Cx<float4>::ld(row[j + k * M]);
+#pragma unroll
+        for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], tw[j * k]);
+        Dft<R, true>::run(v);
+        T* pa = ga + (long long)y * prm.gs[2] + j;
+        T* pb = gb + (long long)y * prm.gs[2] + j;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                IO<T>::store1(pa + c * prm.gs[1] + m * M, prm.gw[c] * v[m].re.x);
+                if (b_valid) IO<T>::store1(pb + c * prm.gs[1] + m * M, prm.gw[c] * v[m].re.y);
+            }
+        }
+    }
+}
+
+// ---- one tile pair, start to finish ------------------------------------------------------------
+template <int P, typename T, bool LUMA3, class Ctx>
+TFC_HD void pair_process(const Ctx& ctx, const Params& prm, int tile_a, int tile_b, bool b_valid, float4* s,
+                         const float4* tw, float2& accA, float2& accP) {
+    using Pl = Plan<P>;
+    constexpr int LD = PairCfg<P>::LD, LP = ilog2_c(P), L2 = P / Pl::R1;
+    static_assert(Pl::R3 == 1, "pair path supports two-pass plans");
+    const TileCoord ta = decode_tile(prm, tile_a), tb = decode_tile(prm, tile_b);
+    pair_load<P, T, LUMA3>(ctx, prm, ta, tb, s);
+    ctx.sync();
+    pair_rows_first<P>(ctx, s, tw);
+    ctx.sync();
+    pair_rows_second<P>(ctx, s);
+    ctx.sync();
+    fft_pass<P, Pl::R1, P, false>(ctx, s, LD, 1, LP, tw);   // columns: thread-fast = column
+    ctx.sync();
+    fft_pass<P, Pl::R2, L2, false>(ctx, s, LD, 1, LP, tw);
+    ctx.sync();
+    pair_bins<P>(ctx, prm, s, accA, accP);
+    ctx.sync();
+    if (prm.grad != nullptr) {
+        pair_cols_inv_pass<P, Pl::R2, L2>(ctx, s, tw);
+        ctx.sync();
+        pair_cols_inv_pass<P, Pl::R1, P>(ctx, s, tw);
+        ctx.sync();
+        fft_pass<P, Pl::R2, L2, true>(ctx, s, 1, LD, LP, tw);
+        ctx.sync();
+        pair_rows_last<P, T, LUMA3>(ctx, prm, ta, tb, b_valid, s, tw);
+        ctx.sync();
+    }
+}
+
+TFC_HD bool pair_supported(const Params& prm) {
+    return prm.p == 64 && !(prm.flags & (TFCFFT_LOG_MAGNITUDE | TFCFFT_FULL_SPECTRUM | TFCFFT_FORCE_SPLIT | TFCFFT_FORCE_GENERIC));
+}
+
+}  // namespace tfcfft

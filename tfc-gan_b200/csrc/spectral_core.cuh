@@ -58,6 +58,7 @@ template <> struct IO<float> {
     TFC_HD static void store4(float* p, const float* v) {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     }
+    TFC_HD static void store1(float* p, float v) { *p = v; }
     // (x * 255) in fp32, truncated toward zero, wrapped mod 256
     TFC_HD static int quant(float x) {
 #ifdef __CUDA_ARCH__
@@ -84,6 +85,7 @@ template <> struct IO<__half> {
         t.y = *reinterpret_cast<const unsigned*>(&b);
         *reinterpret_cast<uint2*>(p) = t;
     }
+    TFC_HD static void store1(__half* p, float v) { *p = __float2half_rn(v); }
     // fp16 * 255 rounded to fp16 (the exact fp32 product rounded once == the fp16 product)
     TFC_HD static int quant(float x) {
         const float t = __half2float(__float2half_rn(x * 255.0f));
@@ -104,6 +106,7 @@ template <> struct IO<__nv_bfloat16> {
         for (int i = 0; i < 4; ++i) h[i] = __float2bfloat16_rn(v[i]);
         *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(h);
     }
+    TFC_HD static void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
     TFC_HD static int quant(float x) { return IO<float>::quant(x); }  // NumPy has no bf16: fp32 rule
     TFC_HD static float __uint_as_float_hd(unsigned u) {
         float f;
@@ -118,6 +121,7 @@ template <> struct IO<uint8_t> {
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
     TFC_HD static void store4(uint8_t*, const float*) {}  // no gradient for integer inputs
+    TFC_HD static void store1(uint8_t*, float) {}
     TFC_HD static int quant(float x) { return (int)x; }   // already an 8-bit code
 };
 

@@ -11,6 +11,7 @@
 //
 // Roofline / algorithmic bytes are documented in DESIGN.md.
 #pragma once
+#include "pair_tile.cuh"
 #include "spectral_core.cuh"
 
 namespace tfcfft {
@@ -118,6 +119,69 @@ __global__ void __launch_bounds__(ResidentCfg<P>::NT) resident_kernel(const __gr
         if (threadIdx.x == 0) {
             prm.partials[2 * tile] = a;
             prm.partials[2 * tile + 1] = p;
+        }
+    }
+    finish(prm, gridDim.x);
+}
+
+// Block sum of four floats; result valid in thread 0.
+__device__ __forceinline__ void block_sum4(float& a, float& b, float& c, float& d) {
+    __shared__ float red4[4][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+        c += __shfl_down_sync(0xffffffffu, c, o);
+        d += __shfl_down_sync(0xffffffffu, d, o);
+    }
+    if (lane == 0) {
+        red4[0][wid] = a;
+        red4[1][wid] = b;
+        red4[2][wid] = c;
+        red4[3][wid] = d;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        a = lane < nw ? red4[0][lane] : 0.f;
+        b = lane < nw ? red4[1][lane] : 0.f;
+        c = lane < nw ? red4[2][lane] : 0.f;
+        d = lane < nw ? red4[3][lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, o);
+            b += __shfl_down_sync(0xffffffffu, b, o);
+            c += __shfl_down_sync(0xffffffffu, c, o);
+            d += __shfl_down_sync(0xffffffffu, d, o);
+        }
+    }
+    __syncthreads();
+}
+
+// Packed tile-pair kernel (pair_tile.cuh): persistent CTAs, each iteration transforms two tiles.
+template <int P, typename T, bool LUMA3>
+__global__ void __launch_bounds__(PairCfg<P>::NT) pair_kernel(const __grid_constant__ Params prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* s = reinterpret_cast<float4*>(smem_raw);
+    float4* tw = s + P * PairCfg<P>::LD;
+    const BlockCtx ctx{(int)threadIdx.x, (int)blockDim.x};
+    fill_twiddles4<P>(ctx, tw);
+    ctx.sync();
+    const int npairs = (prm.tiles_total + 1) >> 1;
+    for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+        const int ta = 2 * pr;
+        const bool b_valid = ta + 1 < prm.tiles_total;
+        const int tb = b_valid ? ta + 1 : ta;
+        float2 accA = make_float2(0.f, 0.f), accP = make_float2(0.f, 0.f);
+        pair_process<P, T, LUMA3>(ctx, prm, ta, tb, b_valid, s, tw, accA, accP);
+        block_sum4(accA.x, accA.y, accP.x, accP.y);
+        if (threadIdx.x == 0) {
+            prm.partials[2 * ta] = accA.x;
+            prm.partials[2 * ta + 1] = accP.x;
+            if (b_valid) {
+                prm.partials[2 * tb] = accA.y;
+                prm.partials[2 * tb + 1] = accP.y;
+            }
         }
     }
     finish(prm, gridDim.x);

@@ -60,6 +60,25 @@ int launch_resident(const Params& prm, cudaStream_t st) {
 }
 
 template <int P, typename T, bool LUMA3>
+int launch_pair(const Params& prm, cudaStream_t st) {
+    auto kernel = pair_kernel<P, T, LUMA3>;
+    constexpr size_t smem = PairCfg<P>::SMEM;
+    constexpr int nt = PairCfg<P>::NT;
+    if (int rc = set_smem(kernel, smem)) return rc;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    const long long npairs = ((long long)prm.tiles_total + 1) / 2;
+    const long long cap = (long long)device_info().sms * per_sm;
+    const int grid = (int)(npairs < cap ? npairs : cap);
+    kernel<<<grid, nt, smem, st>>>(prm);
+    g_launches++;
+    TFC_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int P, typename T, bool LUMA3>
 int launch_split(Params prm, cudaStream_t st) {
     if constexpr (P >= 64) {
         using Sp = Split<P>;
@@ -94,6 +113,9 @@ template <int P, typename T, bool LUMA3>
 int launch(const Params& prm, bool split, cudaStream_t st) {
     if (split) return launch_split<P, T, LUMA3>(prm, st);
     if constexpr (P <= 128) {
+        if constexpr (P == 64) {
+            if (pair_supported(prm)) return launch_pair<P, T, LUMA3>(prm, st);
+        }
         return launch_resident<P, T, LUMA3>(prm, st);
     } else {
         return TFCFFT_ERR_SHAPE;

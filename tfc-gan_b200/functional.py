@@ -36,6 +36,7 @@ class SpectralConfig:
     input_scale: float = 1.0
     quantize: bool = False       # reference-as-shipped uint8 wrap + integer luma; forward only
     force_split: bool = False    # testing: route 64/128 patches through the split kernels
+    force_generic: bool = False  # testing: bypass the packed 64x64 fast path
 
     def flags(self) -> int:
         if self.channels not in ("luma", "rgb"):
@@ -63,6 +64,8 @@ class SpectralConfig:
             f |= _lib.QUANTIZE_U8
         if self.force_split:
             f |= _lib.FORCE_SPLIT
+        if self.force_generic:
+            f |= _lib.FORCE_GENERIC
         return f
 
 
