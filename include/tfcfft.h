@@ -107,6 +107,11 @@ int tfcfft_loss(const tfcfft_desc* d, const void* fake, const void* real, float*
 int tfcfft_grad_scale(void* dst, const void* src, int32_t dtype, int64_t numel, const float* dev_scale,
                       float host_scale, void* stream);
 
+/* DEBUG / profiling aid, not part of the stable surface: while `device_buffer` is non-NULL the packed
+ * 64x64 kernel records clock64() at its stage boundaries for the first 6 tile pairs of every CTA
+ * (16 int64 per pair: 11 stage stamps, [14] = SM id, [15] = globaltimer).  Pass NULL to switch off. */
+void tfcfft_debug_trace(void* device_buffer);
+
 /* Number of kernels this library has launched in this process since the last reset. */
 int64_t tfcfft_launch_count(void);
 void tfcfft_launch_count_reset(void);

@@ -36,6 +36,7 @@ EXPORTS = (
     "tfcfft_workspace_init",
     "tfcfft_loss",
     "tfcfft_grad_scale",
+    "tfcfft_debug_trace",
     "tfcfft_launch_count",
     "tfcfft_launch_count_reset",
 )
@@ -94,6 +95,8 @@ def bind(lib):
     lib.tfcfft_loss.argtypes = [dp, vp, vp, f32p, f32p, vp, vp, ctypes.c_size_t, vp]
     lib.tfcfft_grad_scale.restype = ctypes.c_int
     lib.tfcfft_grad_scale.argtypes = [vp, vp, ctypes.c_int32, ctypes.c_int64, f32p, ctypes.c_float, vp]
+    lib.tfcfft_debug_trace.restype = None
+    lib.tfcfft_debug_trace.argtypes = [vp]
     lib.tfcfft_launch_count.restype = ctypes.c_int64
     lib.tfcfft_launch_count.argtypes = []
     lib.tfcfft_launch_count_reset.restype = None

@@ -219,11 +219,26 @@ TFC_HD int neg_pos(int q) { return pos_of_freq<P>((P - freq_of_pos<P>(q)) & (P -
 struct SerialCtx {
     int tid = 0, nthreads = 1;
     TFC_HD void sync() const {}
+    TFC_HD void mark(int) const {}
 };
 #ifdef __CUDACC__
 struct BlockCtx {
     int tid, nthreads;
     __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ void mark(int) const {}
+};
+// Block size known at compile time: the task loops get constant trip counts and unroll, so the loads of
+// a thread's next task overlap the arithmetic of the current one.  `trace` (debug) records clock64 at
+// stage boundaries.
+template <int NT>
+struct BlockCtxT {
+    int tid;
+    static constexpr int nthreads = NT;
+    long long* trace;
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ void mark(int k) const {
+        if (trace != nullptr && tid == 0) trace[k] = clock64();
+    }
 };
 #endif
 

@@ -17,9 +17,12 @@ namespace tfcfft {
 
 template <int P>
 struct PairCfg {
-    static constexpr int NT = 256;
-    static constexpr int LD = P + 1;  // float4 row pitch, odd: row and column walks are conflict-free
-    static constexpr size_t SMEM = ((size_t)P * LD + P) * sizeof(float4);
+    static constexpr int LD = P + 1;          // float4 row pitch, odd: row and column walks are conflict-free
+    static constexpr int NT_COMPUTE = 512;    // 16 warps transform the current pair
+    static constexpr int NT_LOAD = 256;       // 8 warps stream the next pair from HBM into the other buffer
+    static constexpr int NT = NT_COMPUTE + NT_LOAD;
+    static constexpr size_t TILE_BYTES = (size_t)P * LD * sizeof(float4);
+    static constexpr size_t SMEM = 2 * TILE_BYTES + (size_t)P * sizeof(float4);  // two work buffers + twiddles
 };
 
 // ---- MUFU-level approximations (1-2 ulp), exact libm on the host emulation -------------------
@@ -151,24 +154,94 @@ TFC_HD void fill_twiddles4(const Ctx& ctx, float4* tw) {
 }
 
 // ---- stage 0: global -> luma -> packed tile pair ----------------------------------------------
+// Base pointers of the four source tiles (fake A, real A, fake B, real B), computed once per pair.
+template <typename T>
+struct PairSrc {
+    const T* p[4];
+    int sh[4], sc[4];  // row / channel strides in elements (tile-local offsets fit 32 bits)
+};
+template <int P, typename T>
+TFC_HD PairSrc<T> pair_src(const Params& prm, const TileCoord& ta, const TileCoord& tb) {
+    PairSrc<T> r;
+    r.p[0] = tile_ptr<T>(prm.fake, prm.fs, ta, P);
+    r.p[1] = tile_ptr<T>(prm.real, prm.rs, ta, P);
+    r.p[2] = tile_ptr<T>(prm.fake, prm.fs, tb, P);
+    r.p[3] = tile_ptr<T>(prm.real, prm.rs, tb, P);
+    r.sh[0] = r.sh[2] = (int)prm.fs[2];
+    r.sh[1] = r.sh[3] = (int)prm.rs[2];
+    r.sc[0] = r.sc[2] = (int)prm.fs[1];
+    r.sc[1] = r.sc[3] = (int)prm.rs[1];
+    return r;
+}
+
 template <int P, typename T, bool LUMA3, class Ctx>
 TFC_HD void pair_load(const Ctx& ctx, const Params& prm, const TileCoord& ta, const TileCoord& tb, float4* s) {
-    constexpr int LD = PairCfg<P>::LD, XV = P / 4;
-    const T* fa = tile_ptr<T>(prm.fake, prm.fs, ta, P);
-    const T* ra = tile_ptr<T>(prm.real, prm.rs, ta, P);
-    const T* fb = tile_ptr<T>(prm.fake, prm.fs, tb, P);
-    const T* rb = tile_ptr<T>(prm.real, prm.rs, tb, P);
+    constexpr int LD = PairCfg<P>::LD, XV = P / 4, NC = LUMA3 ? 3 : 1;
+    const PairSrc<T> src = pair_src<P, T>(prm, ta, tb);
+    const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
+    const float2 w0 = p_dup(prm.lw[0]), w1 = p_dup(prm.lw[1]), w2 = p_dup(prm.lw[2]);
     for (int it = ctx.tid; it < P * XV; it += ctx.nthreads) {
         const int x = (it % XV) * 4, y = it / XV;
-        float vfa[4], vra[4], vfb[4], vrb[4];
-        load_px4<T, LUMA3>(prm, fa, prm.fs, y, x, vfa);
-        load_px4<T, LUMA3>(prm, ra, prm.rs, y, x, vra);
-        load_px4<T, LUMA3>(prm, fb, prm.fs, y, x, vfb);
-        load_px4<T, LUMA3>(prm, rb, prm.rs, y, x, vrb);
         float4* row = s + y * LD;
+        float2 v[2][4];  // [fake | real][pixel] = (tile A, tile B)
+        // two half-items (fake A+B, then real A+B): 2*NC 128-bit loads in flight per thread each
 #pragma unroll
-        for (int i = 0; i < 4; ++i) row[swz(x + i)] = make_float4(vfa[i], vfb[i], vra[i], vrb[i]);
+        for (int h = 0; h < 2; ++h) {
+            float raw[2][NC][4];
+#pragma unroll
+            for (int ab = 0; ab < 2; ++ab)
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const int w = h + 2 * ab;
+                    IO<T>::load4(src.p[w] + y * src.sh[w] + c * src.sc[w] + x, raw[ab][c]);
+                }
+            if (!quant) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float2 f = p_mul(w0, make_float2(raw[0][0][i], raw[1][0][i]));
+                    if constexpr (LUMA3) {
+                        f = p_fma(w1, make_float2(raw[0][1][i], raw[1][1][i]), f);
+                        f = p_fma(w2, make_float2(raw[0][2][i], raw[1][2][i]), f);
+                    }
+                    v[h][i] = f;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float q[2];
+#pragma unroll
+                    for (int ab = 0; ab < 2; ++ab) {
+                        if constexpr (LUMA3)
+                            q[ab] = (float)((19595 * IO<T>::quant(raw[ab][0][i]) + 38470 * IO<T>::quant(raw[ab][1][i]) +
+                                             7471 * IO<T>::quant(raw[ab][2][i]) + 0x8000) >> 16);
+                        else
+                            q[ab] = (float)IO<T>::quant(raw[ab][0][i]);
+                    }
+                    v[h][i] = make_float2(q[0], q[1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) row[swz(x + i)] = make_float4(v[0][i].x, v[0][i].y, v[1][i].x, v[1][i].y);
     }
+}
+
+// Pulls the next pair's source lines into L2 while the current pair is being transformed, so the next
+// load stage sees L2 latency instead of HBM latency.  No registers or shared memory are held.
+template <int P, typename T, bool LUMA3, class Ctx>
+TFC_HD void pair_prefetch_l2(const Ctx& ctx, const Params& prm, const TileCoord& ta, const TileCoord& tb) {
+#ifdef __CUDA_ARCH__
+    constexpr int NC = LUMA3 ? 3 : 1;
+    constexpr int EPL = 128 / (int)sizeof(T);              // elements per 128-byte line
+    constexpr int LPR = (P + EPL - 1) / EPL;               // lines per tile row
+    const PairSrc<T> src = pair_src<P, T>(prm, ta, tb);
+    for (int it = ctx.tid; it < 4 * NC * P * LPR; it += ctx.nthreads) {
+        const int l = it % LPR, y = (it / LPR) % P, wc = it / (LPR * P);
+        const int w = wc & 3, c = wc >> 2;
+        const T* q = src.p[w] + y * src.sh[w] + c * src.sc[w] + l * EPL;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    }
+#endif
 }
 
 // ---- stages 1+2: forward row passes.  The first works in place on the swizzled addresses (each
@@ -207,37 +280,41 @@ TFC_HD void pair_rows_second(const Ctx& ctx, float4* s) {
 }
 
 // ---- loss pass over exactly the half-plane bins -------------------------------------------------
+// P*P/2 work items: P*(P/2-1) regular bins (columns kx = 1..P/2-1, one item per bin; the mirror position
+// is zeroed for the inverse row passes) followed by P items for the two self-conjugate columns kx = 0 and
+// kx = P/2 (an item owns rows ky and -ky; the four self-conjugate bins of a column pair up as one item).
 template <int P, class Ctx>
 TFC_HD void pair_bins(const Ctx& ctx, const Params& prm, float4* s, float2& accA, float2& accP) {
-    constexpr int LD = PairCfg<P>::LD, H = P / 2;
+    constexpr int LD = PairCfg<P>::LD, H = P / 2, NREG = P * (H - 1);
     const bool mse = (prm.flags & TFCFFT_DIST_MSE) != 0, phase = !(prm.flags & TFCFFT_NO_PHASE);
     const bool want_grad = prm.grad != nullptr;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    // regular columns kx = 1 .. P/2-1: one item per bin, mirror position zeroed for the inverse rows
-    for (int it = ctx.tid; it < P * (H - 1); it += ctx.nthreads) {
-        const int qy = it % P, kx = 1 + it / P;  // consecutive threads: consecutive row positions
-        const int qx = pos_of_freq<P>(kx), qxm = pos_of_freq<P>(P - kx), qym = neg_pos<P>(qy);
-        float4* pk = s + qy * LD + qx;
-        float4* pm = s + qym * LD + qxm;
-        const c2 g = bin_eval_pair(prm, mse, phase, Cx<float4>::ld(*pk), Cx<float4>::ld(*pm), accA, accP);
-        if (want_grad) {
-            *pk = Cx<float4>::st(g);
-            *pm = zero;
+    for (int it = ctx.tid; it < P * H; it += ctx.nthreads) {
+        if (it < NREG) {
+            const int qy = it % P, kx = 1 + it / P;  // consecutive threads: consecutive row positions
+            const int qx = pos_of_freq<P>(kx), qxm = pos_of_freq<P>(P - kx), qym = neg_pos<P>(qy);
+            float4* pk = s + qy * LD + qx;
+            float4* pm = s + qym * LD + qxm;
+            const c2 g = bin_eval_pair(prm, mse, phase, Cx<float4>::ld(*pk), Cx<float4>::ld(*pm), accA, accP);
+            if (want_grad) {
+                *pk = Cx<float4>::st(g);
+                *pm = zero;
+            }
+        } else {
+            const int sp = it - NREG, r = sp % H;
+            const int qx = pos_of_freq<P>((sp / H) * H);
+            // r == 0: the two self-conjugate bins ky = 0 and ky = P/2; else the pair (ky, -ky) = (r, P - r)
+            const int qy = pos_of_freq<P>(r), qym = pos_of_freq<P>(r == 0 ? H : P - r);
+            float4* pk = s + qy * LD + qx;
+            float4* pm = s + qym * LD + qx;
+            const c2 zk = Cx<float4>::ld(*pk), zm = Cx<float4>::ld(*pm);
+            const c2 g = bin_eval_pair(prm, mse, phase, zk, r == 0 ? zk : zm, accA, accP);
+            const c2 g2 = bin_eval_pair(prm, mse, phase, zm, r == 0 ? zm : zk, accA, accP);
+            if (want_grad) {
+                *pk = Cx<float4>::st(g);
+                *pm = Cx<float4>::st(g2);
+            }
         }
-    }
-    // self-conjugate columns kx = 0 and kx = P/2: the item owns rows ky and -ky
-    for (int it = ctx.tid; it < 2 * (H + 1); it += ctx.nthreads) {
-        const int ky = it % (H + 1), qx = pos_of_freq<P>((it / (H + 1)) * H);
-        const int qy = pos_of_freq<P>(ky), qym = pos_of_freq<P>((P - ky) & (P - 1));
-        float4* pk = s + qy * LD + qx;
-        float4* pm = s + qym * LD + qx;
-        const c2 zk = Cx<float4>::ld(*pk), zm = Cx<float4>::ld(*pm);
-        const c2 g = bin_eval_pair(prm, mse, phase, zk, zm, accA, accP);
-        if (qym != qy) {
-            const c2 g2 = bin_eval_pair(prm, mse, phase, zm, zk, accA, accP);
-            if (want_grad) *pm = Cx<float4>::st(g2);
-        }
-        if (want_grad) *pk = Cx<float4>::st(g);
     }
 }
 
@@ -295,36 +372,54 @@ TFC_HD void pair_rows_last(const Ctx& ctx, const Params& prm, const TileCoord& t
     }
 }
 
-// ---- one tile pair, start to finish ------------------------------------------------------------
+// ---- one tile pair: everything after the load stage -------------------------------------------
 template <int P, typename T, bool LUMA3, class Ctx>
-TFC_HD void pair_process(const Ctx& ctx, const Params& prm, int tile_a, int tile_b, bool b_valid, float4* s,
-                         const float4* tw, float2& accA, float2& accP) {
+TFC_HD void pair_compute(const Ctx& ctx, const Params& prm, const TileCoord& ta, const TileCoord& tb, bool b_valid,
+                         float4* s, const float4* tw, float2& accA, float2& accP) {
     using Pl = Plan<P>;
     constexpr int LD = PairCfg<P>::LD, LP = ilog2_c(P), L2 = P / Pl::R1;
     static_assert(Pl::R3 == 1, "pair path supports two-pass plans");
-    const TileCoord ta = decode_tile(prm, tile_a), tb = decode_tile(prm, tile_b);
-    pair_load<P, T, LUMA3>(ctx, prm, ta, tb, s);
-    ctx.sync();
+    ctx.mark(1);
     pair_rows_first<P>(ctx, s, tw);
     ctx.sync();
+    ctx.mark(2);
     pair_rows_second<P>(ctx, s);
     ctx.sync();
+    ctx.mark(3);
     fft_pass<P, Pl::R1, P, false>(ctx, s, LD, 1, LP, tw);   // columns: thread-fast = column
     ctx.sync();
+    ctx.mark(4);
     fft_pass<P, Pl::R2, L2, false>(ctx, s, LD, 1, LP, tw);
     ctx.sync();
+    ctx.mark(5);
     pair_bins<P>(ctx, prm, s, accA, accP);
     ctx.sync();
+    ctx.mark(6);
     if (prm.grad != nullptr) {
         pair_cols_inv_pass<P, Pl::R2, L2>(ctx, s, tw);
         ctx.sync();
+        ctx.mark(7);
         pair_cols_inv_pass<P, Pl::R1, P>(ctx, s, tw);
         ctx.sync();
+        ctx.mark(8);
         fft_pass<P, Pl::R2, L2, true>(ctx, s, 1, LD, LP, tw);
         ctx.sync();
+        ctx.mark(9);
         pair_rows_last<P, T, LUMA3>(ctx, prm, ta, tb, b_valid, s, tw);
         ctx.sync();
+        ctx.mark(10);
     }
+}
+
+// load + compute by the same threads (CPU emulation; the kernel splits the two across warp roles)
+template <int P, typename T, bool LUMA3, class Ctx>
+TFC_HD void pair_process(const Ctx& ctx, const Params& prm, int tile_a, int tile_b, bool b_valid, float4* s,
+                         const float4* tw, float2& accA, float2& accP) {
+    const TileCoord ta = decode_tile(prm, tile_a), tb = decode_tile(prm, tile_b);
+    ctx.mark(0);
+    pair_load<P, T, LUMA3>(ctx, prm, ta, tb, s);
+    ctx.sync();
+    pair_compute<P, T, LUMA3>(ctx, prm, ta, tb, b_valid, s, tw, accA, accP);
 }
 
 TFC_HD bool pair_supported(const Params& prm) {

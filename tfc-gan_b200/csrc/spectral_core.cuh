@@ -43,6 +43,7 @@ struct Params {
     float2* zws;           // split path: spectrum workspace [chunk_tiles][P][P]
     int tile_base;         // split path: first tile of this chunk
     int chunk_tiles;
+    long long* trace;      // debug: per-CTA stage timestamps (tfcfft_debug_trace), normally nullptr
 };
 
 // ---------------------------------------------------------------------------------------------

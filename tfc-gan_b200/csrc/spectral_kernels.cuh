@@ -124,10 +124,31 @@ __global__ void __launch_bounds__(ResidentCfg<P>::NT) resident_kernel(const __gr
     finish(prm, gridDim.x);
 }
 
-// Block sum of four floats; result valid in thread 0.
-__device__ __forceinline__ void block_sum4(float& a, float& b, float& c, float& d) {
-    __shared__ float red4[4][32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+// ---- named barriers (bar.sync / bar.arrive with explicit participant counts) ---------------------
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Execution context of one warp-role group: compile-time size, its own named barrier.
+template <int NT, int BAR>
+struct GroupCtx {
+    int tid;
+    static constexpr int nthreads = NT;
+    long long* trace;
+    __device__ __forceinline__ void sync() const { bar_sync(BAR, NT); }
+    __device__ __forceinline__ void mark(int k) const {
+        if (trace != nullptr && tid == 0) trace[k] = clock64();
+    }
+};
+
+// Sum of four floats over a group of NT threads (NT/32 <= 32 warps); result valid in group thread 0.
+template <int NT, int BAR>
+__device__ __forceinline__ void group_sum4(int tid, float* red /* [4][32] */, float& a, float& b, float& c, float& d) {
+    const int lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_down_sync(0xffffffffu, a, o);
@@ -136,17 +157,17 @@ __device__ __forceinline__ void block_sum4(float& a, float& b, float& c, float& 
         d += __shfl_down_sync(0xffffffffu, d, o);
     }
     if (lane == 0) {
-        red4[0][wid] = a;
-        red4[1][wid] = b;
-        red4[2][wid] = c;
-        red4[3][wid] = d;
+        red[0 * 32 + wid] = a;
+        red[1 * 32 + wid] = b;
+        red[2 * 32 + wid] = c;
+        red[3 * 32 + wid] = d;
     }
-    __syncthreads();
+    bar_sync(BAR, NT);
     if (wid == 0) {
-        a = lane < nw ? red4[0][lane] : 0.f;
-        b = lane < nw ? red4[1][lane] : 0.f;
-        c = lane < nw ? red4[2][lane] : 0.f;
-        d = lane < nw ? red4[3][lane] : 0.f;
+        a = lane < NW ? red[0 * 32 + lane] : 0.f;
+        b = lane < NW ? red[1 * 32 + lane] : 0.f;
+        c = lane < NW ? red[2 * 32 + lane] : 0.f;
+        d = lane < NW ? red[3 * 32 + lane] : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             a += __shfl_down_sync(0xffffffffu, a, o);
@@ -155,32 +176,79 @@ __device__ __forceinline__ void block_sum4(float& a, float& b, float& c, float& 
             d += __shfl_down_sync(0xffffffffu, d, o);
         }
     }
-    __syncthreads();
+    bar_sync(BAR, NT);
 }
 
-// Packed tile-pair kernel (pair_tile.cuh): persistent CTAs, each iteration transforms two tiles.
+// Packed tile-pair kernel (pair_tile.cuh), warp-specialised and persistent: one CTA per SM.
+//   warps 0..15  (compute): transform the pair resident in work buffer b = i & 1 -- row/column FFTs, loss,
+//                           spectral gradient, inverse FFTs, gradient store;
+//   warps 16..23 (load):    stream pair i+1 from HBM (coalesced 128-bit loads), fold luma, pack (A, B) and
+//                           fill the other work buffer, so HBM latency and the transforms overlap.
+// Hand-off with named barriers: FULL[b] (loaders arrive, compute waits), EMPTY[b] (compute arrives after its
+// last read of buffer b, loaders wait before overwriting it).  Shared memory per pair (66.5 KB) is what
+// bounds the number of pairs in flight; two buffers + one transform at a time with 16 warps keeps every
+// stage short instead of interleaving three slow CTAs.
 template <int P, typename T, bool LUMA3>
-__global__ void __launch_bounds__(PairCfg<P>::NT) pair_kernel(const __grid_constant__ Params prm) {
+__global__ void __launch_bounds__(PairCfg<P>::NT, 1) pair_kernel(const __grid_constant__ Params prm) {
+    using Cfg = PairCfg<P>;
+    constexpr int BAR_COMPUTE = 1, BAR_FULL = 2, BAR_EMPTY = 4;  // ids 2,3 and 4,5
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* s = reinterpret_cast<float4*>(smem_raw);
-    float4* tw = s + P * PairCfg<P>::LD;
-    const BlockCtx ctx{(int)threadIdx.x, (int)blockDim.x};
-    fill_twiddles4<P>(ctx, tw);
-    ctx.sync();
+    float4* buf0 = reinterpret_cast<float4*>(smem_raw);
+    float4* buf1 = buf0 + P * Cfg::LD;
+    float4* tw = buf1 + P * Cfg::LD;
+    __shared__ float red[4 * 32];
+    {
+        const BlockCtx all{(int)threadIdx.x, (int)blockDim.x};
+        fill_twiddles4<P>(all, tw);
+    }
+    __syncthreads();
     const int npairs = (prm.tiles_total + 1) >> 1;
-    for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
-        const int ta = 2 * pr;
-        const bool b_valid = ta + 1 < prm.tiles_total;
-        const int tb = b_valid ? ta + 1 : ta;
-        float2 accA = make_float2(0.f, 0.f), accP = make_float2(0.f, 0.f);
-        pair_process<P, T, LUMA3>(ctx, prm, ta, tb, b_valid, s, tw, accA, accP);
-        block_sum4(accA.x, accA.y, accP.x, accP.y);
-        if (threadIdx.x == 0) {
-            prm.partials[2 * ta] = accA.x;
-            prm.partials[2 * ta + 1] = accP.x;
-            if (b_valid) {
-                prm.partials[2 * tb] = accA.y;
-                prm.partials[2 * tb + 1] = accP.y;
+    if (threadIdx.x >= Cfg::NT_COMPUTE) {
+        // ---------------- loader warps ----------------
+        const GroupCtx<Cfg::NT_LOAD, 6> ctx{(int)threadIdx.x - Cfg::NT_COMPUTE, nullptr};
+        int iter = 0;
+        for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++iter) {
+            const int b = iter & 1;
+            const int ta = 2 * pr, tb = ta + 1 < prm.tiles_total ? ta + 1 : ta;
+            bar_sync(BAR_EMPTY + b, Cfg::NT);  // buffer b has been consumed (primed for the first two pairs)
+            pair_load<P, T, LUMA3>(ctx, prm, decode_tile(prm, ta), decode_tile(prm, tb), b ? buf1 : buf0);
+            bar_arrive(BAR_FULL + b, Cfg::NT);
+        }
+    } else {
+        // ---------------- compute warps ----------------
+        GroupCtx<Cfg::NT_COMPUTE, BAR_COMPUTE> ctx{(int)threadIdx.x, nullptr};
+        bar_arrive(BAR_EMPTY + 0, Cfg::NT);  // both buffers start empty
+        bar_arrive(BAR_EMPTY + 1, Cfg::NT);
+        int iter = 0;
+        for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++iter) {
+            const int b = iter & 1;
+            const int ta = 2 * pr;
+            const bool b_valid = ta + 1 < prm.tiles_total;
+            const int tb = b_valid ? ta + 1 : ta;
+            float4* s = b ? buf1 : buf0;
+            float2 accA = make_float2(0.f, 0.f), accP = make_float2(0.f, 0.f);
+            ctx.trace = (prm.trace != nullptr && iter < 6) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
+            ctx.mark(0);
+            bar_sync(BAR_FULL + b, Cfg::NT);  // the loaders have filled buffer b
+            pair_compute<P, T, LUMA3>(ctx, prm, decode_tile(prm, ta), decode_tile(prm, tb), b_valid, s, tw, accA, accP);
+            // pair_compute ends with a group barrier: every read of buffer b is done
+            if (pr + 2 * (int)gridDim.x < npairs) bar_arrive(BAR_EMPTY + b, Cfg::NT);
+            group_sum4<Cfg::NT_COMPUTE, BAR_COMPUTE>(ctx.tid, red, accA.x, accA.y, accP.x, accP.y);
+            if (ctx.tid == 0) {
+                prm.partials[2 * ta] = accA.x;
+                prm.partials[2 * ta + 1] = accP.x;
+                if (b_valid) {
+                    prm.partials[2 * tb] = accA.y;
+                    prm.partials[2 * tb + 1] = accP.y;
+                }
+                if (ctx.trace != nullptr) {
+                    unsigned smid;
+                    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                    ctx.trace[14] = smid;
+                    unsigned long long gt;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                    ctx.trace[15] = (long long)gt;
+                }
             }
         }
     }

@@ -13,6 +13,7 @@ using namespace tfcfft;
 namespace {
 
 std::atomic<long long> g_launches{0};
+std::atomic<long long*> g_trace{nullptr};  // debug only (tfcfft_debug_trace)
 
 struct DeviceInfo {
     int sms = 0;
@@ -65,12 +66,8 @@ int launch_pair(const Params& prm, cudaStream_t st) {
     constexpr size_t smem = PairCfg<P>::SMEM;
     constexpr int nt = PairCfg<P>::NT;
     if (int rc = set_smem(kernel, smem)) return rc;
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem);
-    if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) per_sm = 1;
     const long long npairs = ((long long)prm.tiles_total + 1) / 2;
-    const long long cap = (long long)device_info().sms * per_sm;
+    const long long cap = device_info().sms;  // persistent, warp-specialised: one CTA per SM
     const int grid = (int)(npairs < cap ? npairs : cap);
     kernel<<<grid, nt, smem, st>>>(prm);
     g_launches++;
@@ -173,7 +170,8 @@ int tfcfft_loss(const tfcfft_desc* d, const void* fake, const void* real, float*
     if ((rc = check_grad_args(d, grad_fake))) return rc;
     if ((rc = check_alignment(d, fake, real, grad_fake))) return rc;
     if (!workspace || workspace_bytes < g.ws_bytes || ((uintptr_t)workspace & 255)) return TFCFFT_ERR_WORKSPACE;
-    const Params prm = make_params(d, g, fake, real, grad_fake, out, per_image, workspace);
+    Params prm = make_params(d, g, fake, real, grad_fake, out, per_image, workspace);
+    prm.trace = g_trace.load();
     cudaStream_t st = (cudaStream_t)stream;
     switch (g.p) {
         case 16: return launch_t<16>(prm, g.split, g.luma3, d->dtype, st);
@@ -213,6 +211,8 @@ int tfcfft_grad_scale(void* dst, const void* src, int32_t dtype, int64_t numel, 
     TFC_LAUNCH_CHECK();
     return 0;
 }
+
+void tfcfft_debug_trace(void* device_buffer) { g_trace.store((long long*)device_buffer); }
 
 int64_t tfcfft_launch_count(void) { return g_launches.load(); }
 void tfcfft_launch_count_reset(void) { g_launches.store(0); }
