@@ -102,6 +102,20 @@ int tfcfft_workspace_init(void* workspace, size_t workspace_bytes, void* stream)
 int tfcfft_loss(const tfcfft_desc* d, const void* fake, const void* real, float* out, float* per_image,
                 void* grad_fake, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Materialised spectra: the differentiable counterpart of the reference's fft_components
+ * (TFCGAN_multigpu_patchFFT_16P.py:293-319; global variant TFCGAN_multigpu_globalFFT.py:266-284) and of
+ * make_spectra / sample_spectra (patchFFT_16P.py:284-289, 378-388).  d->grid must be 1 (the tensor IS the
+ * patch).  Outputs are float [N][C'][P][W], W = P/2+1 (or P with FULL_SPECTRUM), C' = 1 (luma) or 3 (rgb);
+ * with LOG_MAGNITUDE the amplitude is log|F|.  fftshift != 0 stores them in np.fft.fftshift order over both
+ * axes like the reference (:279).  y and any output pointer may be NULL. */
+int tfcfft_spectra(const tfcfft_desc* d, const void* x, const void* y, float* amp_x, float* pha_x, float* amp_y,
+                   float* pha_y, int fftshift, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of tfcfft_spectra for `x`: grad_x = d L / d x given d L / d amp_x and d L / d pha_x
+ * (either may be NULL); d->grad_stride describes grad_x. */
+int tfcfft_spectra_bwd(const tfcfft_desc* d, const void* x, const float* grad_amp, const float* grad_pha,
+                       void* grad_x, int fftshift, void* workspace, size_t workspace_bytes, void* stream);
+
 /* dst[i] = src[i] * host_scale * (*dev_scale)   (dev_scale may be NULL; dst may equal src);
  * numel elements of `dtype`, both 16-byte aligned. */
 int tfcfft_grad_scale(void* dst, const void* src, int32_t dtype, int64_t numel, const float* dev_scale,

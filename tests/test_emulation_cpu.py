@@ -123,3 +123,53 @@ def test_packed_pair_path_matches_generic_path(opt):
     np.testing.assert_allclose(o1[:3], o2[:3], rtol=2e-6)
     np.testing.assert_allclose(p1, p2, rtol=2e-6)
     assert l2rel(g1, g2) <= 2e-5
+
+
+@pytest.mark.parametrize("side", [64, 256])
+@pytest.mark.parametrize("opt", [dict(), dict(channels="rgb"), dict(spectrum="full", log_magnitude=True)])
+def test_emulated_spectra_match_fft_components(side, opt):
+    """tfcfft_spectra == differentiable fft_components (amp / phase, fftshift-ed half plane or full log plane)."""
+    from util import emulate_spectra, emulate_spectra_bwd
+
+    x, y = make_pair("tanh", 23, (2, 3, side, side), "float32")
+    rc, ax, px, ay, py = emulate_spectra(x, flags_of(**opt), input_scale=255.0, shift=True, y=y)
+    assert rc == 0
+    full = opt.get("spectrum") == "full"
+    for arr, (a_emu, p_emu) in ((x, (ax, px)), (y, (ay, py))):
+        t = oracle.r1_differentiable._prepare(torch.from_numpy(arr), opt.get("channels", "luma"), 255.0, False, torch.float64)
+        F = torch.fft.fft2(t) if full else torch.fft.rfft2(t)
+        F = torch.fft.fftshift(F, dim=(-2, -1))
+        amp = F.abs().log() if opt.get("log_magnitude") else F.abs()
+        np.testing.assert_allclose(a_emu, amp.numpy(), rtol=2e-4, atol=2e-3 if not opt.get("log_magnitude") else 2e-4)
+        # phase of tiny bins is rounding noise: compare where the amplitude is not negligible
+        big = F.abs().numpy() > 1e-3 * F.abs().numpy().max()
+        dphi = np.angle(np.exp(1j * (p_emu - torch.angle(F).numpy())))
+        assert np.abs(dphi[big]).max() < 2e-3
+    # backward against autograd for a random cotangent
+    rs = np.random.RandomState(0)
+    ga = rs.normal(size=ax.shape).astype(np.float32)
+    gp = (rs.normal(size=px.shape) * 0.0 if opt.get("log_magnitude") else rs.normal(size=px.shape)).astype(np.float32)
+    rc, g = emulate_spectra_bwd(x, ga, gp, flags_of(**opt), input_scale=255.0, shift=True)
+    assert rc == 0
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    t = oracle.r1_differentiable._prepare(xt, opt.get("channels", "luma"), 255.0, False, torch.float64)
+    F = torch.fft.fftshift(torch.fft.fft2(t) if full else torch.fft.rfft2(t), dim=(-2, -1))
+    amp = F.abs().log() if opt.get("log_magnitude") else F.abs()
+    loss = (amp * torch.from_numpy(ga).double()).sum() + (torch.angle(F) * torch.from_numpy(gp).double()).sum()
+    loss.backward()
+    assert l2rel(g, xt.grad.numpy()) <= 1e-3
+
+
+def test_emulated_spectra_quantised_match_reference_golden():
+    from util import emulate_spectra
+
+    case = next(c for c in GOLD["cases"] if c["name"] == "p16_uniform_11_float32")
+    fake, _ = make_pair(case["kind"], case["seed"], (case["n"], 3, 256, 256), case["dtype"])
+    patch = np.ascontiguousarray(fake[:, :, 64:128, 64:128])  # B6
+    rc, amp, pha, _, _ = emulate_spectra(patch, flags_of(quantize=True), shift=True)
+    assert rc == 0
+    gold = np.load(os.path.join(HERE, "golden", "golden_arrays.npz"))
+    np.testing.assert_allclose(amp, gold["p16_uniform_11_float32_amp_B6"], rtol=1e-5, atol=0.05)
+    ga = gold["p16_uniform_11_float32_amp_B6"]
+    dphi = np.angle(np.exp(1j * (pha - gold["p16_uniform_11_float32_pha_B6"])))
+    assert np.abs(dphi[ga > 1.0]).max() < 1e-3

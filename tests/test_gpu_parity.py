@@ -281,3 +281,45 @@ def test_errors_raise():
         tfc.spectral_loss(x[:0], x[:0], grid=4)
     with pytest.raises(RuntimeError, match="shape"):
         tfc.spectral_loss(torch.zeros(1, 3, 256, 128, device="cuda"), torch.zeros(1, 3, 256, 128, device="cuda"), grid=1)
+
+
+@pytest.mark.parametrize("side", [64, 128, 256])
+def test_fft_components_materialised_and_differentiable(side):
+    """compat.fft_components: (AMP, PHA) [N,1,p,p/2+1], fftshift-ed, with a gradient."""
+    from tfc_gan_b200 import compat
+
+    x, _ = make_pair("tanh", 29, (2, 3, side, side), "float32")
+    xt = cu(x).requires_grad_(True)
+    amp, pha = compat.fft_components(xt)
+    assert amp.shape == (2, 1, side, side // 2 + 1) and pha.shape == amp.shape
+    ra, rp = oracle.fft_components_r1(torch.from_numpy(x), input_scale=255.0, shift=True)
+    np.testing.assert_allclose(amp.detach().cpu().numpy(), ra.numpy(), rtol=2e-4, atol=2e-3)
+    big = ra.numpy() > 1e-3 * ra.numpy().max()
+    dphi = np.angle(np.exp(1j * (pha.detach().cpu().numpy() - rp.numpy())))
+    assert np.abs(dphi[big]).max() < 2e-3
+    # a downstream loss on the spectra back-propagates to x (e.g. the triplet-on-spectra variants)
+    w = torch.linspace(0.5, 1.5, amp.numel(), device="cuda").reshape(amp.shape)
+    (amp * w).sum().backward()
+    xd = torch.from_numpy(x).double().requires_grad_(True)
+    a64, _ = oracle.fft_components_r1(xd, input_scale=255.0, shift=True)
+    (a64 * w.cpu().double()).sum().backward()
+    assert l2rel(xt.grad.cpu().numpy(), xd.grad.numpy()) <= GRAD_TOL
+
+
+def test_fft_components_r0_mode_matches_reference_spectra():
+    from tfc_gan_b200 import compat
+
+    case = next(c for c in GOLD["cases"] if c["name"] == "p16_uniform_11_float32")
+    fake, _ = make_pair(case["kind"], case["seed"], (case["n"], 3, 256, 256), case["dtype"])
+    compat.set_mode("r0")
+    try:
+        amp, pha = compat.fft_components(compat.make_16_patches(cu(fake))[5])  # a strided view: patch B6
+        spec = compat.sample_spectra(cu(fake)[:1])
+    finally:
+        compat.set_mode("r1")
+    ga, gp = ARR["p16_uniform_11_float32_amp_B6"], ARR["p16_uniform_11_float32_pha_B6"]
+    np.testing.assert_allclose(amp.cpu().numpy(), ga, rtol=1e-5, atol=0.05)
+    dphi = np.angle(np.exp(1j * (pha.cpu().numpy() - gp)))
+    assert np.abs(dphi[ga > 1.0]).max() < 1e-3
+    ref = oracle.make_spectra_r0(oracle.gray_u8(fake[:1])[0])
+    np.testing.assert_allclose(spec[0, 0].cpu().numpy(), ref, rtol=1e-4, atol=1e-3)

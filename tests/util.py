@@ -55,6 +55,36 @@ def emulate(fake: np.ndarray, real: np.ndarray, grid: int, flags: int, weight=1.
     return rc, out, per, g
 
 
+def emulate_spectra(x: np.ndarray, flags: int, input_scale=1.0, shift=True, y=None):
+    """CPU twin of tfcfft_spectra.  Returns (rc, amp_x, pha_x[, amp_y, pha_y])."""
+    lib = emu_lib()
+    lib.tfcfft_emulate_spectra.restype = ctypes.c_int
+    lib.tfcfft_emulate_spectra.argtypes = [ctypes.POINTER(L.Desc)] + [ctypes.c_void_p] * 6 + [ctypes.c_int]
+    n, c, p, _ = x.shape
+    cp = 3 if (flags & L.CHANNELS_RGB and c == 3) else 1
+    w = p if flags & L.FULL_SPECTRUM else p // 2 + 1
+    outs = [np.zeros((n, cp, p, w), np.float32) for _ in range(4)]
+    d = L.make_desc(NP_DTYPES[str(x.dtype)], 1, flags, x.shape, _strides(x), _strides(y if y is not None else x), None,
+                    1.0, input_scale)
+    rc = lib.tfcfft_emulate_spectra(ctypes.byref(d), x.ctypes.data, y.ctypes.data if y is not None else None,
+                                    outs[0].ctypes.data, outs[1].ctypes.data, outs[2].ctypes.data, outs[3].ctypes.data,
+                                    int(shift))
+    return (rc, *outs)
+
+
+def emulate_spectra_bwd(x: np.ndarray, g_amp, g_pha, flags: int, input_scale=1.0, shift=True):
+    lib = emu_lib()
+    lib.tfcfft_emulate_spectra_bwd.restype = ctypes.c_int
+    lib.tfcfft_emulate_spectra_bwd.argtypes = [ctypes.POINTER(L.Desc)] + [ctypes.c_void_p] * 4 + [ctypes.c_int]
+    g = np.zeros_like(x)
+    d = L.make_desc(NP_DTYPES[str(x.dtype)], 1, flags, x.shape, _strides(x), _strides(x), _strides(g), 1.0, input_scale)
+    ga = np.ascontiguousarray(g_amp, np.float32) if g_amp is not None else None
+    gp = np.ascontiguousarray(g_pha, np.float32) if g_pha is not None else None
+    rc = lib.tfcfft_emulate_spectra_bwd(ctypes.byref(d), x.ctypes.data, ga.ctypes.data if ga is not None else None,
+                                        gp.ctypes.data if gp is not None else None, g.ctypes.data, int(shift))
+    return rc, g
+
+
 def l2rel(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)

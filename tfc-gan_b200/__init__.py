@@ -10,6 +10,7 @@ from .functional import (  # noqa: F401
     SpectralConfig,
     launch_count,
     reset_launch_count,
+    spectral_components,
     spectral_loss,
     spectral_loss_and_grad,
     spectral_terms_per_image,
@@ -17,6 +18,6 @@ from .functional import (  # noqa: F401
 from .modules import SpectralLoss  # noqa: F401
 
 __all__ = [
-    "SpectralConfig", "SpectralLoss", "spectral_loss", "spectral_loss_and_grad", "spectral_terms_per_image",
+    "SpectralConfig", "SpectralLoss", "spectral_loss", "spectral_components", "spectral_loss_and_grad", "spectral_terms_per_image",
     "launch_count", "reset_launch_count", "compat", "dist",
 ]

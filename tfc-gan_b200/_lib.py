@@ -35,6 +35,8 @@ EXPORTS = (
     "tfcfft_workspace_bytes",
     "tfcfft_workspace_init",
     "tfcfft_loss",
+    "tfcfft_spectra",
+    "tfcfft_spectra_bwd",
     "tfcfft_grad_scale",
     "tfcfft_debug_trace",
     "tfcfft_launch_count",
@@ -93,6 +95,10 @@ def bind(lib):
     lib.tfcfft_workspace_init.argtypes = [vp, ctypes.c_size_t, vp]
     lib.tfcfft_loss.restype = ctypes.c_int
     lib.tfcfft_loss.argtypes = [dp, vp, vp, f32p, f32p, vp, vp, ctypes.c_size_t, vp]
+    lib.tfcfft_spectra.restype = ctypes.c_int
+    lib.tfcfft_spectra.argtypes = [dp, vp, vp, f32p, f32p, f32p, f32p, ctypes.c_int, vp, ctypes.c_size_t, vp]
+    lib.tfcfft_spectra_bwd.restype = ctypes.c_int
+    lib.tfcfft_spectra_bwd.argtypes = [dp, vp, f32p, f32p, vp, ctypes.c_int, vp, ctypes.c_size_t, vp]
     lib.tfcfft_grad_scale.restype = ctypes.c_int
     lib.tfcfft_grad_scale.argtypes = [vp, vp, ctypes.c_int32, ctypes.c_int64, f32p, ctypes.c_float, vp]
     lib.tfcfft_debug_trace.restype = None

@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import torch
 
-from .functional import SpectralConfig, spectral_loss, spectral_terms_per_image
+from .functional import SpectralConfig, spectral_components, spectral_loss, spectral_terms_per_image
 
 _MODE = {"mode": "r1", "input_scale": 255.0}
 
@@ -32,6 +32,24 @@ def _cfg(grid, patch_reduce="mean", weight=1.0):
     if _MODE["mode"] == "r0":
         return SpectralConfig(grid=grid, patch_reduce=patch_reduce, weight=weight, quantize=True)
     return SpectralConfig(grid=grid, patch_reduce=patch_reduce, weight=weight, input_scale=_MODE["input_scale"])
+
+
+def fft_components(thermal_tensor, patch=True):
+    """``fft_components(x, patch=True)`` (``TFC-GAN-FFT/TFCGAN_multigpu_patchFFT_16P.py:293-319``; global
+    variants ``TFCGAN_multigpu_globalFFT.py:266-284``): ``[N,3,p,p]`` -> ``(AMP, PHA)`` each ``[N,1,p,p/2+1]`` fp32,
+    fftshift-ed like the reference.  Shapes come from the tensor (``patch`` is accepted and ignored; upstream it
+    only selected hard-coded reshape constants).  Differentiable in ``"r1"`` mode."""
+    if _MODE["mode"] == "r0":
+        return spectral_components(thermal_tensor, quantize=True)
+    return spectral_components(thermal_tensor, input_scale=_MODE["input_scale"])
+
+
+def sample_spectra(thermal_tensor):
+    """``sample_spectra`` / ``FFT_Components.make_spectra`` (``...patchFFT_16P.py:284-289,378-388``):
+    ``log|fftshift(fft2(L))|`` of every image, ``[N,1,H,W]`` (``-inf`` where a bin is exactly zero)."""
+    kw = dict(quantize=True) if _MODE["mode"] == "r0" else dict(input_scale=_MODE["input_scale"])
+    amp, _ = spectral_components(thermal_tensor, spectrum="full", log_magnitude=True, **kw)
+    return amp
 
 
 def make_16_patches(B):

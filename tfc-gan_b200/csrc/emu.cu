@@ -101,6 +101,17 @@ void run_t(const Params& prm, bool split, bool luma3, int dtype) {
 
 }  // namespace
 
+static void run_all(Params& prm, const Geometry& g, int dtype) {
+    switch (g.p) {
+        case 16: run_t<16>(prm, g.split, g.luma3, dtype); break;
+        case 32: run_t<32>(prm, g.split, g.luma3, dtype); break;
+        case 64: run_t<64>(prm, g.split, g.luma3, dtype); break;
+        case 128: run_t<128>(prm, g.split, g.luma3, dtype); break;
+        case 256: run_t<256>(prm, g.split, g.luma3, dtype); break;
+        case 512: run_t<512>(prm, g.split, g.luma3, dtype); break;
+    }
+}
+
 // Same contract as tfcfft_loss, but every pointer is HOST memory and no workspace is passed in.
 extern "C" int tfcfft_emulate(const tfcfft_desc* d, const void* fake, const void* real, float* out, float* per_image,
                               void* grad_fake) {
@@ -112,14 +123,7 @@ extern "C" int tfcfft_emulate(const tfcfft_desc* d, const void* fake, const void
     if ((rc = check_alignment(d, fake, real, grad_fake))) return rc;
     std::vector<char> ws(g.ws_bytes, 0);
     Params prm = make_params(d, g, fake, real, grad_fake, out, per_image, ws.data());
-    switch (g.p) {
-        case 16: run_t<16>(prm, g.split, g.luma3, d->dtype); break;
-        case 32: run_t<32>(prm, g.split, g.luma3, d->dtype); break;
-        case 64: run_t<64>(prm, g.split, g.luma3, d->dtype); break;
-        case 128: run_t<128>(prm, g.split, g.luma3, d->dtype); break;
-        case 256: run_t<256>(prm, g.split, g.luma3, d->dtype); break;
-        case 512: run_t<512>(prm, g.split, g.luma3, d->dtype); break;
-    }
+    run_all(prm, g, d->dtype);
     double sa = 0.0, sp = 0.0;
     for (int img = 0; img < prm.n; ++img) {
         double a, p;
@@ -132,5 +136,45 @@ extern "C" int tfcfft_emulate(const tfcfft_desc* d, const void* fake, const void
         sp += p;
     }
     write_outputs(prm, sa, sp);
+    return TFCFFT_OK;
+}
+
+// Host-memory twins of tfcfft_spectra / tfcfft_spectra_bwd.
+extern "C" int tfcfft_emulate_spectra(const tfcfft_desc* d, const void* x, const void* y, float* amp_x, float* pha_x,
+                                      float* amp_y, float* pha_y, int fftshift) {
+    Geometry g;
+    int rc = validate_desc(d, &g);
+    if (rc) return rc;
+    if (d->grid != 1) return TFCFFT_ERR_SHAPE;
+    if (!x) return TFCFFT_ERR_NULL;
+    std::vector<char> ws(g.ws_bytes, 0);
+    float out[4];
+    Params prm = make_params(d, g, x, y ? y : x, nullptr, out, nullptr, ws.data());
+    prm.spec_mode = 1;
+    prm.spec_shift = fftshift != 0;
+    prm.spec_out[0] = amp_x;
+    prm.spec_out[1] = pha_x;
+    prm.spec_out[2] = y ? amp_y : nullptr;
+    prm.spec_out[3] = y ? pha_y : nullptr;
+    run_all(prm, g, d->dtype);
+    return TFCFFT_OK;
+}
+
+extern "C" int tfcfft_emulate_spectra_bwd(const tfcfft_desc* d, const void* x, const float* grad_amp, const float* grad_pha,
+                                          void* grad_x, int fftshift) {
+    Geometry g;
+    int rc = validate_desc(d, &g);
+    if (rc) return rc;
+    if (d->grid != 1) return TFCFFT_ERR_SHAPE;
+    if (!x || !grad_x) return TFCFFT_ERR_NULL;
+    if ((rc = check_grad_args(d, grad_x))) return rc;
+    std::vector<char> ws(g.ws_bytes, 0);
+    float out[4];
+    Params prm = make_params(d, g, x, x, grad_x, out, nullptr, ws.data());
+    prm.spec_mode = 2;
+    prm.spec_shift = fftshift != 0;
+    prm.spec_gin[0] = grad_amp;
+    prm.spec_gin[1] = grad_pha;
+    run_all(prm, g, d->dtype);
     return TFCFFT_OK;
 }

@@ -219,12 +219,14 @@ TFC_HD int neg_pos(int q) { return pos_of_freq<P>((P - freq_of_pos<P>(q)) & (P -
 struct SerialCtx {
     int tid = 0, nthreads = 1;
     TFC_HD void sync() const {}
+    TFC_HD void warp_sync() const {}
     TFC_HD void mark(int) const {}
 };
 #ifdef __CUDACC__
 struct BlockCtx {
     int tid, nthreads;
     __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
     __device__ __forceinline__ void mark(int) const {}
 };
 // Block size known at compile time: the task loops get constant trip counts and unroll, so the loads of
@@ -236,6 +238,7 @@ struct BlockCtxT {
     static constexpr int nthreads = NT;
     long long* trace;
     __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
     __device__ __forceinline__ void mark(int k) const {
         if (trace != nullptr && tid == 0) trace[k] = clock64();
     }

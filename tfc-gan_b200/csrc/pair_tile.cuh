@@ -289,30 +289,56 @@ TFC_HD void pair_bins(const Ctx& ctx, const Params& prm, float4* s, float2& accA
     const bool mse = (prm.flags & TFCFFT_DIST_MSE) != 0, phase = !(prm.flags & TFCFFT_NO_PHASE);
     const bool want_grad = prm.grad != nullptr;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int it = ctx.tid; it < P * H; it += ctx.nthreads) {
-        if (it < NREG) {
-            const int qy = it % P, kx = 1 + it / P;  // consecutive threads: consecutive row positions
-            const int qx = pos_of_freq<P>(kx), qxm = pos_of_freq<P>(P - kx), qym = neg_pos<P>(qy);
-            float4* pk = s + qy * LD + qx;
-            float4* pm = s + qym * LD + qxm;
-            const c2 g = bin_eval_pair(prm, mse, phase, Cx<float4>::ld(*pk), Cx<float4>::ld(*pm), accA, accP);
-            if (want_grad) {
-                *pk = Cx<float4>::st(g);
-                *pm = zero;
+    // two items per iteration: their (long, serial) dependency chains interleave
+    for (int it0 = ctx.tid; it0 < P * H; it0 += 2 * ctx.nthreads) {
+        float4* pk[2];
+        float4* pm[2];
+        c2 zk[2], zm[2];
+        bool live[2], reg[2], selfpair[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int it = it0 + u * ctx.nthreads;
+            live[u] = it < P * H;
+            reg[u] = it < NREG;
+            selfpair[u] = false;
+            int qy, qx, qym, qxm;
+            if (reg[u] || !live[u]) {
+                const int iq = live[u] ? it : 0;
+                qy = iq % P;  // consecutive threads: consecutive row positions
+                const int kx = 1 + iq / P;
+                qx = pos_of_freq<P>(kx);
+                qxm = pos_of_freq<P>(P - kx);
+                qym = neg_pos<P>(qy);
+            } else {
+                const int sp = it - NREG, r = sp % H;
+                qx = qxm = pos_of_freq<P>((sp / H) * H);
+                // r == 0: the two self-conjugate bins ky = 0 and ky = P/2; else the pair (ky, -ky) = (r, P - r)
+                qy = pos_of_freq<P>(r);
+                qym = pos_of_freq<P>(r == 0 ? H : P - r);
+                selfpair[u] = (r == 0);
             }
-        } else {
-            const int sp = it - NREG, r = sp % H;
-            const int qx = pos_of_freq<P>((sp / H) * H);
-            // r == 0: the two self-conjugate bins ky = 0 and ky = P/2; else the pair (ky, -ky) = (r, P - r)
-            const int qy = pos_of_freq<P>(r), qym = pos_of_freq<P>(r == 0 ? H : P - r);
-            float4* pk = s + qy * LD + qx;
-            float4* pm = s + qym * LD + qx;
-            const c2 zk = Cx<float4>::ld(*pk), zm = Cx<float4>::ld(*pm);
-            const c2 g = bin_eval_pair(prm, mse, phase, zk, r == 0 ? zk : zm, accA, accP);
-            const c2 g2 = bin_eval_pair(prm, mse, phase, zm, r == 0 ? zm : zk, accA, accP);
-            if (want_grad) {
-                *pk = Cx<float4>::st(g);
-                *pm = Cx<float4>::st(g2);
+            pk[u] = s + qy * LD + qx;
+            pm[u] = s + qym * LD + qxm;
+            zk[u] = Cx<float4>::ld(*pk[u]);
+            zm[u] = Cx<float4>::ld(*pm[u]);
+        }
+        c2 g[2], g2[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!live[u]) continue;
+            if (reg[u]) {
+                g[u] = bin_eval_pair(prm, mse, phase, zk[u], zm[u], accA, accP);
+            } else {
+                g[u] = bin_eval_pair(prm, mse, phase, zk[u], selfpair[u] ? zk[u] : zm[u], accA, accP);
+                g2[u] = bin_eval_pair(prm, mse, phase, zm[u], selfpair[u] ? zm[u] : zk[u], accA, accP);
+            }
+        }
+        if (want_grad) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (!live[u]) continue;
+                *pk[u] = Cx<float4>::st(g[u]);
+                *pm[u] = reg[u] ? zero : Cx<float4>::st(g2[u]);
             }
         }
     }
@@ -342,32 +368,69 @@ TFC_HD void pair_cols_inv_pass(const Ctx& ctx, float4* s, const float4* tw) {
     }
 }
 
-// ---- last inverse row pass: real part -> gradient in global memory ----------------------------
-template <int P, typename T, bool LUMA3, class Ctx>
-TFC_HD void pair_rows_last(const Ctx& ctx, const Params& prm, const TileCoord& ta, const TileCoord& tb, bool b_valid,
-                           const float4* s, const float4* tw) {
+// ---- last inverse row pass: the real parts (the two gradient tiles) stay in shared memory ---------
+// Output pixel x of row y goes to float4 slot swz(x) as (gA, gB, -, -).  The eight tasks of a row sit in
+// eight adjacent lanes of one warp; a warp-level barrier separates their reads from the swizzled writes.
+template <int P, class Ctx>
+TFC_HD void pair_rows_last(const Ctx& ctx, float4* s, const float4* tw) {
     constexpr int R = Plan<P>::R1, M = P / R, LD = PairCfg<P>::LD;
-    constexpr int NC = LUMA3 ? 3 : 1;
-    T* ga = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, ta, P));
-    T* gb = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tb, P));
+    static_assert(M <= 32 && (32 % M) == 0, "the tasks of one row must share a warp");
     for (int t = ctx.tid; t < P * M; t += ctx.nthreads) {
-        const int j = t % M, y = t / M;  // consecutive threads: consecutive pixels of one row
-        const float4* row = s + y * LD;
+        const int j = t % M, y = t / M;
+        float4* row = s + y * LD;
+#ifndef __CUDA_ARCH__
+        // serial emulation: tasks of a row run one after the other, so they read a snapshot of the row
+        static thread_local float4 snap[P];
+        if (j == 0)
+            for (int q = 0; q < P; ++q) snap[q] = row[q];
+        const float4* src = snap;
+#else
+        const float4* src = row;
+#endif
         c2 v[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) v[k] = Cx<float4>::ld(row[j + k * M]);
+        for (int k = 0; k < R; ++k) v[k] = Cx<float4>::ld(src[j + k * M]);
 #pragma unroll
         for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], tw[j * k]);
         Dft<R, true>::run(v);
-        T* pa = ga + (long long)y * prm.gs[2] + j;
-        T* pb = gb + (long long)y * prm.gs[2] + j;
+        ctx.warp_sync();
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            float2* dst = reinterpret_cast<float2*>(row + swz(j + m * M));
+            *dst = v[m].re;
+        }
+    }
+}
+
+// ---- gradient store: shared memory -> global, coalesced 128-bit stores -----------------------------
+// Runs on the loader warps of the kernel (off the transform's critical path).
+template <int P, typename T, bool LUMA3, class Ctx>
+TFC_HD void pair_store(const Ctx& ctx, const Params& prm, const TileCoord& ta, const TileCoord& tb, bool b_valid,
+                       const float4* s) {
+    constexpr int LD = PairCfg<P>::LD, XV = P / 4, NC = LUMA3 ? 3 : 1;
+    T* ga = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, ta, P));
+    T* gb = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tb, P));
+    const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
+    for (int it = ctx.tid; it < P * XV; it += ctx.nthreads) {
+        const int x = (it % XV) * 4, y = it / XV;
+        const float4* row = s + y * LD;
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 g = *reinterpret_cast<const float2*>(row + swz(x + i));
+            a[i] = g.x;
+            b[i] = g.y;
+        }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
+            float va[4], vb[4];
 #pragma unroll
-            for (int m = 0; m < R; ++m) {
-                IO<T>::store1(pa + c * prm.gs[1] + m * M, prm.gw[c] * v[m].re.x);
-                if (b_valid) IO<T>::store1(pb + c * prm.gs[1] + m * M, prm.gw[c] * v[m].re.y);
+            for (int i = 0; i < 4; ++i) {
+                va[i] = prm.gw[c] * a[i];
+                vb[i] = prm.gw[c] * b[i];
             }
+            IO<T>::store4(ga + y * sh + c * sc + x, va);
+            if (b_valid) IO<T>::store4(gb + y * sh + c * sc + x, vb);
         }
     }
 }
@@ -405,7 +468,7 @@ TFC_HD void pair_compute(const Ctx& ctx, const Params& prm, const TileCoord& ta,
         fft_pass<P, Pl::R2, L2, true>(ctx, s, 1, LD, LP, tw);
         ctx.sync();
         ctx.mark(9);
-        pair_rows_last<P, T, LUMA3>(ctx, prm, ta, tb, b_valid, s, tw);
+        pair_rows_last<P>(ctx, s, tw);
         ctx.sync();
         ctx.mark(10);
     }
@@ -420,10 +483,12 @@ TFC_HD void pair_process(const Ctx& ctx, const Params& prm, int tile_a, int tile
     pair_load<P, T, LUMA3>(ctx, prm, ta, tb, s);
     ctx.sync();
     pair_compute<P, T, LUMA3>(ctx, prm, ta, tb, b_valid, s, tw, accA, accP);
+    if (prm.grad != nullptr) pair_store<P, T, LUMA3>(ctx, prm, ta, tb, b_valid, s);
+    ctx.sync();
 }
 
 TFC_HD bool pair_supported(const Params& prm) {
-    return prm.p == 64 && !(prm.flags & (TFCFFT_LOG_MAGNITUDE | TFCFFT_FULL_SPECTRUM | TFCFFT_FORCE_SPLIT | TFCFFT_FORCE_GENERIC));
+    return prm.p == 64 && prm.spec_mode == 0 && !(prm.flags & (TFCFFT_LOG_MAGNITUDE | TFCFFT_FULL_SPECTRUM | TFCFFT_FORCE_SPLIT | TFCFFT_FORCE_GENERIC));
 }
 
 }  // namespace tfcfft

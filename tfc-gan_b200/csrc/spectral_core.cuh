@@ -44,6 +44,11 @@ struct Params {
     int tile_base;         // split path: first tile of this chunk
     int chunk_tiles;
     long long* trace;      // debug: per-CTA stage timestamps (tfcfft_debug_trace), normally nullptr
+    // spectra materialisation (fft_components / make_spectra): grid == 1, tile = n * C' + ch
+    int spec_mode;         // 0 loss, 1 emit amp / phase of both inputs, 2 backward from d/d(amp, phase)
+    int spec_shift;        // outputs (and incoming gradients) in np.fft.fftshift order over both axes
+    float* spec_out[4];    // emit: amp(fake), pha(fake), amp(real), pha(real); [tiles][P][W]; may be null
+    const float* spec_gin[2];  // backward: d loss / d amp, d loss / d pha of `fake`; may be null
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -291,12 +296,73 @@ struct SlabCols {
     }
 };
 
+// ---- spectra materialisation (reference fft_components, patchFFT_16P.py:293-319; make_spectra :284-289) --
+template <int P>
+TFC_HD long long spec_index(const Params& prm, int tile, int kr, int kc) {
+    const bool full = (prm.flags & TFCFFT_FULL_SPECTRUM) != 0;
+    const int w = full ? P : P / 2 + 1;
+    int r = kr, c = kc;
+    if (prm.spec_shift) {  // np.fft.fftshift: out[(i + n/2) % n] = in[i]
+        r = (kr + P / 2) % P;
+        c = (kc + w / 2) % w;
+    }
+    return ((long long)tile * P + r) * w + c;
+}
+
+// zk = Z(k), zm = Z(-k) at half-plane bin k = (kr, kc): write amplitude / phase of F (and R).
+template <int P>
+TFC_HD void bin_emit(const Params& prm, int tile, int kr, int kc, float2 zk, float2 zm, bool mirror) {
+    const float fx = zk.x + zm.x, fy = zk.y - zm.y;  // 2F
+    const float rx = zk.y + zm.y, ry = zm.x - zk.x;  // 2R
+    const bool lg = (prm.flags & TFCFFT_LOG_MAGNITUDE) != 0;
+    float af = 0.5f * sqrtf(fx * fx + fy * fy), ar = 0.5f * sqrtf(rx * rx + ry * ry);
+    if (lg) {
+        af = logf(af);
+        ar = logf(ar);
+    }
+    const float pf = atan2f(fy, fx), pr = atan2f(ry, rx);
+    const long long i = spec_index<P>(prm, tile, kr, kc);
+    if (prm.spec_out[0]) prm.spec_out[0][i] = af;
+    if (prm.spec_out[1]) prm.spec_out[1][i] = pf;
+    if (prm.spec_out[2]) prm.spec_out[2][i] = ar;
+    if (prm.spec_out[3]) prm.spec_out[3][i] = pr;
+    if (mirror) {  // full plane: bin -k has the conjugate value
+        const long long m = spec_index<P>(prm, tile, (P - kr) & (P - 1), (P - kc) & (P - 1));
+        if (prm.spec_out[0]) prm.spec_out[0][m] = af;
+        if (prm.spec_out[1]) prm.spec_out[1][m] = atan2f(-fy, fx);
+        if (prm.spec_out[2]) prm.spec_out[2][m] = ar;
+        if (prm.spec_out[3]) prm.spec_out[3][m] = atan2f(-ry, rx);
+    }
+}
+
+// Spectral gradient of bin k from incoming d/d amp, d/d phase (chain rule of abs / log / angle).
+template <int P>
+TFC_HD float2 bin_spec_bwd(const Params& prm, int tile, int kr, int kc, float2 zk, float2 zm, bool mirror) {
+    const float fx = zk.x + zm.x, fy = zk.y - zm.y;  // 2F
+    const float f2 = sqrtf(fx * fx + fy * fy);
+    const float finv = f2 > 0.f ? 1.0f / f2 : 0.f;
+    const long long i = spec_index<P>(prm, tile, kr, kc);
+    float ga = prm.spec_gin[0] ? prm.spec_gin[0][i] : 0.f;
+    float gp = prm.spec_gin[1] ? prm.spec_gin[1][i] : 0.f;
+    if (mirror) {  // F(-k) = conj F(k): same amplitude, negated phase
+        const long long m = spec_index<P>(prm, tile, (P - kr) & (P - 1), (P - kc) & (P - 1));
+        if (prm.spec_gin[0]) ga += prm.spec_gin[0][m];
+        if (prm.spec_gin[1]) gp -= prm.spec_gin[1][m];
+    }
+    float ca = ga * finv;                                     // d|F|/dF = F2/|F2|
+    if (prm.flags & TFCFFT_LOG_MAGNITUDE) ca *= 2.f * finv;   // d log|F|/dF = 2 F2/|F2|^2
+    const float cp = gp * 2.f * finv * finv;                  // d angle/dF = 2 i F2/|F2|^2
+    return make_float2(ca * fx - cp * fy, ca * fy + cp * fx);
+}
+
 // Loss + spectral gradient over the spectrum held in s (rows = row positions, stride ld).
 // Every half-plane bin is owned by exactly one item, which also owns its mirror position.
 template <int P, class Cols, class Ctx>
-TFC_HD void bin_pass(const Ctx& ctx, const Params& prm, float2* s, int ld, const Cols& cm, int ncols, float& accA, float& accP) {
+TFC_HD void bin_pass(const Ctx& ctx, const Params& prm, int tile, float2* s, int ld, const Cols& cm, int ncols, float& accA,
+                     float& accP) {
     const bool want_grad = prm.grad != nullptr;
     const bool full = (prm.flags & TFCFFT_FULL_SPECTRUM) != 0;
+    const int mode = prm.spec_mode;
     for (int it = ctx.tid; it < P * ncols; it += ctx.nthreads) {
         const int cl = it % ncols, qr = it / ncols;
         const int kc = cm.freq(cl);
@@ -304,13 +370,20 @@ TFC_HD void bin_pass(const Ctx& ctx, const Params& prm, float2* s, int ld, const
         const int kr = freq_of_pos<P>(qr);
         const bool special = (kc == 0) || (kc == P / 2);  // self-conjugate columns
         if (special && kr > P / 2) continue;
-        const int qrm = pos_of_freq<P>((P - kr) & (P - 1));
+        const int krm = (P - kr) & (P - 1);
+        const int qrm = pos_of_freq<P>(krm);
         const int clm = cm.partner(cl);
         float2* pk = s + qr * ld + cl;
         float2* pm = s + qrm * ld + clm;
         const float2 zk = *pk, zm = *pm;
+        if (mode == 1) {
+            bin_emit<P>(prm, tile, kr, kc, zk, zm, full && !special);
+            if (special && pm != pk) bin_emit<P>(prm, tile, krm, kc, zm, zk, false);
+            continue;
+        }
         const float mult = (full && !special) ? 2.f : 1.f;
-        const float2 g = bin_eval(prm, zk, zm, mult, accA, accP);
+        const float2 g = mode == 2 ? bin_spec_bwd<P>(prm, tile, kr, kc, zk, zm, full && !special)
+                                   : bin_eval(prm, zk, zm, mult, accA, accP);
         if (!special) {
             if (want_grad) {
                 *pk = g;
@@ -318,7 +391,8 @@ TFC_HD void bin_pass(const Ctx& ctx, const Params& prm, float2* s, int ld, const
             }
         } else {
             if (pm != pk) {  // the mirrored row of the same column is a half-plane bin of its own
-                const float2 g2 = bin_eval(prm, zm, zk, mult, accA, accP);
+                const float2 g2 = mode == 2 ? bin_spec_bwd<P>(prm, tile, krm, kc, zm, zk, false)
+                                            : bin_eval(prm, zm, zk, mult, accA, accP);
                 if (want_grad) *pm = g2;
             }
             if (want_grad) *pk = g;
@@ -338,7 +412,7 @@ TFC_HD void tile_process(const Ctx& ctx, const Params& prm, int tile, float2* s,
     ctx.sync();
     fft_lines<P, false>(ctx, s, 1, LD, LP, tw);   // rows: thread-fast index = row
     fft_lines<P, false>(ctx, s, LD, 1, LP, tw);   // columns: thread-fast index = column
-    bin_pass<P>(ctx, prm, s, LD, TileCols<P>(), P, accA, accP);
+    bin_pass<P>(ctx, prm, tile, s, LD, TileCols<P>(), P, accA, accP);
     ctx.sync();
     if (prm.grad != nullptr) {
         fft_lines<P, true>(ctx, s, LD, 1, LP, tw);
@@ -392,7 +466,7 @@ TFC_HD void split_cols(const Ctx& ctx, const Params& prm, int lt, int pair, floa
     }
     ctx.sync();
     fft_lines<P, false>(ctx, s, ld, 1, ilog2(ncols), tw);
-    bin_pass<P>(ctx, prm, s, ld, cm, ncols, accA, accP);
+    bin_pass<P>(ctx, prm, prm.tile_base + lt, s, ld, cm, ncols, accA, accP);
     ctx.sync();
     if (prm.grad != nullptr) {
         fft_lines<P, true>(ctx, s, ld, 1, ilog2(ncols), tw);

@@ -139,6 +139,7 @@ struct GroupCtx {
     static constexpr int nthreads = NT;
     long long* trace;
     __device__ __forceinline__ void sync() const { bar_sync(BAR, NT); }
+    __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
     __device__ __forceinline__ void mark(int k) const {
         if (trace != nullptr && tid == 0) trace[k] = clock64();
     }
@@ -184,14 +185,15 @@ __device__ __forceinline__ void group_sum4(int tid, float* red /* [4][32] */, fl
 //                           spectral gradient, inverse FFTs, gradient store;
 //   warps 16..23 (load):    stream pair i+1 from HBM (coalesced 128-bit loads), fold luma, pack (A, B) and
 //                           fill the other work buffer, so HBM latency and the transforms overlap.
-// Hand-off with named barriers: FULL[b] (loaders arrive, compute waits), EMPTY[b] (compute arrives after its
-// last read of buffer b, loaders wait before overwriting it).  Shared memory per pair (66.5 KB) is what
+//                           and write the finished gradient tiles of pair i-1 out with 128-bit stores.
+// Hand-off with named barriers: FULL[b] (loaders arrive, compute waits), DONE[b] (compute arrives when
+// buffer b holds the gradient tiles, loaders wait, store them and refill the buffer).  Shared memory per pair (66.5 KB) is what
 // bounds the number of pairs in flight; two buffers + one transform at a time with 16 warps keeps every
 // stage short instead of interleaving three slow CTAs.
 template <int P, typename T, bool LUMA3>
 __global__ void __launch_bounds__(PairCfg<P>::NT, 1) pair_kernel(const __grid_constant__ Params prm) {
     using Cfg = PairCfg<P>;
-    constexpr int BAR_COMPUTE = 1, BAR_FULL = 2, BAR_EMPTY = 4;  // ids 2,3 and 4,5
+    constexpr int BAR_COMPUTE = 1, BAR_FULL = 2, BAR_DONE = 4;  // ids 2,3 and 4,5; 6 = loader group
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* buf0 = reinterpret_cast<float4*>(smem_raw);
     float4* buf1 = buf0 + P * Cfg::LD;
@@ -203,22 +205,40 @@ __global__ void __launch_bounds__(PairCfg<P>::NT, 1) pair_kernel(const __grid_co
     }
     __syncthreads();
     const int npairs = (prm.tiles_total + 1) >> 1;
+    const bool want_grad = prm.grad != nullptr;
     if (threadIdx.x >= Cfg::NT_COMPUTE) {
-        // ---------------- loader warps ----------------
+        // ---------------- loader / storer warps ----------------
         const GroupCtx<Cfg::NT_LOAD, 6> ctx{(int)threadIdx.x - Cfg::NT_COMPUTE, nullptr};
-        int iter = 0;
-        for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++iter) {
+        int iter = 0, pr = blockIdx.x;
+        for (; pr < npairs; pr += gridDim.x, ++iter) {
             const int b = iter & 1;
+            float4* s = b ? buf1 : buf0;
+            if (iter >= 2) {
+                // buffer b holds the finished gradient tiles of pair iter-2: write them out, then reuse it
+                bar_sync(BAR_DONE + b, Cfg::NT);
+                if (want_grad) {
+                    const int pa = 2 * (pr - 2 * (int)gridDim.x), pb = pa + 1 < prm.tiles_total ? pa + 1 : pa;
+                    pair_store<P, T, LUMA3>(ctx, prm, decode_tile(prm, pa), decode_tile(prm, pb), pb != pa, s);
+                    bar_sync(6, Cfg::NT_LOAD);  // all loader reads of buffer b precede its refill
+                }
+            }
             const int ta = 2 * pr, tb = ta + 1 < prm.tiles_total ? ta + 1 : ta;
-            bar_sync(BAR_EMPTY + b, Cfg::NT);  // buffer b has been consumed (primed for the first two pairs)
-            pair_load<P, T, LUMA3>(ctx, prm, decode_tile(prm, ta), decode_tile(prm, tb), b ? buf1 : buf0);
+            pair_load<P, T, LUMA3>(ctx, prm, decode_tile(prm, ta), decode_tile(prm, tb), s);
             bar_arrive(BAR_FULL + b, Cfg::NT);
+        }
+        // drain: the last (up to) two pairs of this CTA
+        for (int back = (iter >= 2 ? 2 : iter); back >= 1; --back) {
+            const int it2 = iter - back, b = it2 & 1;
+            const int p2 = (int)blockIdx.x + it2 * (int)gridDim.x;
+            bar_sync(BAR_DONE + b, Cfg::NT);
+            if (want_grad) {
+                const int pa = 2 * p2, pb = pa + 1 < prm.tiles_total ? pa + 1 : pa;
+                pair_store<P, T, LUMA3>(ctx, prm, decode_tile(prm, pa), decode_tile(prm, pb), pb != pa, b ? buf1 : buf0);
+            }
         }
     } else {
         // ---------------- compute warps ----------------
         GroupCtx<Cfg::NT_COMPUTE, BAR_COMPUTE> ctx{(int)threadIdx.x, nullptr};
-        bar_arrive(BAR_EMPTY + 0, Cfg::NT);  // both buffers start empty
-        bar_arrive(BAR_EMPTY + 1, Cfg::NT);
         int iter = 0;
         for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++iter) {
             const int b = iter & 1;
@@ -231,8 +251,8 @@ __global__ void __launch_bounds__(PairCfg<P>::NT, 1) pair_kernel(const __grid_co
             ctx.mark(0);
             bar_sync(BAR_FULL + b, Cfg::NT);  // the loaders have filled buffer b
             pair_compute<P, T, LUMA3>(ctx, prm, decode_tile(prm, ta), decode_tile(prm, tb), b_valid, s, tw, accA, accP);
-            // pair_compute ends with a group barrier: every read of buffer b is done
-            if (pr + 2 * (int)gridDim.x < npairs) bar_arrive(BAR_EMPTY + b, Cfg::NT);
+            // pair_compute ends with a group barrier: buffer b now holds the gradient tiles (or is dead)
+            bar_arrive(BAR_DONE + b, Cfg::NT);
             group_sum4<Cfg::NT_COMPUTE, BAR_COMPUTE>(ctx.tid, red, accA.x, accA.y, accP.x, accP.y);
             if (ctx.tid == 0) {
                 prm.partials[2 * ta] = accA.x;

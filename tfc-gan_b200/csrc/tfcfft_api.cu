@@ -161,6 +161,62 @@ int tfcfft_workspace_init(void* workspace, size_t workspace_bytes, void* stream)
     return e == cudaSuccess ? 0 : (int)e;
 }
 
+static int dispatch(const Params& prm, const Geometry& g, int dtype, cudaStream_t st) {
+    switch (g.p) {
+        case 16: return launch_t<16>(prm, g.split, g.luma3, dtype, st);
+        case 32: return launch_t<32>(prm, g.split, g.luma3, dtype, st);
+        case 64: return launch_t<64>(prm, g.split, g.luma3, dtype, st);
+        case 128: return launch_t<128>(prm, g.split, g.luma3, dtype, st);
+        case 256: return launch_t<256>(prm, g.split, g.luma3, dtype, st);
+        case 512: return launch_t<512>(prm, g.split, g.luma3, dtype, st);
+    }
+    return TFCFFT_ERR_SHAPE;
+}
+
+// shared argument checks of the two spectra entry points; the scalar outputs of the reduction tail land in
+// the workspace header (nobody reads them)
+static int spectra_common(const tfcfft_desc* d, const void* x, const void* y, void* grad, void* workspace,
+                          size_t workspace_bytes, Geometry* g, Params* prm) {
+    int rc = validate_desc(d, g);
+    if (rc) return rc;
+    if (d->grid != 1) return TFCFFT_ERR_SHAPE;
+    if (!x) return TFCFFT_ERR_NULL;
+    if ((rc = check_grad_args(d, grad))) return rc;
+    if ((rc = check_alignment(d, x, y ? y : x, grad))) return rc;
+    if (!workspace || workspace_bytes < g->ws_bytes || ((uintptr_t)workspace & 255)) return TFCFFT_ERR_WORKSPACE;
+    float* scratch_out = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 64);
+    *prm = make_params(d, *g, x, y ? y : x, grad, scratch_out, nullptr, workspace);
+    return 0;
+}
+
+int tfcfft_spectra(const tfcfft_desc* d, const void* x, const void* y, float* amp_x, float* pha_x, float* amp_y,
+                   float* pha_y, int fftshift, void* workspace, size_t workspace_bytes, void* stream) {
+    Geometry g;
+    Params prm;
+    if (int rc = spectra_common(d, x, y, nullptr, workspace, workspace_bytes, &g, &prm)) return rc;
+    prm.spec_mode = 1;
+    prm.spec_shift = fftshift != 0;
+    prm.spec_out[0] = amp_x;
+    prm.spec_out[1] = pha_x;
+    prm.spec_out[2] = y ? amp_y : nullptr;
+    prm.spec_out[3] = y ? pha_y : nullptr;
+    return dispatch(prm, g, d->dtype, (cudaStream_t)stream);
+}
+
+int tfcfft_spectra_bwd(const tfcfft_desc* d, const void* x, const float* grad_amp, const float* grad_pha, void* grad_x,
+                       int fftshift, void* workspace, size_t workspace_bytes, void* stream) {
+    Geometry g;
+    Params prm;
+    if (!grad_x) return TFCFFT_ERR_NULL;
+    if (int rc = spectra_common(d, x, nullptr, grad_x, workspace, workspace_bytes, &g, &prm)) return rc;
+    prm.spec_mode = 2;
+    prm.spec_shift = fftshift != 0;
+    prm.spec_gin[0] = grad_amp;
+    prm.spec_gin[1] = grad_pha;
+    // the generic kernels scale the outgoing gradient by gw = (luma weight) * input_scale: exactly d x'/d x
+    return dispatch(prm, g, d->dtype, (cudaStream_t)stream);
+}
+
 int tfcfft_loss(const tfcfft_desc* d, const void* fake, const void* real, float* out, float* per_image, void* grad_fake,
                 void* workspace, size_t workspace_bytes, void* stream) {
     Geometry g;
@@ -173,15 +229,7 @@ int tfcfft_loss(const tfcfft_desc* d, const void* fake, const void* real, float*
     Params prm = make_params(d, g, fake, real, grad_fake, out, per_image, workspace);
     prm.trace = g_trace.load();
     cudaStream_t st = (cudaStream_t)stream;
-    switch (g.p) {
-        case 16: return launch_t<16>(prm, g.split, g.luma3, d->dtype, st);
-        case 32: return launch_t<32>(prm, g.split, g.luma3, d->dtype, st);
-        case 64: return launch_t<64>(prm, g.split, g.luma3, d->dtype, st);
-        case 128: return launch_t<128>(prm, g.split, g.luma3, d->dtype, st);
-        case 256: return launch_t<256>(prm, g.split, g.luma3, d->dtype, st);
-        case 512: return launch_t<512>(prm, g.split, g.luma3, d->dtype, st);
-    }
-    return TFCFFT_ERR_SHAPE;
+    return dispatch(prm, g, d->dtype, st);
 }
 
 int tfcfft_grad_scale(void* dst, const void* src, int32_t dtype, int64_t numel, const float* dev_scale, float host_scale,

@@ -208,6 +208,89 @@ def spectral_terms_per_image(fake, real, *, config: SpectralConfig | None = None
     return per
 
 
+def _spectra_desc(x, cfg: SpectralConfig, grad=None):
+    if cfg.grid != 1:
+        raise ValueError("spectra are materialised per tensor: pass the patch itself (grid must be 1)")
+    return _lib.make_desc(_DTYPES[x.dtype], 1, cfg.flags(), x.shape, x.stride(), x.stride(),
+                          grad.stride() if grad is not None else None, 1.0, cfg.input_scale)
+
+
+def _spectra_shape(x, cfg: SpectralConfig):
+    n, c, p, _ = x.shape
+    cp = 3 if (cfg.channels == "rgb" and c == 3) else 1
+    return (n, cp, p, p if cfg.spectrum == "full" else p // 2 + 1)
+
+
+def _prep1(x):
+    if x.dim() != 4:
+        raise ValueError("expected a 4-D NCHW tensor")
+    if not x.is_cuda:
+        raise RuntimeError("tfcfft runs on CUDA tensors only (no CPU fallback)")
+    if x.dtype not in _DTYPES:
+        x = x.float()
+    return x if _acceptable(x) else x.contiguous()
+
+
+class _SpectraFn(torch.autograd.Function):
+    """amp / phase of rfft2 (or fft2) of every image: differentiable ``fft_components``."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, shift):
+        xp = _prep1(x.detach())
+        lib = _lib.load()
+        dev = xp.device
+        with torch.cuda.device(dev):
+            stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+            shape = _spectra_shape(xp, cfg)
+            amp = torch.empty(shape, dtype=torch.float32, device=dev)
+            pha = torch.empty(shape, dtype=torch.float32, device=dev)
+            desc = _spectra_desc(xp, cfg)
+            nbytes = lib.tfcfft_workspace_bytes(ctypes.byref(desc))
+            if nbytes == 0:
+                _lib.check(lib.tfcfft_validate(ctypes.byref(desc)), "tfcfft_validate")
+            ws = _workspace(dev, stream_ptr, nbytes)
+            _lib.check(lib.tfcfft_spectra(ctypes.byref(desc), xp.data_ptr(), None, amp.data_ptr(), pha.data_ptr(), None,
+                                          None, int(shift), ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream_ptr)),
+                       "tfcfft_spectra")
+        ctx.cfg, ctx.shift, ctx.in_dtype = cfg, shift, x.dtype
+        ctx.differentiable = not cfg.quantize and xp.dtype != torch.uint8
+        if ctx.differentiable:
+            ctx.save_for_backward(xp)
+        return amp, pha
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_amp, g_pha):
+        if not ctx.differentiable or not ctx.needs_input_grad[0]:
+            return None, None, None
+        (xp,) = ctx.saved_tensors
+        lib = _lib.load()
+        dev = xp.device
+        with torch.cuda.device(dev):
+            stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+            g_amp = g_amp.contiguous().float()
+            g_pha = g_pha.contiguous().float()
+            grad = torch.empty(xp.shape, dtype=xp.dtype, device=dev)
+            desc = _spectra_desc(xp, ctx.cfg, grad)
+            nbytes = lib.tfcfft_workspace_bytes(ctypes.byref(desc))
+            ws = _workspace(dev, stream_ptr, nbytes)
+            _lib.check(lib.tfcfft_spectra_bwd(ctypes.byref(desc), xp.data_ptr(), g_amp.data_ptr(), g_pha.data_ptr(),
+                                              grad.data_ptr(), int(ctx.shift), ws.data_ptr(), ws.numel(),
+                                              ctypes.c_void_p(stream_ptr)),
+                       "tfcfft_spectra_bwd")
+        return (grad if grad.dtype == ctx.in_dtype else grad.to(ctx.in_dtype)), None, None
+
+
+def spectral_components(x, *, channels: str = "luma", input_scale: float = 1.0, spectrum: str = "half",
+                        log_magnitude: bool = False, quantize: bool = False, fftshift: bool = True):
+    """``(AMP, PHA)`` of every image of ``x`` ``[N,C,P,P]`` -> two fp32 ``[N,C',P,P/2+1]`` tensors (``P`` wide for
+    ``spectrum="full"``), optionally fftshift-ed over both axes like the reference's ``fft_components``
+    (``TFC-GAN-FFT/TFCGAN_multigpu_patchFFT_16P.py:271-319``).  Differentiable w.r.t. ``x``."""
+    cfg = SpectralConfig(grid=1, channels=channels, input_scale=input_scale, spectrum=spectrum,
+                         log_magnitude=log_magnitude, quantize=quantize)
+    return _SpectraFn.apply(x, cfg, bool(fftshift))
+
+
 def launch_count() -> int:
     """Kernels launched by ``libtfcfft.so`` in this process since the last reset."""
     return int(_lib.load().tfcfft_launch_count())

@@ -36,6 +36,11 @@ for i, nm in enumerate(names):
     tot += v.mean()
     print(f"  {nm:7s} {v.mean():9.0f} {np.percentile(v,10):9.0f} {np.percentile(v,90):9.0f}")
 print(f"  total   {tot:9.0f}")
+print("per pair-iteration mean stage cycles:")
+for it in range(6):
+    m = valid[:, it]
+    if m.any():
+        print(f"  it{it}: " + " ".join(f"{nm}={d[:, it, i][m].mean():.0f}" for i, nm in enumerate(names)))
 gt = t[:, :, 15].astype(np.float64)
 g0 = gt[valid].min()
 for it in range(6):
