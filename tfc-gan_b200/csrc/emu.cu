@@ -33,8 +33,9 @@ template <int P, typename T, bool LUMA3>
 void run_pair(Params prm) {
     if constexpr (P == 64) {
         SerialCtx ctx;
-        std::vector<float4> s((size_t)P * PairCfg<P>::LD), tw(P);
+        std::vector<float4> s((size_t)P * PairCfg<P>::LD), tw(2 * P);
         fill_twiddles4<P>(ctx, tw.data());
+        fill_row_twiddles4<P>(ctx, tw.data(), tw.data() + P);
         for (int ta = 0; ta < prm.tiles_total; ta += 2) {
             const bool b_valid = ta + 1 < prm.tiles_total;
             const int tb = b_valid ? ta + 1 : ta;

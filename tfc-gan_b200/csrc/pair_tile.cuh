@@ -22,7 +22,7 @@ struct PairCfg {
     static constexpr int NT_LOAD = 256;       // 8 warps stream the next pair from HBM into the other buffer
     static constexpr int NT = NT_COMPUTE + NT_LOAD;
     static constexpr size_t TILE_BYTES = (size_t)P * LD * sizeof(float4);
-    static constexpr size_t SMEM = 2 * TILE_BYTES + (size_t)P * sizeof(float4);  // two work buffers + twiddles
+    static constexpr size_t SMEM = 2 * TILE_BYTES + 2 * (size_t)P * sizeof(float4);  // two work buffers + 2 twiddle tables
 };
 
 // ---- MUFU-level approximations (1-2 ulp), exact libm on the host emulation -------------------
@@ -153,6 +153,14 @@ TFC_HD void fill_twiddles4(const Ctx& ctx, float4* tw) {
     }
 }
 
+// Row-pass copy of the twiddles, laid out [k][j] = W_P^{j k}: the M lanes of a row read consecutive float4
+// (the plain table would be read with stride k: bank conflicts for even k).
+template <int P, class Ctx>
+TFC_HD void fill_row_twiddles4(const Ctx& ctx, const float4* tw, float4* twr) {
+    constexpr int R = Plan<P>::R1, M = P / R;
+    for (int t = ctx.tid; t < R * M; t += ctx.nthreads) twr[t] = tw[((t / M) * (t % M)) % P];
+}
+
 // ---- stage 0: global -> luma -> packed tile pair ----------------------------------------------
 // Base pointers of the four source tiles (fake A, real A, fake B, real B), computed once per pair.
 template <typename T>
@@ -248,7 +256,7 @@ TFC_HD void pair_prefetch_l2(const Ctx& ctx, const Params& prm, const TileCoord&
 // task rewrites exactly the words it read); the second owns whole groups of R2 positions, reads them
 // through the swizzle and writes plain positions, which removes the swizzle for free. ------------
 template <int P, class Ctx>
-TFC_HD void pair_rows_first(const Ctx& ctx, float4* s, const float4* tw) {
+TFC_HD void pair_rows_first(const Ctx& ctx, float4* s, const float4* twr) {
     constexpr int R = Plan<P>::R1, M = P / R, LD = PairCfg<P>::LD;
     for (int t = ctx.tid; t < P * M; t += ctx.nthreads) {
         const int j = t % M, y = t / M;  // consecutive threads: consecutive columns of one row
@@ -258,7 +266,7 @@ TFC_HD void pair_rows_first(const Ctx& ctx, float4* s, const float4* tw) {
         for (int m = 0; m < R; ++m) v[m] = Cx<float4>::ld(row[swz(j + m * M)]);
         Dft<R, false>::run(v);
 #pragma unroll
-        for (int k = 1; k < R; ++k) v[k] = cmul(v[k], tw[j * k]);
+        for (int k = 1; k < R; ++k) v[k] = cmul(v[k], twr[k * M + j]);
 #pragma unroll
         for (int k = 0; k < R; ++k) row[swz(j + k * M)] = Cx<float4>::st(v[k]);
     }
@@ -372,7 +380,7 @@ TFC_HD void pair_cols_inv_pass(const Ctx& ctx, float4* s, const float4* tw) {
 // Output pixel x of row y goes to float4 slot swz(x) as (gA, gB, -, -).  The eight tasks of a row sit in
 // eight adjacent lanes of one warp; a warp-level barrier separates their reads from the swizzled writes.
 template <int P, class Ctx>
-TFC_HD void pair_rows_last(const Ctx& ctx, float4* s, const float4* tw) {
+TFC_HD void pair_rows_last(const Ctx& ctx, float4* s, const float4* twr) {
     constexpr int R = Plan<P>::R1, M = P / R, LD = PairCfg<P>::LD;
     static_assert(M <= 32 && (32 % M) == 0, "the tasks of one row must share a warp");
     for (int t = ctx.tid; t < P * M; t += ctx.nthreads) {
@@ -391,7 +399,7 @@ TFC_HD void pair_rows_last(const Ctx& ctx, float4* s, const float4* tw) {
 #pragma unroll
         for (int k = 0; k < R; ++k) v[k] = Cx<float4>::ld(src[j + k * M]);
 #pragma unroll
-        for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], tw[j * k]);
+        for (int k = 1; k < R; ++k) v[k] = cmulc(v[k], twr[k * M + j]);
         Dft<R, true>::run(v);
         ctx.warp_sync();
 #pragma unroll
@@ -443,7 +451,7 @@ TFC_HD void pair_compute(const Ctx& ctx, const Params& prm, const TileCoord& ta,
     constexpr int LD = PairCfg<P>::LD, LP = ilog2_c(P), L2 = P / Pl::R1;
     static_assert(Pl::R3 == 1, "pair path supports two-pass plans");
     ctx.mark(1);
-    pair_rows_first<P>(ctx, s, tw);
+    pair_rows_first<P>(ctx, s, tw + P);
     ctx.sync();
     ctx.mark(2);
     pair_rows_second<P>(ctx, s);
@@ -468,7 +476,7 @@ TFC_HD void pair_compute(const Ctx& ctx, const Params& prm, const TileCoord& ta,
         fft_pass<P, Pl::R2, L2, true>(ctx, s, 1, LD, LP, tw);
         ctx.sync();
         ctx.mark(9);
-        pair_rows_last<P>(ctx, s, tw);
+        pair_rows_last<P>(ctx, s, tw + P);
         ctx.sync();
         ctx.mark(10);
     }

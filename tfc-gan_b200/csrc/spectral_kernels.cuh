@@ -202,6 +202,8 @@ __global__ void __launch_bounds__(PairCfg<P>::NT, 1) pair_kernel(const __grid_co
     {
         const BlockCtx all{(int)threadIdx.x, (int)blockDim.x};
         fill_twiddles4<P>(all, tw);
+        __syncthreads();
+        fill_row_twiddles4<P>(all, tw, tw + P);
     }
     __syncthreads();
     const int npairs = (prm.tiles_total + 1) >> 1;
