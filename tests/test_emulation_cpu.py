@@ -31,6 +31,9 @@ CASES = [
     (512, 1, dict()),
     (256, 4, dict(force_split=True)),
     (256, 2, dict(force_split=True, channels="rgb")),
+    (256, 1, dict(force_split=True)),
+    (256, 2, dict(force_generic=True)),
+    (256, 1, dict(channels="rgb", distance="mse")),
 ]
 
 

@@ -56,6 +56,10 @@ CASES = [
     (256, 4, dict(force_generic=True)),                 # generic resident kernel (the default is the packed pair path)
     (256, 4, dict(force_split=True)),                   # split kernels on a size the resident path also covers
     (256, 2, dict(force_split=True, channels="rgb")),
+    (256, 1, dict(force_split=True)),                   # the split kernels at their native size
+    (256, 2, dict(force_generic=True)),                 # generic resident kernel at 128 x 128
+    (256, 1, dict(distance="mse", channels="rgb")),     # sub-tile path (D = 4), other modes
+    (256, 2, dict(use_phase=False, patch_reduce="sum")),  # sub-tile path (D = 2)
 ]
 
 

@@ -11,6 +11,7 @@
 
 #include "host_common.h"
 #include "pair_tile.cuh"
+#include "sub_tile.cuh"
 
 using namespace tfcfft;
 
@@ -51,6 +52,44 @@ void run_pair(Params prm) {
     }
 }
 
+template <typename T, bool LUMA3>
+void run_sub(Params prm) {
+    SerialCtx ctx;
+    const int D = prm.sub_d, npp = D * D / 2;
+    std::vector<float4> s((size_t)64 * 65), tw(128);
+    fill_twiddles4<64>(ctx, tw.data());
+    fill_row_twiddles4<64>(ctx, tw.data(), tw.data() + 64);
+    for (int base = 0; base < prm.tiles_total; base += prm.chunk_tiles) {
+        prm.tile_base = base;
+        prm.chunk_now = prm.tiles_total - base < prm.chunk_tiles ? prm.tiles_total - base : prm.chunk_tiles;
+        for (int u = 0; u < prm.chunk_now * npp; ++u) {
+            const SubUnit su = sub_unit(u, D);
+            sub_load<T, LUMA3>(ctx, prm, decode_tile(prm, base + su.tile_local), su, s.data());
+            sub_compute_fwd(ctx, s.data(), tw.data());
+            spec_store(ctx, s.data(), sub_plane(prm, su));
+        }
+        for (int lt = 0; lt < prm.chunk_now; ++lt) {
+            float4* ws_tile = reinterpret_cast<float4*>(prm.zws) + (long long)lt * npp * 4096;
+            for (int part = 0; part < 9; ++part) {
+                float a = 0.f, p = 0.f;
+                for (int item = part * 256; item < (part + 1) * 256 && item < kCombineItems; ++item) {
+                    if (D == 2) combine_item<2>(prm, ws_tile, item, a, p);
+                    else combine_item<4>(prm, ws_tile, item, a, p);
+                }
+                prm.partials[2 * ((size_t)(base + lt) * 9 + part)] = a;
+                prm.partials[2 * ((size_t)(base + lt) * 9 + part) + 1] = p;
+            }
+        }
+        if (prm.grad)
+            for (int u = 0; u < prm.chunk_now * npp; ++u) {
+                const SubUnit su = sub_unit(u, D);
+                spec_load(ctx, sub_plane(prm, su), s.data());
+                sub_compute_inv(ctx, s.data(), tw.data());
+                sub_store<T, LUMA3>(ctx, prm, decode_tile(prm, base + su.tile_local), su, s.data());
+            }
+    }
+}
+
 template <int P, typename T, bool LUMA3>
 void run_split(Params prm) {
     if constexpr (P >= 64) {
@@ -79,7 +118,8 @@ void run_split(Params prm) {
 
 template <int P, typename T, bool LUMA3>
 void run(const Params& prm, bool split) {
-    if (split) run_split<P, T, LUMA3>(prm);
+    if ((P == 128 || P == 256) && prm.sub_d > 1) run_sub<T, LUMA3>(prm);
+    else if (split) run_split<P, T, LUMA3>(prm);
     else if (P == 64 && pair_supported(prm)) run_pair<P, T, LUMA3>(prm);
     else if constexpr (P <= 128) run_resident<P, T, LUMA3>(prm);
 }
@@ -144,7 +184,7 @@ extern "C" int tfcfft_emulate(const tfcfft_desc* d, const void* fake, const void
 extern "C" int tfcfft_emulate_spectra(const tfcfft_desc* d, const void* x, const void* y, float* amp_x, float* pha_x,
                                       float* amp_y, float* pha_y, int fftshift) {
     Geometry g;
-    int rc = validate_desc(d, &g);
+    int rc = validate_desc(d, &g, false);
     if (rc) return rc;
     if (d->grid != 1) return TFCFFT_ERR_SHAPE;
     if (!x) return TFCFFT_ERR_NULL;
@@ -164,7 +204,7 @@ extern "C" int tfcfft_emulate_spectra(const tfcfft_desc* d, const void* x, const
 extern "C" int tfcfft_emulate_spectra_bwd(const tfcfft_desc* d, const void* x, const float* grad_amp, const float* grad_pha,
                                           void* grad_x, int fftshift) {
     Geometry g;
-    int rc = validate_desc(d, &g);
+    int rc = validate_desc(d, &g, false);
     if (rc) return rc;
     if (d->grid != 1) return TFCFFT_ERR_SHAPE;
     if (!x || !grad_x) return TFCFFT_ERR_NULL;

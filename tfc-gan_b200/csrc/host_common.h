@@ -25,7 +25,8 @@ struct Geometry {
     int p;            // patch side
     int cprime;       // spectra per tile position
     bool luma3;       // 3 channels folded to luma
-    bool split;       // split path (P >= 256 or forced)
+    bool split;       // split path (P = 512, spectra at P >= 256, or forced)
+    bool sub;         // sub-tile path (P = 128 / 256): packed 64 x 64 kernels + combine kernel
     int parts;        // partial sums per tile
     long long tiles_total;
     long long chunk_tiles;
@@ -42,7 +43,7 @@ inline int split_parts(int p) {
     }
 }
 
-inline int validate_desc(const tfcfft_desc* d, Geometry* geo) {
+inline int validate_desc(const tfcfft_desc* d, Geometry* geo, bool allow_sub = true) {
     if (!d) return TFCFFT_ERR_NULL;
     if (d->struct_size != sizeof(tfcfft_desc)) return TFCFFT_ERR_STRUCT;
     if (elem_size(d->dtype) == 0) return TFCFFT_ERR_DTYPE;
@@ -69,13 +70,14 @@ inline int validate_desc(const tfcfft_desc* d, Geometry* geo) {
         geo->p = (int)p;
         geo->luma3 = (d->c == 3) && !(d->flags & TFCFFT_CHANNELS_RGB);
         geo->cprime = (d->c == 3 && !geo->luma3) ? 3 : 1;
-        geo->split = (p >= 256) || (d->flags & TFCFFT_FORCE_SPLIT);
-        geo->parts = geo->split ? split_parts((int)p) : 1;
+        geo->sub = allow_sub && (p == 128 || p == 256) && !(d->flags & (TFCFFT_FORCE_SPLIT | TFCFFT_FORCE_GENERIC));
+        geo->split = !geo->sub && ((p >= 256) || (d->flags & TFCFFT_FORCE_SPLIT));
+        geo->parts = geo->sub ? 9 : geo->split ? split_parts((int)p) : 1;
         geo->tiles_total = (long long)d->n * geo->cprime * d->grid * d->grid;
         geo->partial_bytes = align_up((size_t)geo->tiles_total * geo->parts * 2 * sizeof(float), 256);
         geo->chunk_tiles = 0;
         size_t z = 0;
-        if (geo->split) {
+        if (geo->split || geo->sub) {
             const size_t per_tile = (size_t)p * p * sizeof(float2);
             long long ct = (long long)(kWsChunkBytes / per_tile);
             if (ct < 1) ct = 1;
@@ -145,7 +147,8 @@ inline Params make_params(const tfcfft_desc* d, const Geometry& g, const void* f
     p.parts = g.parts;
     p.out = out;
     p.per_image = per_image;
-    p.zws = g.split ? reinterpret_cast<float2*>(w + kWsHeader + g.partial_bytes) : nullptr;
+    p.zws = (g.split || g.sub) ? reinterpret_cast<float2*>(w + kWsHeader + g.partial_bytes) : nullptr;
+    p.sub_d = g.sub ? g.p / 64 : 0;
     p.tile_base = 0;
     p.chunk_tiles = (int)g.chunk_tiles;
     return p;

@@ -44,6 +44,10 @@ struct Params {
     int tile_base;         // split path: first tile of this chunk
     int chunk_tiles;
     long long* trace;      // debug: per-CTA stage timestamps (tfcfft_debug_trace), normally nullptr
+    // sub-tile path (P = 128 / 256): the tile is decimated into D x D interleaved 64 x 64 sub-images
+    int sub_d;             // 0 / 1: not used; 2 or 4
+    int pair_mode;         // sub_pair_kernel: 1 sub-images -> spectra in zws, 2 zws -> gradient
+    int chunk_now;         // tiles in the chunk being processed by this launch
     // spectra materialisation (fft_components / make_spectra): grid == 1, tile = n * C' + ch
     int spec_mode;         // 0 loss, 1 emit amp / phase of both inputs, 2 backward from d/d(amp, phase)
     int spec_shift;        // outputs (and incoming gradients) in np.fft.fftshift order over both axes
@@ -65,6 +69,11 @@ template <> struct IO<float> {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     }
     TFC_HD static void store1(float* p, float v) { *p = v; }
+    TFC_HD static void load2(const float* p, float* v) {
+        const float2 t = *reinterpret_cast<const float2*>(p);
+        v[0] = t.x; v[1] = t.y;
+    }
+    TFC_HD static void store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
     // (x * 255) in fp32, truncated toward zero, wrapped mod 256
     TFC_HD static int quant(float x) {
 #ifdef __CUDA_ARCH__
@@ -92,6 +101,11 @@ template <> struct IO<__half> {
         *reinterpret_cast<uint2*>(p) = t;
     }
     TFC_HD static void store1(__half* p, float v) { *p = __float2half_rn(v); }
+    TFC_HD static void load2(const __half* p, float* v) {
+        const __half2 t = *reinterpret_cast<const __half2*>(p);
+        v[0] = __low2float(t); v[1] = __high2float(t);
+    }
+    TFC_HD static void store2(__half* p, float a, float b) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b); }
     // fp16 * 255 rounded to fp16 (the exact fp32 product rounded once == the fp16 product)
     TFC_HD static int quant(float x) {
         const float t = __half2float(__float2half_rn(x * 255.0f));
@@ -113,6 +127,14 @@ template <> struct IO<__nv_bfloat16> {
         *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(h);
     }
     TFC_HD static void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+    TFC_HD static void load2(const __nv_bfloat16* p, float* v) {
+        const unsigned t = *reinterpret_cast<const unsigned*>(p);
+        v[0] = __uint_as_float_hd(t << 16); v[1] = __uint_as_float_hd(t & 0xFFFF0000u);
+    }
+    TFC_HD static void store2(__nv_bfloat16* p, float a, float b) {
+        p[0] = __float2bfloat16_rn(a);
+        p[1] = __float2bfloat16_rn(b);
+    }
     TFC_HD static int quant(float x) { return IO<float>::quant(x); }  // NumPy has no bf16: fp32 rule
     TFC_HD static float __uint_as_float_hd(unsigned u) {
         float f;
@@ -128,6 +150,8 @@ template <> struct IO<uint8_t> {
     }
     TFC_HD static void store4(uint8_t*, const float*) {}  // no gradient for integer inputs
     TFC_HD static void store1(uint8_t*, float) {}
+    TFC_HD static void load2(const uint8_t* p, float* v) { v[0] = p[0]; v[1] = p[1]; }
+    TFC_HD static void store2(uint8_t*, float, float) {}
     TFC_HD static int quant(float x) { return (int)x; }   // already an 8-bit code
 };
 

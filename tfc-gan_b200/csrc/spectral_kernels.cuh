@@ -12,6 +12,7 @@
 // Roofline / algorithmic bytes are documented in DESIGN.md.
 #pragma once
 #include "pair_tile.cuh"
+#include "sub_tile.cuh"
 #include "spectral_core.cuh"
 
 namespace tfcfft {
@@ -275,6 +276,87 @@ __global__ void __launch_bounds__(PairCfg<P>::NT, 1) pair_kernel(const __grid_co
         }
     }
     finish(prm, gridDim.x);
+}
+
+// Sub-tile path, launches 1 and 3 (sub_tile.cuh): the warp-specialised pair pipeline with the loss pass
+// removed.  mode 1: sub-image pairs of fake / real -> forward 64 x 64 transforms -> sub-spectra planes in the
+// workspace; mode 2: gradient sub-spectra planes -> inverse transforms -> gradient sub-images.
+template <typename T, bool LUMA3>
+__global__ void __launch_bounds__(PairCfg<64>::NT, 1) sub_pair_kernel(const __grid_constant__ Params prm) {
+    using Cfg = PairCfg<64>;
+    constexpr int P = 64;
+    constexpr int BAR_COMPUTE = 1, BAR_FULL = 2, BAR_DONE = 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* buf0 = reinterpret_cast<float4*>(smem_raw);
+    float4* buf1 = buf0 + P * Cfg::LD;
+    float4* tw = buf1 + P * Cfg::LD;
+    {
+        const BlockCtx all{(int)threadIdx.x, (int)blockDim.x};
+        fill_twiddles4<P>(all, tw);
+        __syncthreads();
+        fill_row_twiddles4<P>(all, tw, tw + P);
+    }
+    __syncthreads();
+    const int D = prm.sub_d, mode = prm.pair_mode;
+    const int nunits = prm.chunk_now * (D * D / 2);
+    if (threadIdx.x >= Cfg::NT_COMPUTE) {
+        const GroupCtx<Cfg::NT_LOAD, 6> ctx{(int)threadIdx.x - Cfg::NT_COMPUTE, nullptr};
+        auto write_back = [&](int u, const float4* s) {
+            const SubUnit su = sub_unit(u, D);
+            if (mode == 1) spec_store(ctx, s, sub_plane(prm, su));
+            else sub_store<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
+        };
+        int iter = 0, u = blockIdx.x;
+        for (; u < nunits; u += gridDim.x, ++iter) {
+            const int b = iter & 1;
+            float4* s = b ? buf1 : buf0;
+            if (iter >= 2) {
+                bar_sync(BAR_DONE + b, Cfg::NT);
+                write_back(u - 2 * (int)gridDim.x, s);
+                bar_sync(6, Cfg::NT_LOAD);
+            }
+            const SubUnit su = sub_unit(u, D);
+            if (mode == 1) sub_load<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
+            else spec_load(ctx, sub_plane(prm, su), s);
+            bar_arrive(BAR_FULL + b, Cfg::NT);
+        }
+        for (int back = (iter >= 2 ? 2 : iter); back >= 1; --back) {
+            const int it2 = iter - back, b = it2 & 1;
+            bar_sync(BAR_DONE + b, Cfg::NT);
+            write_back((int)blockIdx.x + it2 * (int)gridDim.x, b ? buf1 : buf0);
+        }
+    } else {
+        const GroupCtx<Cfg::NT_COMPUTE, BAR_COMPUTE> ctx{(int)threadIdx.x, nullptr};
+        int iter = 0;
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++iter) {
+            const int b = iter & 1;
+            float4* s = b ? buf1 : buf0;
+            bar_sync(BAR_FULL + b, Cfg::NT);
+            if (mode == 1) sub_compute_fwd(ctx, s, tw);
+            else sub_compute_inv(ctx, s, tw);
+            bar_arrive(BAR_DONE + b, Cfg::NT);
+        }
+    }
+}
+
+// Sub-tile path, launch 2: per-position D x D butterflies, loss, spectral gradient (registers + L2 only).
+template <int D>
+__global__ void __launch_bounds__(256) combine_kernel(const __grid_constant__ Params prm) {
+    constexpr int PARTS = 9;  // ceil(kCombineItems / 256)
+    const int lt = blockIdx.x / PARTS, part = blockIdx.x % PARTS;
+    const int item = part * 256 + (int)threadIdx.x;
+    float a = 0.f, p = 0.f;
+    if (item < kCombineItems) {
+        float4* ws_tile = reinterpret_cast<float4*>(prm.zws) + (long long)lt * (D * D / 2) * 4096;
+        combine_item<D>(prm, ws_tile, item, a, p);
+    }
+    block_sum2(a, p);
+    if (threadIdx.x == 0) {
+        const long long slot = (long long)(prm.tile_base + lt) * PARTS + part;
+        prm.partials[2 * slot] = a;
+        prm.partials[2 * slot + 1] = p;
+    }
+    finish(prm, (unsigned)prm.tiles_total * PARTS);
 }
 
 template <int P, typename T, bool LUMA3>

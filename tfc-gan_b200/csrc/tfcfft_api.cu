@@ -75,6 +75,36 @@ int launch_pair(const Params& prm, cudaStream_t st) {
     return 0;
 }
 
+template <typename T, bool LUMA3>
+int launch_sub(Params prm, cudaStream_t st) {
+    auto kp = sub_pair_kernel<T, LUMA3>;
+    constexpr size_t smem = PairCfg<64>::SMEM;
+    if (int rc = set_smem(kp, smem)) return rc;
+    const int D = prm.sub_d, npp = D * D / 2;
+    const int sms = device_info().sms;
+    for (int base = 0; base < prm.tiles_total; base += prm.chunk_tiles) {
+        prm.tile_base = base;
+        prm.chunk_now = prm.tiles_total - base < prm.chunk_tiles ? prm.tiles_total - base : prm.chunk_tiles;
+        const int units = prm.chunk_now * npp;
+        const int grid = units < sms ? units : sms;
+        prm.pair_mode = 1;
+        kp<<<grid, PairCfg<64>::NT, smem, st>>>(prm);
+        g_launches++;
+        TFC_LAUNCH_CHECK();
+        if (D == 2) combine_kernel<2><<<prm.chunk_now * 9, 256, 0, st>>>(prm);
+        else combine_kernel<4><<<prm.chunk_now * 9, 256, 0, st>>>(prm);
+        g_launches++;
+        TFC_LAUNCH_CHECK();
+        if (prm.grad) {
+            prm.pair_mode = 2;
+            kp<<<grid, PairCfg<64>::NT, smem, st>>>(prm);
+            g_launches++;
+            TFC_LAUNCH_CHECK();
+        }
+    }
+    return 0;
+}
+
 template <int P, typename T, bool LUMA3>
 int launch_split(Params prm, cudaStream_t st) {
     if constexpr (P >= 64) {
@@ -108,6 +138,9 @@ int launch_split(Params prm, cudaStream_t st) {
 
 template <int P, typename T, bool LUMA3>
 int launch(const Params& prm, bool split, cudaStream_t st) {
+    if constexpr (P == 128 || P == 256) {
+        if (prm.sub_d > 1) return launch_sub<T, LUMA3>(prm, st);
+    }
     if (split) return launch_split<P, T, LUMA3>(prm, st);
     if constexpr (P <= 128) {
         if constexpr (P == 64) {
@@ -177,7 +210,7 @@ static int dispatch(const Params& prm, const Geometry& g, int dtype, cudaStream_
 // the workspace header (nobody reads them)
 static int spectra_common(const tfcfft_desc* d, const void* x, const void* y, void* grad, void* workspace,
                           size_t workspace_bytes, Geometry* g, Params* prm) {
-    int rc = validate_desc(d, g);
+    int rc = validate_desc(d, g, /*allow_sub=*/false);
     if (rc) return rc;
     if (d->grid != 1) return TFCFFT_ERR_SHAPE;
     if (!x) return TFCFFT_ERR_NULL;
