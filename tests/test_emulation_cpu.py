@@ -43,7 +43,7 @@ def test_emulation_matches_r1(side, grid, opt):
     fake, real = make_pair("uniform", 7, (n, 3, side, side), "float32")
     rc, out, per, g = emulate(fake, real, grid, flags_of(**opt), weight=0.7, input_scale=3.0)
     assert rc == 0
-    okw = {k: v for k, v in opt.items() if k != "force_split"}
+    okw = {k: v for k, v in opt.items() if not k.startswith("force_")}
     l, a, p, gr = oracle.spectral_loss_and_grad_r1(fake, real, grid=grid, weight=0.7, input_scale=3.0, **okw)
     assert out[0] == pytest.approx(l, rel=1e-5)
     assert out[1] == pytest.approx(a, rel=1e-5)
