@@ -281,9 +281,14 @@ __global__ void __launch_bounds__(PairCfg<P>::NT, 1) pair_kernel(const __grid_co
 // Sub-tile path, launches 1 and 3 (sub_tile.cuh): the warp-specialised pair pipeline with the loss pass
 // removed.  mode 1: sub-image pairs of fake / real -> forward 64 x 64 transforms -> sub-spectra planes in the
 // workspace; mode 2: gradient sub-spectra planes -> inverse transforms -> gradient sub-images.
+// Roles as in pair_kernel: 16 compute warps + 8 loader / storer warps.
+struct SubCfg {
+    static constexpr int LD = 65;
+    static constexpr int NT_COMPUTE = 512, NT_LOAD = 256, NT = NT_COMPUTE + NT_LOAD;
+};
 template <typename T, bool LUMA3>
-__global__ void __launch_bounds__(PairCfg<64>::NT, 1) sub_pair_kernel(const __grid_constant__ Params prm) {
-    using Cfg = PairCfg<64>;
+__global__ void __launch_bounds__(SubCfg::NT, 1) sub_pair_kernel(const __grid_constant__ Params prm) {
+    using Cfg = SubCfg;
     constexpr int P = 64;
     constexpr int BAR_COMPUTE = 1, BAR_FULL = 2, BAR_DONE = 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -310,14 +315,22 @@ __global__ void __launch_bounds__(PairCfg<64>::NT, 1) sub_pair_kernel(const __gr
         for (; u < nunits; u += gridDim.x, ++iter) {
             const int b = iter & 1;
             float4* s = b ? buf1 : buf0;
+            long long* tr = (prm.trace != nullptr && iter < 6 && ctx.tid == 0) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
+            if (tr) tr[4] = clock64();
             if (iter >= 2) {
                 bar_sync(BAR_DONE + b, Cfg::NT);
+                if (tr) tr[5] = clock64();
                 write_back(u - 2 * (int)gridDim.x, s);
                 bar_sync(6, Cfg::NT_LOAD);
             }
+            if (tr) tr[6] = clock64();
             const SubUnit su = sub_unit(u, D);
-            if (mode == 1) sub_load<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
-            else spec_load(ctx, sub_plane(prm, su), s);
+            if (mode == 1) {
+                sub_load<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
+            } else {
+                spec_load(ctx, sub_plane(prm, su), s);
+            }
+            if (tr) tr[7] = clock64();
             bar_arrive(BAR_FULL + b, Cfg::NT);
         }
         for (int back = (iter >= 2 ? 2 : iter); back >= 1; --back) {
@@ -331,9 +344,16 @@ __global__ void __launch_bounds__(PairCfg<64>::NT, 1) sub_pair_kernel(const __gr
         for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++iter) {
             const int b = iter & 1;
             float4* s = b ? buf1 : buf0;
+            long long* tr = (prm.trace != nullptr && iter < 6 && ctx.tid == 0) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
+            if (tr) tr[0] = clock64();
             bar_sync(BAR_FULL + b, Cfg::NT);
+            if (tr) tr[1] = clock64();
             if (mode == 1) sub_compute_fwd(ctx, s, tw);
             else sub_compute_inv(ctx, s, tw);
+            if (tr) {
+                tr[2] = clock64();
+                tr[15] = 1;
+            }
             bar_arrive(BAR_DONE + b, Cfg::NT);
         }
     }
@@ -341,7 +361,7 @@ __global__ void __launch_bounds__(PairCfg<64>::NT, 1) sub_pair_kernel(const __gr
 
 // Sub-tile path, launch 2: per-position D x D butterflies, loss, spectral gradient (registers + L2 only).
 template <int D>
-__global__ void __launch_bounds__(256) combine_kernel(const __grid_constant__ Params prm) {
+__global__ void __launch_bounds__(256, 2) combine_kernel(const __grid_constant__ Params prm) {
     constexpr int PARTS = 9;  // ceil(kCombineItems / 256)
     const int lt = blockIdx.x / PARTS, part = blockIdx.x % PARTS;
     const int item = part * 256 + (int)threadIdx.x;

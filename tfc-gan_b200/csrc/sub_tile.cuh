@@ -41,29 +41,31 @@ TFC_HD void sub_load(const Ctx& ctx, const Params& prm, const TileCoord& tc, con
     const T* rp = tile_ptr<T>(prm.real, prm.rs, tc, P);
     const int fsh = (int)prm.fs[2], fsc = (int)prm.fs[1], rsh = (int)prm.rs[2], rsc = (int)prm.rs[1];
     const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
+    // one sub-image column b per lane (consecutive lanes -> consecutive 8-byte pairs of the source row), four
+    // rows a, a+16, a+32, a+48 per thread in flight
     for (int it = ctx.tid; it < 64 * 16; it += ctx.nthreads) {
-        const int b0 = (it % 16) * 4, a = it / 16;
-        const int y = D * a + su.p;
-        float4* row = s + a * LD;
-        float raw[2][NC][4][2];  // [fake|real][channel][b][lane]
+        const int b = it & 63, a0 = it >> 6;
+        const int x = D * b + 2 * su.i;
+        float raw[4][2][NC][2];  // [row][fake|real][channel][lane]
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
+        for (int r = 0; r < 4; ++r) {
+            const int y = D * (a0 + 16 * r) + su.p;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int x = D * (b0 + b) + 2 * su.i;
-                IO<T>::load2(fp + y * fsh + c * fsc + x, raw[0][c][b]);
-                IO<T>::load2(rp + y * rsh + c * rsc + x, raw[1][c][b]);
+            for (int c = 0; c < NC; ++c) {
+                IO<T>::load2(fp + y * fsh + c * fsc + x, raw[r][0][c]);
+                IO<T>::load2(rp + y * rsh + c * rsc + x, raw[r][1][c]);
             }
+        }
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int r = 0; r < 4; ++r) {
             float2 v[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (!quant) {
-                    float2 f = p_mul(p_dup(prm.lw[0]), make_float2(raw[h][0][b][0], raw[h][0][b][1]));
+                    float2 f = p_mul(p_dup(prm.lw[0]), make_float2(raw[r][h][0][0], raw[r][h][0][1]));
                     if constexpr (LUMA3) {
-                        f = p_fma(p_dup(prm.lw[1]), make_float2(raw[h][1][b][0], raw[h][1][b][1]), f);
-                        f = p_fma(p_dup(prm.lw[2]), make_float2(raw[h][2][b][0], raw[h][2][b][1]), f);
+                        f = p_fma(p_dup(prm.lw[1]), make_float2(raw[r][h][1][0], raw[r][h][1][1]), f);
+                        f = p_fma(p_dup(prm.lw[2]), make_float2(raw[r][h][2][0], raw[r][h][2][1]), f);
                     }
                     v[h] = f;
                 } else {
@@ -71,17 +73,36 @@ TFC_HD void sub_load(const Ctx& ctx, const Params& prm, const TileCoord& tc, con
 #pragma unroll
                     for (int l = 0; l < 2; ++l) {
                         if constexpr (LUMA3)
-                            q[l] = (float)((19595 * IO<T>::quant(raw[h][0][b][l]) + 38470 * IO<T>::quant(raw[h][1][b][l]) +
-                                            7471 * IO<T>::quant(raw[h][2][b][l]) + 0x8000) >> 16);
+                            q[l] = (float)((19595 * IO<T>::quant(raw[r][h][0][l]) + 38470 * IO<T>::quant(raw[r][h][1][l]) +
+                                            7471 * IO<T>::quant(raw[r][h][2][l]) + 0x8000) >> 16);
                         else
-                            q[l] = (float)IO<T>::quant(raw[h][0][b][l]);
+                            q[l] = (float)IO<T>::quant(raw[r][h][0][l]);
                     }
                     v[h] = make_float2(q[0], q[1]);
                 }
             }
-            row[swz(b0 + b)] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+            s[(a0 + 16 * r) * LD + swz(b)] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
         }
     }
+}
+
+// Pulls the source rows of a later unit into L2 (full rows: the sibling lane pairs of the same row phase share
+// them), so the loader's dependent load rounds see L2 latency instead of HBM latency.
+template <typename T, bool LUMA3, class Ctx>
+TFC_HD void sub_prefetch_l2(const Ctx& ctx, const Params& prm, const TileCoord& tc, const SubUnit& su) {
+#ifdef __CUDA_ARCH__
+    constexpr int NC = LUMA3 ? 3 : 1, EPL = 128 / (int)sizeof(T);
+    const int D = prm.sub_d, P = 64 * D, lpr = (P + EPL - 1) / EPL;
+    const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, P);
+    const T* rp = tile_ptr<T>(prm.real, prm.rs, tc, P);
+    for (int it = ctx.tid; it < 2 * NC * 64 * lpr; it += ctx.nthreads) {
+        const int l = it % lpr, a = (it / lpr) % 64, hc = it / (lpr * 64);
+        const int h = hc & 1, c = hc >> 1;
+        const T* q = (h ? rp + (D * a + su.p) * (int)prm.rs[2] + c * (int)prm.rs[1]
+                        : fp + (D * a + su.p) * (int)prm.fs[2] + c * (int)prm.fs[1]) + l * EPL;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    }
+#endif
 }
 
 // ---- gradient sub-image pair (staged at the swizzled slots by pair_rows_last) -> global ------------
@@ -92,13 +113,12 @@ TFC_HD void sub_store(const Ctx& ctx, const Params& prm, const TileCoord& tc, co
     T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, P));
     const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
     for (int it = ctx.tid; it < 64 * 16; it += ctx.nthreads) {
-        const int b0 = (it % 16) * 4, a = it / 16;
-        const int y = D * a + su.p;
-        const float4* row = s + a * LD;
+        const int b = it & 63, a0 = it >> 6;  // consecutive lanes: consecutive 8-byte pairs of the gradient row
+        const int x = D * b + 2 * su.i;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const float2 g = *reinterpret_cast<const float2*>(row + swz(b0 + b));
-            const int x = D * (b0 + b) + 2 * su.i;
+        for (int r = 0; r < 4; ++r) {
+            const int a = a0 + 16 * r, y = D * a + su.p;
+            const float2 g = *reinterpret_cast<const float2*>(s + a * LD + swz(b));
 #pragma unroll
             for (int c = 0; c < NC; ++c) IO<T>::store2(gp + y * sh + c * sc + x, prm.gw[c] * g.x, prm.gw[c] * g.y);
         }
@@ -278,30 +298,80 @@ TFC_HD void combine_item(const Params& prm, float4* ws_tile, int item, float& ac
         for (int be = 0; be < D; ++be) zp[al][be] = t[be];
     }
     float2 ga[D][D], gp[D][D];  // gp: gradient of the partner entries, in the permuted index space
+    const bool generic = (prm.flags & (TFCFFT_LOG_MAGNITUDE | TFCFFT_FULL_SPECTRUM)) != 0;
+    if (generic) {
 #pragma unroll
-    for (int al = 0; al < D; ++al)
+        for (int al = 0; al < D; ++al)
 #pragma unroll
-        for (int be = 0; be < D; ++be) {
-            const int alB = kyA ? D - 1 - al : (D - al) % D;
-            const int beB = kxA ? D - 1 - be : (D - be) % D;
-            float2 gk = make_float2(0.f, 0.f), gm = make_float2(0.f, 0.f);
-            const bool skip = self && (al * D + be) > (alB * D + beB);  // each unordered pair once
-            if (!skip) {
-                const bool selfbin = self && al == alB && be == beB;
-                const int kxf = kxA + 64 * be;
-                const float2 zk = za[al][be], zm = zp[al][be];
-                if (kxf == 0 || kxf == P / 2) {  // self-conjugate column: k and -k are both half-plane bins
-                    gk = bin_eval(prm, zk, zm, 1.f, accA, accP);
-                    if (!selfbin) gm = bin_eval(prm, zm, zk, 1.f, accA, accP);
-                } else if (kxf < P / 2) {
-                    gk = bin_eval(prm, zk, zm, full ? 2.f : 1.f, accA, accP);
-                } else {
-                    gm = bin_eval(prm, zm, zk, full ? 2.f : 1.f, accA, accP);
+            for (int be = 0; be < D; ++be) {
+                const int alB = kyA ? D - 1 - al : (D - al) % D;
+                const int beB = kxA ? D - 1 - be : (D - be) % D;
+                float2 gk = make_float2(0.f, 0.f), gm = make_float2(0.f, 0.f);
+                const bool skip = self && (al * D + be) > (alB * D + beB);  // each unordered pair once
+                if (!skip) {
+                    const bool selfbin = self && al == alB && be == beB;
+                    const int kxf = kxA + 64 * be;
+                    const float2 zk = za[al][be], zm = zp[al][be];
+                    if (kxf == 0 || kxf == P / 2) {  // self-conjugate column: k and -k are both half-plane bins
+                        gk = bin_eval(prm, zk, zm, 1.f, accA, accP);
+                        if (!selfbin) gm = bin_eval(prm, zm, zk, 1.f, accA, accP);
+                    } else if (kxf < P / 2) {
+                        gk = bin_eval(prm, zk, zm, full ? 2.f : 1.f, accA, accP);
+                    } else {
+                        gm = bin_eval(prm, zm, zk, full ? 2.f : 1.f, accA, accP);
+                    }
+                }
+                ga[al][be] = gk;
+                gp[al][be] = gm;
+            }
+    } else {
+        // default modes: two entries (be, be+1) per packed evaluation, MUFU / polynomial transcendental path
+        const bool mse = (prm.flags & TFCFFT_DIST_MSE) != 0, phase = !(prm.flags & TFCFFT_NO_PHASE);
+        float2 pA = make_float2(0.f, 0.f), pP = make_float2(0.f, 0.f);
+        const float2 z0 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int al = 0; al < D; ++al)
+#pragma unroll
+            for (int bp = 0; bp < D / 2; ++bp) {
+                const int alB = kyA ? D - 1 - al : (D - al) % D;
+                bool isM[2], both[2], live[2];
+                c2 zk, zm;
+                float2 k_[2], m_[2];
+#pragma unroll
+                for (int l = 0; l < 2; ++l) {
+                    const int be = 2 * bp + l;
+                    const int beB = kxA ? D - 1 - be : (D - be) % D;
+                    const int kxf = kxA + 64 * be;
+                    live[l] = !(self && (al * D + be) > (alB * D + beB));
+                    const bool special = (kxf == 0 || kxf == P / 2);
+                    both[l] = live[l] && special && !(self && al == alB && be == beB);
+                    isM[l] = !special && kxf > P / 2;
+                    k_[l] = live[l] ? (isM[l] ? zp[al][be] : za[al][be]) : z0;
+                    m_[l] = live[l] ? (isM[l] ? za[al][be] : zp[al][be]) : z0;
+                }
+                zk = make_c2(make_float2(k_[0].x, k_[1].x), make_float2(k_[0].y, k_[1].y));
+                zm = make_c2(make_float2(m_[0].x, m_[1].x), make_float2(m_[0].y, m_[1].y));
+                const c2 g = bin_eval_pair(prm, mse, phase, zk, zm, pA, pP);
+                c2 g2 = make_c2(z0, z0);
+                if (both[0] || both[1]) {  // self-conjugate columns only: evaluate the mirrored bin as well
+                    const c2 zk2 = make_c2(make_float2(both[0] ? m_[0].x : 0.f, both[1] ? m_[1].x : 0.f),
+                                           make_float2(both[0] ? m_[0].y : 0.f, both[1] ? m_[1].y : 0.f));
+                    const c2 zm2 = make_c2(make_float2(both[0] ? k_[0].x : 0.f, both[1] ? k_[1].x : 0.f),
+                                           make_float2(both[0] ? k_[0].y : 0.f, both[1] ? k_[1].y : 0.f));
+                    g2 = bin_eval_pair(prm, mse, phase, zk2, zm2, pA, pP);
+                }
+#pragma unroll
+                for (int l = 0; l < 2; ++l) {
+                    const int be = 2 * bp + l;
+                    const float2 gl = l ? make_float2(g.re.y, g.im.y) : make_float2(g.re.x, g.im.x);
+                    const float2 g2l = l ? make_float2(g2.re.y, g2.im.y) : make_float2(g2.re.x, g2.im.x);
+                    ga[al][be] = live[l] ? (isM[l] ? z0 : gl) : z0;
+                    gp[al][be] = live[l] ? (isM[l] ? gl : (both[l] ? g2l : z0)) : z0;
                 }
             }
-            ga[al][be] = gk;
-            gp[al][be] = gm;
-        }
+        accA += pA.x + pA.y;
+        accP += pP.x + pP.y;
+    }
     if (!want_grad) return;
     // undo the permutation: gb[a][b] = gp[perm(a)][perm(b)]
     float2 gb[D][D];

@@ -88,7 +88,7 @@ int launch_sub(Params prm, cudaStream_t st) {
         const int units = prm.chunk_now * npp;
         const int grid = units < sms ? units : sms;
         prm.pair_mode = 1;
-        kp<<<grid, PairCfg<64>::NT, smem, st>>>(prm);
+        kp<<<grid, SubCfg::NT, smem, st>>>(prm);
         g_launches++;
         TFC_LAUNCH_CHECK();
         if (D == 2) combine_kernel<2><<<prm.chunk_now * 9, 256, 0, st>>>(prm);
@@ -97,7 +97,7 @@ int launch_sub(Params prm, cudaStream_t st) {
         TFC_LAUNCH_CHECK();
         if (prm.grad) {
             prm.pair_mode = 2;
-            kp<<<grid, PairCfg<64>::NT, smem, st>>>(prm);
+            kp<<<grid, SubCfg::NT, smem, st>>>(prm);
             g_launches++;
             TFC_LAUNCH_CHECK();
         }
