@@ -316,6 +316,8 @@ def run_ours(args, wl):
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if not os.environ.get("TFCFFT_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout; rank 0 prints exactly one line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
