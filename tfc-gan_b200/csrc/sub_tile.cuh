@@ -243,7 +243,84 @@ TFC_HD void combine_inv(float2 (&v)[D][D], int ky, int kx) {
     }
 }
 
-constexpr int kCombineItems = 64 * 31 + 2 * 33;  // position pairs {(ky',kx'), -(ky',kx')} of the 64 x 64 sub-grid
+// ---- the same butterflies on two positions at once (lane x = position A, lane y = its partner B) ----
+TFC_HD c2 cmul2(c2 a, c2 w) {  // per-lane a * w
+    return make_c2(p_fma(a.re, w.re, p_neg(p_mul(a.im, w.im))), p_fma(a.re, w.im, p_mul(a.im, w.re)));
+}
+TFC_HD c2 cmulc2(c2 a, c2 w) {  // per-lane a * conj(w)
+    return make_c2(p_fma(a.re, w.re, p_mul(a.im, w.im)), p_fma(a.im, w.re, p_neg(p_mul(a.re, w.im))));
+}
+TFC_HD c2 cis_neg2(float fa, float fb) {
+    const float2 a = cis_neg(fa), b = cis_neg(fb);
+    return make_c2(make_float2(a.x, b.x), make_float2(a.y, b.y));
+}
+template <int D>
+TFC_HD void combine_fwd2(c2 (&v)[D][D], int kyA, int kxA, int kyB, int kxB) {
+    constexpr int P = 64 * D;
+    const c2 wy = cis_neg2((float)kyA / (float)P, (float)kyB / (float)P);
+    const c2 wx = cis_neg2((float)kxA / (float)P, (float)kxB / (float)P);
+#pragma unroll
+    for (int p = 0; p < D; ++p) {
+        c2 w = wx;
+#pragma unroll
+        for (int q = 1; q < D; ++q) {
+            v[p][q] = cmul2(v[p][q], w);
+            if (q + 1 < D) w = cmul2(w, wx);
+        }
+        Dft<D, false>::run(v[p]);
+    }
+#pragma unroll
+    for (int be = 0; be < D; ++be) {
+        c2 col[D];
+        c2 w = wy;
+#pragma unroll
+        for (int p = 0; p < D; ++p) col[p] = v[p][be];
+#pragma unroll
+        for (int p = 1; p < D; ++p) {
+            col[p] = cmul2(col[p], w);
+            if (p + 1 < D) w = cmul2(w, wy);
+        }
+        Dft<D, false>::run(col);
+#pragma unroll
+        for (int al = 0; al < D; ++al) v[al][be] = col[al];
+    }
+}
+template <int D>
+TFC_HD void combine_inv2(c2 (&v)[D][D], int kyA, int kxA, int kyB, int kxB) {
+    constexpr int P = 64 * D;
+    const c2 wy = cis_neg2((float)kyA / (float)P, (float)kyB / (float)P);
+    const c2 wx = cis_neg2((float)kxA / (float)P, (float)kxB / (float)P);
+#pragma unroll
+    for (int be = 0; be < D; ++be) {
+        c2 col[D];
+#pragma unroll
+        for (int al = 0; al < D; ++al) col[al] = v[al][be];
+        Dft<D, true>::run(col);
+        c2 w = wy;
+#pragma unroll
+        for (int p = 1; p < D; ++p) {
+            col[p] = cmulc2(col[p], w);
+            if (p + 1 < D) w = cmul2(w, wy);
+        }
+#pragma unroll
+        for (int p = 0; p < D; ++p) v[p][be] = col[p];
+    }
+#pragma unroll
+    for (int p = 0; p < D; ++p) {
+        Dft<D, true>::run(v[p]);
+        c2 w = wx;
+#pragma unroll
+        for (int q = 1; q < D; ++q) {
+            v[p][q] = cmulc2(v[p][q], w);
+            if (q + 1 < D) w = cmul2(w, wx);
+        }
+    }
+}
+
+// position pairs {(ky',kx'), -(ky',kx')} of the 64 x 64 sub-grid: 64 x 32 slots walk the half-plane column
+// POSITIONS in memory order (4 consecutive float4 = 64 contiguous bytes per group; slot j = 0 is the kx' = 0
+// column, handled with kx' = 32 by the 66 items that pair rows instead)
+constexpr int kCombineItems = 64 * 32 + 2 * 33;
 
 // One position pair of one tile: load the D^2 sub-spectra at both positions, combine, evaluate every
 // full-size half-plane bin they contain, un-combine the spectral gradient, store back.
@@ -251,11 +328,13 @@ template <int D>
 TFC_HD void combine_item(const Params& prm, float4* ws_tile, int item, float& accA, float& accP) {
     constexpr int P = 64 * D, NPP = D * D / 2, HD = D / 2;
     int kyA, kxA;
-    if (item < 64 * 31) {
-        kyA = freq_of_pos<64>(item & 63);  // consecutive items: consecutive row positions
-        kxA = 1 + (item >> 6);
+    if (item < 64 * 32) {
+        const int j = item & 31;
+        if (j == 0) return;
+        kyA = freq_of_pos<64>(item >> 5);
+        kxA = freq_of_pos<64>((j >> 2) * 8 + (j & 3));  // 1 .. 31
     } else {
-        const int sp = item - 64 * 31;
+        const int sp = item - 64 * 32;
         kxA = (sp / 33) * 32;
         kyA = sp % 33;
     }
@@ -274,8 +353,22 @@ TFC_HD void combine_item(const Params& prm, float4* ws_tile, int item, float& ac
         zb[p][q] = make_float2(b.x, b.z);
         zb[p][q + 1] = make_float2(b.y, b.w);
     }
-    combine_fwd<D>(za, kyA, kxA);
-    combine_fwd<D>(zb, kyB, kxB);
+    {
+        c2 z2[D][D];
+#pragma unroll
+        for (int p = 0; p < D; ++p)
+#pragma unroll
+            for (int q = 0; q < D; ++q)
+                z2[p][q] = make_c2(make_float2(za[p][q].x, zb[p][q].x), make_float2(za[p][q].y, zb[p][q].y));
+        combine_fwd2<D>(z2, kyA, kxA, kyB, kxB);
+#pragma unroll
+        for (int p = 0; p < D; ++p)
+#pragma unroll
+            for (int q = 0; q < D; ++q) {
+                za[p][q] = make_float2(z2[p][q].re.x, z2[p][q].im.x);
+                zb[p][q] = make_float2(z2[p][q].re.y, z2[p][q].im.y);
+            }
+    }
     const bool want_grad = prm.grad != nullptr;
     const bool full = (prm.flags & TFCFFT_FULL_SPECTRUM) != 0;
     // The partner of the full frequency (kyA + 64 al, kxA + 64 be) sits in position B at (alB, beB) with
@@ -393,8 +486,22 @@ TFC_HD void combine_item(const Params& prm, float4* ws_tile, int item, float& ac
 #pragma unroll
             for (int be = 0; be < D; ++be) ga[al][be] = cadd(ga[al][be], gb[al][be]);
     }
-    combine_inv<D>(ga, kyA, kxA);
-    if (!self) combine_inv<D>(gb, kyB, kxB);
+    {
+        c2 g2[D][D];
+#pragma unroll
+        for (int p = 0; p < D; ++p)
+#pragma unroll
+            for (int q = 0; q < D; ++q)
+                g2[p][q] = make_c2(make_float2(ga[p][q].x, gb[p][q].x), make_float2(ga[p][q].y, gb[p][q].y));
+        combine_inv2<D>(g2, kyA, kxA, kyB, kxB);
+#pragma unroll
+        for (int p = 0; p < D; ++p)
+#pragma unroll
+            for (int q = 0; q < D; ++q) {
+                ga[p][q] = make_float2(g2[p][q].re.x, g2[p][q].im.x);
+                gb[p][q] = make_float2(g2[p][q].re.y, g2[p][q].im.y);
+            }
+    }
 #pragma unroll
     for (int pl = 0; pl < NPP; ++pl) {
         const int p = pl / HD, q = 2 * (pl % HD);
