@@ -14,9 +14,13 @@ cfg = tfc.SpectralConfig(grid=grid, weight=0.01, input_scale=255.0)
 for _ in range(3):
     tfc.spectral_loss_and_grad(fake, real, config=cfg)
 buf = torch.zeros(148 * 6 * 16, dtype=torch.int64, device="cuda")
-for mode_name in ("both launches (mode 2 overwrites mode 1)",):
+for mode_name in ("forward launch only (mode 1)", "both launches (mode 2 overwrites mode 1)"):
+    buf.zero_()
     lib.tfcfft_debug_trace(ctypes.c_void_p(buf.data_ptr()))
-    tfc.spectral_loss_and_grad(fake, real, config=cfg)
+    if mode_name.startswith("forward"):
+        tfc.spectral_terms_per_image(fake, real, config=cfg)
+    else:
+        tfc.spectral_loss_and_grad(fake, real, config=cfg)
     torch.cuda.synchronize()
     lib.tfcfft_debug_trace(None)
     t = buf.cpu().numpy().reshape(148, 6, 16).astype(np.float64)
