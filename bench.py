@@ -220,7 +220,8 @@ def time_kernel_path(tfc, torch, wl, steps, warmup, barrier):
         f = torch.empty(wl["batch"], 3, wl["side"], wl["side"], device=dev).uniform_(-1, 1, generator=g)
         r = torch.empty_like(f).uniform_(-1, 1, generator=g)
         pool.append((f, r))
-    cfg = tfc.SpectralConfig(grid=wl["grid"], channels=wl["channels"], weight=0.01, input_scale=255.0)
+    cfg = tfc.SpectralConfig(grid=wl["grid"], channels=wl["channels"], weight=0.01, input_scale=255.0,
+                             use_line=bool(os.environ.get("TFCFFT_BENCH_USE_LINE")))
     sink = None
     for i in range(warmup):
         f, r = pool[i % pool_n]

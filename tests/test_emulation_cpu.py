@@ -176,3 +176,17 @@ def test_emulated_spectra_quantised_match_reference_golden():
     ga = gold["p16_uniform_11_float32_amp_B6"]
     dphi = np.angle(np.exp(1j * (pha - gold["p16_uniform_11_float32_pha_B6"])))
     assert np.abs(dphi[ga > 1.0]).max() < 1e-3
+
+
+@pytest.mark.parametrize("opt", [dict(), dict(channels="rgb", distance="mse"), dict(use_phase=False)])
+def test_thread_per_line_path_matches_oracle_and_pair_path(opt):
+    """The register-resident 64-point line kernel (USE_LINE) against R1 and against the packed pair path."""
+    fake, real = make_pair("tanh", 19, (3, 3, 128, 128), "float32")  # grid=2 -> 64x64 tiles
+    rc, o1, p1, g1 = emulate(fake, real, 2, flags_of(use_line=True, **opt), input_scale=255.0)
+    rc2, o2, p2, g2 = emulate(fake, real, 2, flags_of(**opt), input_scale=255.0)
+    assert rc == 0 and rc2 == 0
+    l, a, p, gr = oracle.spectral_loss_and_grad_r1(fake, real, grid=2, input_scale=255.0, **opt)
+    assert o1[0] == pytest.approx(l, rel=1e-5)
+    assert l2rel(g1, gr) <= 1e-3
+    np.testing.assert_allclose(o1[:3], o2[:3], rtol=2e-6)
+    assert l2rel(g1, g2) <= 2e-5

@@ -54,6 +54,8 @@ CASES = [
     (64, 4, dict(spectrum="full")),
     (64, 1, dict()),
     (256, 4, dict(force_generic=True)),                 # generic resident kernel (the default is the packed pair path)
+    (256, 4, dict(use_line=True)),                      # thread-per-line kernel
+    (256, 4, dict(use_line=True, channels="rgb", distance="mse")),
     (256, 4, dict(force_split=True)),                   # split kernels on a size the resident path also covers
     (256, 2, dict(force_split=True, channels="rgb")),
     (256, 1, dict(force_split=True)),                   # the split kernels at their native size

@@ -12,6 +12,7 @@
 #include "host_common.h"
 #include "pair_tile.cuh"
 #include "sub_tile.cuh"
+#include "line_tile.cuh"
 
 using namespace tfcfft;
 
@@ -25,6 +26,18 @@ void run_resident(Params prm) {
     for (int tile = 0; tile < prm.tiles_total; ++tile) {
         float a = 0.f, p = 0.f;
         tile_process<P, T, LUMA3>(ctx, prm, tile, s.data(), tw.data(), a, p);
+        prm.partials[2 * tile] = a;
+        prm.partials[2 * tile + 1] = p;
+    }
+}
+
+template <typename T, bool LUMA3>
+void run_line(Params prm) {
+    SerialCtx ctx;
+    std::vector<float2> s((size_t)64 * LineCfg::LD);
+    for (int tile = 0; tile < prm.tiles_total; ++tile) {
+        float a = 0.f, p = 0.f;
+        line_process<T, LUMA3>(ctx, prm, tile, s.data(), a, p);
         prm.partials[2 * tile] = a;
         prm.partials[2 * tile + 1] = p;
     }
@@ -120,6 +133,7 @@ template <int P, typename T, bool LUMA3>
 void run(const Params& prm, bool split) {
     if ((P == 128 || P == 256) && prm.sub_d > 1) run_sub<T, LUMA3>(prm);
     else if (split) run_split<P, T, LUMA3>(prm);
+    else if (P == 64 && pair_supported(prm) && (prm.flags & TFCFFT_USE_LINE)) run_line<T, LUMA3>(prm);
     else if (P == 64 && pair_supported(prm)) run_pair<P, T, LUMA3>(prm);
     else if constexpr (P <= 128) run_resident<P, T, LUMA3>(prm);
 }

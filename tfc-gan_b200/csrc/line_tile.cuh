@@ -1,0 +1,306 @@
+// line_tile.cuh -- 64 x 64 tiles with one thread per transform line (register-resident 64-point FFTs).
+//
+// Why: the packed pair kernel (pair_tile.cuh) is bounded by shared-memory round trips -- every radix-8 pass
+// moves the whole tile through shared memory and ends in a block barrier (profiles/r01_*: ~11.5 k shared
+// wavefronts and 9 barriers per pair).  Here a thread owns a whole 64-point line: it reads the line once,
+// runs the complete 8 x 8 Cooley-Tukey factorisation in registers with compile-time twiddles (no twiddle
+// table, no index arithmetic, natural-order output) and writes it back once.  Shared-memory traffic per tile
+// drops ~2.3x and the instruction count ~1.8x; parallelism comes from instruction-level parallelism inside a
+// thread (64 independent elements) and from six independent 64-thread CTAs per SM.
+//
+// One CTA (64 threads) = one tile: cooperative coalesced load + luma -> rows -> columns -> half-plane loss +
+// spectral gradient -> inverse columns (33 non-zero ones) -> inverse rows -> coalesced gradient store.
+#pragma once
+#include "pair_tile.cuh"
+
+namespace tfcfft {
+
+struct LineCfg {
+    static constexpr int NT = 64;
+    static constexpr int LD = 65;  // float2 row pitch: lanes = rows and lanes = columns are both conflict-free
+    static constexpr size_t SMEM = (size_t)64 * LD * sizeof(float2);
+};
+
+constexpr float kCos64[64] = {
+    1.f, 0.995184727f, 0.98078528f, 0.956940336f, 0.923879533f, 0.881921264f, 0.831469612f, 0.773010453f,
+    0.707106781f, 0.634393284f, 0.555570233f, 0.471396737f, 0.382683432f, 0.290284677f, 0.195090322f, 0.0980171403f,
+    0.f, -0.0980171403f, -0.195090322f, -0.290284677f, -0.382683432f, -0.471396737f, -0.555570233f, -0.634393284f,
+    -0.707106781f, -0.773010453f, -0.831469612f, -0.881921264f, -0.923879533f, -0.956940336f, -0.98078528f, -0.995184727f,
+    -1.f, -0.995184727f, -0.98078528f, -0.956940336f, -0.923879533f, -0.881921264f, -0.831469612f, -0.773010453f,
+    -0.707106781f, -0.634393284f, -0.555570233f, -0.471396737f, -0.382683432f, -0.290284677f, -0.195090322f, -0.0980171403f,
+    0.f, 0.0980171403f, 0.195090322f, 0.290284677f, 0.382683432f, 0.471396737f, 0.555570233f, 0.634393284f,
+    0.707106781f, 0.773010453f, 0.831469612f, 0.881921264f, 0.923879533f, 0.956940336f, 0.98078528f, 0.995184727f};
+constexpr float kSin64[64] = {
+    0.f, 0.0980171403f, 0.195090322f, 0.290284677f, 0.382683432f, 0.471396737f, 0.555570233f, 0.634393284f,
+    0.707106781f, 0.773010453f, 0.831469612f, 0.881921264f, 0.923879533f, 0.956940336f, 0.98078528f, 0.995184727f,
+    1.f, 0.995184727f, 0.98078528f, 0.956940336f, 0.923879533f, 0.881921264f, 0.831469612f, 0.773010453f,
+    0.707106781f, 0.634393284f, 0.555570233f, 0.471396737f, 0.382683432f, 0.290284677f, 0.195090322f, 0.0980171403f,
+    0.f, -0.0980171403f, -0.195090322f, -0.290284677f, -0.382683432f, -0.471396737f, -0.555570233f, -0.634393284f,
+    -0.707106781f, -0.773010453f, -0.831469612f, -0.881921264f, -0.923879533f, -0.956940336f, -0.98078528f, -0.995184727f,
+    -1.f, -0.995184727f, -0.98078528f, -0.956940336f, -0.923879533f, -0.881921264f, -0.831469612f, -0.773010453f,
+    -0.707106781f, -0.634393284f, -0.555570233f, -0.471396737f, -0.382683432f, -0.290284677f, -0.195090322f, -0.0980171403f};
+
+// a * W_64^K (INV: conjugate twiddle), K compile-time
+template <int K, bool INV>
+TFC_HD float2 mul_w64(float2 a) {
+    constexpr int k = K & 63;
+    constexpr float c8 = 0.707106781186547524f;
+    if constexpr (k == 0) return a;
+    else if constexpr (k == 16) return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+    else if constexpr (k == 32) return make_float2(-a.x, -a.y);
+    else if constexpr (k == 48) return INV ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+    else if constexpr (k == 8) return INV ? make_float2((a.x - a.y) * c8, (a.x + a.y) * c8) : make_float2((a.x + a.y) * c8, (a.y - a.x) * c8);
+    else {
+        constexpr float wr = kCos64[k];
+        constexpr float wi = INV ? kSin64[k] : -kSin64[k];
+        return make_float2(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
+    }
+}
+
+template <bool INV, int N1, int K2>
+TFC_HD void fft64_twiddle_row(float2* v) {  // v[N1 + 8*k2] *= W64^{N1*k2} for k2 = K2 .. 7
+    if constexpr (K2 < 8) {
+        v[N1 + 8 * K2] = mul_w64<N1 * K2, INV>(v[N1 + 8 * K2]);
+        fft64_twiddle_row<INV, N1, K2 + 1>(v);
+    }
+}
+template <bool INV, int N1>
+TFC_HD void fft64_twiddles(float2* v) {
+    if constexpr (N1 < 8) {
+        fft64_twiddle_row<INV, N1, 1>(v);
+        fft64_twiddles<INV, N1 + 1>(v);
+    }
+}
+
+// In-register 64-point DFT.  Input natural order v[n]; output X[k2 + 8*k1] is left in slot k1 + 8*k2
+// (i.e. slot s holds frequency fft64_freq(s) = (s >> 3) + 8 * (s & 7)); callers rename when they store.
+template <bool INV>
+TFC_HD void fft64(float2* v) {
+    // step 1: for each n1, 8-point DFT over n2 of x[n1 + 8 n2]  ->  Y[n1][k2] in slot n1 + 8 k2
+#pragma unroll
+    for (int n1 = 0; n1 < 8; ++n1) {
+        float2 u[8];
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) u[n2] = v[n1 + 8 * n2];
+        Dft<8, INV>::run(u);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) v[n1 + 8 * k2] = u[k2];
+    }
+    // step 2: Y[n1][k2] *= W64^{n1 k2}
+    fft64_twiddles<INV, 1>(v);
+    // step 3: for each k2, 8-point DFT over n1  ->  X[k2 + 8 k1] in slot k1 + 8 k2
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) Dft<8, INV>::run(v + 8 * k2);
+}
+TFC_HD constexpr int fft64_freq(int slot) { return (slot >> 3) + 8 * (slot & 7); }
+
+// physical slot of pixel x inside a freshly loaded row: the loader's four-pixel 64-bit stores of a half-warp
+// land on 16 consecutive slots
+TFC_HD constexpr int line_slot(int x) { return (x >> 2) + 16 * (x & 3); }
+
+// ---- load: global -> luma -> complex tile (z = fake + i real) ------------------------------------
+template <typename T, bool LUMA3, class Ctx>
+TFC_HD void line_load(const Ctx& ctx, const Params& prm, const TileCoord& tc, float2* s) {
+    constexpr int LD = LineCfg::LD, NC = LUMA3 ? 3 : 1;
+    const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, 64);
+    const T* rp = tile_ptr<T>(prm.real, prm.rs, tc, 64);
+    const int fsh = (int)prm.fs[2], fsc = (int)prm.fs[1], rsh = (int)prm.rs[2], rsc = (int)prm.rs[1];
+    const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
+    for (int it0 = ctx.tid; it0 < 64 * 16; it0 += 2 * ctx.nthreads) {
+        float raw[2][2][NC][4];  // [item][fake|real][channel][pixel]: 4*NC 128-bit loads in flight
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int it = it0 + u * ctx.nthreads, x = (it & 15) * 4, y = it >> 4;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                IO<T>::load4(fp + y * fsh + c * fsc + x, raw[u][0][c]);
+                IO<T>::load4(rp + y * rsh + c * rsc + x, raw[u][1][c]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int it = it0 + u * ctx.nthreads, x4 = it & 15, y = it >> 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float z[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (!quant) {
+                        float f = prm.lw[0] * raw[u][h][0][i];
+                        if constexpr (LUMA3) f = fmaf(prm.lw[2], raw[u][h][2][i], fmaf(prm.lw[1], raw[u][h][1][i], f));
+                        z[h] = f;
+                    } else if constexpr (LUMA3) {
+                        z[h] = (float)((19595 * IO<T>::quant(raw[u][h][0][i]) + 38470 * IO<T>::quant(raw[u][h][1][i]) +
+                                        7471 * IO<T>::quant(raw[u][h][2][i]) + 0x8000) >> 16);
+                    } else {
+                        z[h] = (float)IO<T>::quant(raw[u][h][0][i]);
+                    }
+                }
+                s[y * LD + x4 + 16 * i] = make_float2(z[0], z[1]);  // == line_slot(4*x4 + i)
+            }
+        }
+    }
+}
+
+// ---- forward rows / columns: one thread per line ----------------------------------------------------
+template <class Ctx>
+TFC_HD void line_rows_fwd(const Ctx& ctx, float2* s) {
+    constexpr int LD = LineCfg::LD;
+    for (int y = ctx.tid; y < 64; y += ctx.nthreads) {
+        float2* row = s + y * LD;
+        float2 v[64];
+#pragma unroll
+        for (int x = 0; x < 64; ++x) v[x] = row[line_slot(x)];
+        fft64<false>(v);
+#pragma unroll
+        for (int sl = 0; sl < 64; ++sl) row[fft64_freq(sl)] = v[sl];
+    }
+}
+template <class Ctx>
+TFC_HD void line_cols_fwd(const Ctx& ctx, float2* s) {
+    constexpr int LD = LineCfg::LD;
+    for (int x = ctx.tid; x < 64; x += ctx.nthreads) {
+        float2* col = s + x;
+        float2 v[64];
+#pragma unroll
+        for (int y = 0; y < 64; ++y) v[y] = col[y * LD];
+        fft64<false>(v);
+#pragma unroll
+        for (int sl = 0; sl < 64; ++sl) col[fft64_freq(sl) * LD] = v[sl];
+    }
+}
+
+// ---- loss + spectral gradient over the half plane (natural frequency order) ------------------------
+template <class Ctx>
+TFC_HD void line_bins(const Ctx& ctx, const Params& prm, float2* s, float& accA, float& accP) {
+    constexpr int LD = LineCfg::LD, NREG = 64 * 31;
+    const bool mse = (prm.flags & TFCFFT_DIST_MSE) != 0, phase = !(prm.flags & TFCFFT_NO_PHASE);
+    const bool want_grad = prm.grad != nullptr;
+    const float2 z0 = make_float2(0.f, 0.f);
+    float2 pA = z0, pP = z0;
+    // two regular bins per packed evaluation
+    for (int it0 = ctx.tid; it0 < NREG; it0 += 2 * ctx.nthreads) {
+        float2* pk[2];
+        float2* pm[2];
+        float2 zk[2], zm[2];
+        bool live[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int it = it0 + u * ctx.nthreads;
+            live[u] = it < NREG;
+            const int iq = live[u] ? it : 0;
+            const int ky = iq & 63, kx = 1 + (iq >> 6);  // consecutive threads: consecutive rows
+            pk[u] = s + ky * LD + kx;
+            pm[u] = s + ((64 - ky) & 63) * LD + (64 - kx);
+            zk[u] = live[u] ? *pk[u] : z0;
+            zm[u] = live[u] ? *pm[u] : z0;
+        }
+        const c2 g = bin_eval_pair(prm, mse, phase, make_c2(make_float2(zk[0].x, zk[1].x), make_float2(zk[0].y, zk[1].y)),
+                                   make_c2(make_float2(zm[0].x, zm[1].x), make_float2(zm[0].y, zm[1].y)), pA, pP);
+        if (want_grad) {
+            if (live[0]) {
+                *pk[0] = make_float2(g.re.x, g.im.x);
+                *pm[0] = z0;
+            }
+            if (live[1]) {
+                *pk[1] = make_float2(g.re.y, g.im.y);
+                *pm[1] = z0;
+            }
+        }
+    }
+    // self-conjugate columns kx = 0, 32: an item owns rows (ky, -ky); its two bins are the two packed lanes
+    for (int sp = ctx.tid; sp < 64; sp += ctx.nthreads) {
+        const int kx = (sp >> 5) * 32, r = sp & 31;
+        const int ky = r, kym = r == 0 ? 32 : 64 - r;  // r == 0: the two self-conjugate bins ky = 0 and 32
+        float2* pk = s + ky * LD + kx;
+        float2* pm = s + kym * LD + kx;
+        const float2 a = *pk, b = *pm;
+        // lane 0: bin at pk with partner (itself when r == 0); lane 1: bin at pm with its partner
+        const float2 pa = r == 0 ? a : b, pb = r == 0 ? b : a;
+        const c2 g = bin_eval_pair(prm, mse, phase, make_c2(make_float2(a.x, b.x), make_float2(a.y, b.y)),
+                                   make_c2(make_float2(pa.x, pb.x), make_float2(pa.y, pb.y)), pA, pP);
+        if (want_grad) {
+            *pk = make_float2(g.re.x, g.im.x);
+            *pm = make_float2(g.re.y, g.im.y);
+        }
+    }
+    accA += pA.x + pA.y;
+    accP += pP.x + pP.y;
+}
+
+// ---- inverse columns (kx = 0..32 only) and rows -------------------------------------------------------
+template <class Ctx>
+TFC_HD void line_cols_inv(const Ctx& ctx, float2* s) {
+    constexpr int LD = LineCfg::LD;
+    for (int x = ctx.tid; x < 33; x += ctx.nthreads) {
+        float2* col = s + x;
+        float2 v[64];
+#pragma unroll
+        for (int y = 0; y < 64; ++y) v[y] = col[y * LD];
+        fft64<true>(v);
+#pragma unroll
+        for (int sl = 0; sl < 64; ++sl) col[fft64_freq(sl) * LD] = v[sl];
+    }
+}
+// rows: columns 33..63 hold exact zeros (written by line_bins); the real part is the gradient, left in the
+// row as floats g[x] at float index x (the row is reused as a float array)
+template <class Ctx>
+TFC_HD void line_rows_inv(const Ctx& ctx, float2* s) {
+    constexpr int LD = LineCfg::LD;
+    for (int y = ctx.tid; y < 64; y += ctx.nthreads) {
+        float2* row = s + y * LD;
+        float2 v[64];
+#pragma unroll
+        for (int k = 0; k < 64; ++k) v[k] = k <= 32 ? row[k] : make_float2(0.f, 0.f);
+        fft64<true>(v);
+        float* g = reinterpret_cast<float*>(row);
+#pragma unroll
+        for (int m = 0; m < 32; ++m) {  // pixel x lives in slot (x >> 3) + 8 * (x & 7)
+            const int x0 = 2 * m, x1 = 2 * m + 1;
+            const float a = v[(x0 >> 3) + 8 * (x0 & 7)].x, b = v[(x1 >> 3) + 8 * (x1 & 7)].x;
+            *reinterpret_cast<float2*>(g + 2 * m) = make_float2(a, b);
+        }
+    }
+}
+
+// ---- gradient store: rows of floats -> global, 128-bit stores ----------------------------------------
+template <typename T, bool LUMA3, class Ctx>
+TFC_HD void line_store(const Ctx& ctx, const Params& prm, const TileCoord& tc, const float2* s) {
+    constexpr int LD = LineCfg::LD, NC = LUMA3 ? 3 : 1;
+    T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, 64));
+    const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
+    for (int it = ctx.tid; it < 64 * 16; it += ctx.nthreads) {
+        const int x = (it & 15) * 4, y = it >> 4;
+        const float* g = reinterpret_cast<const float*>(s + y * LD) + x;
+        const float2 lo = *reinterpret_cast<const float2*>(g), hi = *reinterpret_cast<const float2*>(g + 2);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const float v[4] = {prm.gw[c] * lo.x, prm.gw[c] * lo.y, prm.gw[c] * hi.x, prm.gw[c] * hi.y};
+            IO<T>::store4(gp + y * sh + c * sc + x, v);
+        }
+    }
+}
+
+// ---- one tile ---------------------------------------------------------------------------------------
+template <typename T, bool LUMA3, class Ctx>
+TFC_HD void line_process(const Ctx& ctx, const Params& prm, int tile, float2* s, float& accA, float& accP) {
+    const TileCoord tc = decode_tile(prm, tile);
+    line_load<T, LUMA3>(ctx, prm, tc, s);
+    ctx.sync();
+    line_rows_fwd(ctx, s);
+    ctx.sync();
+    line_cols_fwd(ctx, s);
+    ctx.sync();
+    line_bins(ctx, prm, s, accA, accP);
+    ctx.sync();
+    if (prm.grad != nullptr) {
+        line_cols_inv(ctx, s);
+        ctx.sync();
+        line_rows_inv(ctx, s);
+        ctx.sync();
+        line_store<T, LUMA3>(ctx, prm, tc, s);
+        ctx.sync();
+    }
+}
+
+}  // namespace tfcfft

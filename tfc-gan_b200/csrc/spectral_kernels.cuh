@@ -13,6 +13,7 @@
 #pragma once
 #include "pair_tile.cuh"
 #include "sub_tile.cuh"
+#include "line_tile.cuh"
 #include "spectral_core.cuh"
 
 namespace tfcfft {
@@ -273,6 +274,24 @@ __global__ void __launch_bounds__(PairCfg<P>::NT, 1) pair_kernel(const __grid_co
                     ctx.trace[15] = (long long)gt;
                 }
             }
+        }
+    }
+    finish(prm, gridDim.x);
+}
+
+// Thread-per-line kernel for 64 x 64 tiles (line_tile.cuh): 64 threads = one tile, six CTAs per SM.
+template <typename T, bool LUMA3>
+__global__ void __launch_bounds__(LineCfg::NT, 6) line_kernel(const __grid_constant__ Params prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    const BlockCtxT<LineCfg::NT> ctx{(int)threadIdx.x, nullptr};
+    for (int tile = blockIdx.x; tile < prm.tiles_total; tile += gridDim.x) {
+        float a = 0.f, p = 0.f;
+        line_process<T, LUMA3>(ctx, prm, tile, s, a, p);
+        block_sum2(a, p);
+        if (threadIdx.x == 0) {
+            prm.partials[2 * tile] = a;
+            prm.partials[2 * tile + 1] = p;
         }
     }
     finish(prm, gridDim.x);

@@ -76,6 +76,23 @@ int launch_pair(const Params& prm, cudaStream_t st) {
 }
 
 template <typename T, bool LUMA3>
+int launch_line(const Params& prm, cudaStream_t st) {
+    auto kernel = line_kernel<T, LUMA3>;
+    constexpr size_t smem = LineCfg::SMEM;
+    if (int rc = set_smem(kernel, smem)) return rc;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, LineCfg::NT, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    const long long cap = (long long)device_info().sms * per_sm;
+    const int grid = (int)(prm.tiles_total < cap ? prm.tiles_total : cap);
+    kernel<<<grid, LineCfg::NT, smem, st>>>(prm);
+    g_launches++;
+    TFC_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename T, bool LUMA3>
 int launch_sub(Params prm, cudaStream_t st) {
     auto kp = sub_pair_kernel<T, LUMA3>;
     constexpr size_t smem = PairCfg<64>::SMEM;
@@ -144,7 +161,10 @@ int launch(const Params& prm, bool split, cudaStream_t st) {
     if (split) return launch_split<P, T, LUMA3>(prm, st);
     if constexpr (P <= 128) {
         if constexpr (P == 64) {
-            if (pair_supported(prm)) return launch_pair<P, T, LUMA3>(prm, st);
+            if (pair_supported(prm)) {
+                if (prm.flags & TFCFFT_USE_LINE) return launch_line<T, LUMA3>(prm, st);
+                return launch_pair<P, T, LUMA3>(prm, st);
+            }
         }
         return launch_resident<P, T, LUMA3>(prm, st);
     } else {

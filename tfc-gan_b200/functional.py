@@ -37,6 +37,7 @@ class SpectralConfig:
     quantize: bool = False       # reference-as-shipped uint8 wrap + integer luma; forward only
     force_split: bool = False    # testing: route 64/128 patches through the split kernels
     force_generic: bool = False  # testing: bypass the packed 64x64 fast path
+    use_line: bool = False       # testing: 64x64 tiles through the thread-per-line kernel
 
     def flags(self) -> int:
         if self.channels not in ("luma", "rgb"):
@@ -66,6 +67,8 @@ class SpectralConfig:
             f |= _lib.FORCE_SPLIT
         if self.force_generic:
             f |= _lib.FORCE_GENERIC
+        if self.use_line:
+            f |= _lib.USE_LINE
         return f
 
 
