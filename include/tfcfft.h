@@ -49,6 +49,7 @@ enum tfcfft_dtype { TFCFFT_F32 = 0, TFCFFT_F16 = 1, TFCFFT_BF16 = 2, TFCFFT_U8 =
 #define TFCFFT_FULL_SPECTRUM (1u << 5) /* mean over the full P x P plane (fft2) not P x (P/2+1)   */
 #define TFCFFT_QUANTIZE_U8   (1u << 6) /* reference-as-shipped input path: uint8 wrap + integer
                                           luma (patchFFT_16P.py:300); forward only               */
+#define TFCFFT_USE_PAIR      (1u << 28) /* testing: 64x64 tiles through the packed pair kernel            */
 #define TFCFFT_USE_LINE      (1u << 29) /* testing: 64x64 tiles through the thread-per-line kernel        */
 #define TFCFFT_FORCE_GENERIC (1u << 30) /* testing: bypass the packed 64x64 fast path                */
 #define TFCFFT_FORCE_SPLIT   (1u << 31) /* testing: route P = 64 / 128 through the split path     */

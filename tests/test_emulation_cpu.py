@@ -120,7 +120,7 @@ def test_packed_pair_path_matches_generic_path(opt):
     """The packed 64x64 tile-pair fast path and the generic resident path are two implementations of the
     same algebra; odd tile counts exercise the duplicated last lane."""
     fake, real = make_pair("tanh", 17, (3, 3, 64, 64), "float32")  # grid=1: 3 (luma) or 9 (rgb) tiles, odd
-    rc, o1, p1, g1 = emulate(fake, real, 1, flags_of(**opt), input_scale=255.0)
+    rc, o1, p1, g1 = emulate(fake, real, 1, flags_of(use_pair=True, **opt), input_scale=255.0)
     rc2, o2, p2, g2 = emulate(fake, real, 1, flags_of(force_generic=True, **opt), input_scale=255.0)
     assert rc == 0 and rc2 == 0
     np.testing.assert_allclose(o1[:3], o2[:3], rtol=2e-6)
@@ -183,7 +183,7 @@ def test_thread_per_line_path_matches_oracle_and_pair_path(opt):
     """The register-resident 64-point line kernel (USE_LINE) against R1 and against the packed pair path."""
     fake, real = make_pair("tanh", 19, (3, 3, 128, 128), "float32")  # grid=2 -> 64x64 tiles
     rc, o1, p1, g1 = emulate(fake, real, 2, flags_of(use_line=True, **opt), input_scale=255.0)
-    rc2, o2, p2, g2 = emulate(fake, real, 2, flags_of(**opt), input_scale=255.0)
+    rc2, o2, p2, g2 = emulate(fake, real, 2, flags_of(use_pair=True, **opt), input_scale=255.0)
     assert rc == 0 and rc2 == 0
     l, a, p, gr = oracle.spectral_loss_and_grad_r1(fake, real, grid=2, input_scale=255.0, **opt)
     assert o1[0] == pytest.approx(l, rel=1e-5)

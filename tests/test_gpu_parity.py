@@ -55,7 +55,7 @@ CASES = [
     (64, 1, dict()),
     (256, 4, dict(force_generic=True)),                 # generic resident kernel (the default is the packed pair path)
     (256, 4, dict(use_line=True)),                      # thread-per-line kernel
-    (256, 4, dict(use_line=True, channels="rgb", distance="mse")),
+    (256, 4, dict(use_pair=True, channels="rgb", distance="mse")),   # pair kernel on single-channel tiles
     (256, 4, dict(force_split=True)),                   # split kernels on a size the resident path also covers
     (256, 2, dict(force_split=True, channels="rgb")),
     (256, 1, dict(force_split=True)),                   # the split kernels at their native size
@@ -71,7 +71,7 @@ def test_loss_and_gradient_match_oracle(side, grid, opt, kind):
     n = 3 if side <= 256 else 2
     fake, real = make_pair(kind, 101, (n, 3, side, side), "float32")
     loss, terms, grad = run_cuda(fake, real, grid=grid, weight=0.01, input_scale=255.0, **opt)
-    okw = {k: v for k, v in opt.items() if not k.startswith("force_")}
+    okw = {k: v for k, v in opt.items() if not (k.startswith("force_") or k.startswith("use_l") or k == "use_pair")}
     l, a, p, g = oracle.spectral_loss_and_grad_r1(fake, real, grid=grid, weight=0.01, input_scale=255.0, **okw)
     assert loss == pytest.approx(l, rel=LOSS_TOL)
     assert terms[0] == pytest.approx(a, rel=LOSS_TOL)

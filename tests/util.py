@@ -17,10 +17,10 @@ NP_DTYPES = {"float32": L.F32, "float16": L.F16, "uint8": L.U8}
 
 
 def flags_of(channels="luma", use_phase=True, distance="l1", patch_reduce="mean", log_magnitude=False,
-             spectrum="half", quantize=False, force_split=False, force_generic=False, use_line=False):
+             spectrum="half", quantize=False, force_split=False, force_generic=False, use_line=False, use_pair=False):
     return tfc.SpectralConfig(channels=channels, use_phase=use_phase, distance=distance, patch_reduce=patch_reduce,
                               log_magnitude=log_magnitude, spectrum=spectrum, quantize=quantize,
-                              force_split=force_split, force_generic=force_generic, use_line=use_line).flags()
+                              force_split=force_split, force_generic=force_generic, use_line=use_line, use_pair=use_pair).flags()
 
 
 _EMU = None

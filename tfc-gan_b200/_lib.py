@@ -24,6 +24,7 @@ PATCH_SUM = 1 << 3
 LOG_MAGNITUDE = 1 << 4
 FULL_SPECTRUM = 1 << 5
 QUANTIZE_U8 = 1 << 6
+USE_PAIR = 1 << 28
 USE_LINE = 1 << 29
 FORCE_GENERIC = 1 << 30
 FORCE_SPLIT = 1 << 31

@@ -34,8 +34,21 @@ constexpr float kSin32[32] = {
     0.f, -0.195090322f, -0.382683432f, -0.555570233f, -0.707106781f, -0.831469612f, -0.923879533f, -0.98078528f,
     -1.f, -0.98078528f, -0.923879533f, -0.831469612f, -0.707106781f, -0.555570233f, -0.382683432f, -0.195090322f};
 
-TFC_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-TFC_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / subtract as ONE packed f32x2 instruction (FADD2) on sm_100a: (re, im) are the two lanes
+TFC_HD float2 cadd(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+TFC_HD float2 csub(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    return __fadd2_rn(a, make_float2(-b.x, -b.y));
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
 // a * w
 TFC_HD float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
 // a * conj(w)

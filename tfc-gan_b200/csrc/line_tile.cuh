@@ -106,10 +106,11 @@ TFC_HD void line_load(const Ctx& ctx, const Params& prm, const TileCoord& tc, fl
     const T* rp = tile_ptr<T>(prm.real, prm.rs, tc, 64);
     const int fsh = (int)prm.fs[2], fsc = (int)prm.fs[1], rsh = (int)prm.rs[2], rsc = (int)prm.rs[1];
     const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
-    for (int it0 = ctx.tid; it0 < 64 * 16; it0 += 2 * ctx.nthreads) {
-        float raw[2][2][NC][4];  // [item][fake|real][channel][pixel]: 4*NC 128-bit loads in flight
+    constexpr int NI = 4;  // items in flight per thread: 2*NC*NI 128-bit loads (the FFT registers are idle here)
+    for (int it0 = ctx.tid; it0 < 64 * 16; it0 += NI * ctx.nthreads) {
+        float raw[NI][2][NC][4];  // [item][fake|real][channel][pixel]
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < NI; ++u) {
             const int it = it0 + u * ctx.nthreads, x = (it & 15) * 4, y = it >> 4;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
@@ -118,7 +119,7 @@ TFC_HD void line_load(const Ctx& ctx, const Params& prm, const TileCoord& tc, fl
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < NI; ++u) {
             const int it = it0 + u * ctx.nthreads, x4 = it & 15, y = it >> 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {

@@ -38,6 +38,7 @@ class SpectralConfig:
     force_split: bool = False    # testing: route 64/128 patches through the split kernels
     force_generic: bool = False  # testing: bypass the packed 64x64 fast path
     use_line: bool = False       # testing: 64x64 tiles through the thread-per-line kernel
+    use_pair: bool = False       # testing: 64x64 tiles through the packed pair kernel
 
     def flags(self) -> int:
         if self.channels not in ("luma", "rgb"):
@@ -69,6 +70,8 @@ class SpectralConfig:
             f |= _lib.FORCE_GENERIC
         if self.use_line:
             f |= _lib.USE_LINE
+        if self.use_pair:
+            f |= _lib.USE_PAIR
         return f
 
 
