@@ -182,7 +182,7 @@ def test_emulated_spectra_quantised_match_reference_golden():
 def test_thread_per_line_path_matches_oracle_and_pair_path(opt):
     """The register-resident 64-point line kernel (USE_LINE) against R1 and against the packed pair path."""
     fake, real = make_pair("tanh", 19, (3, 3, 128, 128), "float32")  # grid=2 -> 64x64 tiles
-    rc, o1, p1, g1 = emulate(fake, real, 2, flags_of(use_line=True, **opt), input_scale=255.0)
+    rc, o1, p1, g1 = emulate(fake, real, 2, flags_of(**opt), input_scale=255.0)
     rc2, o2, p2, g2 = emulate(fake, real, 2, flags_of(use_pair=True, **opt), input_scale=255.0)
     assert rc == 0 and rc2 == 0
     l, a, p, gr = oracle.spectral_loss_and_grad_r1(fake, real, grid=2, input_scale=255.0, **opt)

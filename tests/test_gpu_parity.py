@@ -53,8 +53,8 @@ CASES = [
     (128, 4, dict()),
     (64, 4, dict(spectrum="full")),
     (64, 1, dict()),
-    (256, 4, dict(force_generic=True)),                 # generic resident kernel (the default is the packed pair path)
-    (256, 4, dict(use_line=True)),                      # thread-per-line kernel
+    (256, 4, dict(force_generic=True)),                 # generic resident kernel
+    (256, 4, dict(use_pair=True)),                      # packed pair kernel (the default is the thread-per-line kernel)
     (256, 4, dict(use_pair=True, channels="rgb", distance="mse")),   # pair kernel on single-channel tiles
     (256, 4, dict(force_split=True)),                   # split kernels on a size the resident path also covers
     (256, 2, dict(force_split=True, channels="rgb")),
@@ -83,7 +83,7 @@ def test_phase_dominated_gradient():
     """input_scale = 1 on [-1,1] data: |F| is small, the phase term dominates the gradient -- the hardest
     case for the fast atan2 / rsqrt of the packed path."""
     fake, real = make_pair("uniform", 55, (2, 3, 256, 256), "float32")
-    for opt in (dict(), dict(force_generic=True)):
+    for opt in (dict(), dict(use_pair=True), dict(force_generic=True)):
         loss, terms, grad = run_cuda(fake, real, grid=4, **opt)
         l, a, p, g = oracle.spectral_loss_and_grad_r1(fake, real, grid=4)
         assert loss == pytest.approx(l, rel=LOSS_TOL)
@@ -237,7 +237,8 @@ def test_fast_paths_agree_with_generic_kernels_at_scale():
     g = torch.Generator(device="cuda").manual_seed(13)
     f = torch.empty(48, 3, 256, 256, device="cuda").uniform_(-1, 1, generator=g)
     r = torch.empty(48, 3, 256, 256, device="cuda").uniform_(-1, 1, generator=g)
-    for grid, ref_opt in ((4, dict(force_generic=True)), (2, dict(force_generic=True)), (1, dict(force_split=True))):
+    for grid, ref_opt in ((4, dict(force_generic=True)), (4, dict(use_pair=True)), (2, dict(force_generic=True)),
+                          (1, dict(force_split=True))):
         l1, t1, g1 = tfc.spectral_loss_and_grad(f, r, grid=grid, input_scale=255.0)
         l2, t2, g2 = tfc.spectral_loss_and_grad(f, r, grid=grid, input_scale=255.0, **ref_opt)
         assert l1.item() == pytest.approx(l2.item(), rel=2e-6)

@@ -133,7 +133,7 @@ template <int P, typename T, bool LUMA3>
 void run(const Params& prm, bool split) {
     if ((P == 128 || P == 256) && prm.sub_d > 1) run_sub<T, LUMA3>(prm);
     else if (split) run_split<P, T, LUMA3>(prm);
-    else if (P == 64 && pair_supported(prm) && ((prm.flags & TFCFFT_USE_LINE) || (!LUMA3 && !(prm.flags & TFCFFT_USE_PAIR)))) run_line<T, LUMA3>(prm);
+    else if (P == 64 && pair_supported(prm) && !(prm.flags & TFCFFT_USE_PAIR)) run_line<T, LUMA3>(prm);
     else if (P == 64 && pair_supported(prm)) run_pair<P, T, LUMA3>(prm);
     else if constexpr (P <= 128) run_resident<P, T, LUMA3>(prm);
 }

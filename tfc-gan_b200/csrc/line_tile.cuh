@@ -209,31 +209,45 @@ TFC_HD void line_bins(const Ctx& ctx, const Params& prm, float2* s, float& accA,
             }
         }
     }
-    // self-conjugate columns kx = 0, 32: an item owns rows (ky, -ky); its two bins are the two packed lanes
-    for (int sp = ctx.tid; sp < 64; sp += ctx.nthreads) {
-        const int kx = (sp >> 5) * 32, r = sp & 31;
-        const int ky = r, kym = r == 0 ? 32 : 64 - r;  // r == 0: the two self-conjugate bins ky = 0 and 32
-        float2* pk = s + ky * LD + kx;
-        float2* pm = s + kym * LD + kx;
-        const float2 a = *pk, b = *pm;
-        // lane 0: bin at pk with partner (itself when r == 0); lane 1: bin at pm with its partner
-        const float2 pa = r == 0 ? a : b, pb = r == 0 ? b : a;
-        const c2 g = bin_eval_pair(prm, mse, phase, make_c2(make_float2(a.x, b.x), make_float2(a.y, b.y)),
-                                   make_c2(make_float2(pa.x, pb.x), make_float2(pa.y, pb.y)), pA, pP);
-        if (want_grad) {
-            *pk = make_float2(g.re.x, g.im.x);
-            *pm = make_float2(g.re.y, g.im.y);
+    // self-conjugate columns kx = 0 and kx = 32: item r owns rows (ky, -ky) = (r, 64 - r) of BOTH columns (r == 0: the
+    // two self-conjugate rows 0 and 32); the two bins of a column are the two packed lanes.
+    // Only the REAL part of these two columns' inverse column transforms reaches the (real) gradient, so their
+    // spectral gradients are Hermitian-symmetrised, Hs(ky) = (G(ky) + conj G(-ky)) / 2, and the two real-output
+    // transforms are packed into ONE complex line c = Hs_0 + i Hs_32 stored in column 0: the inverse column phase
+    // then has exactly 32 lines (one warp) and leaves (u_0(y), u_32(y)) in column 0.
+    for (int r = ctx.tid; r < 32; r += ctx.nthreads) {
+        const int ky = r, kym = r == 0 ? 32 : 64 - r;
+        float2 hs[2][2];  // [column][row ky | row kym]
+#pragma unroll
+        for (int cidx = 0; cidx < 2; ++cidx) {
+            const int kx = cidx * 32;
+            const float2 a = s[ky * LD + kx], b = s[kym * LD + kx];
+            const float2 pa = r == 0 ? a : b, pb = r == 0 ? b : a;
+            const c2 g = bin_eval_pair(prm, mse, phase, make_c2(make_float2(a.x, b.x), make_float2(a.y, b.y)),
+                                       make_c2(make_float2(pa.x, pb.x), make_float2(pa.y, pb.y)), pA, pP);
+            const float2 gk = make_float2(g.re.x, g.im.x), gm = make_float2(g.re.y, g.im.y);
+            if (r == 0) {  // rows 0 and 32 are their own mirrors: Hs = Re G
+                hs[cidx][0] = make_float2(gk.x, 0.f);
+                hs[cidx][1] = make_float2(gm.x, 0.f);
+            } else {
+                hs[cidx][0] = make_float2(0.5f * (gk.x + gm.x), 0.5f * (gk.y - gm.y));
+                hs[cidx][1] = make_float2(hs[cidx][0].x, -hs[cidx][0].y);
+            }
+        }
+        if (want_grad) {  // c = Hs_0 + i Hs_32
+            s[ky * LD] = make_float2(hs[0][0].x - hs[1][0].y, hs[0][0].y + hs[1][0].x);
+            s[kym * LD] = make_float2(hs[0][1].x - hs[1][1].y, hs[0][1].y + hs[1][1].x);
         }
     }
     accA += pA.x + pA.y;
     accP += pP.x + pP.y;
 }
 
-// ---- inverse columns (kx = 0..32 only) and rows -------------------------------------------------------
+// ---- inverse columns (32 lines: kx = 1..31 and the packed pair {0, 32}) and rows -------------------------------------------------------
 template <class Ctx>
 TFC_HD void line_cols_inv(const Ctx& ctx, float2* s) {
     constexpr int LD = LineCfg::LD;
-    for (int x = ctx.tid; x < 33; x += ctx.nthreads) {
+    for (int x = ctx.tid; x < 32; x += ctx.nthreads) {  // line 0 = the packed columns 0 and 32
         float2* col = s + x;
         float2 v[64];
 #pragma unroll
@@ -252,7 +266,12 @@ TFC_HD void line_rows_inv(const Ctx& ctx, float2* s) {
         float2* row = s + y * LD;
         float2 v[64];
 #pragma unroll
-        for (int k = 0; k < 64; ++k) v[k] = k <= 32 ? row[k] : make_float2(0.f, 0.f);
+        for (int k = 0; k < 64; ++k) v[k] = (k >= 1 && k < 32) ? row[k] : make_float2(0.f, 0.f);
+        {
+            const float2 u = row[0];  // (u_0(y), u_32(y)): real inverse transforms of columns 0 and 32
+            v[0] = make_float2(u.x, 0.f);
+            v[32] = make_float2(u.y, 0.f);
+        }
         fft64<true>(v);
         float* g = reinterpret_cast<float*>(row);
 #pragma unroll
