@@ -47,7 +47,8 @@ WORKLOADS = {
     "global-fft-512-b32": dict(grid=1, side=512, batch=32, channels="luma"),      # configs[4]
 }
 DEFAULT_WORKLOAD = "global-fft-256-b64"
-VARIANTS = ["patch16-fft-256-b256", "patch4-fft-256-b256", "patch16-fft-256-b256-rgb", "global-fft-256-b64-rgb"]
+VARIANTS = ["patch16-fft-256-b256", "patch4-fft-256-b256", "patch16-fft-256-b256-rgb", "global-fft-256-b64-rgb",
+            "patch16-fft-512-b64", "global-fft-512-b32"]
 L2_BYTES = 126 << 20
 
 
