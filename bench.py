@@ -45,15 +45,16 @@ WORKLOADS = {
     "patch16-fft-256-b256-rgb": dict(grid=4, side=256, batch=256, channels="rgb"),
     "patch16-fft-512-b64": dict(grid=4, side=512, batch=64, channels="luma"),     # configs[4]
     "global-fft-512-b32": dict(grid=1, side=512, batch=32, channels="luma"),      # configs[4]
+    "patch16-fft-256-b256-f16": dict(grid=4, side=256, batch=256, channels="luma", dtype="f16"),  # HalfTensor I/O
 }
 DEFAULT_WORKLOAD = "global-fft-256-b64"
 VARIANTS = ["patch16-fft-256-b256", "patch4-fft-256-b256", "patch16-fft-256-b256-rgb", "global-fft-256-b64-rgb",
-            "patch16-fft-512-b64", "global-fft-512-b32"]
+            "patch16-fft-512-b64", "global-fft-512-b32", "patch16-fft-256-b256-f16"]
 L2_BYTES = 126 << 20
 
 
-def bytes_per_image(side: int) -> int:
-    return 3 * 3 * side * side * 4  # read fake + read real + write grad, fp32 RGB
+def bytes_per_image(side: int, dtype: str = "f32") -> int:
+    return 3 * 3 * side * side * (2 if dtype == "f16" else 4)  # read fake + read real + write grad, RGB
 
 
 def peaks():
@@ -220,6 +221,8 @@ def time_kernel_path(tfc, torch, wl, steps, warmup, barrier):
     for _ in range(pool_n):
         f = torch.empty(wl["batch"], 3, wl["side"], wl["side"], device=dev).uniform_(-1, 1, generator=g)
         r = torch.empty_like(f).uniform_(-1, 1, generator=g)
+        if wl.get("dtype") == "f16":
+            f, r = f.half(), r.half()
         pool.append((f, r))
     cfg = tfc.SpectralConfig(grid=wl["grid"], channels=wl["channels"], weight=0.01, input_scale=255.0,
                              use_line=bool(os.environ.get("TFCFFT_BENCH_USE_LINE")))
@@ -347,12 +350,12 @@ def run_ours(args, wl):
     e2e_value = world * wl["batch"] * e2e_steps / e_secs
 
     peak, peak_src = peaks()
-    bpi = bytes_per_image(wl["side"])
+    bpi = bytes_per_image(wl["side"], wl.get("dtype", "f32"))
     achieved = (wl["batch"] * args.steps * bpi / secs) / 1e9  # per GPU
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": wl.get("dtype", "f32"), "data": "synthetic",
         "config": {
             "workload": args.workload, "grid": wl["grid"], "side": wl["side"], "channels": wl["channels"],
             "per_gpu_batch": wl["batch"], "global_batch": world * wl["batch"], "parallelism": f"dp{world}",
@@ -375,7 +378,8 @@ def run_ours(args, wl):
             w = WORKLOADS[name]
             s, _, _ = time_kernel_path(tfc, torch, w, max(10, args.steps // 4), 3, barrier)
             ips = w["batch"] * max(10, args.steps // 4) / s
-            var[name] = {"value": ips, "unit": UNIT, "roofline_frac": ips * bytes_per_image(w["side"]) / 1e9 / peak}
+            var[name] = {"value": ips, "unit": UNIT,
+                         "roofline_frac": ips * bytes_per_image(w["side"], w.get("dtype", "f32")) / 1e9 / peak}
         line["variants"] = var
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_arm(wl, 12.0)

@@ -234,24 +234,6 @@ TFC_HD void pair_load(const Ctx& ctx, const Params& prm, const TileCoord& ta, co
     }
 }
 
-// Pulls the next pair's source lines into L2 while the current pair is being transformed, so the next
-// load stage sees L2 latency instead of HBM latency.  No registers or shared memory are held.
-template <int P, typename T, bool LUMA3, class Ctx>
-TFC_HD void pair_prefetch_l2(const Ctx& ctx, const Params& prm, const TileCoord& ta, const TileCoord& tb) {
-#ifdef __CUDA_ARCH__
-    constexpr int NC = LUMA3 ? 3 : 1;
-    constexpr int EPL = 128 / (int)sizeof(T);              // elements per 128-byte line
-    constexpr int LPR = (P + EPL - 1) / EPL;               // lines per tile row
-    const PairSrc<T> src = pair_src<P, T>(prm, ta, tb);
-    for (int it = ctx.tid; it < 4 * NC * P * LPR; it += ctx.nthreads) {
-        const int l = it % LPR, y = (it / LPR) % P, wc = it / (LPR * P);
-        const int w = wc & 3, c = wc >> 2;
-        const T* q = src.p[w] + y * src.sh[w] + c * src.sc[w] + l * EPL;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-    }
-#endif
-}
-
 // ---- stages 1+2: forward row passes.  The first works in place on the swizzled addresses (each
 // task rewrites exactly the words it read); the second owns whole groups of R2 positions, reads them
 // through the swizzle and writes plain positions, which removes the swizzle for free. ------------

@@ -86,25 +86,6 @@ TFC_HD void sub_load(const Ctx& ctx, const Params& prm, const TileCoord& tc, con
     }
 }
 
-// Pulls the source rows of a later unit into L2 (full rows: the sibling lane pairs of the same row phase share
-// them), so the loader's dependent load rounds see L2 latency instead of HBM latency.
-template <typename T, bool LUMA3, class Ctx>
-TFC_HD void sub_prefetch_l2(const Ctx& ctx, const Params& prm, const TileCoord& tc, const SubUnit& su) {
-#ifdef __CUDA_ARCH__
-    constexpr int NC = LUMA3 ? 3 : 1, EPL = 128 / (int)sizeof(T);
-    const int D = prm.sub_d, P = 64 * D, lpr = (P + EPL - 1) / EPL;
-    const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, P);
-    const T* rp = tile_ptr<T>(prm.real, prm.rs, tc, P);
-    for (int it = ctx.tid; it < 2 * NC * 64 * lpr; it += ctx.nthreads) {
-        const int l = it % lpr, a = (it / lpr) % 64, hc = it / (lpr * 64);
-        const int h = hc & 1, c = hc >> 1;
-        const T* q = (h ? rp + (D * a + su.p) * (int)prm.rs[2] + c * (int)prm.rs[1]
-                        : fp + (D * a + su.p) * (int)prm.fs[2] + c * (int)prm.fs[1]) + l * EPL;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-    }
-#endif
-}
-
 // ---- gradient sub-image pair (staged at the swizzled slots by pair_rows_last) -> global ------------
 template <typename T, bool LUMA3, class Ctx>
 TFC_HD void sub_store(const Ctx& ctx, const Params& prm, const TileCoord& tc, const SubUnit& su, const float4* s) {
@@ -163,9 +144,6 @@ TFC_HD void sub_compute_inv(const Ctx& ctx, float4* s, const float4* tw) {
 }
 
 // ---- D-point butterflies over small register arrays ------------------------------------------------
-template <int D, bool INV>
-TFC_HD void small_dft(float2* v) { Dft<D, INV>::run(v); }
-
 TFC_HD float2 cis_neg(float frac) {  // e^{-2 pi i frac}
     float sn, cs;
 #ifdef __CUDA_ARCH__
@@ -178,72 +156,8 @@ TFC_HD float2 cis_neg(float frac) {  // e^{-2 pi i frac}
     return make_float2(cs, -sn);
 }
 
-// S[p][q] (sub-spectra at one position) -> Z[al][be] (full-size spectrum entries), in place
-template <int D>
-TFC_HD void combine_fwd(float2 (&v)[D][D], int ky, int kx) {
-    constexpr int P = 64 * D;
-    const float2 wy = cis_neg((float)ky / (float)P), wx = cis_neg((float)kx / (float)P);
-    // along q: twiddle W_P^{q kx}, then D-point DFT q -> be
-#pragma unroll
-    for (int p = 0; p < D; ++p) {
-        float2 w = wx;
-#pragma unroll
-        for (int q = 1; q < D; ++q) {
-            v[p][q] = cmul(v[p][q], w);
-            w = cmul(w, wx);
-        }
-        small_dft<D, false>(v[p]);
-    }
-    // along p: twiddle W_P^{p ky}, then D-point DFT p -> al
-#pragma unroll
-    for (int be = 0; be < D; ++be) {
-        float2 col[D];
-        float2 w = wy;
-#pragma unroll
-        for (int p = 0; p < D; ++p) col[p] = v[p][be];
-#pragma unroll
-        for (int p = 1; p < D; ++p) {
-            col[p] = cmul(col[p], w);
-            w = cmul(w, wy);
-        }
-        small_dft<D, false>(col);
-#pragma unroll
-        for (int al = 0; al < D; ++al) v[al][be] = col[al];
-    }
-}
-// G[al][be] -> H[p][q] (the adjoint of combine_fwd, unnormalised)
-template <int D>
-TFC_HD void combine_inv(float2 (&v)[D][D], int ky, int kx) {
-    constexpr int P = 64 * D;
-    const float2 wy = cis_neg((float)ky / (float)P), wx = cis_neg((float)kx / (float)P);
-#pragma unroll
-    for (int be = 0; be < D; ++be) {
-        float2 col[D];
-#pragma unroll
-        for (int al = 0; al < D; ++al) col[al] = v[al][be];
-        small_dft<D, true>(col);
-        float2 w = wy;
-#pragma unroll
-        for (int p = 1; p < D; ++p) {
-            col[p] = cmulc(col[p], w);
-            w = cmul(w, wy);
-        }
-#pragma unroll
-        for (int p = 0; p < D; ++p) v[p][be] = col[p];
-    }
-#pragma unroll
-    for (int p = 0; p < D; ++p) {
-        small_dft<D, true>(v[p]);
-        float2 w = wx;
-#pragma unroll
-        for (int q = 1; q < D; ++q) {
-            v[p][q] = cmulc(v[p][q], w);
-            w = cmul(w, wx);
-        }
-    }
-}
-
-// ---- the same butterflies on two positions at once (lane x = position A, lane y = its partner B) ----
+// ---- D x D butterflies on two positions at once (lane x = position A, lane y = its partner B) ----
+// forward: S[p][q] (sub-spectra) -> Z[al][be] (full-size spectrum entries); inverse: the unnormalised adjoint
 TFC_HD c2 cmul2(c2 a, c2 w) {  // per-lane a * w
     return make_c2(p_fma(a.re, w.re, p_neg(p_mul(a.im, w.im))), p_fma(a.re, w.im, p_mul(a.im, w.re)));
 }
