@@ -107,6 +107,7 @@ TFC_HD void line_load(const Ctx& ctx, const Params& prm, const TileCoord& tc, fl
     const int fsh = (int)prm.fs[2], fsc = (int)prm.fs[1], rsh = (int)prm.rs[2], rsc = (int)prm.rs[1];
     const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
     constexpr int NI = 4;  // items in flight per thread: 2*NC*NI 128-bit loads (the FFT registers are idle here)
+#pragma unroll 1
     for (int it0 = ctx.tid; it0 < 64 * 16; it0 += NI * ctx.nthreads) {
         float raw[NI][2][NC][4];  // [item][fake|real][channel][pixel]
 #pragma unroll
@@ -179,7 +180,9 @@ TFC_HD void line_bins(const Ctx& ctx, const Params& prm, float2* s, float& accA,
     const bool want_grad = prm.grad != nullptr;
     const float2 z0 = make_float2(0.f, 0.f);
     float2 pA = z0, pP = z0;
-    // two regular bins per packed evaluation
+    // two regular bins per packed evaluation.  Kept as a real loop: the kernel is instruction-fetch sensitive
+    // (straight-line 64-point transforms), the loss code should not be replicated 16 times
+#pragma unroll 1
     for (int it0 = ctx.tid; it0 < NREG; it0 += 2 * ctx.nthreads) {
         float2* pk[2];
         float2* pm[2];
@@ -289,6 +292,7 @@ TFC_HD void line_store(const Ctx& ctx, const Params& prm, const TileCoord& tc, c
     constexpr int LD = LineCfg::LD, NC = LUMA3 ? 3 : 1;
     T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, 64));
     const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
+#pragma unroll 2
     for (int it = ctx.tid; it < 64 * 16; it += ctx.nthreads) {
         const int x = (it & 15) * 4, y = it >> 4;
         const float* g = reinterpret_cast<const float*>(s + y * LD) + x;
@@ -301,25 +305,52 @@ TFC_HD void line_store(const Ctx& ctx, const Params& prm, const TileCoord& tc, c
     }
 }
 
+// Pull the next tile's source lines into L2 shortly before they are needed (late enough to survive in L2, early
+// enough to turn the load phase's four dependent HBM round trips into L2 hits).
+template <typename T, bool LUMA3, class Ctx>
+TFC_HD void line_prefetch_l2(const Ctx& ctx, const Params& prm, const TileCoord& tc) {
+#ifdef __CUDA_ARCH__
+    constexpr int NC = LUMA3 ? 3 : 1, EPL = 128 / (int)sizeof(T), LPR = (64 + EPL - 1) / EPL;
+    const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, 64);
+    const T* rp = tile_ptr<T>(prm.real, prm.rs, tc, 64);
+    for (int it = ctx.tid; it < 2 * NC * 64 * LPR; it += ctx.nthreads) {
+        const int l = it % LPR, y = (it / LPR) & 63, hc = it / (LPR * 64);
+        const int h = hc & 1, c = hc >> 1;
+        const T* q = (h ? rp + y * (int)prm.rs[2] + c * (int)prm.rs[1] : fp + y * (int)prm.fs[2] + c * (int)prm.fs[1]) + l * EPL;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    }
+#endif
+}
+
 // ---- one tile ---------------------------------------------------------------------------------------
 template <typename T, bool LUMA3, class Ctx>
-TFC_HD void line_process(const Ctx& ctx, const Params& prm, int tile, float2* s, float& accA, float& accP) {
+TFC_HD void line_process(const Ctx& ctx, const Params& prm, int tile, float2* s, float& accA, float& accP,
+                         int next_tile = -1) {
     const TileCoord tc = decode_tile(prm, tile);
+    ctx.mark(0);
     line_load<T, LUMA3>(ctx, prm, tc, s);
     ctx.sync();
+    ctx.mark(1);
     line_rows_fwd(ctx, s);
     ctx.sync();
+    ctx.mark(2);
     line_cols_fwd(ctx, s);
     ctx.sync();
+    ctx.mark(3);
     line_bins(ctx, prm, s, accA, accP);
     ctx.sync();
+    ctx.mark(4);
     if (prm.grad != nullptr) {
         line_cols_inv(ctx, s);
+        if (next_tile >= 0) line_prefetch_l2<T, LUMA3>(ctx, prm, decode_tile(prm, next_tile));
         ctx.sync();
+        ctx.mark(5);
         line_rows_inv(ctx, s);
         ctx.sync();
+        ctx.mark(6);
         line_store<T, LUMA3>(ctx, prm, tc, s);
         ctx.sync();
+        ctx.mark(7);
     }
 }
 

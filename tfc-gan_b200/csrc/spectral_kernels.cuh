@@ -284,14 +284,18 @@ template <typename T, bool LUMA3>
 __global__ void __launch_bounds__(LineCfg::NT, 6) line_kernel(const __grid_constant__ Params prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
-    const BlockCtxT<LineCfg::NT> ctx{(int)threadIdx.x, nullptr};
-    for (int tile = blockIdx.x; tile < prm.tiles_total; tile += gridDim.x) {
+    BlockCtxT<LineCfg::NT> ctx{(int)threadIdx.x, nullptr};
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < prm.tiles_total; tile += gridDim.x, ++iter) {
         float a = 0.f, p = 0.f;
-        line_process<T, LUMA3>(ctx, prm, tile, s, a, p);
+        ctx.trace = (prm.trace != nullptr && iter < 6) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
+        const int nt = tile + (int)gridDim.x;
+        line_process<T, LUMA3>(ctx, prm, tile, s, a, p, nt < prm.tiles_total ? nt : -1);
         block_sum2(a, p);
         if (threadIdx.x == 0) {
             prm.partials[2 * tile] = a;
             prm.partials[2 * tile + 1] = p;
+            if (ctx.trace != nullptr) ctx.trace[15] = 1;
         }
     }
     finish(prm, gridDim.x);

@@ -234,6 +234,26 @@ TFC_HD void combine_inv2(c2 (&v)[D][D], int kyA, int kxA, int kyB, int kxB) {
 // position pairs {(ky',kx'), -(ky',kx')} of the 64 x 64 sub-grid: 64 x 32 slots walk the half-plane column
 // POSITIONS in memory order (4 consecutive float4 = 64 contiguous bytes per group; slot j = 0 is the kx' = 0
 // column, handled with kx' = 32 by the 66 items that pair rows instead)
+// Out-of-line copy of the packed bin evaluation: combine_item calls it from 8 (D = 4) fully unrolled entry
+// pairs; inlining it there made the kernel instruction-fetch bound (ncu: no_instruction 3.9 per issue).
+#ifdef __CUDA_ARCH__
+__device__ __noinline__
+#else
+inline
+#endif
+c2 bin_eval_pair_call(const Params& prm, bool mse, bool phase, c2 zk, c2 zm, float2& accA, float2& accP) {
+    return bin_eval_pair(prm, mse, phase, zk, zm, accA, accP);
+}
+
+#ifdef __CUDA_ARCH__
+__device__ __noinline__
+#else
+inline
+#endif
+float2 bin_eval_call(const Params& prm, float2 zk, float2 zm, float mult, float& accA, float& accP) {
+    return bin_eval(prm, zk, zm, mult, accA, accP);
+}
+
 constexpr int kCombineItems = 64 * 32 + 2 * 33;
 
 // One position pair of one tile: load the D^2 sub-spectra at both positions, combine, evaluate every
@@ -320,12 +340,12 @@ TFC_HD void combine_item(const Params& prm, float4* ws_tile, int item, float& ac
                     const int kxf = kxA + 64 * be;
                     const float2 zk = za[al][be], zm = zp[al][be];
                     if (kxf == 0 || kxf == P / 2) {  // self-conjugate column: k and -k are both half-plane bins
-                        gk = bin_eval(prm, zk, zm, 1.f, accA, accP);
-                        if (!selfbin) gm = bin_eval(prm, zm, zk, 1.f, accA, accP);
+                        gk = bin_eval_call(prm, zk, zm, 1.f, accA, accP);
+                        if (!selfbin) gm = bin_eval_call(prm, zm, zk, 1.f, accA, accP);
                     } else if (kxf < P / 2) {
-                        gk = bin_eval(prm, zk, zm, full ? 2.f : 1.f, accA, accP);
+                        gk = bin_eval_call(prm, zk, zm, full ? 2.f : 1.f, accA, accP);
                     } else {
-                        gm = bin_eval(prm, zm, zk, full ? 2.f : 1.f, accA, accP);
+                        gm = bin_eval_call(prm, zm, zk, full ? 2.f : 1.f, accA, accP);
                     }
                 }
                 ga[al][be] = gk;
@@ -358,14 +378,14 @@ TFC_HD void combine_item(const Params& prm, float4* ws_tile, int item, float& ac
                 }
                 zk = make_c2(make_float2(k_[0].x, k_[1].x), make_float2(k_[0].y, k_[1].y));
                 zm = make_c2(make_float2(m_[0].x, m_[1].x), make_float2(m_[0].y, m_[1].y));
-                const c2 g = bin_eval_pair(prm, mse, phase, zk, zm, pA, pP);
+                const c2 g = bin_eval_pair_call(prm, mse, phase, zk, zm, pA, pP);
                 c2 g2 = make_c2(z0, z0);
                 if (both[0] || both[1]) {  // self-conjugate columns only: evaluate the mirrored bin as well
                     const c2 zk2 = make_c2(make_float2(both[0] ? m_[0].x : 0.f, both[1] ? m_[1].x : 0.f),
                                            make_float2(both[0] ? m_[0].y : 0.f, both[1] ? m_[1].y : 0.f));
                     const c2 zm2 = make_c2(make_float2(both[0] ? k_[0].x : 0.f, both[1] ? k_[1].x : 0.f),
                                            make_float2(both[0] ? k_[0].y : 0.f, both[1] ? k_[1].y : 0.f));
-                    g2 = bin_eval_pair(prm, mse, phase, zk2, zm2, pA, pP);
+                    g2 = bin_eval_pair_call(prm, mse, phase, zk2, zm2, pA, pP);
                 }
 #pragma unroll
                 for (int l = 0; l < 2; ++l) {
