@@ -69,20 +69,13 @@ template <typename T, bool LUMA3>
 void run_sub(Params prm) {
     SerialCtx ctx;
     const int D = prm.sub_d, npp = D * D / 2;
-    std::vector<float4> s((size_t)64 * 65), tw(128);
-    fill_twiddles4<64>(ctx, tw.data());
-    fill_row_twiddles4<64>(ctx, tw.data(), tw.data() + 64);
+    std::vector<float2> s((size_t)2 * 64 * SubCfg::LD);
     for (int base = 0; base < prm.tiles_total; base += prm.chunk_tiles) {
         prm.tile_base = base;
         prm.chunk_now = prm.tiles_total - base < prm.chunk_tiles ? prm.tiles_total - base : prm.chunk_tiles;
-        for (int u = 0; u < prm.chunk_now * npp; ++u) {
-            const SubUnit su = sub_unit(u, D);
-            sub_load<T, LUMA3>(ctx, prm, decode_tile(prm, base + su.tile_local), su, s.data());
-            sub_compute_fwd(ctx, s.data(), tw.data());
-            spec_store(ctx, s.data(), sub_plane(prm, su));
-        }
+        for (int u = 0; u < prm.chunk_now * npp; ++u) sub_fwd_process<T, LUMA3>(ctx, prm, u, s.data());
         for (int lt = 0; lt < prm.chunk_now; ++lt) {
-            float4* ws_tile = reinterpret_cast<float4*>(prm.zws) + (long long)lt * npp * 4096;
+            float2* ws_tile = sub_plane(prm, lt, 0);
             for (int part = 0; part < 9; ++part) {
                 float a = 0.f, p = 0.f;
                 for (int item = part * 256; item < (part + 1) * 256 && item < kCombineItems; ++item) {
@@ -94,12 +87,7 @@ void run_sub(Params prm) {
             }
         }
         if (prm.grad)
-            for (int u = 0; u < prm.chunk_now * npp; ++u) {
-                const SubUnit su = sub_unit(u, D);
-                spec_load(ctx, sub_plane(prm, su), s.data());
-                sub_compute_inv(ctx, s.data(), tw.data());
-                sub_store<T, LUMA3>(ctx, prm, decode_tile(prm, base + su.tile_local), su, s.data());
-            }
+            for (int u = 0; u < prm.chunk_now * npp; ++u) sub_inv_process<T, LUMA3>(ctx, prm, u, s.data());
     }
 }
 

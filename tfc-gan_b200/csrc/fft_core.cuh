@@ -253,7 +253,11 @@ struct BlockCtxT {
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
     __device__ __forceinline__ void mark(int k) const {
-        if (trace != nullptr && tid == 0) trace[k] = clock64();
+        if (trace != nullptr && tid == 0) {  // global nanosecond timer: comparable across SMs
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            trace[k] = (long long)t;
+        }
     }
 };
 #endif

@@ -301,84 +301,33 @@ __global__ void __launch_bounds__(LineCfg::NT, 6) line_kernel(const __grid_const
     finish(prm, gridDim.x);
 }
 
-// Sub-tile path, launches 1 and 3 (sub_tile.cuh): the warp-specialised pair pipeline with the loss pass
-// removed.  mode 1: sub-image pairs of fake / real -> forward 64 x 64 transforms -> sub-spectra planes in the
-// workspace; mode 2: gradient sub-spectra planes -> inverse transforms -> gradient sub-images.
-// Roles as in pair_kernel: 16 compute warps + 8 loader / storer warps.
-struct SubCfg {
-    static constexpr int LD = 65;
-    static constexpr int NT_COMPUTE = 512, NT_LOAD = 256, NT = NT_COMPUTE + NT_LOAD;
-};
+// Sub-tile path, launches 1 and 3 (sub_tile.cuh): thread-per-line 64 x 64 transforms of the D x D decimated
+// sub-images.  Forward: one CTA = one sub-image PAIR (adjacent pixel columns, so the source rows are read as
+// 8-byte pairs), two 64-thread groups with a work tile each.  Inverse: one 64-thread CTA = one packed plane.
 template <typename T, bool LUMA3>
-__global__ void __launch_bounds__(SubCfg::NT, 1) sub_pair_kernel(const __grid_constant__ Params prm) {
-    using Cfg = SubCfg;
-    constexpr int P = 64;
-    constexpr int BAR_COMPUTE = 1, BAR_FULL = 2, BAR_DONE = 4;
+__global__ void __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd_kernel(const __grid_constant__ Params prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* buf0 = reinterpret_cast<float4*>(smem_raw);
-    float4* buf1 = buf0 + P * Cfg::LD;
-    float4* tw = buf1 + P * Cfg::LD;
-    {
-        const BlockCtx all{(int)threadIdx.x, (int)blockDim.x};
-        fill_twiddles4<P>(all, tw);
-        __syncthreads();
-        fill_row_twiddles4<P>(all, tw, tw + P);
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    BlockCtxT<SubCfg::NT_FWD> ctx{(int)threadIdx.x, nullptr};
+    const int nunits = prm.chunk_now * (prm.sub_d * prm.sub_d / 2);
+    int iter = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++iter) {
+        ctx.trace = (prm.trace != nullptr && iter < 6) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
+        sub_fwd_process<T, LUMA3>(ctx, prm, u, s);
+        if (ctx.trace != nullptr && threadIdx.x == 0) ctx.trace[15] = 1;
     }
-    __syncthreads();
-    const int D = prm.sub_d, mode = prm.pair_mode;
-    const int nunits = prm.chunk_now * (D * D / 2);
-    if (threadIdx.x >= Cfg::NT_COMPUTE) {
-        const GroupCtx<Cfg::NT_LOAD, 6> ctx{(int)threadIdx.x - Cfg::NT_COMPUTE, nullptr};
-        auto write_back = [&](int u, const float4* s) {
-            const SubUnit su = sub_unit(u, D);
-            if (mode == 1) spec_store(ctx, s, sub_plane(prm, su));
-            else sub_store<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
-        };
-        int iter = 0, u = blockIdx.x;
-        for (; u < nunits; u += gridDim.x, ++iter) {
-            const int b = iter & 1;
-            float4* s = b ? buf1 : buf0;
-            long long* tr = (prm.trace != nullptr && iter < 6 && ctx.tid == 0) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
-            if (tr) tr[4] = clock64();
-            if (iter >= 2) {
-                bar_sync(BAR_DONE + b, Cfg::NT);
-                if (tr) tr[5] = clock64();
-                write_back(u - 2 * (int)gridDim.x, s);
-                bar_sync(6, Cfg::NT_LOAD);
-            }
-            if (tr) tr[6] = clock64();
-            const SubUnit su = sub_unit(u, D);
-            if (mode == 1) {
-                sub_load<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
-            } else {
-                spec_load(ctx, sub_plane(prm, su), s);
-            }
-            if (tr) tr[7] = clock64();
-            bar_arrive(BAR_FULL + b, Cfg::NT);
-        }
-        for (int back = (iter >= 2 ? 2 : iter); back >= 1; --back) {
-            const int it2 = iter - back, b = it2 & 1;
-            bar_sync(BAR_DONE + b, Cfg::NT);
-            write_back((int)blockIdx.x + it2 * (int)gridDim.x, b ? buf1 : buf0);
-        }
-    } else {
-        const GroupCtx<Cfg::NT_COMPUTE, BAR_COMPUTE> ctx{(int)threadIdx.x, nullptr};
-        int iter = 0;
-        for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++iter) {
-            const int b = iter & 1;
-            float4* s = b ? buf1 : buf0;
-            long long* tr = (prm.trace != nullptr && iter < 6 && ctx.tid == 0) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
-            if (tr) tr[0] = clock64();
-            bar_sync(BAR_FULL + b, Cfg::NT);
-            if (tr) tr[1] = clock64();
-            if (mode == 1) sub_compute_fwd(ctx, s, tw);
-            else sub_compute_inv(ctx, s, tw);
-            if (tr) {
-                tr[2] = clock64();
-                tr[15] = 1;
-            }
-            bar_arrive(BAR_DONE + b, Cfg::NT);
-        }
+}
+template <typename T, bool LUMA3>
+__global__ void __launch_bounds__(SubCfg::NT_INV, 6) sub_inv_kernel(const __grid_constant__ Params prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    BlockCtxT<SubCfg::NT_INV> ctx{(int)threadIdx.x, nullptr};
+    const int nunits = prm.chunk_now * (prm.sub_d * prm.sub_d / 2);
+    int iter = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++iter) {
+        ctx.trace = (prm.trace != nullptr && iter < 6) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
+        sub_inv_process<T, LUMA3>(ctx, prm, u, s);
+        if (ctx.trace != nullptr && threadIdx.x == 0) ctx.trace[15] = 1;
     }
 }
 
@@ -390,7 +339,7 @@ __global__ void __launch_bounds__(256, 2) combine_kernel(const __grid_constant__
     const int item = part * 256 + (int)threadIdx.x;
     float a = 0.f, p = 0.f;
     if (item < kCombineItems) {
-        float4* ws_tile = reinterpret_cast<float4*>(prm.zws) + (long long)lt * (D * D / 2) * 4096;
+        float2* ws_tile = sub_plane(prm, lt, 0);
         combine_item<D>(prm, ws_tile, item, a, p);
     }
     block_sum2(a, p);

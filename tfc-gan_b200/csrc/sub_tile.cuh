@@ -1,23 +1,36 @@
-// sub_tile.cuh -- 128 x 128 and 256 x 256 tiles on top of the packed 64 x 64 machinery.
+// sub_tile.cuh -- 128 x 128 and 256 x 256 tiles on top of the thread-per-line 64 x 64 machinery.
 //
 // A P x P tile (P = 64 D, D = 2 or 4) is decimated in both dimensions into D x D interleaved sub-images
 // s_pq[a, b] = x[D a + p, D b + q].  The 2-D DFT factors exactly (decimation in time):
 //     Z[ky' + 64 al, kx' + 64 be] = sum_{p,q} W_D^{p al + q be} * W_P^{p ky' + q kx'} * S_pq[ky', kx']
-// so the heavy work -- D^2 independent 64 x 64 complex transforms -- runs in the packed, warp-specialised pair
-// kernel (two sub-images with adjacent pixels q = 2i, 2i+1 are the two f32x2 lanes), and the cross-sub-image
-// step is a D x D butterfly per frequency position done in registers by `combine_kernel`, which also meets
-// Z(k) with Z(-k), evaluates the loss and the spectral gradient, and applies the inverse butterfly.  The three
-// launches exchange the sub-spectra through an L2-sized workspace chunk (P*P*8 bytes per tile):
-//   pair_kernel(mode 1): sub-images -> S_pq          (HBM read of fake / real)
-//   combine_kernel<D>:   S_pq -> Z -> loss, G -> H_pq (L2 only)
-//   pair_kernel(mode 2): H_pq -> gradient sub-images  (HBM write of grad)
+// so the heavy work -- D^2 independent 64 x 64 complex transforms -- runs on the register-resident 64-point
+// line transforms of line_tile.cuh, and the cross-sub-image step is a D x D butterfly per frequency position
+// done in registers by `combine_kernel`, which also meets Z(k) with Z(-k), evaluates the loss and the spectral
+// gradient, and applies the inverse butterfly.  Three launches exchange the sub-spectra through an L2-sized
+// workspace chunk (P*P*8 bytes per tile, D^2 planes of 64 x 64 float2 in natural frequency order):
+//   sub_fwd_kernel:      sub-images -> S_pq                      (HBM read of fake / real)
+//   combine_kernel<D>:   S_pq -> Z -> loss, G -> H_pq -> C_pi    (L2 only)
+//   sub_inv_kernel:      C_pi -> gradient sub-image pairs        (HBM write of grad)
+// Only the REAL part of the inverse sub-image transforms reaches the gradient, so combine_kernel Hermitian-
+// symmetrises each H_pq, Hs(k) = (H(k) + conj H(-k)) / 2, and packs two of them into one complex plane
+// C_pi = Hs_{p,2i} + i Hs_{p,2i+1}: the inverse launch runs D^2/2 complex transforms whose real / imaginary
+// outputs are the gradients of two horizontally adjacent pixels.
 #pragma once
-#include "pair_tile.cuh"
+#include "line_tile.cuh"
 
 namespace tfcfft {
 
+struct SubCfg {
+    static constexpr int LD = LineCfg::LD;
+    static constexpr int NT_FWD = 128;  // two 64-thread groups, one sub-image of the pair each
+    static constexpr int NT_INV = 64;
+    static constexpr int LOAD_NI = 4;  // rows in flight per thread in the forward load (8 measured the same)
+    static constexpr size_t SMEM_FWD = (size_t)2 * 64 * LD * sizeof(float2);
+    static constexpr size_t SMEM_INV = (size_t)64 * LD * sizeof(float2);
+};
+
 struct SubUnit {
-    int tile_local, plane, p, i;  // tile within the chunk, pair plane, sub-image row phase, lane-pair index
+    int tile_local, plane, p, i;  // tile within the chunk, pair plane, sub-image row phase, column-pair index
 };
 TFC_HD SubUnit sub_unit(int u, int d) {
     const int npp = d * d / 2, hd = d / 2;
@@ -28,119 +41,160 @@ TFC_HD SubUnit sub_unit(int u, int d) {
     r.i = r.plane % hd;
     return r;
 }
-TFC_HD float4* sub_plane(const Params& prm, const SubUnit& su) {
-    return reinterpret_cast<float4*>(prm.zws) + ((long long)su.tile_local * (prm.sub_d * prm.sub_d / 2) + su.plane) * 4096;
+// workspace plane `plane` (float2[64][64]) of a chunk-local tile
+TFC_HD float2* sub_plane(const Params& prm, int tile_local, int plane) {
+    return reinterpret_cast<float2*>(prm.zws) + ((long long)tile_local * (prm.sub_d * prm.sub_d) + plane) * 4096;
 }
 
-// ---- sub-image pair -> packed work tile (same swizzled layout as pair_load) ----------------------
+// ---- forward launch: sub-image pair (columns q = 2i, 2i+1 of row phase p) -> two complex work tiles ------
 template <typename T, bool LUMA3, class Ctx>
-TFC_HD void sub_load(const Ctx& ctx, const Params& prm, const TileCoord& tc, const SubUnit& su, float4* s) {
-    constexpr int LD = 65, NC = LUMA3 ? 3 : 1;
+TFC_HD void sub_fwd_load(const Ctx& ctx, const Params& prm, const TileCoord& tc, const SubUnit& su, float2* s) {
+    constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1, NI = SubCfg::LOAD_NI;
     const int D = prm.sub_d, P = 64 * D;
     const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, P);
     const T* rp = tile_ptr<T>(prm.real, prm.rs, tc, P);
     const int fsh = (int)prm.fs[2], fsc = (int)prm.fs[1], rsh = (int)prm.rs[2], rsc = (int)prm.rs[1];
     const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
-    // one sub-image column b per lane (consecutive lanes -> consecutive 8-byte pairs of the source row), four
-    // rows a, a+16, a+32, a+48 per thread in flight
-    for (int it = ctx.tid; it < 64 * 16; it += ctx.nthreads) {
-        const int b = it & 63, a0 = it >> 6;
-        const int x = D * b + 2 * su.i;
-        float raw[4][2][NC][2];  // [row][fake|real][channel][lane]
+    // one sub-image column b per lane (consecutive lanes -> consecutive 8-byte pixel pairs of the source row),
+    // NI rows per thread in flight
+#pragma unroll 1
+    for (int it0 = ctx.tid; it0 < 4096; it0 += NI * ctx.nthreads) {
+        float raw[NI][2][NC][2];  // [item][fake|real][channel][A|B]
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int y = D * (a0 + 16 * r) + su.p;
+        for (int u = 0; u < NI; ++u) {
+            const int it = it0 + u * ctx.nthreads, b = it & 63, a = it >> 6;
+            const int x = D * b + 2 * su.i, y = D * a + su.p;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                IO<T>::load2(fp + y * fsh + c * fsc + x, raw[r][0][c]);
-                IO<T>::load2(rp + y * rsh + c * rsc + x, raw[r][1][c]);
+                IO<T>::load2(fp + y * fsh + c * fsc + x, raw[u][0][c]);
+                IO<T>::load2(rp + y * rsh + c * rsc + x, raw[u][1][c]);
             }
         }
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            float2 v[2];
+        for (int u = 0; u < NI; ++u) {
+            const int it = it0 + u * ctx.nthreads, b = it & 63, a = it >> 6;
+            float z[2][2];  // [fake|real][A|B]
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (!quant) {
-                    float2 f = p_mul(p_dup(prm.lw[0]), make_float2(raw[r][h][0][0], raw[r][h][0][1]));
-                    if constexpr (LUMA3) {
-                        f = p_fma(p_dup(prm.lw[1]), make_float2(raw[r][h][1][0], raw[r][h][1][1]), f);
-                        f = p_fma(p_dup(prm.lw[2]), make_float2(raw[r][h][2][0], raw[r][h][2][1]), f);
-                    }
-                    v[h] = f;
-                } else {
-                    float q[2];
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int l = 0; l < 2; ++l) {
-                        if constexpr (LUMA3)
-                            q[l] = (float)((19595 * IO<T>::quant(raw[r][h][0][l]) + 38470 * IO<T>::quant(raw[r][h][1][l]) +
-                                            7471 * IO<T>::quant(raw[r][h][2][l]) + 0x8000) >> 16);
-                        else
-                            q[l] = (float)IO<T>::quant(raw[r][h][0][l]);
+                for (int l = 0; l < 2; ++l) {
+                    if (!quant) {
+                        float f = prm.lw[0] * raw[u][h][0][l];
+                        if constexpr (LUMA3) f = fmaf(prm.lw[2], raw[u][h][2][l], fmaf(prm.lw[1], raw[u][h][1][l], f));
+                        z[h][l] = f;
+                    } else if constexpr (LUMA3) {
+                        z[h][l] = (float)((19595 * IO<T>::quant(raw[u][h][0][l]) + 38470 * IO<T>::quant(raw[u][h][1][l]) +
+                                           7471 * IO<T>::quant(raw[u][h][2][l]) + 0x8000) >> 16);
+                    } else {
+                        z[h][l] = (float)IO<T>::quant(raw[u][h][0][l]);
                     }
-                    v[h] = make_float2(q[0], q[1]);
                 }
-            }
-            s[(a0 + 16 * r) * LD + swz(b)] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+            s[a * LD + b] = make_float2(z[0][0], z[1][0]);
+            s[64 * LD + a * LD + b] = make_float2(z[0][1], z[1][1]);
         }
     }
 }
+// rows of both work tiles, one thread per row
+template <class Ctx>
+TFC_HD void sub_fwd_rows(const Ctx& ctx, float2* s) {
+    constexpr int LD = SubCfg::LD;
+    for (int l = ctx.tid; l < 128; l += ctx.nthreads) {
+        float2* row = s + l * LD;  // tile (l >> 6), row (l & 63): the two tiles are contiguous
+        float2 v[64];
+#pragma unroll
+        for (int x = 0; x < 64; ++x) v[x] = row[x];
+        fft64<false>(v);
+#pragma unroll
+        for (int sl = 0; sl < 64; ++sl) row[fft64_freq(sl)] = v[sl];
+    }
+}
+// columns, one thread per column, written straight to the workspace planes (coalesced across the column index)
+template <class Ctx>
+TFC_HD void sub_fwd_cols_store(const Ctx& ctx, const Params& prm, const SubUnit& su, const float2* s) {
+    constexpr int LD = SubCfg::LD;
+    for (int l = ctx.tid; l < 128; l += ctx.nthreads) {
+        const int t = l >> 6, x = l & 63;
+        const float2* col = s + t * 64 * LD + x;
+        float2 v[64];
+#pragma unroll
+        for (int y = 0; y < 64; ++y) v[y] = col[y * LD];
+        fft64<false>(v);
+        float2* plane = sub_plane(prm, su.tile_local, su.p * prm.sub_d + 2 * su.i + t) + x;
+#pragma unroll
+        for (int sl = 0; sl < 64; ++sl) plane[fft64_freq(sl) * 64] = v[sl];
+    }
+}
 
-// ---- gradient sub-image pair (staged at the swizzled slots by pair_rows_last) -> global ------------
+// ---- inverse launch: packed plane C_pi -> gradients of the sub-image pair ----------------------------
+template <class Ctx>
+TFC_HD void sub_inv_cols(const Ctx& ctx, const Params& prm, const SubUnit& su, float2* s) {
+    constexpr int LD = SubCfg::LD;
+    for (int x = ctx.tid; x < 64; x += ctx.nthreads) {
+        const float2* plane = sub_plane(prm, su.tile_local, su.plane) + x;
+        float2 v[64];
+#pragma unroll
+        for (int y = 0; y < 64; ++y) v[y] = plane[y * 64];
+        fft64<true>(v);
+#pragma unroll
+        for (int sl = 0; sl < 64; ++sl) s[fft64_freq(sl) * LD + x] = v[sl];
+    }
+}
+template <class Ctx>
+TFC_HD void sub_inv_rows(const Ctx& ctx, float2* s) {
+    constexpr int LD = SubCfg::LD;
+    for (int a = ctx.tid; a < 64; a += ctx.nthreads) {
+        float2* row = s + a * LD;
+        float2 v[64];
+#pragma unroll
+        for (int k = 0; k < 64; ++k) v[k] = row[k];
+        fft64<true>(v);
+#pragma unroll
+        for (int sl = 0; sl < 64; ++sl) row[fft64_freq(sl)] = v[sl];  // (grad of pixel 2i, grad of pixel 2i+1)
+    }
+}
 template <typename T, bool LUMA3, class Ctx>
-TFC_HD void sub_store(const Ctx& ctx, const Params& prm, const TileCoord& tc, const SubUnit& su, const float4* s) {
-    constexpr int LD = 65, NC = LUMA3 ? 3 : 1;
+TFC_HD void sub_inv_store(const Ctx& ctx, const Params& prm, const TileCoord& tc, const SubUnit& su, const float2* s) {
+    constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1;
     const int D = prm.sub_d, P = 64 * D;
     T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, P));
     const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
-    for (int it = ctx.tid; it < 64 * 16; it += ctx.nthreads) {
-        const int b = it & 63, a0 = it >> 6;  // consecutive lanes: consecutive 8-byte pairs of the gradient row
-        const int x = D * b + 2 * su.i;
+#pragma unroll 4
+    for (int it = ctx.tid; it < 4096; it += ctx.nthreads) {
+        const int b = it & 63, a = it >> 6;  // consecutive lanes: consecutive 8-byte pairs of the gradient row
+        const int x = D * b + 2 * su.i, y = D * a + su.p;
+        const float2 g = s[a * LD + b];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int a = a0 + 16 * r, y = D * a + su.p;
-            const float2 g = *reinterpret_cast<const float2*>(s + a * LD + swz(b));
-#pragma unroll
-            for (int c = 0; c < NC; ++c) IO<T>::store2(gp + y * sh + c * sc + x, prm.gw[c] * g.x, prm.gw[c] * g.y);
-        }
+        for (int c = 0; c < NC; ++c) IO<T>::store2(gp + y * sh + c * sc + x, prm.gw[c] * g.x, prm.gw[c] * g.y);
     }
 }
 
-// ---- spectrum plane <-> work tile (plain pitch-65 layout, positions as the pair passes leave them) --
-template <class Ctx>
-TFC_HD void spec_store(const Ctx& ctx, const float4* s, float4* plane) {
-    for (int it = ctx.tid; it < 4096; it += ctx.nthreads) plane[it] = s[(it >> 6) * 65 + (it & 63)];
+template <typename T, bool LUMA3, class Ctx>
+TFC_HD void sub_fwd_process(const Ctx& ctx, const Params& prm, int u, float2* s) {
+    const SubUnit su = sub_unit(u, prm.sub_d);
+    ctx.mark(0);
+    sub_fwd_load<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
+    ctx.sync();
+    ctx.mark(1);
+    sub_fwd_rows(ctx, s);
+    ctx.sync();
+    ctx.mark(2);
+    sub_fwd_cols_store(ctx, prm, su, s);
+    ctx.sync();
+    ctx.mark(3);
 }
-template <class Ctx>
-TFC_HD void spec_load(const Ctx& ctx, const float4* plane, float4* s) {
-    for (int it = ctx.tid; it < 4096; it += ctx.nthreads) s[(it >> 6) * 65 + (it & 63)] = plane[it];
-}
-
-// forward transform of a loaded pair: rows then columns (the loss pass happens in combine_kernel)
-template <class Ctx>
-TFC_HD void sub_compute_fwd(const Ctx& ctx, float4* s, const float4* tw) {
-    using Pl = Plan<64>;
-    pair_rows_first<64>(ctx, s, tw + 64);
+template <typename T, bool LUMA3, class Ctx>
+TFC_HD void sub_inv_process(const Ctx& ctx, const Params& prm, int u, float2* s) {
+    const SubUnit su = sub_unit(u, prm.sub_d);
+    ctx.mark(0);
+    sub_inv_cols(ctx, prm, su, s);
     ctx.sync();
-    pair_rows_second<64>(ctx, s);
+    ctx.mark(1);
+    sub_inv_rows(ctx, s);
     ctx.sync();
-    fft_pass<64, Pl::R1, 64, false>(ctx, s, 65, 1, 6, tw);
+    ctx.mark(2);
+    sub_inv_store<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
     ctx.sync();
-    fft_pass<64, Pl::R2, 8, false>(ctx, s, 65, 1, 6, tw);
-    ctx.sync();
-}
-// inverse transform of a pair of H_pq planes: all 64 columns, then rows; real parts staged for the store
-template <class Ctx>
-TFC_HD void sub_compute_inv(const Ctx& ctx, float4* s, const float4* tw) {
-    using Pl = Plan<64>;
-    fft_pass<64, Pl::R2, 8, true>(ctx, s, 65, 1, 6, tw);
-    ctx.sync();
-    fft_pass<64, Pl::R1, 64, true>(ctx, s, 65, 1, 6, tw);
-    ctx.sync();
-    fft_pass<64, Pl::R2, 8, true>(ctx, s, 1, 65, 6, tw);
-    ctx.sync();
-    pair_rows_last<64>(ctx, s, tw + 64);
-    ctx.sync();
+    ctx.mark(3);
 }
 
 // ---- D-point butterflies over small register arrays ------------------------------------------------
@@ -231,9 +285,9 @@ TFC_HD void combine_inv2(c2 (&v)[D][D], int kyA, int kxA, int kyB, int kxB) {
     }
 }
 
-// position pairs {(ky',kx'), -(ky',kx')} of the 64 x 64 sub-grid: 64 x 32 slots walk the half-plane column
-// POSITIONS in memory order (4 consecutive float4 = 64 contiguous bytes per group; slot j = 0 is the kx' = 0
-// column, handled with kx' = 32 by the 66 items that pair rows instead)
+// position pairs {(ky',kx'), -(ky',kx')} of the 64 x 64 sub-grid: 64 x 32 slots walk the half-plane columns
+// kx' = 1..31 in memory order (slot j = 0 is idle: the kx' = 0 column is handled, with kx' = 32, by the 66
+// items that pair rows instead)
 // Out-of-line copy of the packed bin evaluation: combine_item calls it from 8 (D = 4) fully unrolled entry
 // pairs; inlining it there made the kernel instruction-fetch bound (ncu: no_instruction 3.9 per issue).
 #ifdef __CUDA_ARCH__
@@ -259,14 +313,13 @@ constexpr int kCombineItems = 64 * 32 + 2 * 33;
 // One position pair of one tile: load the D^2 sub-spectra at both positions, combine, evaluate every
 // full-size half-plane bin they contain, un-combine the spectral gradient, store back.
 template <int D>
-TFC_HD void combine_item(const Params& prm, float4* ws_tile, int item, float& accA, float& accP) {
-    constexpr int P = 64 * D, NPP = D * D / 2, HD = D / 2;
+TFC_HD void combine_item(const Params& prm, float2* ws_tile, int item, float& accA, float& accP) {
+    constexpr int P = 64 * D, HD = D / 2;
     int kyA, kxA;
     if (item < 64 * 32) {
-        const int j = item & 31;
-        if (j == 0) return;
-        kyA = freq_of_pos<64>(item >> 5);
-        kxA = freq_of_pos<64>((j >> 2) * 8 + (j & 3));  // 1 .. 31
+        kxA = item & 31;  // 1 .. 31
+        if (kxA == 0) return;
+        kyA = item >> 5;
     } else {
         const int sp = item - 64 * 32;
         kxA = (sp / 33) * 32;
@@ -274,19 +327,15 @@ TFC_HD void combine_item(const Params& prm, float4* ws_tile, int item, float& ac
     }
     const int kyB = (64 - kyA) & 63, kxB = (64 - kxA) & 63;
     const bool self = (kyA == kyB) && (kxA == kxB);
-    const int offA = pos_of_freq<64>(kyA) * 64 + pos_of_freq<64>(kxA);
-    const int offB = pos_of_freq<64>(kyB) * 64 + pos_of_freq<64>(kxB);
+    const int offA = kyA * 64 + kxA, offB = kyB * 64 + kxB;
     float2 za[D][D], zb[D][D];
 #pragma unroll
-    for (int pl = 0; pl < NPP; ++pl) {
-        const int p = pl / HD, q = 2 * (pl % HD);
-        const float4 a = ws_tile[pl * 4096 + offA];
-        const float4 b = ws_tile[pl * 4096 + offB];
-        za[p][q] = make_float2(a.x, a.z);
-        za[p][q + 1] = make_float2(a.y, a.w);
-        zb[p][q] = make_float2(b.x, b.z);
-        zb[p][q + 1] = make_float2(b.y, b.w);
-    }
+    for (int p = 0; p < D; ++p)
+#pragma unroll
+        for (int q = 0; q < D; ++q) {
+            za[p][q] = ws_tile[(p * D + q) * 4096 + offA];
+            zb[p][q] = ws_tile[(p * D + q) * 4096 + offB];
+        }
     {
         c2 z2[D][D];
 #pragma unroll
@@ -436,12 +485,24 @@ TFC_HD void combine_item(const Params& prm, float4* ws_tile, int item, float& ac
                 gb[p][q] = make_float2(g2[p][q].re.y, g2[p][q].im.y);
             }
     }
+    // Hermitian-symmetrise each H_pq over the position pair and pack two of them per complex plane (in place:
+    // this item owns positions A and B of every plane)
 #pragma unroll
-    for (int pl = 0; pl < NPP; ++pl) {
-        const int p = pl / HD, q = 2 * (pl % HD);
-        ws_tile[pl * 4096 + offA] = make_float4(ga[p][q].x, ga[p][q + 1].x, ga[p][q].y, ga[p][q + 1].y);
-        if (!self) ws_tile[pl * 4096 + offB] = make_float4(gb[p][q].x, gb[p][q + 1].x, gb[p][q].y, gb[p][q + 1].y);
-    }
+    for (int p = 0; p < D; ++p)
+#pragma unroll
+        for (int i = 0; i < HD; ++i) {
+            float2 h0, h1;  // Hs_{p,2i}(A), Hs_{p,2i+1}(A); Hs(B) = conj Hs(A)
+            if (self) {
+                h0 = make_float2(ga[p][2 * i].x, 0.f);
+                h1 = make_float2(ga[p][2 * i + 1].x, 0.f);
+            } else {
+                h0 = make_float2(0.5f * (ga[p][2 * i].x + gb[p][2 * i].x), 0.5f * (ga[p][2 * i].y - gb[p][2 * i].y));
+                h1 = make_float2(0.5f * (ga[p][2 * i + 1].x + gb[p][2 * i + 1].x), 0.5f * (ga[p][2 * i + 1].y - gb[p][2 * i + 1].y));
+            }
+            float2* plane = ws_tile + (p * HD + i) * 4096;
+            plane[offA] = make_float2(h0.x - h1.y, h0.y + h1.x);
+            if (!self) plane[offB] = make_float2(h0.x + h1.y, h1.x - h0.y);
+        }
 }
 
 TFC_HD bool sub_supported(const Params& prm) {

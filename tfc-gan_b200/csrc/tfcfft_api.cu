@@ -94,18 +94,28 @@ int launch_line(const Params& prm, cudaStream_t st) {
 
 template <typename T, bool LUMA3>
 int launch_sub(Params prm, cudaStream_t st) {
-    auto kp = sub_pair_kernel<T, LUMA3>;
-    constexpr size_t smem = PairCfg<64>::SMEM;
-    if (int rc = set_smem(kp, smem)) return rc;
+    auto kf = sub_fwd_kernel<T, LUMA3>;
+    auto ki = sub_inv_kernel<T, LUMA3>;
+    if (int rc = set_smem(kf, SubCfg::SMEM_FWD)) return rc;
+    if (int rc = set_smem(ki, SubCfg::SMEM_INV)) return rc;
+    static int per_sm_f = 0, per_sm_i = 0;
+    if (!per_sm_f) {
+        int f = 0, i = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f, kf, SubCfg::NT_FWD, SubCfg::SMEM_FWD);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&i, ki, SubCfg::NT_INV, SubCfg::SMEM_INV);
+        if (e != cudaSuccess) return (int)e;
+        per_sm_i = i < 1 ? 1 : i;
+        per_sm_f = f < 1 ? 1 : f;
+    }
     const int D = prm.sub_d, npp = D * D / 2;
     const int sms = device_info().sms;
     for (int base = 0; base < prm.tiles_total; base += prm.chunk_tiles) {
         prm.tile_base = base;
         prm.chunk_now = prm.tiles_total - base < prm.chunk_tiles ? prm.tiles_total - base : prm.chunk_tiles;
         const int units = prm.chunk_now * npp;
-        const int grid = units < sms ? units : sms;
-        prm.pair_mode = 1;
-        kp<<<grid, SubCfg::NT, smem, st>>>(prm);
+        const int grid_f = units < sms * per_sm_f ? units : sms * per_sm_f;
+        const int grid_i = units < sms * per_sm_i ? units : sms * per_sm_i;
+        kf<<<grid_f, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st>>>(prm);
         g_launches++;
         TFC_LAUNCH_CHECK();
         if (D == 2) combine_kernel<2><<<prm.chunk_now * 9, 256, 0, st>>>(prm);
@@ -113,8 +123,7 @@ int launch_sub(Params prm, cudaStream_t st) {
         g_launches++;
         TFC_LAUNCH_CHECK();
         if (prm.grad) {
-            prm.pair_mode = 2;
-            kp<<<grid, SubCfg::NT, smem, st>>>(prm);
+            ki<<<grid_i, SubCfg::NT_INV, SubCfg::SMEM_INV, st>>>(prm);
             g_launches++;
             TFC_LAUNCH_CHECK();
         }
