@@ -76,14 +76,14 @@ void run_sub(Params prm) {
         for (int u = 0; u < prm.chunk_now * npp; ++u) sub_fwd_process<T, LUMA3>(ctx, prm, u, s.data());
         for (int lt = 0; lt < prm.chunk_now; ++lt) {
             float2* ws_tile = sub_plane(prm, lt, 0);
-            for (int part = 0; part < 9; ++part) {
+            for (int part = 0; part < kCombineParts; ++part) {
                 float a = 0.f, p = 0.f;
-                for (int item = part * 256; item < (part + 1) * 256 && item < kCombineItems; ++item) {
+                for (int item = part * kCombineThreads; item < (part + 1) * kCombineThreads && item < kCombineItems; ++item) {
                     if (D == 2) combine_item<2>(prm, ws_tile, item, a, p);
                     else combine_item<4>(prm, ws_tile, item, a, p);
                 }
-                prm.partials[2 * ((size_t)(base + lt) * 9 + part)] = a;
-                prm.partials[2 * ((size_t)(base + lt) * 9 + part) + 1] = p;
+                prm.partials[2 * ((size_t)(base + lt) * kCombineParts + part)] = a;
+                prm.partials[2 * ((size_t)(base + lt) * kCombineParts + part) + 1] = p;
             }
         }
         if (prm.grad)

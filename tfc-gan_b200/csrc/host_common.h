@@ -72,7 +72,7 @@ inline int validate_desc(const tfcfft_desc* d, Geometry* geo, bool allow_sub = t
         geo->cprime = (d->c == 3 && !geo->luma3) ? 3 : 1;
         geo->sub = allow_sub && (p == 128 || p == 256) && !(d->flags & (TFCFFT_FORCE_SPLIT | TFCFFT_FORCE_GENERIC));
         geo->split = !geo->sub && ((p >= 256) || (d->flags & TFCFFT_FORCE_SPLIT));
-        geo->parts = geo->sub ? 9 : geo->split ? split_parts((int)p) : 1;
+        geo->parts = geo->sub ? kCombineParts : geo->split ? split_parts((int)p) : 1;
         geo->tiles_total = (long long)d->n * geo->cprime * d->grid * d->grid;
         geo->partial_bytes = align_up((size_t)geo->tiles_total * geo->parts * 2 * sizeof(float), 256);
         geo->chunk_tiles = 0;

@@ -58,6 +58,14 @@ struct Params {
 // ---------------------------------------------------------------------------------------------
 // element IO per dtype: 4 consecutive pixels, quantisation (torchvision to_pil_image semantics)
 // ---------------------------------------------------------------------------------------------
+// Sub-tile path (sub_tile.cuh), launch 2: work items per tile and how they are cut into CTAs / partial sums
+constexpr int kCombineItems = 64 * 32 + 2 * 33;
+#ifndef TFCFFT_COMBINE_THREADS
+#define TFCFFT_COMBINE_THREADS 128
+#endif
+constexpr int kCombineThreads = TFCFFT_COMBINE_THREADS;  // one item per thread
+constexpr int kCombineParts = (kCombineItems + kCombineThreads - 1) / kCombineThreads;  // CTAs (= partial sums) per tile
+
 template <typename T> struct IO;
 
 // Pixel tensors are read once and gradients written once per call: mark them streaming (ld/st.global.cs) so they

@@ -333,10 +333,10 @@ __global__ void __launch_bounds__(SubCfg::NT_INV, 6) sub_inv_kernel(const __grid
 
 // Sub-tile path, launch 2: per-position D x D butterflies, loss, spectral gradient (registers + L2 only).
 template <int D>
-__global__ void __launch_bounds__(256, 2) combine_kernel(const __grid_constant__ Params prm) {
-    constexpr int PARTS = 9;  // ceil(kCombineItems / 256)
+__global__ void __launch_bounds__(kCombineThreads, 512 / kCombineThreads) combine_kernel(const __grid_constant__ Params prm) {
+    constexpr int PARTS = kCombineParts;
     const int lt = blockIdx.x / PARTS, part = blockIdx.x % PARTS;
-    const int item = part * 256 + (int)threadIdx.x;
+    const int item = part * kCombineThreads + (int)threadIdx.x;
     float a = 0.f, p = 0.f;
     if (item < kCombineItems) {
         float2* ws_tile = sub_plane(prm, lt, 0);

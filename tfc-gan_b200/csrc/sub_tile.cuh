@@ -296,7 +296,27 @@ __device__ __noinline__
 inline
 #endif
 c2 bin_eval_pair_call(const Params& prm, bool mse, bool phase, c2 zk, c2 zm, float2& accA, float2& accP) {
-    return bin_eval_pair(prm, mse, phase, zk, zm, accA, accP);
+    return bin_eval_pair(prm, mse, phase, zk, zm, accA, accP);  // rare path (self-conjugate columns)
+}
+
+// two independent packed evaluations per call; everything by value (register ABI: no local-memory traffic)
+struct QuadEval {
+    c2 g0, g1;
+    float2 a, p;  // loss-term increments
+};
+#ifdef __CUDA_ARCH__
+__device__ __noinline__
+#else
+inline
+#endif
+QuadEval bin_eval_quad_call(const Params& prm, bool mse, bool phase, c2 zk0, c2 zm0, c2 zk1, c2 zm1) {
+    QuadEval r;
+    float2 a0 = make_float2(0.f, 0.f), p0 = a0, a1 = a0, p1 = a0;  // separate accumulators: independent chains
+    r.g0 = bin_eval_pair(prm, mse, phase, zk0, zm0, a0, p0);
+    r.g1 = bin_eval_pair(prm, mse, phase, zk1, zm1, a1, p1);
+    r.a = p_add(a0, a1);
+    r.p = p_add(p0, p1);
+    return r;
 }
 
 #ifdef __CUDA_ARCH__
@@ -307,8 +327,6 @@ inline
 float2 bin_eval_call(const Params& prm, float2 zk, float2 zm, float mult, float& accA, float& accP) {
     return bin_eval(prm, zk, zm, mult, accA, accP);
 }
-
-constexpr int kCombineItems = 64 * 32 + 2 * 33;
 
 // One position pair of one tile: load the D^2 sub-spectra at both positions, combine, evaluate every
 // full-size half-plane bin they contain, un-combine the spectral gradient, store back.
@@ -401,50 +419,64 @@ TFC_HD void combine_item(const Params& prm, float2* ws_tile, int item, float& ac
                 gp[al][be] = gm;
             }
     } else {
-        // default modes: two entries (be, be+1) per packed evaluation, MUFU / polynomial transcendental path
+        // default modes: two entries (be, be+1) per packed evaluation, two packed evaluations per out-of-line call
+        // (independent dependency chains: the call is latency-bound on MUFU / polynomial chains otherwise)
         const bool mse = (prm.flags & TFCFFT_DIST_MSE) != 0, phase = !(prm.flags & TFCFFT_NO_PHASE);
         float2 pA = make_float2(0.f, 0.f), pP = make_float2(0.f, 0.f);
         const float2 z0 = make_float2(0.f, 0.f);
+        constexpr int NE = D * D / 2;  // packed evaluations: entry pairs (al, 2 bp), (al, 2 bp + 1)
 #pragma unroll
-        for (int al = 0; al < D; ++al)
+        for (int e0 = 0; e0 < NE; e0 += 2) {
+            bool isM[2][2], both[2][2], live[2][2];
+            float2 k_[2][2], m_[2][2];
+            c2 zk[2], zm[2], g[2];
 #pragma unroll
-            for (int bp = 0; bp < D / 2; ++bp) {
+            for (int h = 0; h < 2; ++h) {
+                const int al = (e0 + h) / HD, bp = (e0 + h) % HD;
                 const int alB = kyA ? D - 1 - al : (D - al) % D;
-                bool isM[2], both[2], live[2];
-                c2 zk, zm;
-                float2 k_[2], m_[2];
 #pragma unroll
                 for (int l = 0; l < 2; ++l) {
                     const int be = 2 * bp + l;
                     const int beB = kxA ? D - 1 - be : (D - be) % D;
                     const int kxf = kxA + 64 * be;
-                    live[l] = !(self && (al * D + be) > (alB * D + beB));
+                    live[h][l] = !(self && (al * D + be) > (alB * D + beB));
                     const bool special = (kxf == 0 || kxf == P / 2);
-                    both[l] = live[l] && special && !(self && al == alB && be == beB);
-                    isM[l] = !special && kxf > P / 2;
-                    k_[l] = live[l] ? (isM[l] ? zp[al][be] : za[al][be]) : z0;
-                    m_[l] = live[l] ? (isM[l] ? za[al][be] : zp[al][be]) : z0;
+                    both[h][l] = live[h][l] && special && !(self && al == alB && be == beB);
+                    isM[h][l] = !special && kxf > P / 2;
+                    k_[h][l] = live[h][l] ? (isM[h][l] ? zp[al][be] : za[al][be]) : z0;
+                    m_[h][l] = live[h][l] ? (isM[h][l] ? za[al][be] : zp[al][be]) : z0;
                 }
-                zk = make_c2(make_float2(k_[0].x, k_[1].x), make_float2(k_[0].y, k_[1].y));
-                zm = make_c2(make_float2(m_[0].x, m_[1].x), make_float2(m_[0].y, m_[1].y));
-                const c2 g = bin_eval_pair_call(prm, mse, phase, zk, zm, pA, pP);
+                zk[h] = make_c2(make_float2(k_[h][0].x, k_[h][1].x), make_float2(k_[h][0].y, k_[h][1].y));
+                zm[h] = make_c2(make_float2(m_[h][0].x, m_[h][1].x), make_float2(m_[h][0].y, m_[h][1].y));
+            }
+            {
+                const QuadEval q = bin_eval_quad_call(prm, mse, phase, zk[0], zm[0], zk[1], zm[1]);
+                g[0] = q.g0;
+                g[1] = q.g1;
+                pA = p_add(pA, q.a);
+                pP = p_add(pP, q.p);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int al = (e0 + h) / HD, bp = (e0 + h) % HD;
                 c2 g2 = make_c2(z0, z0);
-                if (both[0] || both[1]) {  // self-conjugate columns only: evaluate the mirrored bin as well
-                    const c2 zk2 = make_c2(make_float2(both[0] ? m_[0].x : 0.f, both[1] ? m_[1].x : 0.f),
-                                           make_float2(both[0] ? m_[0].y : 0.f, both[1] ? m_[1].y : 0.f));
-                    const c2 zm2 = make_c2(make_float2(both[0] ? k_[0].x : 0.f, both[1] ? k_[1].x : 0.f),
-                                           make_float2(both[0] ? k_[0].y : 0.f, both[1] ? k_[1].y : 0.f));
+                if (both[h][0] || both[h][1]) {  // self-conjugate columns only: evaluate the mirrored bin as well
+                    const c2 zk2 = make_c2(make_float2(both[h][0] ? m_[h][0].x : 0.f, both[h][1] ? m_[h][1].x : 0.f),
+                                           make_float2(both[h][0] ? m_[h][0].y : 0.f, both[h][1] ? m_[h][1].y : 0.f));
+                    const c2 zm2 = make_c2(make_float2(both[h][0] ? k_[h][0].x : 0.f, both[h][1] ? k_[h][1].x : 0.f),
+                                           make_float2(both[h][0] ? k_[h][0].y : 0.f, both[h][1] ? k_[h][1].y : 0.f));
                     g2 = bin_eval_pair_call(prm, mse, phase, zk2, zm2, pA, pP);
                 }
 #pragma unroll
                 for (int l = 0; l < 2; ++l) {
                     const int be = 2 * bp + l;
-                    const float2 gl = l ? make_float2(g.re.y, g.im.y) : make_float2(g.re.x, g.im.x);
+                    const float2 gl = l ? make_float2(g[h].re.y, g[h].im.y) : make_float2(g[h].re.x, g[h].im.x);
                     const float2 g2l = l ? make_float2(g2.re.y, g2.im.y) : make_float2(g2.re.x, g2.im.x);
-                    ga[al][be] = live[l] ? (isM[l] ? z0 : gl) : z0;
-                    gp[al][be] = live[l] ? (isM[l] ? gl : (both[l] ? g2l : z0)) : z0;
+                    ga[al][be] = live[h][l] ? (isM[h][l] ? z0 : gl) : z0;
+                    gp[al][be] = live[h][l] ? (isM[h][l] ? gl : (both[h][l] ? g2l : z0)) : z0;
                 }
             }
+        }
         accA += pA.x + pA.y;
         accP += pP.x + pP.y;
     }

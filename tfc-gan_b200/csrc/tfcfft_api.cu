@@ -118,8 +118,8 @@ int launch_sub(Params prm, cudaStream_t st) {
         kf<<<grid_f, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st>>>(prm);
         g_launches++;
         TFC_LAUNCH_CHECK();
-        if (D == 2) combine_kernel<2><<<prm.chunk_now * 9, 256, 0, st>>>(prm);
-        else combine_kernel<4><<<prm.chunk_now * 9, 256, 0, st>>>(prm);
+        if (D == 2) combine_kernel<2><<<prm.chunk_now * kCombineParts, kCombineThreads, 0, st>>>(prm);
+        else combine_kernel<4><<<prm.chunk_now * kCombineParts, kCombineThreads, 0, st>>>(prm);
         g_launches++;
         TFC_LAUNCH_CHECK();
         if (prm.grad) {
