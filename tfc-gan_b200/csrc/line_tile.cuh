@@ -19,6 +19,10 @@ struct LineCfg {
     static constexpr int NT = 64;
     static constexpr int LD = 65;  // float2 row pitch: lanes = rows and lanes = columns are both conflict-free
     static constexpr size_t SMEM = (size_t)64 * LD * sizeof(float2);
+#ifndef TFCFFT_LINE_BIN_EVALS
+#define TFCFFT_LINE_BIN_EVALS 1
+#endif
+    static constexpr int BIN_EVALS = TFCFFT_LINE_BIN_EVALS;  // packed bin evaluations in flight per thread (2 measured no faster)
 };
 
 constexpr float kCos64[64] = {
@@ -180,35 +184,51 @@ TFC_HD void line_bins(const Ctx& ctx, const Params& prm, float2* s, float& accA,
     const bool want_grad = prm.grad != nullptr;
     const float2 z0 = make_float2(0.f, 0.f);
     float2 pA = z0, pP = z0;
-    // two regular bins per packed evaluation.  Kept as a real loop: the kernel is instruction-fetch sensitive
+    // two regular bins per packed evaluation, NE independent packed evaluations per iteration (their MUFU /
+    // polynomial dependency chains interleave).  Kept as a real loop: the kernel is instruction-fetch sensitive
     // (straight-line 64-point transforms), the loss code should not be replicated 16 times
+    constexpr int NE = LineCfg::BIN_EVALS;
 #pragma unroll 1
-    for (int it0 = ctx.tid; it0 < NREG; it0 += 2 * ctx.nthreads) {
-        float2* pk[2];
-        float2* pm[2];
-        float2 zk[2], zm[2];
-        bool live[2];
+    for (int it0 = ctx.tid; it0 < NREG; it0 += 2 * NE * ctx.nthreads) {
+        float2* pk[NE][2];
+        float2* pm[NE][2];
+        float2 zk[NE][2], zm[NE][2];
+        bool live[NE][2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int it = it0 + u * ctx.nthreads;
-            live[u] = it < NREG;
-            const int iq = live[u] ? it : 0;
-            const int ky = iq & 63, kx = 1 + (iq >> 6);  // consecutive threads: consecutive rows
-            pk[u] = s + ky * LD + kx;
-            pm[u] = s + ((64 - ky) & 63) * LD + (64 - kx);
-            zk[u] = live[u] ? *pk[u] : z0;
-            zm[u] = live[u] ? *pm[u] : z0;
-        }
-        const c2 g = bin_eval_pair(prm, mse, phase, make_c2(make_float2(zk[0].x, zk[1].x), make_float2(zk[0].y, zk[1].y)),
-                                   make_c2(make_float2(zm[0].x, zm[1].x), make_float2(zm[0].y, zm[1].y)), pA, pP);
-        if (want_grad) {
-            if (live[0]) {
-                *pk[0] = make_float2(g.re.x, g.im.x);
-                *pm[0] = z0;
+        for (int e = 0; e < NE; ++e)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int it = it0 + (2 * e + u) * ctx.nthreads;
+                live[e][u] = it < NREG;
+                const int iq = live[e][u] ? it : 0;
+                const int ky = iq & 63, kx = 1 + (iq >> 6);  // consecutive threads: consecutive rows
+                pk[e][u] = s + ky * LD + kx;
+                pm[e][u] = s + ((64 - ky) & 63) * LD + (64 - kx);
+                zk[e][u] = live[e][u] ? *pk[e][u] : z0;
+                zm[e][u] = live[e][u] ? *pm[e][u] : z0;
             }
-            if (live[1]) {
-                *pk[1] = make_float2(g.re.y, g.im.y);
-                *pm[1] = z0;
+        c2 g[NE];
+        float2 qA[NE], qP[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            qA[e] = z0;
+            qP[e] = z0;
+            g[e] = bin_eval_pair(prm, mse, phase, make_c2(make_float2(zk[e][0].x, zk[e][1].x), make_float2(zk[e][0].y, zk[e][1].y)),
+                                 make_c2(make_float2(zm[e][0].x, zm[e][1].x), make_float2(zm[e][0].y, zm[e][1].y)), qA[e], qP[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            pA = p_add(pA, qA[e]);
+            pP = p_add(pP, qP[e]);
+            if (want_grad) {
+                if (live[e][0]) {
+                    *pk[e][0] = make_float2(g[e].re.x, g[e].im.x);
+                    *pm[e][0] = z0;
+                }
+                if (live[e][1]) {
+                    *pk[e][1] = make_float2(g[e].re.y, g[e].im.y);
+                    *pm[e][1] = z0;
+                }
             }
         }
     }
