@@ -247,6 +247,32 @@ def time_kernel_path(tfc, torch, wl, steps, warmup, barrier):
     return secs, launches, pool_n
 
 
+def time_triplet(tfc, torch, batch, side, grid, steps, warmup):
+    """Device-timed fused patch-triplet loss + gradient (the first 'next' row of the scope table) on resident inputs
+    rotating over a pool larger than L2.  Algorithmic bytes: anchor + positive + negative reads + gradient write."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    per_batch = 2 * batch * 3 * side * side * 4
+    pool_n = max(2, -(-3 * L2_BYTES // per_batch))
+    g = torch.Generator(device=dev).manual_seed(4321)
+    pool = [(torch.empty(batch, 3, side, side, device=dev).uniform_(-1, 1, generator=g),
+             torch.empty(batch, 3, side, side, device=dev).uniform_(-1, 1, generator=g)) for _ in range(pool_n)]
+    neg = [(5 * i + 3) % (grid * grid) for i in range(grid * grid)]
+    sink = None
+    for i in range(warmup):
+        sink = tfc.patch_triplet_loss_and_grad(*pool[i % pool_n], neg, grid=grid)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        sink = tfc.patch_triplet_loss_and_grad(*pool[(warmup + i) % pool_n], neg, grid=grid)
+    e1.record()
+    torch.cuda.synchronize()
+    assert torch.isfinite(sink[0][0]).item()
+    secs = e0.elapsed_time(e1) / 1e3
+    ips = batch * steps / secs
+    return ips, ips * 4 * 3 * side * side * 4 / 1e9
+
+
 def time_e2e(tfc, torch, wl, steps, warmup, barrier, dist):
     """Public API (nn.Module + backward) with pinned-host inputs copied in and the loss read back
     every step; H2D of step i+1 overlaps the kernels of step i on a second stream."""
@@ -380,6 +406,9 @@ def run_ours(args, wl):
             ips = w["batch"] * max(10, args.steps // 4) / s
             var[name] = {"value": ips, "unit": UNIT,
                          "roofline_frac": ips * bytes_per_image(w["side"], w.get("dtype", "f32")) / 1e9 / peak}
+        ips, gbs = time_triplet(tfc, torch, 256, 256, 4, max(10, args.steps // 4), 3)
+        var["patch16-triplet-256-b256"] = {"value": ips, "unit": UNIT, "roofline_frac": gbs / peak,
+                                           "note": "fused TripletMarginLoss fwd+bwd on 16 patches; 4 tensor passes per image"}
         line["variants"] = var
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_arm(wl, 12.0)

@@ -49,6 +49,7 @@ enum tfcfft_dtype { TFCFFT_F32 = 0, TFCFFT_F16 = 1, TFCFFT_BF16 = 2, TFCFFT_U8 =
 #define TFCFFT_FULL_SPECTRUM (1u << 5) /* mean over the full P x P plane (fft2) not P x (P/2+1)   */
 #define TFCFFT_QUANTIZE_U8   (1u << 6) /* reference-as-shipped input path: uint8 wrap + integer
                                           luma (patchFFT_16P.py:300); forward only               */
+#define TFCFFT_GRAD_ACCUMULATE (1u << 8) /* tfcfft_patch_triplet only: grad_fake += instead of grad_fake =   */
 #define TFCFFT_USE_PAIR      (1u << 28) /* testing: 64x64 tiles through the packed pair kernel            */
 #define TFCFFT_USE_LINE      (1u << 29) /* testing: 64x64 tiles through the thread-per-line kernel        */
 #define TFCFFT_FORCE_GENERIC (1u << 30) /* testing: bypass the packed 64x64 fast path                */
@@ -117,6 +118,25 @@ int tfcfft_spectra(const tfcfft_desc* d, const void* x, const void* y, float* am
  * (either may be NULL); d->grad_stride describes grad_x. */
 int tfcfft_spectra_bwd(const tfcfft_desc* d, const void* x, const float* grad_amp, const float* grad_pha,
                        void* grad_x, int fftshift, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Patch triplet loss of the generator step, forward + backward in one streaming pass (the first "next" row of
+ * the hot-path scope table).  Replaces, for all g*g patches at once,
+ *     triplet_loss(fake_B_i, B_i, random_patches[k_i])      with nn.TripletMarginLoss(margin, p=2)
+ * (TFCGAN_multigpu_patchFFT_16P.py:75, :558-583; 4-patch copies TFCGAN_multigpu_patchFFT.py:474-484 and
+ * TFCGAN_multigpu_globalFFT.py:470-480): distance = || a - b + eps ||_2 over one patch row of one channel,
+ * loss = mean over (n, c, patch, row) of max(margin + d(fake_i, real_i) - d(fake_i, real_{k_i}), 0), which equals
+ * the reference's 1/g^2 * sum of per-patch means.
+ *   d           shape / dtype / strides / weight as for tfcfft_loss; input_scale is ignored; C in 1..4;
+ *               flags: 0 or TFCFFT_GRAD_ACCUMULATE
+ *   negatives   HOST int32[grid*grid]: k_i, the row-major index of the real patch used as negative for patch i
+ *   out         device float[4]: weight*loss, loss, fraction of rows with an active hinge, 0
+ *   grad_fake   device buffer (d->dtype, d->grad_stride) receiving weight * d loss / d fake, or NULL
+ *   workspace   tfcfft_triplet_workspace_bytes() bytes, 256-byte aligned, header zeroed once
+ *               (tfcfft_workspace_init); one workspace per concurrently used stream */
+size_t tfcfft_triplet_workspace_bytes(void);
+int tfcfft_patch_triplet(const tfcfft_desc* d, const void* fake, const void* real, const int32_t* negatives,
+                         float margin, float eps, float* out, void* grad_fake, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* dst[i] = src[i] * host_scale * (*dev_scale)   (dev_scale may be NULL; dst may equal src);
  * numel elements of `dtype`, both 16-byte aligned. */

@@ -1,0 +1,142 @@
+"""Patch triplet loss on the CPU: the oracle against the golden vectors the reference's own
+lines produced (``tests/golden/make_golden_triplet.py``), the kernel arithmetic (serial emulation,
+``libtfcfft_emu.so``) against the oracle, and the host-side argument checks of the C entry point."""
+
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import tfc_gan_b200 as tfc
+from inputs import make_pair
+from oracle import triplet as otri
+from util import emulate_triplet, l2rel
+
+L = tfc._lib
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "golden_triplet.json")))
+ARR = np.load(os.path.join(HERE, "golden", "golden_triplet.npz"))
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
+def test_oracle_matches_reference_lines(case):
+    fake, real = make_pair(case["kind"], case["seed"], (case["n"], 3, 256, 256), case["dtype"])
+    _, loss, _, grad = otri.patch_triplet_loss_and_grad(fake, real, case["negatives"], grid=case["grid"])
+    tol = 1e-12 if case["dtype"] == "float64" else 2e-7  # the fp32 reference runs carry fp32 rounding
+    assert loss == pytest.approx(case["loss"], rel=tol)
+    assert np.sqrt((grad * grad).sum()) == pytest.approx(case["grad_l2"], rel=tol)
+    assert np.abs(grad).sum() == pytest.approx(case["grad_abs_sum"], rel=tol)
+    ref = ARR[case["name"] + "_grad_n0_c1_rows60_70"]
+    assert np.abs(grad[0, 1, 60:70, :] - ref).max() <= 2e-7 * np.abs(grad).max() + 1e-12
+
+
+def test_negative_draw_replays_the_reference_stream():
+    for case in GOLD["cases"]:
+        np.random.seed(case["numpy_seed"])
+        assert otri.draw_negatives(case["grid"] ** 2) == case["negatives"]
+        np.random.seed(case["numpy_seed"])
+        assert tfc.compat.draw_negatives(case["grid"] ** 2) == case["negatives"]
+
+
+def test_oracle_against_torch_autograd_small():
+    rs = np.random.RandomState(3)
+    fake, real = rs.normal(size=(2, 3, 32, 32)), rs.normal(size=(2, 3, 32, 32))
+    neg = [3, 0, 1, 1]
+    f = torch.from_numpy(fake).requires_grad_(True)
+    r = torch.from_numpy(real)
+    crit = torch.nn.TripletMarginLoss(margin=0.7, p=2)
+    tl = lambda t, i: t[:, :, (i // 2) * 16:(i // 2 + 1) * 16, (i % 2) * 16:(i % 2 + 1) * 16]
+    loss = sum(crit(tl(f, i), tl(r, i), tl(r, neg[i])) for i in range(4)) / 4
+    loss.backward()
+    wl, l, _, g = otri.patch_triplet_loss_and_grad(fake, real, neg, grid=2, margin=0.7, weight=2.5)
+    assert l == pytest.approx(float(loss), rel=1e-12)
+    assert wl == pytest.approx(2.5 * float(loss), rel=1e-12)
+    assert l2rel(g, 2.5 * f.grad.numpy()) <= 1e-12
+
+
+EMU_CASES = [(64, 4, "float32"), (64, 2, "float32"), (128, 1, "float32"), (256, 4, "float32"), (256, 2, "float16"), (256, 1, "float32"),
+             (512, 1, "float32"), (512, 4, "float32")]
+
+
+@pytest.mark.parametrize("side,grid,dtype", EMU_CASES, ids=[f"{s}-g{g}-{d}" for s, g, d in EMU_CASES])
+def test_emulated_kernel_arithmetic_matches_oracle(side, grid, dtype):
+    n = 2 if side <= 256 else 1
+    fake, real = make_pair("tanh", 5, (n, 3, side, side), dtype)
+    rs = np.random.RandomState(side + grid)
+    neg = [int(k) for k in rs.randint(grid * grid, size=grid * grid)]
+    rc, out, g = emulate_triplet(fake, real, grid, neg, margin=1.0, weight=0.5)
+    assert rc == 0
+    wl, l, act, gr = otri.patch_triplet_loss_and_grad(fake, real, neg, grid=grid, weight=0.5)
+    assert out[0] == pytest.approx(wl, rel=1e-5)
+    assert out[1] == pytest.approx(l, rel=1e-5)
+    assert out[2] == pytest.approx(act, abs=1e-6)
+    assert l2rel(g.astype(np.float64), gr) <= (2e-3 if dtype == "float16" else 1e-5)
+
+
+def test_emulated_accumulate_and_forward_only():
+    fake, real = make_pair("uniform", 9, (1, 3, 64, 64), "float32")
+    neg = [1, 0, 3, 2]
+    base = np.full_like(fake, 0.25)
+    rc, _, g = emulate_triplet(fake, real, 2, neg, accumulate_into=base.copy())
+    assert rc == 0
+    _, _, _, gr = otri.patch_triplet_loss_and_grad(fake, real, neg, grid=2)
+    assert l2rel(g - 0.25, gr) <= 1e-4
+    rc, out, g = emulate_triplet(fake, real, 2, neg, grad=False)
+    assert rc == 0 and g is None and out[1] > 0
+
+
+def test_degenerate_rows():
+    # fake == real and the negative is the patch itself: d_ap = d_an = eps*sqrt(P) -> hinge = margin, gradient 0
+    x, _ = make_pair("uniform", 2, (1, 1, 32, 32), "float32")
+    rc, out, g = emulate_triplet(x, x.copy(), 2, [0, 1, 2, 3], margin=1.0)
+    assert rc == 0
+    assert out[1] == pytest.approx(1.0, rel=1e-6) and out[2] == pytest.approx(1.0)
+    assert np.abs(g).max() <= 1e-9
+    # eps = 0 on identical tensors: distances are exactly zero, the gradient must stay finite (zero)
+    rc, out, g = emulate_triplet(x, x.copy(), 2, [0, 1, 2, 3], margin=1.0, eps=0.0)
+    assert rc == 0 and np.isfinite(g).all() and np.abs(g).max() == 0.0
+    # a margin so negative that no row is active
+    rc, out, g = emulate_triplet(x, -x, 2, [3, 2, 1, 0], margin=-1e6)
+    assert out[1] == 0.0 and out[2] == 0.0 and np.abs(g).max() == 0.0
+
+
+def desc(shape=(2, 3, 256, 256), grid=4, flags=0, dtype=L.F32):
+    st = (shape[1] * shape[2] * shape[3], shape[2] * shape[3], shape[3], 1)
+    return L.make_desc(dtype, grid, flags, shape, st, st, st, 1.0, 1.0)
+
+
+def call(d, neg, fake=256, real=256, out=256, grad=None, ws=256, ws_bytes=None):
+    lib = L.load()
+    n = (ctypes.c_int32 * len(neg))(*neg) if neg is not None else None
+    nb = lib.tfcfft_triplet_workspace_bytes() if ws_bytes is None else ws_bytes
+    return lib.tfcfft_patch_triplet(ctypes.byref(d), fake, real, n, 1.0, 1e-6, out, grad, ws, nb, None)
+
+
+def test_c_entry_point_rejects_bad_arguments_without_touching_the_gpu():
+    # every call below fails in host-side validation (fake pointers are never dereferenced)
+    assert L.load().tfcfft_triplet_workspace_bytes() >= 256
+    ok16 = list(range(16))
+    assert call(desc(shape=(2, 3, 256, 128)), ok16) == -4        # not square
+    assert call(desc(grid=3), list(range(9))) == -4               # unsupported grid
+    assert call(desc(), ok16[:15] + [16]) == -4                   # negative index out of range
+    assert call(desc(), None) == -1                               # no negatives
+    assert call(desc(flags=L.CHANNELS_RGB), ok16) == -7           # FFT-loss flags do not apply
+    assert call(desc(), ok16, fake=None) == -1
+    assert call(desc(), ok16, fake=260) == -6                     # base not aligned to 4 elements
+    assert call(desc(), ok16, ws=None) == -8
+    assert call(desc(), ok16, ws_bytes=128) == -8
+    assert call(desc(dtype=L.U8), ok16, grad=256) == -9           # no gradient for integer inputs
+    d = desc()
+    d.n = 0
+    assert call(d, ok16) == -10
+
+
+def test_python_layer_validates_negatives_and_device():
+    x = torch.zeros(1, 3, 64, 64)
+    with pytest.raises(RuntimeError):
+        tfc.patch_triplet_loss(x, x, [0] * 16, grid=4)            # CPU tensors: no fallback
+    with pytest.raises(TypeError):
+        tfc.compat.patch_triplet([x] * 3, [x] * 3)

@@ -1,0 +1,176 @@
+"""GPU parity tests of the patch triplet loss: the CUDA kernel, through the C ABI / Python surface,
+against the golden vectors produced by the reference's own lines, against the fp64 oracle, and through
+size-independent properties at full batch size.  Tolerances: loss rel <= 1e-4, gradient L2-rel <= 1e-3."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import tfc_gan_b200 as tfc
+from inputs import make_pair
+from oracle import triplet as otri
+from util import l2rel
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "golden_triplet.json")))
+ARR = np.load(os.path.join(HERE, "golden", "golden_triplet.npz"))
+LOSS_TOL, GRAD_TOL = 1e-4, 1e-3
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
+def test_matches_reference_golden(case):
+    fake, real = make_pair(case["kind"], case["seed"], (case["n"], 3, 256, 256), "float32")
+    f = cu(fake).requires_grad_(True)
+    loss = tfc.patch_triplet_loss(f, cu(real), case["negatives"], grid=case["grid"])
+    loss.backward()
+    g = f.grad.double().cpu().numpy()
+    assert float(loss) == pytest.approx(case["loss"], rel=LOSS_TOL)
+    assert np.sqrt((g * g).sum()) == pytest.approx(case["grad_l2"], rel=GRAD_TOL)
+    ref = ARR[case["name"] + "_grad_n0_c1_rows60_70"]
+    assert l2rel(g[0, 1, 60:70, :], ref) <= GRAD_TOL
+
+
+def test_compat_block_replays_the_reference_draws():
+    case = GOLD["cases"][0]
+    fake, real = make_pair(case["kind"], case["seed"], (case["n"], 3, 256, 256), "float32")
+    f, r = cu(fake), cu(real)
+    np.random.seed(case["numpy_seed"])  # the reference script's NumPy stream
+    loss = tfc.compat.patch_triplet(tfc.compat.make_16_patches(f), tfc.compat.make_16_patches(r))
+    assert float(loss) == pytest.approx(case["loss"], rel=LOSS_TOL)
+    case = next(c for c in GOLD["cases"] if c["grid"] == 2)
+    fake, real = make_pair(case["kind"], case["seed"], (case["n"], 3, 256, 256), "float32")
+    f, r = cu(fake), cu(real)
+    quads = [q.contiguous() for q in tfc.compat.make_4_patches(r)]  # the loader hands out separate quadrants
+    np.random.seed(case["numpy_seed"])
+    loss = tfc.compat.patch_triplet(tfc.compat.make_4_patches(f), quads)
+    assert float(loss) == pytest.approx(case["loss"], rel=LOSS_TOL)
+
+
+CASES = [(256, 4, 3, torch.float32), (256, 2, 2, torch.float32), (512, 4, 1, torch.float32),
+         (512, 2, 1, torch.float32), (512, 1, 1, torch.float32), (64, 4, 5, torch.float32), (128, 2, 3, torch.float16),
+         (256, 4, 2, torch.bfloat16)]
+
+
+@pytest.mark.parametrize("side,grid,n,dtype", CASES, ids=[f"{s}-g{g}-n{n}-{str(d).split('.')[-1]}" for s, g, n, d in CASES])
+def test_loss_and_gradient_match_oracle(side, grid, n, dtype):
+    fake, real = make_pair("tanh", 17 + side + grid, (n, 3, side, side), "float32")
+    f, r = cu(fake, dtype), cu(real, dtype)
+    rs = np.random.RandomState(grid * 1000 + side)
+    neg = [int(k) for k in rs.randint(grid * grid, size=grid * grid)]
+    out, g = tfc.patch_triplet_loss_and_grad(f, r, neg, grid=grid, margin=1.0, weight=0.3)
+    wl, l, act, gr = otri.patch_triplet_loss_and_grad(f.double().cpu().numpy(), r.double().cpu().numpy(), neg, grid=grid, weight=0.3)
+    out = out.cpu().numpy()
+    assert out[0] == pytest.approx(wl, rel=LOSS_TOL)
+    assert out[1] == pytest.approx(l, rel=LOSS_TOL)
+    assert out[2] == pytest.approx(act, abs=2e-5)
+    tol = GRAD_TOL if dtype == torch.float32 else (2e-3 if dtype == torch.float16 else 1e-2)  # output rounding of 16-bit gradients
+    assert l2rel(g.double().cpu().numpy(), gr) <= tol
+    assert g.dtype == dtype
+
+
+def test_global_grid_is_the_degenerate_case():
+    # grid = 1: the only possible negative is the positive itself -> every hinge equals the margin, gradient exactly 0
+    fake, real = make_pair("tanh", 19, (2, 3, 256, 256), "float32")
+    out, g = tfc.patch_triplet_loss_and_grad(cu(fake), cu(real), [0], grid=1, margin=1.0)
+    assert float(out[1]) == pytest.approx(1.0, rel=1e-6) and float(out[2]) == 1.0
+    assert float(g.abs().max()) == 0.0
+
+
+def test_single_channel_views_and_odd_batch():
+    fake, real = make_pair("uniform", 5, (3, 3, 256, 256), "float32")
+    big_f, big_r = cu(fake), cu(real)
+    f, r = big_f[:, 1:2, 128:, 128:], big_r[:, 0:1, :128, 128:]  # strided views, one channel, 128 x 128, grid 2
+    neg = [2, 2, 0, 1]
+    out, g = tfc.patch_triplet_loss_and_grad(f, r, neg, grid=2)
+    _, l, _, gr = otri.patch_triplet_loss_and_grad(f.cpu().numpy(), r.cpu().numpy(), neg, grid=2)
+    assert float(out[1]) == pytest.approx(l, rel=LOSS_TOL)
+    assert l2rel(g.cpu().numpy(), gr) <= GRAD_TOL
+
+
+def test_accumulates_into_the_fft_gradient_in_the_same_pass():
+    fake, real = make_pair("tanh", 23, (4, 3, 256, 256), "float32")
+    f, r = cu(fake), cu(real)
+    neg = list(np.random.RandomState(1).randint(16, size=16))
+    _, _, g_fft = tfc.spectral_loss_and_grad(f, r, grid=4, weight=0.01, input_scale=255.0)
+    _, g_tri = tfc.patch_triplet_loss_and_grad(f, r, neg, grid=4)
+    both = g_fft.clone()
+    out, same = tfc.patch_triplet_loss_and_grad(f, r, neg, grid=4, accumulate_into=both)
+    assert same.data_ptr() == both.data_ptr()
+    assert l2rel(both.cpu().numpy(), (g_fft + g_tri).cpu().numpy()) <= 1e-6
+
+
+def test_backward_scales_by_grad_output_and_module_front_end():
+    fake, real = make_pair("uniform", 29, (2, 3, 256, 256), "float32")
+    r = cu(real)
+    crit = tfc.PatchTripletLoss(grid=4, margin=1.0)
+    f1 = cu(fake).requires_grad_(True)
+    np.random.seed(7)
+    (crit(f1, r) * 1.0).backward()
+    neg = crit.last_negatives
+    f2 = cu(fake).requires_grad_(True)
+    (crit(f2, r, negatives=neg) * 655.36).backward()  # weight x GradScaler-like factor
+    assert l2rel(f2.grad.cpu().numpy(), 655.36 * f1.grad.cpu().numpy()) <= 1e-6
+    # half-precision training tensors: gradient comes back in the input dtype
+    f3 = cu(fake, torch.float16).requires_grad_(True)
+    crit(f3, r.half(), negatives=neg).backward()
+    assert f3.grad.dtype == torch.float16 and l2rel(f3.grad.float().cpu().numpy(), f1.grad.cpu().numpy()) <= 5e-3
+
+
+@pytest.mark.parametrize("grid", [4, 2])
+def test_run_to_run_bit_stable(grid):
+    fake, real = make_pair("uniform", 31, (32, 3, 256, 256), "float32")
+    f, r = cu(fake), cu(real)
+    neg = list(np.random.RandomState(grid).randint(grid * grid, size=grid * grid))
+    outs, grads = [], []
+    for _ in range(3):
+        o, g = tfc.patch_triplet_loss_and_grad(f, r, neg, grid=grid)
+        outs.append(o.cpu().numpy().tobytes())
+        grads.append(g.cpu().numpy().tobytes())
+    assert outs[0] == outs[1] == outs[2]
+    assert grads[0] == grads[1] == grads[2]
+
+
+def test_full_size_properties():
+    g = torch.Generator(device="cuda").manual_seed(3)
+    f = torch.empty(256, 3, 256, 256, device="cuda").uniform_(-1, 1, generator=g)
+    r = torch.empty(256, 3, 256, 256, device="cuda").uniform_(-1, 1, generator=g)
+    ident = list(range(16))
+    # a patch that draws itself as the negative: d_ap == d_an for every row -> loss == margin, gradient == 0
+    out, grad = tfc.patch_triplet_loss_and_grad(f, r, ident, grid=4, margin=0.75)
+    assert float(out[1]) == pytest.approx(0.75, rel=1e-6) and float(out[2]) == 1.0
+    assert float(grad.abs().max()) == 0.0
+    # linear in weight; permuting the batch leaves the loss unchanged (mean over samples)
+    neg = list(np.random.RandomState(11).randint(16, size=16))
+    o1, g1 = tfc.patch_triplet_loss_and_grad(f, r, neg, grid=4, weight=1.0)
+    o2, g2 = tfc.patch_triplet_loss_and_grad(f, r, neg, grid=4, weight=4.0)
+    assert float(o2[0]) == pytest.approx(4.0 * float(o1[0]), rel=1e-6)
+    assert torch.allclose(g2, 4.0 * g1, rtol=1e-6, atol=0)
+    perm = torch.randperm(256, device="cuda", generator=g)
+    o3, g3 = tfc.patch_triplet_loss_and_grad(f[perm].contiguous(), r[perm].contiguous(), neg, grid=4)
+    assert float(o3[1]) == pytest.approx(float(o1[1]), rel=1e-5)
+    assert torch.equal(g3, g1[perm])
+    # against torch's own op on the GPU for one patch (anchor = fake patch 5, negative = real patch neg[5])
+    crit = torch.nn.TripletMarginLoss(margin=1.0, p=2)
+    t = lambda x, i: x[:, :, (i // 4) * 64:(i // 4 + 1) * 64, (i % 4) * 64:(i % 4 + 1) * 64]
+    ref = sum(crit(t(f, i), t(r, i), t(r, neg[i])) for i in range(16)) / 16
+    assert float(o1[1]) == pytest.approx(float(ref), rel=1e-5)
+
+
+def test_errors_raise():
+    f = torch.zeros(2, 3, 256, 256, device="cuda")
+    with pytest.raises(ValueError):
+        tfc.patch_triplet_loss(f, f, [0] * 15, grid=4)
+    with pytest.raises(ValueError):
+        tfc.patch_triplet_loss(f, f, [16] + [0] * 15, grid=4)
+    with pytest.raises(RuntimeError):
+        tfc.patch_triplet_loss(f[:, :, :, :128], f[:, :, :, :128], [0] * 16, grid=4)  # not square

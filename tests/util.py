@@ -89,3 +89,21 @@ def l2rel(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def emulate_triplet(fake: np.ndarray, real: np.ndarray, grid: int, negatives, margin=1.0, eps=1e-6, weight=1.0, grad=True,
+                    accumulate_into=None, dtype_code=None):
+    """CPU twin of tfcfft_patch_triplet (libtfcfft_emu.so).  Returns (rc, out[4], grad)."""
+    lib = emu_lib()
+    lib.tfcfft_emulate_triplet.restype = ctypes.c_int
+    lib.tfcfft_emulate_triplet.argtypes = [ctypes.POINTER(L.Desc), ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32),
+                                           ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
+    code = dtype_code if dtype_code is not None else NP_DTYPES[str(fake.dtype)]
+    out = np.zeros(4, np.float32)
+    g = accumulate_into if accumulate_into is not None else (np.zeros_like(fake) if grad else None)
+    flags = L.GRAD_ACCUMULATE if accumulate_into is not None else 0
+    d = L.make_desc(code, grid, flags, fake.shape, _strides(fake), _strides(real), _strides(g) if g is not None else None, weight, 1.0)
+    neg = (ctypes.c_int32 * len(negatives))(*[int(k) for k in negatives])
+    rc = lib.tfcfft_emulate_triplet(ctypes.byref(d), fake.ctypes.data, real.ctypes.data, neg, margin, eps, out.ctypes.data,
+                                    g.ctypes.data if g is not None else None)
+    return rc, out, g

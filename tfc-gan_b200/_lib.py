@@ -24,6 +24,7 @@ PATCH_SUM = 1 << 3
 LOG_MAGNITUDE = 1 << 4
 FULL_SPECTRUM = 1 << 5
 QUANTIZE_U8 = 1 << 6
+GRAD_ACCUMULATE = 1 << 8
 USE_PAIR = 1 << 28
 USE_LINE = 1 << 29
 FORCE_GENERIC = 1 << 30
@@ -39,6 +40,8 @@ EXPORTS = (
     "tfcfft_loss",
     "tfcfft_spectra",
     "tfcfft_spectra_bwd",
+    "tfcfft_triplet_workspace_bytes",
+    "tfcfft_patch_triplet",
     "tfcfft_grad_scale",
     "tfcfft_debug_trace",
     "tfcfft_launch_count",
@@ -101,6 +104,11 @@ def bind(lib):
     lib.tfcfft_spectra.argtypes = [dp, vp, vp, f32p, f32p, f32p, f32p, ctypes.c_int, vp, ctypes.c_size_t, vp]
     lib.tfcfft_spectra_bwd.restype = ctypes.c_int
     lib.tfcfft_spectra_bwd.argtypes = [dp, vp, f32p, f32p, vp, ctypes.c_int, vp, ctypes.c_size_t, vp]
+    lib.tfcfft_triplet_workspace_bytes.restype = ctypes.c_size_t
+    lib.tfcfft_triplet_workspace_bytes.argtypes = []
+    lib.tfcfft_patch_triplet.restype = ctypes.c_int
+    lib.tfcfft_patch_triplet.argtypes = [dp, vp, vp, ctypes.POINTER(ctypes.c_int32), ctypes.c_float, ctypes.c_float, f32p, vp,
+                                         vp, ctypes.c_size_t, vp]
     lib.tfcfft_grad_scale.restype = ctypes.c_int
     lib.tfcfft_grad_scale.argtypes = [vp, vp, ctypes.c_int32, ctypes.c_int64, f32p, ctypes.c_float, vp]
     lib.tfcfft_debug_trace.restype = None

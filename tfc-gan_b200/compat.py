@@ -17,7 +17,9 @@ from __future__ import annotations
 
 import torch
 
-from .functional import SpectralConfig, spectral_components, spectral_loss, spectral_terms_per_image
+import numpy as np
+
+from .functional import SpectralConfig, patch_triplet_loss, spectral_components, spectral_loss, spectral_terms_per_image
 
 _MODE = {"mode": "r1", "input_scale": 255.0}
 
@@ -113,6 +115,28 @@ def patch4_fft_loss(fake_B, B1, B2, B3, B4):
     """The inline 4-patch block of ``TFCGAN_multigpu_patchFFT.py:498-511`` (patch terms averaged)."""
     real = _assemble((B1, B2, B3, B4), 2)
     return spectral_loss(fake_B, real, config=_cfg(2, "mean"))
+
+
+def draw_negatives(patch_num: int):
+    """The reference's negative sampling, call for call: one ``np.random.randint(patch_num, size=1).item()`` per patch,
+    in patch order (``...patchFFT_16P.py:567-582``) -- seed NumPy the same way and the same negatives come out.  A
+    patch may draw itself, exactly as upstream."""
+    return [np.random.randint(patch_num, size=1).item() for _ in range(patch_num)]
+
+
+def patch_triplet(fake_patches, real_patches, negatives=None, margin: float = 1.0):
+    """The inline patch-triplet block of the generator step (``...patchFFT_16P.py:558-583``; 4-patch copies
+    ``TFCGAN_multigpu_patchFFT.py:474-484``): ``1/n sum_i triplet_loss(fake_B_i, B_i, random_patches[k_i])`` with
+    ``triplet_loss = nn.TripletMarginLoss(margin=1.0, p=2)`` (``:75``).  ``fake_patches`` / ``real_patches`` are the 4
+    or 16 row-major patches (views of a common tensor are used in place); ``negatives`` defaults to
+    :func:`draw_negatives`."""
+    n = len(fake_patches)
+    if n not in (4, 16) or len(real_patches) != n:
+        raise TypeError(f"patch_triplet expects 4 or 16 fake and as many real patches, got {n} / {len(real_patches)}")
+    g = 2 if n == 4 else 4
+    if negatives is None:
+        negatives = draw_negatives(n)
+    return patch_triplet_loss(_assemble(tuple(fake_patches), g), _assemble(tuple(real_patches), g), negatives, grid=g, margin=margin)
 
 
 def global_fft_loss(fake_B, real_B):

@@ -221,3 +221,42 @@ extern "C" int tfcfft_emulate_spectra_bwd(const tfcfft_desc* d, const void* x, c
     run_all(prm, g, d->dtype);
     return TFCFFT_OK;
 }
+
+// Host-memory twin of tfcfft_patch_triplet: one serial "lane" per patch row.
+template <typename T>
+static void run_triplet(const TripletParams& tp) {
+    double sum = 0.0, act = 0.0;
+    for (long long row = 0; row < tp.rows; ++row) {
+        float l = 0.f, a = 0.f;
+        const SerialReduce red;
+        switch (tp.p) {
+            case 16: triplet_row<T, 4>(tp, row, 0, 1, red, l, a); break;
+            case 32: triplet_row<T, 8>(tp, row, 0, 1, red, l, a); break;
+            case 64: triplet_row<T, 16>(tp, row, 0, 1, red, l, a); break;
+            case 128: triplet_row<T, 32>(tp, row, 0, 1, red, l, a); break;
+            case 256: triplet_row<T, 64>(tp, row, 0, 1, red, l, a); break;
+            case 512: triplet_row<T, 128>(tp, row, 0, 1, red, l, a); break;
+        }
+        sum += l;
+        act += a;
+    }
+    triplet_outputs(tp, sum, act);
+}
+
+extern "C" int tfcfft_emulate_triplet(const tfcfft_desc* d, const void* fake, const void* real, const int32_t* negatives,
+                                      float margin, float eps, float* out, void* grad_fake) {
+    int rc = validate_triplet(d, negatives);
+    if (rc) return rc;
+    if (!fake || !real || !out) return TFCFFT_ERR_NULL;
+    if ((rc = check_grad_args(d, grad_fake))) return rc;
+    if ((rc = check_alignment(d, fake, real, grad_fake))) return rc;
+    std::vector<char> ws(kTripletWsBytes, 0);
+    const TripletParams tp = make_triplet_params(d, fake, real, negatives, margin, eps, out, grad_fake, ws.data());
+    switch (d->dtype) {
+        case TFCFFT_F32: run_triplet<float>(tp); break;
+        case TFCFFT_F16: run_triplet<__half>(tp); break;
+        case TFCFFT_BF16: run_triplet<__nv_bfloat16>(tp); break;
+        case TFCFFT_U8: run_triplet<uint8_t>(tp); break;
+    }
+    return TFCFFT_OK;
+}

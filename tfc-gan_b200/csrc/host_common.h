@@ -5,6 +5,7 @@
 #include <cstdint>
 
 #include "spectral_core.cuh"
+#include "triplet.cuh"
 
 namespace tfcfft {
 
@@ -169,6 +170,64 @@ inline const char* status_string(int rc) {
         case TFCFFT_ERR_EMPTY: return "tfcfft: empty batch (N == 0)";
         default: return nullptr;
     }
+}
+
+// ---- patch triplet loss ------------------------------------------------------------------------------------
+constexpr int kTripletMaxBlocks = 4096;
+constexpr size_t kTripletWsBytes = kWsHeader + (size_t)kTripletMaxBlocks * 2 * sizeof(float);
+
+// The descriptor is validated like tfcfft_loss's, with these differences: grid in {1, 2, 4}, patch side a
+// multiple of 16 up to 512 (no transform: no power-of-two rule), only TFCFFT_GRAD_ACCUMULATE as a flag.
+inline int validate_triplet(const tfcfft_desc* d, const int32_t* negatives) {
+    if (!d) return TFCFFT_ERR_NULL;
+    if (d->struct_size != sizeof(tfcfft_desc)) return TFCFFT_ERR_STRUCT;
+    if (elem_size(d->dtype) == 0) return TFCFFT_ERR_DTYPE;
+    if (d->n == 0) return TFCFFT_ERR_EMPTY;
+    if (d->n < 0 || d->n > (1 << 24)) return TFCFFT_ERR_SHAPE;
+    if (d->c < 1 || d->c > 4) return TFCFFT_ERR_SHAPE;
+    if (d->h != d->w || d->h <= 0) return TFCFFT_ERR_SHAPE;
+    if (d->grid != 1 && d->grid != 2 && d->grid != 4) return TFCFFT_ERR_SHAPE;
+    if (d->h % d->grid) return TFCFFT_ERR_SHAPE;
+    const long long p = d->h / d->grid;
+    if (p != 16 && p != 32 && p != 64 && p != 128 && p != 256 && p != 512) return TFCFFT_ERR_SHAPE;
+    if (d->flags & ~TFCFFT_GRAD_ACCUMULATE) return TFCFFT_ERR_FLAGS;
+    if (!negatives) return TFCFFT_ERR_NULL;
+    for (int i = 0; i < d->grid * d->grid; ++i)
+        if (negatives[i] < 0 || negatives[i] >= d->grid * d->grid) return TFCFFT_ERR_SHAPE;
+    for (int t = 0; t < 2; ++t) {
+        const int64_t* st = t ? d->real_stride : d->fake_stride;
+        if (st[3] != 1) return TFCFFT_ERR_STRIDE;
+        for (int i = 0; i < 3; ++i)
+            if (st[i] % 4 != 0 || st[i] < 0) return TFCFFT_ERR_STRIDE;
+    }
+    return TFCFFT_OK;
+}
+
+inline TripletParams make_triplet_params(const tfcfft_desc* d, const void* fake, const void* real, const int32_t* negatives,
+                                         float margin, float eps, float* out, void* grad, void* ws) {
+    TripletParams t{};
+    t.fake = fake;
+    t.real = real;
+    t.grad = grad;
+    for (int i = 0; i < 4; ++i) {
+        t.fs[i] = d->fake_stride[i];
+        t.rs[i] = d->real_stride[i];
+        t.gs[i] = grad ? d->grad_stride[i] : 0;
+    }
+    t.n = (int)d->n; t.c = (int)d->c; t.h = (int)d->h;
+    t.grid = d->grid;
+    t.p = (int)(d->h / d->grid);
+    for (int i = 0; i < 16; ++i) t.neg[i] = i < d->grid * d->grid ? negatives[i] : 0;
+    t.margin = margin;
+    t.eps = eps;
+    t.weight = d->weight;
+    t.rows = (long long)d->n * d->c * d->h * d->grid;
+    t.coef = (float)((double)d->weight / (double)t.rows);
+    t.accumulate = (d->flags & TFCFFT_GRAD_ACCUMULATE) ? 1 : 0;
+    t.counter = reinterpret_cast<unsigned*>(ws);
+    t.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsHeader);
+    t.out = out;
+    return t;
 }
 
 }  // namespace tfcfft

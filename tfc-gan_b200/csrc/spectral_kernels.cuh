@@ -14,6 +14,7 @@
 #include "pair_tile.cuh"
 #include "sub_tile.cuh"
 #include "line_tile.cuh"
+#include "triplet.cuh"
 #include "spectral_core.cuh"
 
 namespace tfcfft {
@@ -410,6 +411,67 @@ __global__ void __launch_bounds__(256) grad_scale_kernel(T* __restrict__ dst, co
     }
     for (long long i = nvec * V + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride)
         dst[i] = (T)((float)src[i] * sc);
+}
+
+// ---- patch triplet loss (triplet.cuh): one lane group per patch row, persistent warps ------------------------
+struct ShflReduce {
+    int lpr;
+    __device__ __forceinline__ float operator()(float v) const {
+        for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+};
+template <typename T, int K>
+__global__ void __launch_bounds__(kTripletThreads) triplet_kernel(const __grid_constant__ TripletParams tp) {
+    const int lpr = tp.p / (4 * K), gpw = 32 / lpr;  // lanes per row, rows per warp pass (rows % gpw == 0 always)
+    const int lane = threadIdx.x & 31, sub = lane / lpr, l = lane - sub * lpr;
+    const long long nwarps = (long long)gridDim.x * (kTripletThreads / 32);
+    const long long warp = (long long)blockIdx.x * (kTripletThreads / 32) + (threadIdx.x >> 5);
+    const ShflReduce red{lpr};
+    float loss = 0.f, act = 0.f;
+    for (long long base = warp * gpw; base < tp.rows; base += nwarps * gpw)
+        triplet_row<T, K>(tp, base + sub, l, lpr, red, loss, act);
+    block_sum2(loss, act);
+    if (threadIdx.x == 0) {
+        tp.partials[2 * blockIdx.x] = loss;
+        tp.partials[2 * blockIdx.x + 1] = act;
+    }
+    // last CTA: fixed-order sum of the per-CTA partials in double, ticket left at zero
+    __shared__ bool last;
+    __shared__ double dred[2][32];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(tp.counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+        a += (double)__ldcg(tp.partials + 2 * i);
+        b += (double)__ldcg(tp.partials + 2 * i + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+        dred[0][threadIdx.x >> 5] = a;
+        dred[1][threadIdx.x >> 5] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = 0.0;
+        b = 0.0;
+        for (int w = 0; w < kTripletThreads / 32; ++w) {
+            a += dred[0][w];
+            b += dred[1][w];
+        }
+        triplet_outputs(tp, a, b);
+        *tp.counter = 0u;
+    }
 }
 
 }  // namespace tfcfft

@@ -201,6 +201,26 @@ int launch_t(const Params& prm, bool split, bool luma3, int dtype, cudaStream_t 
     return TFCFFT_ERR_DTYPE;
 }
 
+template <typename T>
+int launch_triplet(const TripletParams& tp, cudaStream_t st) {
+    const int K = tp.p > 128 ? tp.p / 128 : 1;
+    const int gpw = 32 / (tp.p / (4 * K));
+    const long long warps_needed = (tp.rows + gpw - 1) / gpw;
+    long long blocks = (warps_needed + kTripletThreads / 32 - 1) / (kTripletThreads / 32);
+    const long long cap = (long long)device_info().sms * 8;  // 8 x 256 threads per SM: persistent warps
+    if (blocks > cap) blocks = cap;
+    if (blocks > kTripletMaxBlocks) blocks = kTripletMaxBlocks;
+    switch (K) {
+        case 1: triplet_kernel<T, 1><<<(int)blocks, kTripletThreads, 0, st>>>(tp); break;
+        case 2: triplet_kernel<T, 2><<<(int)blocks, kTripletThreads, 0, st>>>(tp); break;
+        case 4: triplet_kernel<T, 4><<<(int)blocks, kTripletThreads, 0, st>>>(tp); break;
+        default: return TFCFFT_ERR_SHAPE;
+    }
+    g_launches++;
+    TFC_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -296,6 +316,27 @@ int tfcfft_loss(const tfcfft_desc* d, const void* fake, const void* real, float*
     prm.trace = g_trace.load();
     cudaStream_t st = (cudaStream_t)stream;
     return dispatch(prm, g, d->dtype, st);
+}
+
+size_t tfcfft_triplet_workspace_bytes(void) { return kTripletWsBytes; }
+
+int tfcfft_patch_triplet(const tfcfft_desc* d, const void* fake, const void* real, const int32_t* negatives, float margin,
+                         float eps, float* out, void* grad_fake, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = validate_triplet(d, negatives);
+    if (rc) return rc;
+    if (!fake || !real || !out) return TFCFFT_ERR_NULL;
+    if ((rc = check_grad_args(d, grad_fake))) return rc;
+    if ((rc = check_alignment(d, fake, real, grad_fake))) return rc;
+    if (!workspace || workspace_bytes < kTripletWsBytes || ((uintptr_t)workspace & 255)) return TFCFFT_ERR_WORKSPACE;
+    const TripletParams tp = make_triplet_params(d, fake, real, negatives, margin, eps, out, grad_fake, workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (d->dtype) {
+        case TFCFFT_F32: return launch_triplet<float>(tp, st);
+        case TFCFFT_F16: return launch_triplet<__half>(tp, st);
+        case TFCFFT_BF16: return launch_triplet<__nv_bfloat16>(tp, st);
+        case TFCFFT_U8: return launch_triplet<uint8_t>(tp, st);
+    }
+    return TFCFFT_ERR_DTYPE;
 }
 
 int tfcfft_grad_scale(void* dst, const void* src, int32_t dtype, int64_t numel, const float* dev_scale, float host_scale,

@@ -297,6 +297,86 @@ def spectral_components(x, *, channels: str = "luma", input_scale: float = 1.0, 
     return _SpectraFn.apply(x, cfg, bool(fftshift))
 
 
+# ---- patch triplet loss ----------------------------------------------------------------------
+def _check_negatives(negatives, grid: int):
+    neg = [int(k) for k in negatives]
+    if len(neg) != grid * grid or any(k < 0 or k >= grid * grid for k in neg):
+        raise ValueError(f"negatives must hold {grid * grid} patch indices in [0, {grid * grid}), got {neg}")
+    return neg
+
+
+def _launch_triplet(fake, real, grid, negatives, margin, eps, weight, want_grad, accumulate_into=None):
+    lib = _lib.load()
+    dev = fake.device
+    neg = _check_negatives(negatives, grid)
+    with torch.cuda.device(dev):
+        stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        flags = 0
+        if accumulate_into is not None:
+            if accumulate_into.shape != fake.shape or accumulate_into.dtype != fake.dtype or not _acceptable(accumulate_into):
+                raise ValueError("accumulate_into must match fake in shape / dtype and have 16-byte friendly strides")
+            grad, flags = accumulate_into, _lib.GRAD_ACCUMULATE
+        else:
+            grad = torch.empty(fake.shape, dtype=fake.dtype, device=dev) if want_grad else None
+        desc = _lib.make_desc(_DTYPES[fake.dtype], grid, flags, fake.shape, fake.stride(), real.stride(),
+                              grad.stride() if grad is not None else None, weight, 1.0)
+        ws = _workspace(dev, stream_ptr, lib.tfcfft_triplet_workspace_bytes())
+        rc = lib.tfcfft_patch_triplet(ctypes.byref(desc), fake.data_ptr(), real.data_ptr(), (ctypes.c_int32 * len(neg))(*neg),
+                                      float(margin), float(eps), out.data_ptr(), grad.data_ptr() if grad is not None else None,
+                                      ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream_ptr))
+        if rc > 0:
+            _WORKSPACES.pop((dev.index, stream_ptr), None)
+        _lib.check(rc, "tfcfft_patch_triplet")
+    return out, grad
+
+
+class _PatchTripletFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fake, real, grid, negatives, margin, eps, weight):
+        fake_p, real_p = _prep(fake.detach(), real.detach())
+        want_grad = ctx.needs_input_grad[0] and fake_p.dtype != torch.uint8
+        out, grad = _launch_triplet(fake_p, real_p, grid, negatives, margin, eps, weight, want_grad)
+        ctx.has_grad, ctx.in_dtype = want_grad, fake.dtype
+        if want_grad:
+            ctx.save_for_backward(grad)
+        return out[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_loss):
+        if not ctx.has_grad:
+            return (None,) * 7
+        (unit,) = ctx.saved_tensors
+        lib = _lib.load()
+        dev = unit.device
+        with torch.cuda.device(dev):
+            stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+            go = grad_loss.detach().to(device=dev, dtype=torch.float32).contiguous()
+            res = torch.empty_like(unit)
+            _lib.check(lib.tfcfft_grad_scale(res.data_ptr(), unit.data_ptr(), _DTYPES[unit.dtype], unit.numel(), go.data_ptr(),
+                                             1.0, ctypes.c_void_p(stream_ptr)), "tfcfft_grad_scale")
+        if res.dtype != ctx.in_dtype:
+            res = res.to(ctx.in_dtype)
+        return (res,) + (None,) * 6
+
+
+def patch_triplet_loss(fake, real, negatives, *, grid: int = 4, margin: float = 1.0, eps: float = 1e-6, weight: float = 1.0):
+    """``1/g^2 * sum_i TripletMarginLoss(margin, p=2)(fake_patch_i, real_patch_i, real_patch_{negatives[i]})`` for the
+    row-major ``g x g`` patches of ``fake`` / ``real`` ``[N,C,H,H]`` (``TFC-GAN-FFT/TFCGAN_multigpu_patchFFT_16P.py:
+    558-583``), forward and backward in one streaming pass.  0-dim fp32 CUDA tensor; gradient flows to ``fake``."""
+    return _PatchTripletFn.apply(fake, real, int(grid), tuple(int(k) for k in negatives), float(margin), float(eps), float(weight))
+
+
+@torch.no_grad()
+def patch_triplet_loss_and_grad(fake, real, negatives, *, grid: int = 4, margin: float = 1.0, eps: float = 1e-6,
+                                weight: float = 1.0, accumulate_into=None):
+    """The fused pass without autograd: ``(out[4], grad)``; ``out`` = (weight*loss, loss, active-row fraction, 0).
+    With ``accumulate_into`` the gradient is ADDED to that tensor (e.g. the FFT loss gradient) in the same pass."""
+    fake_p, real_p = _prep(fake, real)
+    return _launch_triplet(fake_p, real_p, int(grid), negatives, margin, eps, weight, True, accumulate_into)
+
+
 def launch_count() -> int:
     """Kernels launched by ``libtfcfft.so`` in this process since the last reset."""
     return int(_lib.load().tfcfft_launch_count())

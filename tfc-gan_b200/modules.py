@@ -6,7 +6,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .functional import SpectralConfig, spectral_loss
+from .functional import SpectralConfig, patch_triplet_loss, spectral_loss
 
 
 class SpectralLoss(nn.Module):
@@ -38,3 +38,27 @@ class SpectralLoss(nn.Module):
         c = self.config
         return (f"grid={c.grid}, channels={c.channels!r}, use_phase={c.use_phase}, distance={c.distance!r}, "
                 f"patch_reduce={c.patch_reduce!r}, weight={c.weight}, input_scale={c.input_scale}")
+
+
+class PatchTripletLoss(nn.Module):
+    """``PatchTripletLoss(grid, margin)(fake, real[, negatives]) -> scalar``: the generator step's patch triplet term
+    (``nn.TripletMarginLoss(margin=1.0, p=2)`` on every patch with a randomly drawn real patch as negative,
+    ``TFC-GAN-FFT/TFCGAN_multigpu_patchFFT_16P.py:75,558-583``) for all ``grid x grid`` patches in one fused
+    forward + backward pass.  ``negatives`` (one patch index per patch) defaults to the reference's NumPy draw."""
+
+    def __init__(self, grid: int = 4, margin: float = 1.0, eps: float = 1e-6, weight: float = 1.0):
+        super().__init__()
+        if grid not in (1, 2, 4):
+            raise ValueError("grid must be 1, 2 or 4")
+        self.grid, self.margin, self.eps, self.weight = grid, margin, eps, weight
+        self.last_negatives = None
+
+    def forward(self, fake: torch.Tensor, real: torch.Tensor, negatives=None) -> torch.Tensor:
+        if negatives is None:
+            from .compat import draw_negatives
+            negatives = draw_negatives(self.grid * self.grid)
+        self.last_negatives = list(negatives)
+        return patch_triplet_loss(fake, real, negatives, grid=self.grid, margin=self.margin, eps=self.eps, weight=self.weight)
+
+    def extra_repr(self) -> str:
+        return f"grid={self.grid}, margin={self.margin}, eps={self.eps}, weight={self.weight}"
