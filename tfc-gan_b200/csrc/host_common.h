@@ -217,6 +217,10 @@ inline TripletParams make_triplet_params(const tfcfft_desc* d, const void* fake,
     t.n = (int)d->n; t.c = (int)d->c; t.h = (int)d->h;
     t.grid = d->grid;
     t.p = (int)(d->h / d->grid);
+    auto lg = [](long long v) { int r = 0; while ((1LL << r) < v) ++r; return r; };
+    t.lg_g = lg(d->grid);
+    t.lg_h = lg(d->h);
+    t.lg_p = lg(t.p);
     for (int i = 0; i < 16; ++i) t.neg[i] = i < d->grid * d->grid ? negatives[i] : 0;
     t.margin = margin;
     t.eps = eps;

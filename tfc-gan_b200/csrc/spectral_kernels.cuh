@@ -429,8 +429,18 @@ __global__ void __launch_bounds__(kTripletThreads) triplet_kernel(const __grid_c
     const long long warp = (long long)blockIdx.x * (kTripletThreads / 32) + (threadIdx.x >> 5);
     const ShflReduce red{lpr};
     float loss = 0.f, act = 0.f;
-    for (long long base = warp * gpw; base < tp.rows; base += nwarps * gpw)
-        triplet_row<T, K>(tp, base + sub, l, lpr, red, loss, act);
+    constexpr int R = kTripletRowsInFlight;
+    // a warp owns R * gpw CONSECUTIVE rows per pass (one contiguous window of the tensors is live at a time);
+    // whole warps are in or out of range because rows % gpw == 0
+    for (long long base = warp * gpw * R; base < tp.rows; base += nwarps * gpw * R) {
+        TripletRow<K> tr[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (base + r * gpw < tp.rows) triplet_row_load<T, K>(tp, base + r * gpw + sub, l, lpr, tr[r]);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (base + r * gpw < tp.rows) triplet_row_finish<T, K>(tp, tr[r], l, lpr, red, loss, act);
+    }
     block_sum2(loss, act);
     if (threadIdx.x == 0) {
         tp.partials[2 * blockIdx.x] = loss;

@@ -21,6 +21,7 @@ struct TripletParams {
     void* grad;
     long long fs[4], rs[4], gs[4];
     int n, c, h, grid, p;
+    int lg_g, lg_h, lg_p;  // grid, h and p are powers of two: row decoding is shifts and masks
     int neg[16];       // negative patch index for each patch (row-major patch order)
     float margin, eps;
     float weight;      // out[0] = weight * mean hinge
@@ -33,6 +34,7 @@ struct TripletParams {
 };
 
 constexpr int kTripletThreads = 256;
+constexpr int kTripletRowsInFlight = 1;  // rows per lane group per pass (device kernel)
 
 // product rounded on its own (never contracted into an FMA): a patch that draws itself as its negative must get a
 // gradient of exactly zero, like the reference, and `ca * dp - cn * dn` only cancels exactly with two rounded products
@@ -45,54 +47,73 @@ TFC_HD float mul_rn(float a, float b) {
 #endif
 }
 
+TFC_HD float inv_sqrt(float x) {
+#ifdef __CUDA_ARCH__
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+
 struct SerialReduce {
     TFC_HD float operator()(float v) const { return v; }
 };
 
-// One patch row by a group of `lpr` lanes, K float4 per lane (lane `l` takes float4 l, l + lpr, ...).
-template <typename T, int K, class Reduce>
-TFC_HD void triplet_row(const TripletParams& tp, long long row, int l, int lpr, const Reduce& reduce, float& loss_acc,
-                        float& act_acc) {
+// One patch row by a group of `lpr` lanes, K float4 per lane (lane `l` takes float4 l, l + lpr, ...), in two steps so
+// that a warp can have the loads of several rows in flight before it reduces the first.
+template <int K>
+struct TripletRow {
+    float dp[K][4], dn[K][4];  // anchor - positive + eps, anchor - negative + eps
+    long long goff;            // element offset of the row segment in grad
+};
+
+template <typename T, int K>
+TFC_HD void triplet_row_load(const TripletParams& tp, long long row, int l, int lpr, TripletRow<K>& tr) {
     const int g = tp.grid, P = tp.p;
-    const int px = (int)(row % g);
-    long long t = row / g;
-    const int y = (int)(t % tp.h);
-    t /= tp.h;
-    const int c = (int)(t % tp.c), n = (int)(t / tp.c);
-    const int py = y / P, yin = y - py * P;
-    const int k = tp.neg[py * g + px], ky = k / g, kx = k - ky * g;
+    const int px = (int)(row & (g - 1));
+    const int y = (int)((row >> tp.lg_g) & (tp.h - 1));
+    const unsigned nc = (unsigned)(row >> (tp.lg_g + tp.lg_h));  // n * C + c < 2^27
+    const int n = (int)(nc / (unsigned)tp.c), c = (int)(nc - (unsigned)n * (unsigned)tp.c);
+    const int py = y >> tp.lg_p, yin = y & (P - 1);
+    const int k = tp.neg[(py << tp.lg_g) + px], ky = k >> tp.lg_g, kx = k & (g - 1);
     const T* fp = static_cast<const T*>(tp.fake) + n * tp.fs[0] + c * tp.fs[1] + (long long)y * tp.fs[2] + px * P;
     const T* pp = static_cast<const T*>(tp.real) + n * tp.rs[0] + c * tp.rs[1] + (long long)y * tp.rs[2] + px * P;
     const T* qp = static_cast<const T*>(tp.real) + n * tp.rs[0] + c * tp.rs[1] + (long long)(ky * P + yin) * tp.rs[2] + kx * P;
-    float dp[K][4], dn[K][4];
-    {
-        float f[K][4];
+    tr.goff = n * tp.gs[0] + c * tp.gs[1] + (long long)y * tp.gs[2] + px * P;
+    float f[K][4];
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const int x = 4 * (l + j * lpr);
-            IO<T>::load4(fp + x, f[j]);
-            IO<T>::load4(pp + x, dp[j]);
-            IO<T>::load4(qp + x, dn[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < K; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                dp[j][i] = (f[j][i] - dp[j][i]) + tp.eps;
-                dn[j][i] = (f[j][i] - dn[j][i]) + tp.eps;
-            }
+    for (int j = 0; j < K; ++j) {
+        const int x = 4 * (l + j * lpr);
+        IO<T>::load4(fp + x, f[j]);
+        IO<T>::load4(pp + x, tr.dp[j]);
+        IO<T>::load4(qp + x, tr.dn[j]);
     }
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            tr.dp[j][i] = (f[j][i] - tr.dp[j][i]) + tp.eps;
+            tr.dn[j][i] = (f[j][i] - tr.dn[j][i]) + tp.eps;
+        }
+}
+
+template <typename T, int K, class Reduce>
+TFC_HD void triplet_row_finish(const TripletParams& tp, const TripletRow<K>& tr, int l, int lpr, const Reduce& reduce,
+                               float& loss_acc, float& act_acc) {
     float sap = 0.f, san = 0.f;
 #pragma unroll
     for (int j = 0; j < K; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            sap = fmaf(dp[j][i], dp[j][i], sap);
-            san = fmaf(dn[j][i], dn[j][i], san);
+            sap = fmaf(tr.dp[j][i], tr.dp[j][i], sap);
+            san = fmaf(tr.dn[j][i], tr.dn[j][i], san);
         }
     sap = reduce(sap);
     san = reduce(san);
-    const float dap = sqrtf(sap), dan = sqrtf(san);
+    // one reciprocal square root per distance (MUFU) instead of sqrt + divide: every lane of the group repeats this
+    // scalar tail, and IEEE sqrt / divide sequences made it a third of the kernel's instructions
+    const float iap = sap > 0.f ? inv_sqrt(sap) : 0.f, ian = san > 0.f ? inv_sqrt(san) : 0.f;
+    const float dap = sap * iap, dan = san * ian;
     const float hinge = tp.margin + dap - dan;
     const bool active = hinge >= 0.f;  // torch clamp_min backward passes the gradient where input >= min
     if (l == 0) {
@@ -100,15 +121,15 @@ TFC_HD void triplet_row(const TripletParams& tp, long long row, int l, int lpr, 
         act_acc += active ? 1.f : 0.f;
     }
     if (tp.grad != nullptr) {
-        const float ca = (active && dap > 0.f) ? tp.coef / dap : 0.f;
-        const float cn = (active && dan > 0.f) ? tp.coef / dan : 0.f;
-        T* gp = static_cast<T*>(tp.grad) + n * tp.gs[0] + c * tp.gs[1] + (long long)y * tp.gs[2] + px * P;
+        const float ca = active ? tp.coef * iap : 0.f;
+        const float cn = active ? tp.coef * ian : 0.f;
+        T* gp = static_cast<T*>(tp.grad) + tr.goff;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const int x = 4 * (l + j * lpr);
             float v[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = mul_rn(ca, dp[j][i]) - mul_rn(cn, dn[j][i]);
+            for (int i = 0; i < 4; ++i) v[i] = mul_rn(ca, tr.dp[j][i]) - mul_rn(cn, tr.dn[j][i]);
             if (tp.accumulate) {
                 float old[4];
                 IO<T>::load4(gp + x, old);
@@ -118,6 +139,14 @@ TFC_HD void triplet_row(const TripletParams& tp, long long row, int l, int lpr, 
             IO<T>::store4(gp + x, v);
         }
     }
+}
+
+template <typename T, int K, class Reduce>
+TFC_HD void triplet_row(const TripletParams& tp, long long row, int l, int lpr, const Reduce& reduce, float& loss_acc,
+                        float& act_acc) {
+    TripletRow<K> tr;
+    triplet_row_load<T, K>(tp, row, l, lpr, tr);
+    triplet_row_finish<T, K>(tp, tr, l, lpr, reduce, loss_acc, act_acc);
 }
 
 TFC_HD void triplet_outputs(const TripletParams& tp, double sum, double act) {
