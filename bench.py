@@ -249,7 +249,9 @@ def time_kernel_path(tfc, torch, wl, steps, warmup, barrier):
 
 def time_triplet(tfc, torch, batch, side, grid, steps, warmup):
     """Device-timed fused patch-triplet loss + gradient (the first 'next' row of the scope table) on resident inputs
-    rotating over a pool larger than L2.  Algorithmic bytes: anchor + positive + negative reads + gradient write."""
+    rotating over a pool larger than L2.  Algorithmic bytes: fake read + real read + gradient write (the negative
+    patch is another tile of the same real image: an L2 hit by construction, confirmed by ncu --
+    profiles/r01_ncu_patch_triplet_summary.txt)."""
     dev = torch.device("cuda", torch.cuda.current_device())
     per_batch = 2 * batch * 3 * side * side * 4
     pool_n = max(2, -(-3 * L2_BYTES // per_batch))
@@ -270,7 +272,7 @@ def time_triplet(tfc, torch, batch, side, grid, steps, warmup):
     assert torch.isfinite(sink[0][0]).item()
     secs = e0.elapsed_time(e1) / 1e3
     ips = batch * steps / secs
-    return ips, ips * 4 * 3 * side * side * 4 / 1e9
+    return ips, ips * 3 * 3 * side * side * 4 / 1e9
 
 
 def time_e2e(tfc, torch, wl, steps, warmup, barrier, dist):
@@ -408,7 +410,7 @@ def run_ours(args, wl):
                          "roofline_frac": ips * bytes_per_image(w["side"], w.get("dtype", "f32")) / 1e9 / peak}
         ips, gbs = time_triplet(tfc, torch, 256, 256, 4, max(10, args.steps // 4), 3)
         var["patch16-triplet-256-b256"] = {"value": ips, "unit": UNIT, "roofline_frac": gbs / peak,
-                                           "note": "fused TripletMarginLoss fwd+bwd on 16 patches; 4 tensor passes per image"}
+                                           "note": "fused TripletMarginLoss fwd+bwd on 16 patches; 3 tensor passes per image"}
         line["variants"] = var
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_arm(wl, 12.0)

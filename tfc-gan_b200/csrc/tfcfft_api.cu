@@ -203,7 +203,9 @@ int launch_t(const Params& prm, bool split, bool luma3, int dtype, cudaStream_t 
 
 template <typename T>
 int launch_triplet(const TripletParams& tp, cudaStream_t st) {
-    const int K = tp.p > 128 ? tp.p / 128 : 1;
+    // float4 per lane: 8 lanes per patch row up to 128-pixel rows (the per-row scalar work -- row decoding, shuffles,
+    // rsqrt -- is repeated by every lane of the group; ncu: 80 % issue-slot utilisation with 16 lanes x 1 float4)
+    const int K = tp.p >= 128 ? 4 : tp.p >= 64 ? 2 : 1;
     const int gpw = 32 / (tp.p / (4 * K));
     const long long warps_needed = (tp.rows + gpw - 1) / gpw;
     long long blocks = (warps_needed + kTripletThreads / 32 - 1) / (kTripletThreads / 32);
