@@ -275,6 +275,29 @@ def time_triplet(tfc, torch, batch, side, grid, steps, warmup):
     return ips, ips * 3 * 3 * side * side * 4 / 1e9
 
 
+def time_temperature(tfc, torch, batch, side, steps, warmup):
+    """Device-timed fused temperature triplet loss + gradient (second 'next' row).  Only the red channel takes part:
+    algorithmic bytes = fake.R + positive.R + negative.R reads + grad.R write = 4 planes per image."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    pool_n = max(2, -(-3 * L2_BYTES // (3 * batch * 3 * side * side * 4)))
+    g = torch.Generator(device=dev).manual_seed(777)
+    pool = [tuple(torch.empty(batch, 3, side, side, device=dev).uniform_(0, 1, generator=g) for _ in range(3)) for _ in range(pool_n)]
+    acc = torch.zeros(batch, 3, side, side, device=dev)
+    sink = None
+    for i in range(warmup):
+        sink = tfc.temperature_triplet_loss_and_grad(*pool[i % pool_n], weight=10.0, accumulate_into=acc)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        sink = tfc.temperature_triplet_loss_and_grad(*pool[(warmup + i) % pool_n], weight=10.0, accumulate_into=acc)
+    e1.record()
+    torch.cuda.synchronize()
+    assert torch.isfinite(sink[0][0]).item()
+    ips = batch * steps / (e0.elapsed_time(e1) / 1e3)
+    return ips, ips * 5 * side * side * 4 / 1e9  # accumulate mode also reads the old gradient plane
+
+
 def time_e2e(tfc, torch, wl, steps, warmup, barrier, dist):
     """Public API (nn.Module + backward) with pinned-host inputs copied in and the loss read back
     every step; H2D of step i+1 overlaps the kernels of step i on a second stream."""
@@ -411,6 +434,10 @@ def run_ours(args, wl):
         ips, gbs = time_triplet(tfc, torch, 256, 256, 4, max(10, args.steps // 4), 3)
         var["patch16-triplet-256-b256"] = {"value": ips, "unit": UNIT, "roofline_frac": gbs / peak,
                                            "note": "fused TripletMarginLoss fwd+bwd on 16 patches; 3 tensor passes per image"}
+        ips, gbs = time_temperature(tfc, torch, 256, 256, max(10, args.steps // 4), 3)
+        var["temperature-triplet-256-b256"] = {"value": ips, "unit": UNIT, "roofline_frac": gbs / peak,
+                                               "note": "fused temperature-LUT triplet fwd+bwd (red channel only, accumulating into an "
+                                                       "existing gradient): 5 single-channel planes per image"}
         line["variants"] = var
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_arm(wl, 12.0)

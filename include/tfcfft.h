@@ -50,6 +50,8 @@ enum tfcfft_dtype { TFCFFT_F32 = 0, TFCFFT_F16 = 1, TFCFFT_BF16 = 2, TFCFFT_U8 =
 #define TFCFFT_QUANTIZE_U8   (1u << 6) /* reference-as-shipped input path: uint8 wrap + integer
                                           luma (patchFFT_16P.py:300); forward only               */
 #define TFCFFT_GRAD_ACCUMULATE (1u << 8) /* tfcfft_patch_triplet only: grad_fake += instead of grad_fake =   */
+#define TFCFFT_TEMPS_POSITIVE (1u << 9) /* tfcfft_temperature_triplet only: `positive` is an fp32 tensor of
+                                           temperatures (the loader's T_B), not an image                  */
 #define TFCFFT_USE_PAIR      (1u << 28) /* testing: 64x64 tiles through the packed pair kernel            */
 #define TFCFFT_USE_LINE      (1u << 29) /* testing: 64x64 tiles through the thread-per-line kernel        */
 #define TFCFFT_FORCE_GENERIC (1u << 30) /* testing: bypass the packed 64x64 fast path                */
@@ -137,6 +139,28 @@ size_t tfcfft_triplet_workspace_bytes(void);
 int tfcfft_patch_triplet(const tfcfft_desc* d, const void* fake, const void* real, const int32_t* negatives,
                          float margin, float eps, float* out, void* grad_fake, void* workspace,
                          size_t workspace_bytes, void* stream);
+
+/* Temperature triplet loss of the generator step (second "next" row of the scope table), one streaming pass:
+ *     criterion_temp(vectorize_temps(fake_B), TB, vectorize_temps(B_tf))      nn.TripletMarginLoss(margin, p=2)
+ * (TFCGAN_multigpu_patchFFT_16P.py:80, :254-268, :585-595; TempVector_PyTorch datasets_temp.py:14-35).  A pixel's
+ * temperature is lut[uint8(red channel)], the triplet distance runs over one image row.
+ *   d           shape / dtype / fake_stride / real_stride (= strides of `positive`) / weight; grid is ignored;
+ *               flags: TFCFFT_QUANTIZE_U8 = the reference as shipped (uint8 wrap like ToPILImage + table gather,
+ *               forward only); without it the differentiable variant lut[0] + (lut[255]-lut[0])/255 * input_scale*x;
+ *               TFCFFT_TEMPS_POSITIVE: `positive` already holds temperatures (fp32, the loader's T_B);
+ *               TFCFFT_GRAD_ACCUMULATE
+ *   negative    the augmented real batch (B_tf), same dtype as fake, strides in neg_stride[4]
+ *   lut         HOST float[256] (np.linspace(24, 38, 256) upstream)
+ *   grad_fake   NULL or weight * d loss / d fake; ONLY channel 0 is written (the others receive no gradient:
+ *               zero the buffer first or use TFCFFT_GRAD_ACCUMULATE)
+ *   workspace   as for tfcfft_patch_triplet */
+int tfcfft_temperature_triplet(const tfcfft_desc* d, const void* fake, const void* positive, const void* negative,
+                               const int64_t* neg_stride, const float* lut, float margin, float eps, float* out,
+                               void* grad_fake, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Temperature map alone: out[n][0][y][x] = lut[uint8(x[n][0][y][x])] (fp32, contiguous [N,1,H,W]) -- the reference's
+ * vectorize_temps (patchFFT_16P.py:260-268).  d describes x through fake_stride; no workspace. */
+int tfcfft_vectorize_temps(const tfcfft_desc* d, const void* x, const float* lut, float* out, void* stream);
 
 /* dst[i] = src[i] * host_scale * (*dev_scale)   (dev_scale may be NULL; dst may equal src);
  * numel elements of `dtype`, both 16-byte aligned. */

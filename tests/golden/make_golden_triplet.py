@@ -72,11 +72,37 @@ def main():
                           negatives=negatives, loss=float(loss), grad_l2=float(np.sqrt((g * g).sum())),
                           grad_abs_sum=float(np.abs(g).sum())))
         arrays[name + "_grad_n0_c1_rows60_70"] = g[0, 1, 60:70, :].astype(np.float32)
+    # ---- temperature triplet: vectorize_temps + TempVector_PyTorch + the loss lines (patchFFT_16P.py:254-268, 585-595)
+    from torchvision import transforms
+    FDS = f"{REF}/TFC-GAN-FFT/datasets_temp.py"
+    src_t = lift(FDS, ["TempVector_PyTorch"]) + "\n\n" + lines(F16P, 257, 258, "T = np.linspace(24, 38, num=256)") + "\n\n" + lift(F16P, ["vectorize_temps"])
+    l_fb = lines(F16P, 587, 587, "TFB_ = vectorize_temps(fake_B)")
+    l_tf = lines(F16P, 592, 593, "TBTF = vectorize_temps(B_tf)")
+    l_loss = lines(F16P, 595, 595, "loss_temp_g = criterion_temp(TFB_, TB, TBTF)*lambda_t")
+    torch.Tensor.cuda = lambda self, *a, **k: self  # no GPU here; identity on values
+    for kind, seed, n, dtype in [("uniform", 51, 2, "float32"), ("tanh", 52, 2, "float16"), ("unit", 53, 3, "float32")]:
+        f, r = make_pair(kind, seed, (n, 3, 256, 256), dtype)
+        jit, _ = make_pair(kind, seed + 100, (n, 3, 256, 256), dtype)  # stands in for ColorJitter(real_B): an input of the op
+        ns = dict(np=np, torch=torch, nn=nn, transforms=transforms, opt=types.SimpleNamespace(batch_size=n, img_height=256, img_width=256),
+                  criterion_temp=nn.TripletMarginLoss(margin=1.0, p=2), lambda_t=10,
+                  fake_B=torch.from_numpy(f), real_B=torch.from_numpy(r), B_tf=torch.from_numpy(jit))
+        exec(src_t, ns)
+        # the loader's T_B (datasets_temp.py:65-67): the same table applied to the real image
+        ns["TB"] = torch.stack([torch.Tensor(ns["TempVector_PyTorch"](transforms.ToPILImage()(ns["real_B"][t]).convert("RGB"), ns["d"]).make_pixel_vectors())
+                                for t in range(n)])
+        exec(l_fb, ns)
+        exec(l_tf, ns)
+        exec(l_loss, ns)
+        name = f"temperature_{kind}_{seed}_{dtype}"
+        cases.append(dict(name=name, op="temperature", ref=f"{os.path.relpath(F16P, REF)}:257-268,587-595", kind=kind, seed=seed, n=n,
+                          dtype=dtype, lambda_t=10, loss=float(ns["loss_temp_g"]), temps_sum=float(ns["TFB_"].double().sum()),
+                          tb_sum=float(ns["TB"].double().sum())))
+        arrays[name + "_TFB_n0_rows100_104"] = ns["TFB_"][0, 0, 100:104].numpy()
     json.dump(dict(torch=torch.__version__, numpy=np.__version__, cases=cases), open(os.path.join(HERE, "golden_triplet.json"), "w"),
               indent=1)
     np.savez_compressed(os.path.join(HERE, "golden_triplet.npz"), **arrays)
     for c in cases:
-        print(c["name"], c["loss"], c["negatives"])
+        print(c["name"], c["loss"], c.get("negatives", ""))
 
 
 if __name__ == "__main__":

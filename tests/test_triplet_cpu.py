@@ -13,15 +13,18 @@ import torch
 import tfc_gan_b200 as tfc
 from inputs import make_pair
 from oracle import triplet as otri
-from util import emulate_triplet, l2rel
+from oracle import temperature as otemp
+from util import emulate_temperature, emulate_triplet, l2rel
 
 L = tfc._lib
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "golden_triplet.json")))
 ARR = np.load(os.path.join(HERE, "golden", "golden_triplet.npz"))
+TRI = [c for c in GOLD["cases"] if c.get("op") != "temperature"]
+TEMP = [c for c in GOLD["cases"] if c.get("op") == "temperature"]
 
 
-@pytest.mark.parametrize("case", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
+@pytest.mark.parametrize("case", TRI, ids=[c["name"] for c in TRI])
 def test_oracle_matches_reference_lines(case):
     fake, real = make_pair(case["kind"], case["seed"], (case["n"], 3, 256, 256), case["dtype"])
     _, loss, _, grad = otri.patch_triplet_loss_and_grad(fake, real, case["negatives"], grid=case["grid"])
@@ -34,7 +37,7 @@ def test_oracle_matches_reference_lines(case):
 
 
 def test_negative_draw_replays_the_reference_stream():
-    for case in GOLD["cases"]:
+    for case in TRI:
         np.random.seed(case["numpy_seed"])
         assert otri.draw_negatives(case["grid"] ** 2) == case["negatives"]
         np.random.seed(case["numpy_seed"])
@@ -140,3 +143,74 @@ def test_python_layer_validates_negatives_and_device():
         tfc.patch_triplet_loss(x, x, [0] * 16, grid=4)            # CPU tensors: no fallback
     with pytest.raises(TypeError):
         tfc.compat.patch_triplet([x] * 3, [x] * 3)
+
+
+# ---- temperature triplet --------------------------------------------------------------------
+LUT32 = np.linspace(24, 38, num=256).astype(np.float32)
+
+
+def temp_inputs(case):
+    f, r = make_pair(case["kind"], case["seed"], (case["n"], 3, 256, 256), case["dtype"])
+    j, _ = make_pair(case["kind"], case["seed"] + 100, (case["n"], 3, 256, 256), case["dtype"])
+    return f, r, j
+
+
+@pytest.mark.parametrize("case", TEMP, ids=[c["name"] for c in TEMP])
+def test_temperature_oracle_matches_reference_functions(case):
+    f, r, j = temp_inputs(case)
+    t = otemp.vectorize_temps_r0(f)
+    assert float(t.astype(np.float64).sum()) == case["temps_sum"]                     # bit-exact table gather
+    assert np.array_equal(t[0, 0, 100:104], ARR[case["name"] + "_TFB_n0_rows100_104"])
+    tb = otemp.vectorize_temps_r0(r)
+    assert float(tb.astype(np.float64).sum()) == case["tb_sum"]
+    wl, _, _, g = otemp.temperature_triplet(f, tb, j, positive_is_temps=True, weight=case["lambda_t"])
+    assert g is None and wl == pytest.approx(case["loss"], rel=3e-7)
+
+
+@pytest.mark.parametrize("case", TEMP, ids=[c["name"] for c in TEMP])
+def test_temperature_emulated_kernel_matches_reference_and_oracle(case):
+    f, r, j = temp_inputs(case)
+    tb = otemp.vectorize_temps_r0(r)
+    # as shipped: quantise + table, positive = the loader's temperatures, forward only
+    rc, out, _ = emulate_temperature(f, tb, j, LUT32, flags=L.QUANTIZE_U8 | L.TEMPS_POSITIVE, weight=10.0, grad=False)
+    assert rc == 0 and out[0] == pytest.approx(case["loss"], rel=1e-5)
+    # same thing with the positive given as an image
+    rc, out2, _ = emulate_temperature(f, r, j, LUT32, flags=L.QUANTIZE_U8, weight=10.0, grad=False)
+    assert rc == 0 and out2[0] == pytest.approx(case["loss"], rel=1e-5)
+    # the gradient is refused in quantised mode, like the reference has none
+    rc, _, _ = emulate_temperature(f, r, j, LUT32, flags=L.QUANTIZE_U8)
+    assert rc == -9
+
+
+@pytest.mark.parametrize("side,dtype", [(64, "float32"), (256, "float32"), (256, "float16"), (512, "float32")])
+def test_temperature_differentiable_variant_matches_oracle(side, dtype):
+    f, r = make_pair("unit", 61, (2, 3, side, side), dtype)
+    j, _ = make_pair("unit", 62, (2, 3, side, side), dtype)
+    rc, out, g = emulate_temperature(f, r, j, LUT32, weight=10.0, input_scale=255.0)
+    assert rc == 0
+    wl, l, act, gr = otemp.temperature_triplet(f, r, j, quantize=False, weight=10.0, input_scale=255.0)
+    assert out[0] == pytest.approx(wl, rel=1e-5) and out[1] == pytest.approx(l, rel=1e-5) and out[2] == pytest.approx(act, abs=1e-6)
+    assert np.abs(g[:, 1:]).max() == 0.0                         # only the red channel receives a gradient
+    assert l2rel(g.astype(np.float64), gr) <= (3e-3 if dtype == "float16" else 1e-5)
+
+
+def test_temperature_c_entry_point_argument_checks():
+    lib = L.load()
+    st = (3 * 65536, 65536, 256, 1)
+    d = L.make_desc(L.F32, 1, 0, (2, 3, 256, 256), st, st, st, 1.0, 255.0)
+    lut = (ctypes.c_float * 256)(*LUT32)
+    ns = (ctypes.c_int64 * 4)(*st)
+    nb = lib.tfcfft_triplet_workspace_bytes()
+    f = lib.tfcfft_temperature_triplet
+    assert f(ctypes.byref(d), 256, 256, 256, ns, None, 1.0, 1e-6, 256, None, 256, nb, None) == -1     # no table
+    assert f(ctypes.byref(d), 256, 256, None, ns, lut, 1.0, 1e-6, 256, None, 256, nb, None) == -1    # no negative
+    assert f(ctypes.byref(d), 256, 256, 258, ns, lut, 1.0, 1e-6, 256, None, 256, nb, None) == -6     # misaligned negative
+    assert f(ctypes.byref(d), 256, 256, 256, ns, lut, 1.0, 1e-6, 256, None, 256, 16, None) == -8
+    d.flags = L.CHANNELS_RGB
+    assert f(ctypes.byref(d), 256, 256, 256, ns, lut, 1.0, 1e-6, 256, None, 256, nb, None) == -7
+    d.flags = L.QUANTIZE_U8
+    assert f(ctypes.byref(d), 256, 256, 256, ns, lut, 1.0, 1e-6, 256, 256, 256, nb, None) == -9      # no gradient as shipped
+    d.flags = 0
+    d.h = d.w = 96
+    assert f(ctypes.byref(d), 256, 256, 256, ns, lut, 1.0, 1e-6, 256, None, 256, nb, None) == -4
+    assert lib.tfcfft_vectorize_temps(ctypes.byref(d), 256, lut, 256, None) == -4

@@ -19,6 +19,8 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "golden_triplet.json")))
 ARR = np.load(os.path.join(HERE, "golden", "golden_triplet.npz"))
+TRI = [c for c in GOLD["cases"] if c.get("op") != "temperature"]
+TEMP = [c for c in GOLD["cases"] if c.get("op") == "temperature"]
 LOSS_TOL, GRAD_TOL = 1e-4, 1e-3
 
 
@@ -27,7 +29,7 @@ def cu(a, dtype=None):
     return t if dtype is None else t.to(dtype)
 
 
-@pytest.mark.parametrize("case", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
+@pytest.mark.parametrize("case", TRI, ids=[c["name"] for c in TRI])
 def test_matches_reference_golden(case):
     fake, real = make_pair(case["kind"], case["seed"], (case["n"], 3, 256, 256), "float32")
     f = cu(fake).requires_grad_(True)
@@ -41,13 +43,13 @@ def test_matches_reference_golden(case):
 
 
 def test_compat_block_replays_the_reference_draws():
-    case = GOLD["cases"][0]
+    case = TRI[0]
     fake, real = make_pair(case["kind"], case["seed"], (case["n"], 3, 256, 256), "float32")
     f, r = cu(fake), cu(real)
     np.random.seed(case["numpy_seed"])  # the reference script's NumPy stream
     loss = tfc.compat.patch_triplet(tfc.compat.make_16_patches(f), tfc.compat.make_16_patches(r))
     assert float(loss) == pytest.approx(case["loss"], rel=LOSS_TOL)
-    case = next(c for c in GOLD["cases"] if c["grid"] == 2)
+    case = next(c for c in TRI if c["grid"] == 2)
     fake, real = make_pair(case["kind"], case["seed"], (case["n"], 3, 256, 256), "float32")
     f, r = cu(fake), cu(real)
     quads = [q.contiguous() for q in tfc.compat.make_4_patches(r)]  # the loader hands out separate quadrants
@@ -174,3 +176,69 @@ def test_errors_raise():
         tfc.patch_triplet_loss(f, f, [16] + [0] * 15, grid=4)
     with pytest.raises(RuntimeError):
         tfc.patch_triplet_loss(f[:, :, :, :128], f[:, :, :, :128], [0] * 16, grid=4)  # not square
+
+
+# ---- temperature triplet --------------------------------------------------------------------
+from oracle import temperature as otemp  # noqa: E402
+
+
+def temp_inputs(case):
+    f, r = make_pair(case["kind"], case["seed"], (case["n"], 3, 256, 256), case["dtype"])
+    j, _ = make_pair(case["kind"], case["seed"] + 100, (case["n"], 3, 256, 256), case["dtype"])
+    return f, r, j
+
+
+@pytest.mark.parametrize("case", TEMP, ids=[c["name"] for c in TEMP])
+def test_temperature_block_matches_reference_golden(case):
+    f, r, j = temp_inputs(case)
+    F, R, J = cu(f), cu(r), cu(j)
+    # vectorize_temps: bit-exact against the reference's own function output
+    t = tfc.compat.vectorize_temps(F)
+    assert t.shape == (case["n"], 1, 256, 256) and t.dtype == torch.float32
+    assert float(t.double().sum()) == case["temps_sum"]
+    assert np.array_equal(t[0, 0, 100:104].cpu().numpy(), ARR[case["name"] + "_TFB_n0_rows100_104"])
+    tb = tfc.vectorize_temps(R)[:, 0]                         # what the loader hands out: [N, H, W] temperatures
+    assert float(tb.double().sum()) == case["tb_sum"]
+    tfc.compat.set_mode("r0")
+    try:
+        loss = tfc.compat.temperature_loss(F, tb, J)          # the reference block, lambda_t = 10
+    finally:
+        tfc.compat.set_mode("r1")
+    assert float(loss) == pytest.approx(case["loss"], rel=LOSS_TOL)
+    assert not loss.requires_grad
+
+
+@pytest.mark.parametrize("side,n,dtype", [(256, 3, torch.float32), (512, 1, torch.float32), (64, 4, torch.float32), (256, 2, torch.float16)])
+def test_temperature_differentiable_variant(side, n, dtype):
+    f, r = make_pair("unit", 71 + side, (n, 3, side, side), "float32")
+    j, _ = make_pair("unit", 72 + side, (n, 3, side, side), "float32")
+    F, R, J = cu(f, dtype).requires_grad_(True), cu(r, dtype), cu(j, dtype)
+    loss = tfc.temperature_triplet_loss(F, R, J, weight=10.0, input_scale=255.0)
+    (loss * 3.0).backward()
+    wl, _, _, gr = otemp.temperature_triplet(F.detach().double().cpu().numpy(), R.double().cpu().numpy(), J.double().cpu().numpy(),
+                                             quantize=False, weight=10.0, input_scale=255.0)
+    assert float(loss) == pytest.approx(wl, rel=LOSS_TOL)
+    g = F.grad.double().cpu().numpy()
+    assert np.abs(g[:, 1:]).max() == 0.0
+    assert l2rel(g, 3.0 * gr) <= (GRAD_TOL if dtype == torch.float32 else 3e-3)
+    # positive given as the loader's temperature tensor instead of an image: same numbers
+    tb = (24.0 + (38.0 - 24.0) / 255.0 * 255.0 * R.float()[:, 0]).contiguous()
+    out, _ = tfc.temperature_triplet_loss_and_grad(F.detach(), tb, J, weight=10.0, input_scale=255.0)
+    assert float(out[0]) == pytest.approx(wl, rel=1e-4)
+
+
+def test_temperature_full_size_and_determinism():
+    g = torch.Generator(device="cuda").manual_seed(5)
+    F = torch.empty(256, 3, 256, 256, device="cuda").uniform_(0, 1, generator=g)
+    R = torch.empty(256, 3, 256, 256, device="cuda").uniform_(0, 1, generator=g)
+    J = torch.empty(256, 3, 256, 256, device="cuda").uniform_(0, 1, generator=g)
+    o1, g1 = tfc.temperature_triplet_loss_and_grad(F, R, J, weight=10.0)
+    o2, g2 = tfc.temperature_triplet_loss_and_grad(F, R, J, weight=10.0)
+    assert torch.equal(o1, o2) and torch.equal(g1, g2)
+    # torch's own op on the materialised (linear) temperatures
+    lin = lambda x: 24.0 + 14.0 * x[:, 0:1]
+    ref = 10.0 * torch.nn.TripletMarginLoss(margin=1.0, p=2)(lin(F), lin(R), lin(J))
+    assert float(o1[0]) == pytest.approx(float(ref), rel=1e-5)
+    # negative == positive -> every hinge equals the margin, zero gradient
+    o3, g3 = tfc.temperature_triplet_loss_and_grad(F, R, R, weight=1.0, margin=0.5)
+    assert float(o3[1]) == pytest.approx(0.5, rel=1e-6) and float(g3.abs().max()) == 0.0

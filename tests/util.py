@@ -107,3 +107,20 @@ def emulate_triplet(fake: np.ndarray, real: np.ndarray, grid: int, negatives, ma
     rc = lib.tfcfft_emulate_triplet(ctypes.byref(d), fake.ctypes.data, real.ctypes.data, neg, margin, eps, out.ctypes.data,
                                     g.ctypes.data if g is not None else None)
     return rc, out, g
+
+
+def emulate_temperature(fake, positive, negative, lut, flags=0, margin=1.0, eps=1e-6, weight=1.0, input_scale=1.0, grad=True,
+                        dtype_code=None):
+    """CPU twin of tfcfft_temperature_triplet.  Returns (rc, out[4], grad)."""
+    lib = emu_lib()
+    fn = lib.tfcfft_emulate_temperature_triplet
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.POINTER(L.Desc), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64),
+                   ctypes.POINTER(ctypes.c_float), ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
+    code = dtype_code if dtype_code is not None else NP_DTYPES[str(fake.dtype)]
+    out = np.zeros(4, np.float32)
+    g = np.zeros_like(fake) if grad else None
+    d = L.make_desc(code, 1, flags, fake.shape, _strides(fake), _strides(positive), _strides(g) if g is not None else None, weight, input_scale)
+    rc = fn(ctypes.byref(d), fake.ctypes.data, positive.ctypes.data, negative.ctypes.data, (ctypes.c_int64 * 4)(*_strides(negative)),
+            (ctypes.c_float * 256)(*[float(v) for v in lut]), margin, eps, out.ctypes.data, g.ctypes.data if g is not None else None)
+    return rc, out, g

@@ -25,6 +25,7 @@ LOG_MAGNITUDE = 1 << 4
 FULL_SPECTRUM = 1 << 5
 QUANTIZE_U8 = 1 << 6
 GRAD_ACCUMULATE = 1 << 8
+TEMPS_POSITIVE = 1 << 9
 USE_PAIR = 1 << 28
 USE_LINE = 1 << 29
 FORCE_GENERIC = 1 << 30
@@ -42,6 +43,8 @@ EXPORTS = (
     "tfcfft_spectra_bwd",
     "tfcfft_triplet_workspace_bytes",
     "tfcfft_patch_triplet",
+    "tfcfft_temperature_triplet",
+    "tfcfft_vectorize_temps",
     "tfcfft_grad_scale",
     "tfcfft_debug_trace",
     "tfcfft_launch_count",
@@ -109,6 +112,11 @@ def bind(lib):
     lib.tfcfft_patch_triplet.restype = ctypes.c_int
     lib.tfcfft_patch_triplet.argtypes = [dp, vp, vp, ctypes.POINTER(ctypes.c_int32), ctypes.c_float, ctypes.c_float, f32p, vp,
                                          vp, ctypes.c_size_t, vp]
+    lib.tfcfft_temperature_triplet.restype = ctypes.c_int
+    lib.tfcfft_temperature_triplet.argtypes = [dp, vp, vp, vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_float),
+                                               ctypes.c_float, ctypes.c_float, f32p, vp, vp, ctypes.c_size_t, vp]
+    lib.tfcfft_vectorize_temps.restype = ctypes.c_int
+    lib.tfcfft_vectorize_temps.argtypes = [dp, vp, ctypes.POINTER(ctypes.c_float), f32p, vp]
     lib.tfcfft_grad_scale.restype = ctypes.c_int
     lib.tfcfft_grad_scale.argtypes = [vp, vp, ctypes.c_int32, ctypes.c_int64, f32p, ctypes.c_float, vp]
     lib.tfcfft_debug_trace.restype = None

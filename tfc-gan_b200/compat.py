@@ -19,7 +19,7 @@ import torch
 
 import numpy as np
 
-from .functional import SpectralConfig, patch_triplet_loss, spectral_components, spectral_loss, spectral_terms_per_image
+from .functional import SpectralConfig, patch_triplet_loss, temperature_triplet_loss, vectorize_temps as _vectorize_temps, spectral_components, spectral_loss, spectral_terms_per_image
 
 _MODE = {"mode": "r1", "input_scale": 255.0}
 
@@ -137,6 +137,20 @@ def patch_triplet(fake_patches, real_patches, negatives=None, margin: float = 1.
     if negatives is None:
         negatives = draw_negatives(n)
     return patch_triplet_loss(_assemble(tuple(fake_patches), g), _assemble(tuple(real_patches), g), negatives, grid=g, margin=margin)
+
+
+def vectorize_temps(fake_B):
+    """``vectorize_temps`` (``...patchFFT_16P.py:260-268``): ``[N,1,H,W]`` fp32 temperatures of the red channel."""
+    return _vectorize_temps(fake_B)
+
+
+def temperature_loss(fake_B, TB, B_tf, lambda_t: float = 10.0):
+    """The temperature block of the generator step (``...patchFFT_16P.py:585-595``):
+    ``criterion_temp(vectorize_temps(fake_B), TB, vectorize_temps(B_tf)) * lambda_t`` in one fused pass.  ``TB`` is the
+    loader's ``T_B`` (``[N,H,W]``, reshaped like ``:593``); ``B_tf`` the colour-jittered real batch.  Mode ``"r0"``
+    reproduces the reference (no gradient), ``"r1"`` is differentiable."""
+    return temperature_triplet_loss(fake_B, TB, B_tf, quantize=(_MODE["mode"] == "r0"), weight=lambda_t,
+                                    input_scale=_MODE["input_scale"])
 
 
 def global_fft_loss(fake_B, real_B):

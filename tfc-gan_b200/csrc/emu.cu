@@ -260,3 +260,21 @@ extern "C" int tfcfft_emulate_triplet(const tfcfft_desc* d, const void* fake, co
     }
     return TFCFFT_OK;
 }
+
+extern "C" int tfcfft_emulate_temperature_triplet(const tfcfft_desc* d, const void* fake, const void* positive, const void* negative,
+                                                  const int64_t* neg_stride, const float* lut, float margin, float eps, float* out,
+                                                  void* grad_fake) {
+    int rc = validate_temperature(d, neg_stride);
+    if (rc) return rc;
+    if (!fake || !positive || !negative || !lut || !out) return TFCFFT_ERR_NULL;
+    if ((rc = check_grad_args(d, grad_fake))) return rc;
+    std::vector<char> ws(kTripletWsBytes, 0);
+    const TripletParams tp = make_temperature_params(d, fake, positive, negative, neg_stride, lut, margin, eps, out, grad_fake, ws.data());
+    switch (d->dtype) {
+        case TFCFFT_F32: run_triplet<float>(tp); break;
+        case TFCFFT_F16: run_triplet<__half>(tp); break;
+        case TFCFFT_BF16: run_triplet<__nv_bfloat16>(tp); break;
+        case TFCFFT_U8: run_triplet<uint8_t>(tp); break;
+    }
+    return TFCFFT_OK;
+}

@@ -203,6 +203,29 @@ inline int validate_triplet(const tfcfft_desc* d, const int32_t* negatives) {
     return TFCFFT_OK;
 }
 
+// tfcfft_temperature_triplet: like validate_triplet, but grid is ignored (rows are whole image rows), flags may be
+// QUANTIZE_U8 | GRAD_ACCUMULATE | TEMPS_POSITIVE, and the image side must be a power of two in 16..512
+inline int validate_temperature(const tfcfft_desc* d, const int64_t* neg_stride) {
+    if (!d) return TFCFFT_ERR_NULL;
+    if (d->struct_size != sizeof(tfcfft_desc)) return TFCFFT_ERR_STRUCT;
+    if (elem_size(d->dtype) == 0) return TFCFFT_ERR_DTYPE;
+    if (d->n == 0) return TFCFFT_ERR_EMPTY;
+    if (d->n < 0 || d->n > (1 << 24)) return TFCFFT_ERR_SHAPE;
+    if (d->c < 1 || d->c > 4) return TFCFFT_ERR_SHAPE;
+    if (d->h != d->w) return TFCFFT_ERR_SHAPE;
+    const long long p = d->h;
+    if (p != 16 && p != 32 && p != 64 && p != 128 && p != 256 && p != 512) return TFCFFT_ERR_SHAPE;
+    if (d->flags & ~(TFCFFT_GRAD_ACCUMULATE | TFCFFT_QUANTIZE_U8 | TFCFFT_TEMPS_POSITIVE)) return TFCFFT_ERR_FLAGS;
+    if (!neg_stride) return TFCFFT_ERR_NULL;
+    for (int t = 0; t < 3; ++t) {
+        const int64_t* st = t == 0 ? d->fake_stride : t == 1 ? d->real_stride : neg_stride;
+        if (st[3] != 1) return TFCFFT_ERR_STRIDE;
+        for (int i = 0; i < 3; ++i)
+            if (st[i] % 4 != 0 || st[i] < 0) return TFCFFT_ERR_STRIDE;
+    }
+    return TFCFFT_OK;
+}
+
 inline TripletParams make_triplet_params(const tfcfft_desc* d, const void* fake, const void* real, const int32_t* negatives,
                                          float margin, float eps, float* out, void* grad, void* ws) {
     TripletParams t{};
@@ -231,6 +254,28 @@ inline TripletParams make_triplet_params(const tfcfft_desc* d, const void* fake,
     t.counter = reinterpret_cast<unsigned*>(ws);
     t.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsHeader);
     t.out = out;
+    return t;
+}
+
+inline TripletParams make_temperature_params(const tfcfft_desc* d, const void* fake, const void* positive, const void* negative,
+                                             const int64_t* neg_stride, const float* lut, float margin, float eps, float* out,
+                                             void* grad, void* ws) {
+    tfcfft_desc g1 = *d;
+    g1.grid = 1;
+    g1.flags &= TFCFFT_GRAD_ACCUMULATE;
+    const int32_t self = 0;
+    TripletParams t = make_triplet_params(&g1, fake, positive, &self, margin, eps, out, grad, ws);
+    t.c = 1;  // the red channel only (datasets_temp.py:32)
+    t.rows = (long long)d->n * d->h;
+    t.neg_src = negative;
+    for (int i = 0; i < 4; ++i) t.ns[i] = neg_stride[i];
+    t.mode = (d->flags & TFCFFT_QUANTIZE_U8) ? 1 : 2;
+    t.pos_f32 = (d->flags & TFCFFT_TEMPS_POSITIVE) ? 1 : 0;
+    for (int i = 0; i < 256; ++i) t.lut[i] = lut[i];
+    // differentiable variant: the table's end-to-end linear law on x' = input_scale * x (x' in 0..255)
+    t.lin_b = (lut[255] - lut[0]) / 255.0f * d->input_scale;
+    t.lin_a = lut[0];
+    t.coef = (float)((double)d->weight / (double)t.rows) * (t.mode == 2 ? t.lin_b : 0.f);
     return t;
 }
 

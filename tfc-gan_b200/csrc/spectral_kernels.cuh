@@ -484,4 +484,27 @@ __global__ void __launch_bounds__(kTripletThreads) triplet_kernel(const __grid_c
     }
 }
 
+// temperature map alone (vectorize_temps): red channel -> uint8 like ToPILImage -> table
+struct TempsParams {
+    const void* x;
+    long long xs[4];
+    int n, h;
+    float* out;
+    float lut[256];
+};
+template <typename T>
+__global__ void __launch_bounds__(256) temps_kernel(const __grid_constant__ TempsParams tp) {
+    const long long total4 = (long long)tp.n * tp.h * (tp.h / 4);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int x4 = (int)(i % (tp.h / 4));
+        const long long r = i / (tp.h / 4);
+        const int y = (int)(r % tp.h), n = (int)(r / tp.h);
+        float v[4];
+        IO<T>::load4(static_cast<const T*>(tp.x) + n * tp.xs[0] + (long long)y * tp.xs[2] + 4 * x4, v);
+        const float4 o = make_float4(tp.lut[IO<T>::quant(v[0])], tp.lut[IO<T>::quant(v[1])], tp.lut[IO<T>::quant(v[2])],
+                                     tp.lut[IO<T>::quant(v[3])]);
+        *reinterpret_cast<float4*>(tp.out + 4 * i) = o;
+    }
+}
+
 }  // namespace tfcfft

@@ -343,6 +343,58 @@ int tfcfft_patch_triplet(const tfcfft_desc* d, const void* fake, const void* rea
     return TFCFFT_ERR_DTYPE;
 }
 
+int tfcfft_temperature_triplet(const tfcfft_desc* d, const void* fake, const void* positive, const void* negative,
+                               const int64_t* neg_stride, const float* lut, float margin, float eps, float* out, void* grad_fake,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = validate_temperature(d, neg_stride);
+    if (rc) return rc;
+    if (!fake || !positive || !negative || !lut || !out) return TFCFFT_ERR_NULL;
+    if ((rc = check_grad_args(d, grad_fake))) return rc;
+    if ((rc = check_alignment(d, fake, (d->flags & TFCFFT_TEMPS_POSITIVE) ? fake : positive, grad_fake))) return rc;
+    if ((uintptr_t)negative % (4 * elem_size(d->dtype))) return TFCFFT_ERR_ALIGNMENT;
+    if ((d->flags & TFCFFT_TEMPS_POSITIVE) && ((uintptr_t)positive % 16)) return TFCFFT_ERR_ALIGNMENT;
+    if (!workspace || workspace_bytes < kTripletWsBytes || ((uintptr_t)workspace & 255)) return TFCFFT_ERR_WORKSPACE;
+    const TripletParams tp = make_temperature_params(d, fake, positive, negative, neg_stride, lut, margin, eps, out, grad_fake, workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (d->dtype) {
+        case TFCFFT_F32: return launch_triplet<float>(tp, st);
+        case TFCFFT_F16: return launch_triplet<__half>(tp, st);
+        case TFCFFT_BF16: return launch_triplet<__nv_bfloat16>(tp, st);
+        case TFCFFT_U8: return launch_triplet<uint8_t>(tp, st);
+    }
+    return TFCFFT_ERR_DTYPE;
+}
+
+int tfcfft_vectorize_temps(const tfcfft_desc* d, const void* x, const float* lut, float* out, void* stream) {
+    int64_t st4[4] = {0, 0, 0, 1};
+    int rc = validate_temperature(d, st4);
+    if (rc) return rc;
+    if (!x || !lut || !out) return TFCFFT_ERR_NULL;
+    if ((uintptr_t)x % (4 * elem_size(d->dtype)) || (uintptr_t)out % 16) return TFCFFT_ERR_ALIGNMENT;
+    TempsParams tp{};
+    tp.x = x;
+    for (int i = 0; i < 4; ++i) tp.xs[i] = d->fake_stride[i];
+    tp.n = (int)d->n;
+    tp.h = (int)d->h;
+    tp.out = out;
+    for (int i = 0; i < 256; ++i) tp.lut[i] = lut[i];
+    const long long total4 = (long long)d->n * d->h * (d->h / 4);
+    long long blocks = (total4 + 255) / 256;
+    const long long cap = (long long)device_info().sms * 16;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (d->dtype) {
+        case TFCFFT_F32: temps_kernel<float><<<(int)blocks, 256, 0, st>>>(tp); break;
+        case TFCFFT_F16: temps_kernel<__half><<<(int)blocks, 256, 0, st>>>(tp); break;
+        case TFCFFT_BF16: temps_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>(tp); break;
+        case TFCFFT_U8: temps_kernel<uint8_t><<<(int)blocks, 256, 0, st>>>(tp); break;
+        default: return TFCFFT_ERR_DTYPE;
+    }
+    g_launches++;
+    TFC_LAUNCH_CHECK();
+    return 0;
+}
+
 int tfcfft_grad_scale(void* dst, const void* src, int32_t dtype, int64_t numel, const float* dev_scale, float host_scale,
                       void* stream) {
     if (!dst || !src) return TFCFFT_ERR_NULL;

@@ -23,6 +23,14 @@ struct TripletParams {
     int n, c, h, grid, p;
     int lg_g, lg_h, lg_p;  // grid, h and p are powers of two: row decoding is shifts and masks
     int neg[16];       // negative patch index for each patch (row-major patch order)
+    // temperature variant (tfcfft_temperature_triplet): the negative is a third tensor, values pass through the
+    // temperature map first, only channel 0 takes part (c == 1)
+    const void* neg_src;  // NULL: negative = tile neg[i] of `real`
+    long long ns[4];
+    int mode;          // 0 raw values; 1 lut[uint8(x)] (reference as shipped, no gradient); 2 lin_a + lin_b * x
+    int pos_f32;       // `real` is an fp32 tensor that already holds temperatures (the loader's T_B)
+    float lin_a, lin_b;
+    float lut[256];
     float margin, eps;
     float weight;      // out[0] = weight * mean hinge
     float coef;        // weight / rows: gradient scale of one active row
@@ -59,6 +67,15 @@ struct SerialReduce {
     TFC_HD float operator()(float v) const { return v; }
 };
 
+// temperature of one pixel value (TFCGAN_multigpu_patchFFT_16P.py:257-268, datasets_temp.py:14-35): the reference
+// quantises to uint8 like ToPILImage and gathers from a 256-entry table; the differentiable variant is the
+// table's linear law on the unquantised value
+template <typename T>
+TFC_HD float temp_value(const TripletParams& tp, float raw) {
+    if (tp.mode == 1) return tp.lut[IO<T>::quant(raw)];
+    return fmaf(raw, tp.lin_b, tp.lin_a);
+}
+
 // One patch row by a group of `lpr` lanes, K float4 per lane (lane `l` takes float4 l, l + lpr, ...), in two steps so
 // that a warp can have the loads of several rows in flight before it reduces the first.
 template <int K>
@@ -78,15 +95,28 @@ TFC_HD void triplet_row_load(const TripletParams& tp, long long row, int l, int 
     const int k = tp.neg[(py << tp.lg_g) + px], ky = k >> tp.lg_g, kx = k & (g - 1);
     const T* fp = static_cast<const T*>(tp.fake) + n * tp.fs[0] + c * tp.fs[1] + (long long)y * tp.fs[2] + px * P;
     const T* pp = static_cast<const T*>(tp.real) + n * tp.rs[0] + c * tp.rs[1] + (long long)y * tp.rs[2] + px * P;
-    const T* qp = static_cast<const T*>(tp.real) + n * tp.rs[0] + c * tp.rs[1] + (long long)(ky * P + yin) * tp.rs[2] + kx * P;
+    const T* qp = tp.neg_src == nullptr
+                      ? static_cast<const T*>(tp.real) + n * tp.rs[0] + c * tp.rs[1] + (long long)(ky * P + yin) * tp.rs[2] + kx * P
+                      : static_cast<const T*>(tp.neg_src) + n * tp.ns[0] + c * tp.ns[1] + (long long)y * tp.ns[2] + px * P;
     tr.goff = n * tp.gs[0] + c * tp.gs[1] + (long long)y * tp.gs[2] + px * P;
     float f[K][4];
 #pragma unroll
     for (int j = 0; j < K; ++j) {
         const int x = 4 * (l + j * lpr);
         IO<T>::load4(fp + x, f[j]);
-        IO<T>::load4(pp + x, tr.dp[j]);
+        if (tp.pos_f32) IO<float>::load4(reinterpret_cast<const float*>(tp.real) + (pp - static_cast<const T*>(tp.real)) + x, tr.dp[j]);
+        else IO<T>::load4(pp + x, tr.dp[j]);
         IO<T>::load4(qp + x, tr.dn[j]);
+    }
+    if (tp.mode != 0) {
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                f[j][i] = temp_value<T>(tp, f[j][i]);
+                if (!tp.pos_f32) tr.dp[j][i] = temp_value<T>(tp, tr.dp[j][i]);
+                tr.dn[j][i] = temp_value<T>(tp, tr.dn[j][i]);
+            }
     }
 #pragma unroll
     for (int j = 0; j < K; ++j)

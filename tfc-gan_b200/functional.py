@@ -377,6 +377,126 @@ def patch_triplet_loss_and_grad(fake, real, negatives, *, grid: int = 4, margin:
     return _launch_triplet(fake_p, real_p, int(grid), negatives, margin, eps, weight, True, accumulate_into)
 
 
+# ---- temperature triplet loss ----------------------------------------------------------------
+#: the reference's table: ``T = np.linspace(24, 38, num=256)`` (``TFCGAN_multigpu_patchFFT_16P.py:257``), as fp32
+DEFAULT_TEMPERATURE_LUT = tuple(float(v) for v in __import__("numpy").linspace(24, 38, num=256).astype("float32"))
+
+
+def _lut_array(lut):
+    vals = DEFAULT_TEMPERATURE_LUT if lut is None else tuple(float(v) for v in lut)
+    if len(vals) != 256:
+        raise ValueError("the temperature table must have 256 entries")
+    return (ctypes.c_float * 256)(*vals)
+
+
+def _prep_img(x, like=None):
+    if x.dim() != 4 or x.shape[2] != x.shape[3]:
+        raise ValueError(f"expected a square 4-D NCHW tensor, got {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise RuntimeError("tfcfft runs on CUDA tensors only (no CPU fallback)")
+    if like is not None and x.dtype != like.dtype:
+        x = x.to(like.dtype)
+    if x.dtype not in _DTYPES:
+        x = x.float()
+    return x if _acceptable(x) else x.contiguous()
+
+
+@torch.no_grad()
+def vectorize_temps(x, lut=None):
+    """``[N,C,H,H]`` -> fp32 ``[N,1,H,H]``: ``lut[uint8(red channel)]`` with ToPILImage's uint8 rule -- the reference's
+    ``vectorize_temps`` (``TFCGAN_multigpu_patchFFT_16P.py:260-268``) without the per-sample CPU round trip."""
+    lib = _lib.load()
+    xp = _prep_img(x)
+    dev = xp.device
+    with torch.cuda.device(dev):
+        out = torch.empty((xp.shape[0], 1, xp.shape[2], xp.shape[3]), dtype=torch.float32, device=dev)
+        desc = _lib.make_desc(_DTYPES[xp.dtype], 1, 0, xp.shape, xp.stride(), xp.stride(), None, 1.0, 1.0)
+        _lib.check(lib.tfcfft_vectorize_temps(ctypes.byref(desc), xp.data_ptr(), _lut_array(lut), out.data_ptr(),
+                                              ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "tfcfft_vectorize_temps")
+    return out
+
+
+def _launch_temperature(fake, positive, negative, lut, quantize, margin, eps, weight, input_scale, want_grad, accumulate_into=None):
+    lib = _lib.load()
+    dev = fake.device
+    positive_is_temps = positive.shape[1] == 1 and positive.dtype == torch.float32 and fake.shape[1] != 1
+    flags = (_lib.QUANTIZE_U8 if quantize else 0) | (_lib.TEMPS_POSITIVE if positive_is_temps else 0)
+    with torch.cuda.device(dev):
+        stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        grad = None
+        if accumulate_into is not None:
+            grad, flags = accumulate_into, flags | _lib.GRAD_ACCUMULATE
+        elif want_grad:
+            grad = torch.zeros(fake.shape, dtype=fake.dtype, device=dev)  # only channel 0 receives a gradient
+        desc = _lib.make_desc(_DTYPES[fake.dtype], 1, flags, fake.shape, fake.stride(), positive.stride(),
+                              grad.stride() if grad is not None else None, weight, input_scale)
+        ws = _workspace(dev, stream_ptr, lib.tfcfft_triplet_workspace_bytes())
+        rc = lib.tfcfft_temperature_triplet(ctypes.byref(desc), fake.data_ptr(), positive.data_ptr(), negative.data_ptr(),
+                                            (ctypes.c_int64 * 4)(*negative.stride()), _lut_array(lut), float(margin), float(eps),
+                                            out.data_ptr(), grad.data_ptr() if grad is not None else None, ws.data_ptr(), ws.numel(),
+                                            ctypes.c_void_p(stream_ptr))
+        if rc > 0:
+            _WORKSPACES.pop((dev.index, stream_ptr), None)
+        _lib.check(rc, "tfcfft_temperature_triplet")
+    return out, grad
+
+
+def _prep_temperature(fake, positive, negative):
+    fake = _prep_img(fake)
+    negative = _prep_img(negative, like=fake)
+    if positive.dim() == 3:
+        positive = positive.reshape(positive.shape[0], 1, positive.shape[1], positive.shape[2])  # the reference's reshape (:593)
+    if positive.shape[1] == 1 and fake.shape[1] != 1:
+        positive = positive.float()
+        positive = positive if _acceptable(positive) else positive.contiguous()
+    else:
+        positive = _prep_img(positive, like=fake)
+    if negative.shape != fake.shape or positive.shape[0] != fake.shape[0] or positive.shape[2:] != fake.shape[2:]:
+        raise ValueError("fake, positive and negative must agree in batch and image size")
+    return fake, positive, negative
+
+
+class _TemperatureTripletFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fake, positive, negative, lut, quantize, margin, eps, weight, input_scale):
+        f, p, n = _prep_temperature(fake.detach(), positive.detach(), negative.detach())
+        want_grad = ctx.needs_input_grad[0] and not quantize and f.dtype != torch.uint8
+        out, grad = _launch_temperature(f, p, n, lut, quantize, margin, eps, weight, input_scale, want_grad)
+        ctx.has_grad, ctx.in_dtype = want_grad, fake.dtype
+        if want_grad:
+            ctx.save_for_backward(grad)
+        return out[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_loss):
+        if not ctx.has_grad:
+            return (None,) * 9
+        (unit,) = ctx.saved_tensors
+        res = (unit.float() * grad_loss.detach().float()).to(ctx.in_dtype)
+        return (res,) + (None,) * 8
+
+
+def temperature_triplet_loss(fake, positive, negative, *, lut=None, quantize: bool = False, margin: float = 1.0, eps: float = 1e-6,
+                             weight: float = 1.0, input_scale: float = 255.0):
+    """``weight * TripletMarginLoss(margin, p=2)(temps(fake), temps(positive), temps(negative))`` in one fused pass
+    (``TFCGAN_multigpu_patchFFT_16P.py:585-595``; ``weight`` is the reference's ``lambda_t``).  ``positive`` is either an
+    image batch or the loader's precomputed temperatures ``T_B`` (fp32 ``[N,H,W]`` / ``[N,1,H,W]``).  ``quantize=True``
+    is the reference as shipped (uint8 + table, no gradient); the default is the differentiable linear variant on
+    ``input_scale * x``."""
+    return _TemperatureTripletFn.apply(fake, positive, negative, None if lut is None else tuple(lut), bool(quantize), float(margin),
+                                       float(eps), float(weight), float(input_scale))
+
+
+@torch.no_grad()
+def temperature_triplet_loss_and_grad(fake, positive, negative, *, lut=None, quantize: bool = False, margin: float = 1.0,
+                                      eps: float = 1e-6, weight: float = 1.0, input_scale: float = 255.0, accumulate_into=None):
+    """The fused pass without autograd: ``(out[4], grad_or_None)``."""
+    f, p, n = _prep_temperature(fake, positive, negative)
+    return _launch_temperature(f, p, n, lut, quantize, margin, eps, weight, input_scale, not quantize, accumulate_into)
+
+
 def launch_count() -> int:
     """Kernels launched by ``libtfcfft.so`` in this process since the last reset."""
     return int(_lib.load().tfcfft_launch_count())
