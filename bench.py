@@ -205,7 +205,7 @@ def run_reference(args, wl):
     }
     if "as_shipped_r0_fwd_only_images_per_s" in cb:
         line["as_shipped_r0_fwd_only_images_per_s"] = cb["as_shipped_r0_fwd_only_images_per_s"]
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -445,13 +445,34 @@ def run_ours(args, wl):
         if "as_shipped_r0_fwd_only_images_per_s" in cb:
             line["cpu_baseline"]["as_shipped_r0_fwd_only_images_per_s"] = cb["as_shipped_r0_fwd_only_images_per_s"]
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """Rank 0 must print exactly ONE line on stdout, but native libraries write there too (NCCL prints its version
+    banner with printf when the first communicator comes up).  Keep a private handle to the real stdout for the
+    result line and point file descriptor 1 at stderr for everything else."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
