@@ -302,11 +302,22 @@ __global__ void __launch_bounds__(LineCfg::NT, 6) line_kernel(const __grid_const
     finish(prm, gridDim.x);
 }
 
+// Programmatic dependent launch (sm_90+): the three launches of the sub-tile path are chained with the
+// programmatic-stream-serialization attribute, so the next grid is scheduled while the previous one drains and its
+// CTAs sit in `griddepcontrol.wait` until that grid has completed and flushed -- the launch latency between
+// dependent kernels (~2 us each, a few percent of a 100 us step) overlaps the tail.  Both instructions are no-ops in
+// a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Issued by every CTA when its own work is done: releasing earlier lets the dependent grid's CTAs take SM slots
+// that this grid's not-yet-started CTAs need (measured: 118 us instead of 98 us per step).
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // Sub-tile path, launches 1 and 3 (sub_tile.cuh): thread-per-line 64 x 64 transforms of the D x D decimated
 // sub-images.  Forward: one CTA = one sub-image PAIR (adjacent pixel columns, so the source rows are read as
 // 8-byte pairs), two 64-thread groups with a work tile each.  Inverse: one 64-thread CTA = one packed plane.
 template <typename T, bool LUMA3>
 __global__ void __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd_kernel(const __grid_constant__ Params prm) {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
     BlockCtxT<SubCfg::NT_FWD> ctx{(int)threadIdx.x, nullptr};
@@ -317,9 +328,11 @@ __global__ void __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd_kernel(const __grid
         sub_fwd_process<T, LUMA3>(ctx, prm, u, s);
         if (ctx.trace != nullptr && threadIdx.x == 0) ctx.trace[15] = 1;
     }
+    pdl_release();
 }
 template <typename T, bool LUMA3>
 __global__ void __launch_bounds__(SubCfg::NT_INV, 6) sub_inv_kernel(const __grid_constant__ Params prm) {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
     BlockCtxT<SubCfg::NT_INV> ctx{(int)threadIdx.x, nullptr};
@@ -330,11 +343,13 @@ __global__ void __launch_bounds__(SubCfg::NT_INV, 6) sub_inv_kernel(const __grid
         sub_inv_process<T, LUMA3>(ctx, prm, u, s);
         if (ctx.trace != nullptr && threadIdx.x == 0) ctx.trace[15] = 1;
     }
+    pdl_release();
 }
 
 // Sub-tile path, launch 2: per-position D x D butterflies, loss, spectral gradient (registers + L2 only).
 template <int D>
 __global__ void __launch_bounds__(kCombineThreads, 512 / kCombineThreads) combine_kernel(const __grid_constant__ Params prm) {
+    pdl_wait();
     constexpr int PARTS = kCombineParts;
     const int lt = blockIdx.x / PARTS, part = blockIdx.x % PARTS;
     const int item = part * kCombineThreads + (int)threadIdx.x;
@@ -349,6 +364,7 @@ __global__ void __launch_bounds__(kCombineThreads, 512 / kCombineThreads) combin
         prm.partials[2 * slot] = a;
         prm.partials[2 * slot + 1] = p;
     }
+    pdl_release();
     finish(prm, (unsigned)prm.tiles_total * PARTS);
 }
 

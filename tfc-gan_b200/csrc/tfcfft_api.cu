@@ -92,6 +92,23 @@ int launch_line(const Params& prm, cudaStream_t st) {
     return 0;
 }
 
+// launch with the programmatic-stream-serialization attribute (see pdl_wait_then_release)
+template <class K>
+cudaError_t launch_pdl(K kernel, int grid, int block, size_t smem, cudaStream_t st, const Params& prm) {
+    static const bool off = getenv("TFCFFT_PDL") == nullptr;  // opt-in until it measures faster
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, prm);
+}
+
 template <typename T, bool LUMA3>
 int launch_sub(Params prm, cudaStream_t st) {
     auto kf = sub_fwd_kernel<T, LUMA3>;
@@ -115,17 +132,17 @@ int launch_sub(Params prm, cudaStream_t st) {
         const int units = prm.chunk_now * npp;
         const int grid_f = units < sms * per_sm_f ? units : sms * per_sm_f;
         const int grid_i = units < sms * per_sm_i ? units : sms * per_sm_i;
-        kf<<<grid_f, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st>>>(prm);
+        cudaError_t e = launch_pdl(kf, grid_f, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st, prm);
+        if (e != cudaSuccess) return (int)e;
         g_launches++;
-        TFC_LAUNCH_CHECK();
-        if (D == 2) combine_kernel<2><<<prm.chunk_now * kCombineParts, kCombineThreads, 0, st>>>(prm);
-        else combine_kernel<4><<<prm.chunk_now * kCombineParts, kCombineThreads, 0, st>>>(prm);
+        e = D == 2 ? launch_pdl(combine_kernel<2>, prm.chunk_now * kCombineParts, kCombineThreads, 0, st, prm)
+                   : launch_pdl(combine_kernel<4>, prm.chunk_now * kCombineParts, kCombineThreads, 0, st, prm);
+        if (e != cudaSuccess) return (int)e;
         g_launches++;
-        TFC_LAUNCH_CHECK();
         if (prm.grad) {
-            ki<<<grid_i, SubCfg::NT_INV, SubCfg::SMEM_INV, st>>>(prm);
+            e = launch_pdl(ki, grid_i, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
+            if (e != cudaSuccess) return (int)e;
             g_launches++;
-            TFC_LAUNCH_CHECK();
         }
     }
     return 0;
