@@ -231,6 +231,27 @@ def test_run_to_run_bit_stable(grid):
         assert torch.equal(gr, outs[0][2])
 
 
+@pytest.mark.parametrize("grid,n", [(1, 64), (2, 96)])
+def test_back_to_back_calls_do_not_race_through_the_workspace(grid, n):
+    # The three launches of the sub-tile path are chained with programmatic dependent launch and share one L2
+    # workspace across calls: 40 un-synchronised calls on alternating inputs must reproduce, bit for bit, what each
+    # input gives in isolation.
+    g = torch.Generator(device="cuda").manual_seed(grid)
+    ins = [(torch.empty(n, 3, 256, 256, device="cuda").uniform_(-1, 1, generator=g),
+            torch.empty(n, 3, 256, 256, device="cuda").uniform_(-1, 1, generator=g)) for _ in range(2)]
+    cfg = tfc.SpectralConfig(grid=grid, weight=0.01, input_scale=255.0)
+    ref = []
+    for f, r in ins:
+        loss, terms, grad = tfc.spectral_loss_and_grad(f, r, config=cfg)
+        torch.cuda.synchronize()
+        ref.append((loss.clone(), terms.clone(), grad.clone()))
+    outs = [tfc.spectral_loss_and_grad(*ins[i % 2], config=cfg) for i in range(40)]
+    torch.cuda.synchronize()
+    for i, (loss, terms, grad) in enumerate(outs):
+        assert torch.equal(loss, ref[i % 2][0]) and torch.equal(terms, ref[i % 2][1])
+        assert torch.equal(grad, ref[i % 2][2])
+
+
 def test_fast_paths_agree_with_generic_kernels_at_scale():
     """Packed pair kernel / sub-tile pipeline vs the generic resident / split kernels on a batch that gives every
     persistent CTA several units."""

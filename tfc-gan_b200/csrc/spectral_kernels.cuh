@@ -280,12 +280,23 @@ __global__ void __launch_bounds__(PairCfg<P>::NT, 1) pair_kernel(const __grid_co
     finish(prm, gridDim.x);
 }
 
+// Programmatic dependent launch (sm_90+): consecutive launches of this library are chained with the
+// programmatic-stream-serialization attribute, so the next grid is scheduled while the previous one drains and its
+// CTAs sit in `griddepcontrol.wait` until that grid has completed and flushed -- the launch latency between
+// dependent kernels (~2 us each, a few percent of a 100 us step) overlaps the tail.  Both instructions are no-ops in
+// a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Issued by every CTA when its own work is done: releasing earlier lets the dependent grid's CTAs take SM slots
+// that this grid's not-yet-started CTAs need (measured: 118 us instead of 98 us per step).
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // Thread-per-line kernel for 64 x 64 tiles (line_tile.cuh): 64 threads = one tile, six CTAs per SM.
 template <typename T, bool LUMA3>
 __global__ void __launch_bounds__(LineCfg::NT, 6) line_kernel(const __grid_constant__ Params prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
     BlockCtxT<LineCfg::NT> ctx{(int)threadIdx.x, nullptr};
+    pdl_wait();
     int iter = 0;
     for (int tile = blockIdx.x; tile < prm.tiles_total; tile += gridDim.x, ++iter) {
         float a = 0.f, p = 0.f;
@@ -299,18 +310,9 @@ __global__ void __launch_bounds__(LineCfg::NT, 6) line_kernel(const __grid_const
             if (ctx.trace != nullptr) ctx.trace[15] = 1;
         }
     }
+    pdl_release();
     finish(prm, gridDim.x);
 }
-
-// Programmatic dependent launch (sm_90+): the three launches of the sub-tile path are chained with the
-// programmatic-stream-serialization attribute, so the next grid is scheduled while the previous one drains and its
-// CTAs sit in `griddepcontrol.wait` until that grid has completed and flushed -- the launch latency between
-// dependent kernels (~2 us each, a few percent of a 100 us step) overlaps the tail.  Both instructions are no-ops in
-// a launch without the attribute.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-// Issued by every CTA when its own work is done: releasing earlier lets the dependent grid's CTAs take SM slots
-// that this grid's not-yet-started CTAs need (measured: 118 us instead of 98 us per step).
-__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;"); }
 
 // Sub-tile path, launches 1 and 3 (sub_tile.cuh): thread-per-line 64 x 64 transforms of the D x D decimated
 // sub-images.  Forward: one CTA = one sub-image PAIR (adjacent pixel columns, so the source rows are read as
@@ -374,9 +376,11 @@ __global__ void __launch_bounds__(SplitCfg<P>::NT) split_rows_fwd_kernel(const _
     float2* s = reinterpret_cast<float2*>(smem_raw);
     float2* tw = s + Split<P>::RS * (P + 1);
     const BlockCtx ctx{(int)threadIdx.x, (int)blockDim.x};
-    fill_twiddles<P>(ctx, tw);
+    fill_twiddles<P>(ctx, tw);  // prologue: independent of the previous grid
     ctx.sync();
+    pdl_wait();
     split_rows_fwd<P, T, LUMA3>(ctx, prm, blockIdx.x / Split<P>::ROW_SLABS, blockIdx.x % Split<P>::ROW_SLABS, s, tw);
+    pdl_release();
 }
 
 template <int P>
@@ -387,9 +391,11 @@ __global__ void __launch_bounds__(SplitCfg<P>::NT) split_cols_kernel(const __gri
     const BlockCtx ctx{(int)threadIdx.x, (int)blockDim.x};
     fill_twiddles<P>(ctx, tw);
     ctx.sync();
+    pdl_wait();
     const int lt = blockIdx.x / Split<P>::PARTS, pair = blockIdx.x % Split<P>::PARTS;
     float a = 0.f, p = 0.f;
     split_cols<P>(ctx, prm, lt, pair, s, tw, a, p);
+    pdl_release();
     block_sum2(a, p);
     if (threadIdx.x == 0) {
         const long long slot = (long long)(prm.tile_base + lt) * Split<P>::PARTS + pair;
@@ -407,7 +413,9 @@ __global__ void __launch_bounds__(SplitCfg<P>::NT) split_rows_inv_kernel(const _
     const BlockCtx ctx{(int)threadIdx.x, (int)blockDim.x};
     fill_twiddles<P>(ctx, tw);
     ctx.sync();
+    pdl_wait();
     split_rows_inv<P, T, LUMA3>(ctx, prm, blockIdx.x / Split<P>::ROW_SLABS, blockIdx.x % Split<P>::ROW_SLABS, s, tw);
+    pdl_release();
 }
 
 // dst = src * host_scale * (*dev_scale); 16-byte vectors, grid-stride.
@@ -445,6 +453,7 @@ __global__ void __launch_bounds__(kTripletThreads) triplet_kernel(const __grid_c
     const long long warp = (long long)blockIdx.x * (kTripletThreads / 32) + (threadIdx.x >> 5);
     const ShflReduce red{lpr};
     float loss = 0.f, act = 0.f;
+    pdl_wait();
     constexpr int R = kTripletRowsInFlight;
     // a warp owns R * gpw CONSECUTIVE rows per pass (one contiguous window of the tensors is live at a time);
     // whole warps are in or out of range because rows % gpw == 0
@@ -457,6 +466,7 @@ __global__ void __launch_bounds__(kTripletThreads) triplet_kernel(const __grid_c
         for (int r = 0; r < R; ++r)
             if (base + r * gpw < tp.rows) triplet_row_finish<T, K>(tp, tr[r], l, lpr, red, loss, act);
     }
+    pdl_release();
     block_sum2(loss, act);
     if (threadIdx.x == 0) {
         tp.partials[2 * blockIdx.x] = loss;

@@ -75,27 +75,10 @@ int launch_pair(const Params& prm, cudaStream_t st) {
     return 0;
 }
 
-template <typename T, bool LUMA3>
-int launch_line(const Params& prm, cudaStream_t st) {
-    auto kernel = line_kernel<T, LUMA3>;
-    constexpr size_t smem = LineCfg::SMEM;
-    if (int rc = set_smem(kernel, smem)) return rc;
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, LineCfg::NT, smem);
-    if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) per_sm = 1;
-    const long long cap = (long long)device_info().sms * per_sm;
-    const int grid = (int)(prm.tiles_total < cap ? prm.tiles_total : cap);
-    kernel<<<grid, LineCfg::NT, smem, st>>>(prm);
-    g_launches++;
-    TFC_LAUNCH_CHECK();
-    return 0;
-}
-
-// launch with the programmatic-stream-serialization attribute (see pdl_wait_then_release)
-template <class K>
-cudaError_t launch_pdl(K kernel, int grid, int block, size_t smem, cudaStream_t st, const Params& prm) {
-    static const bool off = getenv("TFCFFT_PDL") == nullptr;  // opt-in until it measures faster
+// launch with the programmatic-stream-serialization attribute (spectral_kernels.cuh: pdl_wait / pdl_release)
+template <class K, class P>
+cudaError_t launch_pdl(K kernel, int grid, int block, size_t smem, cudaStream_t st, const P& prm) {
+    static const bool off = getenv("TFCFFT_NO_PDL") != nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)block);
@@ -107,6 +90,22 @@ cudaError_t launch_pdl(K kernel, int grid, int block, size_t smem, cudaStream_t 
     cfg.attrs = attr;
     cfg.numAttrs = off ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, prm);
+}
+
+template <typename T, bool LUMA3>
+int launch_line(const Params& prm, cudaStream_t st) {
+    auto kernel = line_kernel<T, LUMA3>;
+    constexpr size_t smem = LineCfg::SMEM;
+    if (int rc = set_smem(kernel, smem)) return rc;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, LineCfg::NT, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    const long long cap = (long long)device_info().sms * per_sm;
+    const int grid = (int)(prm.tiles_total < cap ? prm.tiles_total : cap);
+    if (cudaError_t e2 = launch_pdl(kernel, grid, LineCfg::NT, smem, st, prm)) return (int)e2;
+    g_launches++;
+    return 0;
 }
 
 template <typename T, bool LUMA3>
@@ -161,16 +160,13 @@ int launch_split(Params prm, cudaStream_t st) {
         for (int base = 0; base < prm.tiles_total; base += prm.chunk_tiles) {
             prm.tile_base = base;
             const int nt = prm.tiles_total - base < prm.chunk_tiles ? prm.tiles_total - base : prm.chunk_tiles;
-            k1<<<nt * Sp::ROW_SLABS, SplitCfg<P>::NT, SplitCfg<P>::SMEM_ROWS, st>>>(prm);
+            if (cudaError_t e = launch_pdl(k1, nt * Sp::ROW_SLABS, SplitCfg<P>::NT, SplitCfg<P>::SMEM_ROWS, st, prm)) return (int)e;
             g_launches++;
-            TFC_LAUNCH_CHECK();
-            k2<<<nt * Sp::PARTS, SplitCfg<P>::NT, SplitCfg<P>::SMEM_COLS, st>>>(prm);
+            if (cudaError_t e = launch_pdl(k2, nt * Sp::PARTS, SplitCfg<P>::NT, SplitCfg<P>::SMEM_COLS, st, prm)) return (int)e;
             g_launches++;
-            TFC_LAUNCH_CHECK();
             if (prm.grad) {
-                k3<<<nt * Sp::ROW_SLABS, SplitCfg<P>::NT, SplitCfg<P>::SMEM_ROWS, st>>>(prm);
+                if (cudaError_t e = launch_pdl(k3, nt * Sp::ROW_SLABS, SplitCfg<P>::NT, SplitCfg<P>::SMEM_ROWS, st, prm)) return (int)e;
                 g_launches++;
-                TFC_LAUNCH_CHECK();
             }
         }
         return 0;
@@ -236,9 +232,8 @@ int launch_triplet(const TripletParams& tp, cudaStream_t st) {
     const long long cap = (long long)device_info().sms * (per_sm < 1 ? 1 : per_sm) * 4;
     if (blocks > cap) blocks = cap;
     if (blocks > kTripletMaxBlocks) blocks = kTripletMaxBlocks;
-    kernel<<<(int)blocks, kTripletThreads, 0, st>>>(tp);
+    if (cudaError_t e2 = launch_pdl(kernel, (int)blocks, kTripletThreads, 0, st, tp)) return (int)e2;
     g_launches++;
-    TFC_LAUNCH_CHECK();
     return 0;
 }
 
