@@ -167,9 +167,10 @@ int tfcfft_vectorize_temps(const tfcfft_desc* d, const void* x, const float* lut
 int tfcfft_grad_scale(void* dst, const void* src, int32_t dtype, int64_t numel, const float* dev_scale,
                       float host_scale, void* stream);
 
-/* DEBUG / profiling aid, not part of the stable surface: while `device_buffer` is non-NULL the packed
- * 64x64 kernel records clock64() at its stage boundaries for the first 6 tile pairs of every CTA
- * (16 int64 per pair: 11 stage stamps, [14] = SM id, [15] = globaltimer).  Pass NULL to switch off. */
+/* DEBUG / profiling aid, not part of the stable surface: while `device_buffer` is non-NULL the 64x64 line kernel
+ * and the sub-tile launches record the global nanosecond timer at their stage boundaries for the first 6 work
+ * units of every CTA (16 int64 per unit; [15] = 1 when the unit was traced; the packed pair kernel records
+ * clock64).  Read by tools/trace_line.py and tools/trace_sub.py.  Pass NULL to switch off. */
 void tfcfft_debug_trace(void* device_buffer);
 
 /* Number of kernels this library has launched in this process since the last reset. */
