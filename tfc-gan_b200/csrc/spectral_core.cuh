@@ -46,7 +46,6 @@ struct Params {
     long long* trace;      // debug: per-CTA stage timestamps (tfcfft_debug_trace), normally nullptr
     // sub-tile path (P = 128 / 256): the tile is decimated into D x D interleaved 64 x 64 sub-images
     int sub_d;             // 0 / 1: not used; 2 or 4
-    int pair_mode;         // sub_pair_kernel: 1 sub-images -> spectra in zws, 2 zws -> gradient
     int chunk_now;         // tiles in the chunk being processed by this launch
     // spectra materialisation (fft_components / make_spectra): grid == 1, tile = n * C' + ch
     int spec_mode;         // 0 loss, 1 emit amp / phase of both inputs, 2 backward from d/d(amp, phase)

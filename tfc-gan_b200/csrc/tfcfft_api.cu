@@ -186,7 +186,6 @@ int launch(const Params& prm, bool split, cudaStream_t st) {
             if (pair_supported(prm)) {
                 // measured (profiles/): the thread-per-line kernel wins on both luma (1.45 M vs 1.39 M img/s) and
                 // single-channel tiles (0.80 M vs 0.60 M); the packed pair kernel stays selectable for A/B runs
-                // and is the engine of the sub-tile path
                 const bool line = !(prm.flags & TFCFFT_USE_PAIR);
                 if (line) return launch_line<T, LUMA3>(prm, st);
                 return launch_pair<P, T, LUMA3>(prm, st);
