@@ -121,6 +121,15 @@ int tfcfft_spectra(const tfcfft_desc* d, const void* x, const void* y, float* am
 int tfcfft_spectra_bwd(const tfcfft_desc* d, const void* x, const float* grad_amp, const float* grad_pha,
                        void* grad_x, int fftshift, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Regional FFT loss on the reference's two 100 x 256 bands ("hair" rows 0..99, "eyes" rows 100..199 of a 256 x 256
+ * image): regional_fft_loss, TFCGAN_multigpu_patchFFT_withregion_FFT.py:353-402 -- per band the grey -> rfft2 ->
+ * abs / arctan2 -> nn.L1Loss pipeline of the patch losses on a 100 x 129 half spectrum, the two bands summed,
+ * 1/2 (amp + pha).  Arguments as tfcfft_loss (d->grid is ignored, H = W = 256 required; flags: CHANNELS_RGB,
+ * NO_PHASE, DIST_MSE, QUANTIZE_U8); fused forward + backward; out[1], out[2] are the summed amp / pha terms. */
+size_t tfcfft_regional_workspace_bytes(const tfcfft_desc* d);
+int tfcfft_regional_loss(const tfcfft_desc* d, const void* fake, const void* real, float* out, float* per_image,
+                         void* grad_fake, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Patch triplet loss of the generator step, forward + backward in one streaming pass (the first "next" row of
  * the hot-path scope table).  Replaces, for all g*g patches at once,
  *     triplet_loss(fake_B_i, B_i, random_patches[k_i])      with nn.TripletMarginLoss(margin, p=2)

@@ -98,6 +98,17 @@ def main():
                           dtype=dtype, lambda_t=10, loss=float(ns["loss_temp_g"]), temps_sum=float(ns["TFB_"].double().sum()),
                           tb_sum=float(ns["TB"].double().sum())))
         arrays[name + "_TFB_n0_rows100_104"] = ns["TFB_"][0, 0, 100:104].numpy()
+    # ---- regional FFT loss: FFT_Components + regional_fft_loss (patchFFT_withregion_FFT.py:246-265, 353-402)
+    FREG = f"{REF}/TFC-GAN-FFT/TFCGAN_multigpu_patchFFT_withregion_FFT.py"
+    src_r = lift(FREG, ["FFT_Components", "regional_fft_loss"])
+    for kind, seed, n, dtype in [("uniform", 61, 2, "float32"), ("tanh", 62, 2, "float16"), ("lowpass", 63, 3, "float32")]:
+        f, r = make_pair(kind, seed, (n, 3, 256, 256), dtype)
+        ns = dict(np=np, torch=torch, nn=nn, transforms=transforms, opt=types.SimpleNamespace(batch_size=n, img_height=256, img_width=256),
+                  criterion_amp=nn.L1Loss(), criterion_phase=nn.L1Loss())
+        exec(src_r, ns)
+        loss = ns["regional_fft_loss"](torch.from_numpy(f), torch.from_numpy(r))
+        cases.append(dict(name=f"regional_{kind}_{seed}_{dtype}", op="regional", ref=f"{os.path.relpath(FREG, REF)}:246-265,353-402",
+                          kind=kind, seed=seed, n=n, dtype=dtype, loss=float(loss)))
     json.dump(dict(torch=torch.__version__, numpy=np.__version__, cases=cases), open(os.path.join(HERE, "golden_triplet.json"), "w"),
               indent=1)
     np.savez_compressed(os.path.join(HERE, "golden_triplet.npz"), **arrays)

@@ -14,13 +14,15 @@ import tfc_gan_b200 as tfc
 from inputs import make_pair
 from oracle import triplet as otri
 from oracle import temperature as otemp
-from util import emulate_temperature, emulate_triplet, l2rel
+from oracle import regional as oreg
+from util import emulate_regional, emulate_temperature, emulate_triplet, l2rel
 
 L = tfc._lib
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "golden_triplet.json")))
 ARR = np.load(os.path.join(HERE, "golden", "golden_triplet.npz"))
-TRI = [c for c in GOLD["cases"] if c.get("op") != "temperature"]
+TRI = [c for c in GOLD["cases"] if "op" not in c]
+REG = [c for c in GOLD["cases"] if c.get("op") == "regional"]
 TEMP = [c for c in GOLD["cases"] if c.get("op") == "temperature"]
 
 
@@ -214,3 +216,50 @@ def test_temperature_c_entry_point_argument_checks():
     d.h = d.w = 96
     assert f(ctypes.byref(d), 256, 256, 256, ns, lut, 1.0, 1e-6, 256, None, 256, nb, None) == -4
     assert lib.tfcfft_vectorize_temps(ctypes.byref(d), 256, lut, 256, None) == -4
+
+
+# ---- regional FFT loss on the 100 x 256 bands ------------------------------------------------
+@pytest.mark.parametrize("case", REG, ids=[c["name"] for c in REG])
+def test_regional_oracle_and_emulated_kernel_match_the_reference_function(case):
+    f, r = make_pair(case["kind"], case["seed"], (case["n"], 3, 256, 256), case["dtype"])
+    l, _, _ = oreg.regional_loss_r0(f, r)
+    assert float(l) == pytest.approx(case["loss"], rel=2e-6)
+    rc, out, _, _ = emulate_regional(f, r, flags=L.QUANTIZE_U8, grad=False)
+    assert rc == 0 and out[0] == pytest.approx(case["loss"], rel=1e-5)
+    rc, _, _, _ = emulate_regional(f, r, flags=L.QUANTIZE_U8)     # as shipped there is no gradient
+    assert rc == -9
+
+
+REG_OPTS = [dict(), dict(channels="rgb"), dict(distance="mse", use_phase=False), dict(use_phase=False)]
+
+
+@pytest.mark.parametrize("opt", REG_OPTS, ids=["default", "rgb", "mse-amp", "amp-only"])
+def test_regional_emulated_kernel_matches_r1(opt):
+    f, r = make_pair("tanh", 7, (2, 3, 256, 256), "float32")
+    flags = tfc.SpectralConfig(grid=1, **opt).flags()
+    rc, out, per, g = emulate_regional(f, r, flags=flags, weight=0.7, input_scale=3.0)
+    assert rc == 0
+    l, a, p, gr = oreg.regional_loss_and_grad_r1(f, r, weight=0.7, input_scale=3.0, **opt)
+    assert out[0] == pytest.approx(l, rel=1e-5) and out[1] == pytest.approx(a, rel=1e-5)
+    assert out[2] == pytest.approx(p, rel=1e-5, abs=1e-12)
+    assert l2rel(g, gr) <= 1e-3
+    assert np.abs(g[:, :, 200:]).max() == 0.0                      # rows outside the two bands get no gradient
+    assert per[:, 0].mean() == pytest.approx(a, rel=1e-5)
+
+
+def test_regional_single_channel_half_and_argument_checks():
+    f, r = make_pair("uniform", 9, (1, 1, 256, 256), "float16")
+    rc, out, _, g = emulate_regional(f, r, input_scale=255.0)
+    l, _, _, gr = oreg.regional_loss_and_grad_r1(f.astype(np.float64), r.astype(np.float64), input_scale=255.0)
+    assert rc == 0 and out[0] == pytest.approx(l, rel=1e-5) and l2rel(g.astype(np.float64), gr) <= 3e-3
+    lib = L.load()
+    st = (3 * 128 * 128, 128 * 128, 128, 1)
+    d = L.make_desc(L.F32, 1, 0, (2, 3, 128, 128), st, st, st, 1.0, 1.0)
+    assert lib.tfcfft_regional_workspace_bytes(ctypes.byref(d)) == 0
+    assert lib.tfcfft_regional_loss(ctypes.byref(d), 256, 256, 256, None, None, 256, 1 << 20, None) == -4   # bands need 256 x 256
+    st = (3 * 65536, 65536, 256, 1)
+    d = L.make_desc(L.F32, 1, L.LOG_MAGNITUDE, (2, 3, 256, 256), st, st, st, 1.0, 1.0)
+    assert lib.tfcfft_regional_loss(ctypes.byref(d), 256, 256, 256, None, None, 256, 1 << 20, None) == -7
+    d = L.make_desc(L.F32, 1, 0, (2, 3, 256, 256), st, st, st, 1.0, 1.0)
+    assert lib.tfcfft_regional_workspace_bytes(ctypes.byref(d)) >= 256
+    assert lib.tfcfft_regional_loss(ctypes.byref(d), 256, 256, 256, None, None, None, 0, None) == -8

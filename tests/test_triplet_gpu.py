@@ -19,7 +19,8 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "golden_triplet.json")))
 ARR = np.load(os.path.join(HERE, "golden", "golden_triplet.npz"))
-TRI = [c for c in GOLD["cases"] if c.get("op") != "temperature"]
+TRI = [c for c in GOLD["cases"] if "op" not in c]
+REG = [c for c in GOLD["cases"] if c.get("op") == "regional"]
 TEMP = [c for c in GOLD["cases"] if c.get("op") == "temperature"]
 LOSS_TOL, GRAD_TOL = 1e-4, 1e-3
 
@@ -242,3 +243,59 @@ def test_temperature_full_size_and_determinism():
     # negative == positive -> every hinge equals the margin, zero gradient
     o3, g3 = tfc.temperature_triplet_loss_and_grad(F, R, R, weight=1.0, margin=0.5)
     assert float(o3[1]) == pytest.approx(0.5, rel=1e-6) and float(g3.abs().max()) == 0.0
+
+
+
+# ---- regional FFT loss on the 100 x 256 bands ------------------------------------------------
+from oracle import regional as oreg  # noqa: E402
+
+
+@pytest.mark.parametrize("case", REG, ids=[c["name"] for c in REG])
+def test_regional_loss_matches_reference_golden(case):
+    f, r = make_pair(case["kind"], case["seed"], (case["n"], 3, 256, 256), case["dtype"])
+    tfc.compat.set_mode("r0")
+    try:
+        loss = tfc.compat.regional_fft_loss(cu(f), cu(r))
+    finally:
+        tfc.compat.set_mode("r1")
+    assert float(loss) == pytest.approx(case["loss"], rel=LOSS_TOL) and not loss.requires_grad
+
+
+@pytest.mark.parametrize("opt", [dict(), dict(channels="rgb"), dict(distance="mse", use_phase=False)], ids=["default", "rgb", "mse-amp"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_regional_loss_and_gradient_match_oracle(opt, dtype):
+    f, r = make_pair("tanh", 81, (3, 3, 256, 256), "float32")
+    F, R = cu(f, dtype).requires_grad_(True), cu(r, dtype)
+    loss, terms = tfc.regional_spectral_loss(F, R, return_terms=True, weight=0.01, input_scale=255.0, **opt)
+    (loss * 2.0).backward()
+    l, a, p, gr = oreg.regional_loss_and_grad_r1(F.detach().double().cpu().numpy(), R.double().cpu().numpy(), weight=0.01,
+                                                 input_scale=255.0, **opt)
+    assert float(loss) == pytest.approx(l, rel=LOSS_TOL)
+    assert float(terms[0]) == pytest.approx(a, rel=LOSS_TOL)
+    g = F.grad.double().cpu().numpy()
+    assert l2rel(g, 2.0 * gr) <= (GRAD_TOL if dtype == torch.float32 else 3e-3)
+    assert np.abs(g[:, :, 200:]).max() == 0.0
+
+
+def test_regional_full_batch_properties():
+    g = torch.Generator(device="cuda").manual_seed(9)
+    F = torch.empty(64, 3, 256, 256, device="cuda").uniform_(-1, 1, generator=g)
+    R = torch.empty(64, 3, 256, 256, device="cuda").uniform_(-1, 1, generator=g)
+    l1, t1, g1 = tfc.regional_spectral_loss_and_grad(F, R, weight=0.01, input_scale=255.0)
+    l2, t2, g2 = tfc.regional_spectral_loss_and_grad(F, R, weight=0.01, input_scale=255.0)
+    assert torch.equal(l1, l2) and torch.equal(g1, g2)                           # deterministic
+    l0, _, g0 = tfc.regional_spectral_loss_and_grad(F, F.clone(), weight=0.01, input_scale=255.0)
+    assert 0.0 <= float(l0) <= 1e-5 * float(l1)                                   # identical inputs: zero up to fp32 un-mixing noise
+    # the loss only sees rows 0..199: changing the rest changes nothing
+    F2 = F.clone()
+    F2[:, :, 200:] = 0.123
+    l3, _, _ = tfc.regional_spectral_loss_and_grad(F2, R, weight=0.01, input_scale=255.0)
+    assert torch.equal(l1, l3)
+    # torch.fft on the GPU as an independent yard-stick
+    w = torch.tensor([19595.0, 38470.0, 7471.0], device="cuda").view(1, 3, 1, 1) / 65536.0
+    lum = lambda x: (x * 255.0 * w).sum(1)
+    ref = 0.0
+    for lo, hi in ((0, 100), (100, 200)):
+        a, b = torch.fft.rfft2(lum(F)[:, lo:hi]), torch.fft.rfft2(lum(R)[:, lo:hi])
+        ref = ref + (a.abs() - b.abs()).abs().mean() + (torch.angle(a) - torch.angle(b)).abs().mean()
+    assert float(l1) == pytest.approx(0.01 * 0.5 * float(ref), rel=2e-4)

@@ -124,3 +124,18 @@ def emulate_temperature(fake, positive, negative, lut, flags=0, margin=1.0, eps=
     rc = fn(ctypes.byref(d), fake.ctypes.data, positive.ctypes.data, negative.ctypes.data, (ctypes.c_int64 * 4)(*_strides(negative)),
             (ctypes.c_float * 256)(*[float(v) for v in lut]), margin, eps, out.ctypes.data, g.ctypes.data if g is not None else None)
     return rc, out, g
+
+
+def emulate_regional(fake, real, flags=0, weight=1.0, input_scale=1.0, grad=True, dtype_code=None):
+    """CPU twin of tfcfft_regional_loss.  Returns (rc, out[4], per_image, grad)."""
+    lib = emu_lib()
+    lib.tfcfft_emulate_regional.restype = ctypes.c_int
+    lib.tfcfft_emulate_regional.argtypes = [ctypes.POINTER(L.Desc)] + [ctypes.c_void_p] * 5
+    code = dtype_code if dtype_code is not None else NP_DTYPES[str(fake.dtype)]
+    out = np.zeros(4, np.float32)
+    per = np.zeros((fake.shape[0], 2), np.float32)
+    g = np.zeros_like(fake) if grad else None
+    d = L.make_desc(code, 1, flags, fake.shape, _strides(fake), _strides(real), _strides(g) if grad else None, weight, input_scale)
+    rc = lib.tfcfft_emulate_regional(ctypes.byref(d), fake.ctypes.data, real.ctypes.data, out.ctypes.data, per.ctypes.data,
+                                     g.ctypes.data if grad else None)
+    return rc, out, per, g

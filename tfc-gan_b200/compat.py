@@ -19,7 +19,7 @@ import torch
 
 import numpy as np
 
-from .functional import SpectralConfig, patch_triplet_loss, temperature_triplet_loss, vectorize_temps as _vectorize_temps, spectral_components, spectral_loss, spectral_terms_per_image
+from .functional import SpectralConfig, patch_triplet_loss, regional_spectral_loss, temperature_triplet_loss, vectorize_temps as _vectorize_temps, spectral_components, spectral_loss, spectral_terms_per_image
 
 _MODE = {"mode": "r1", "input_scale": 255.0}
 
@@ -151,6 +151,14 @@ def temperature_loss(fake_B, TB, B_tf, lambda_t: float = 10.0):
     reproduces the reference (no gradient), ``"r1"`` is differentiable."""
     return temperature_triplet_loss(fake_B, TB, B_tf, quantize=(_MODE["mode"] == "r0"), weight=lambda_t,
                                     input_scale=_MODE["input_scale"])
+
+
+def regional_fft_loss(fake_B, real_B):
+    """``regional_fft_loss(fake_B, real_B)`` (``TFCGAN_multigpu_patchFFT_withregion_FFT.py:353-402``): hair (rows 0..99) and
+    eyes (rows 100..199) bands, amplitude + phase L1, bands summed, ``1/2 (amp + pha)``."""
+    if _MODE["mode"] == "r0":
+        return regional_spectral_loss(fake_B, real_B, quantize=True)
+    return regional_spectral_loss(fake_B, real_B, input_scale=_MODE["input_scale"])
 
 
 def global_fft_loss(fake_B, real_B):

@@ -278,3 +278,47 @@ extern "C" int tfcfft_emulate_temperature_triplet(const tfcfft_desc* d, const vo
     }
     return TFCFFT_OK;
 }
+
+template <typename T, bool LUMA3>
+static void run_regional(Params prm) {
+    SerialCtx ctx;
+    std::vector<float2> s((size_t)RegCfg::H * RegCfg::LD), tw(RegCfg::W), w100(100);
+    fill_twiddles<RegCfg::W>(ctx, tw.data());
+    reg_fill_w100(ctx, w100.data());
+    for (int unit = 0; unit < prm.tiles_total; ++unit) {
+        float a = 0.f, p = 0.f;
+        regional_process<T, LUMA3>(ctx, prm, unit, s.data(), tw.data(), w100.data(), a, p);
+        prm.partials[2 * unit] = a;
+        prm.partials[2 * unit + 1] = p;
+    }
+}
+
+extern "C" int tfcfft_emulate_regional(const tfcfft_desc* d, const void* fake, const void* real, float* out, float* per_image,
+                                       void* grad_fake) {
+    Geometry g;
+    int rc = validate_regional(d, &g);
+    if (rc) return rc;
+    if (!fake || !real || !out) return TFCFFT_ERR_NULL;
+    if ((rc = check_grad_args(d, grad_fake))) return rc;
+    std::vector<char> ws(g.ws_bytes, 0);
+    Params prm = make_regional_params(d, g, fake, real, grad_fake, out, per_image, ws.data());
+    switch (d->dtype) {
+        case TFCFFT_F32: g.luma3 ? run_regional<float, true>(prm) : run_regional<float, false>(prm); break;
+        case TFCFFT_F16: g.luma3 ? run_regional<__half, true>(prm) : run_regional<__half, false>(prm); break;
+        case TFCFFT_BF16: g.luma3 ? run_regional<__nv_bfloat16, true>(prm) : run_regional<__nv_bfloat16, false>(prm); break;
+        case TFCFFT_U8: g.luma3 ? run_regional<uint8_t, true>(prm) : run_regional<uint8_t, false>(prm); break;
+    }
+    double sa = 0.0, sp = 0.0;
+    for (int img = 0; img < prm.n; ++img) {
+        double a, p;
+        image_sums(prm, img, a, p);
+        if (per_image) {
+            per_image[2 * img] = (float)(a * prm.norm * prm.n);
+            per_image[2 * img + 1] = (float)(p * prm.norm * prm.n);
+        }
+        sa += a;
+        sp += p;
+    }
+    write_outputs(prm, sa, sp);
+    return TFCFFT_OK;
+}

@@ -6,6 +6,7 @@
 
 #include "spectral_core.cuh"
 #include "triplet.cuh"
+#include "regional.cuh"
 
 namespace tfcfft {
 
@@ -170,6 +171,54 @@ inline const char* status_string(int rc) {
         case TFCFFT_ERR_EMPTY: return "tfcfft: empty batch (N == 0)";
         default: return nullptr;
     }
+}
+
+// ---- regional 100 x 256 FFT loss ------------------------------------------------------------------------------
+inline int validate_regional(const tfcfft_desc* d, Geometry* geo) {
+    if (!d) return TFCFFT_ERR_NULL;
+    if (d->struct_size != sizeof(tfcfft_desc)) return TFCFFT_ERR_STRUCT;
+    if (elem_size(d->dtype) == 0) return TFCFFT_ERR_DTYPE;
+    if (d->n == 0) return TFCFFT_ERR_EMPTY;
+    if (d->n < 0 || d->n > (1 << 22)) return TFCFFT_ERR_SHAPE;
+    if (d->c != 1 && d->c != 3) return TFCFFT_ERR_SHAPE;
+    if (d->h != 256 || d->w != 256) return TFCFFT_ERR_SHAPE;  // the reference's bands: rows 0..99 and 100..199 of 256
+    if (d->flags & ~(TFCFFT_CHANNELS_RGB | TFCFFT_NO_PHASE | TFCFFT_DIST_MSE | TFCFFT_QUANTIZE_U8)) return TFCFFT_ERR_FLAGS;
+    if ((d->flags & TFCFFT_QUANTIZE_U8) && (d->flags & TFCFFT_CHANNELS_RGB) && d->c == 3) return TFCFFT_ERR_FLAGS;
+    for (int t = 0; t < 2; ++t) {
+        const int64_t* st = t ? d->real_stride : d->fake_stride;
+        if (st[3] != 1) return TFCFFT_ERR_STRIDE;
+        for (int i = 0; i < 3; ++i)
+            if (st[i] % 4 != 0 || st[i] < 0) return TFCFFT_ERR_STRIDE;
+    }
+    if (geo) {
+        *geo = Geometry{};
+        geo->p = 256;
+        geo->luma3 = (d->c == 3) && !(d->flags & TFCFFT_CHANNELS_RGB);
+        geo->cprime = (d->c == 3 && !geo->luma3) ? 3 : 1;
+        geo->parts = 1;
+        geo->tiles_total = (long long)d->n * geo->cprime * RegCfg::BANDS;
+        geo->partial_bytes = align_up((size_t)geo->tiles_total * 2 * sizeof(float), 256);
+        geo->ws_bytes = kWsHeader + geo->partial_bytes;
+    }
+    return TFCFFT_OK;
+}
+
+inline Params make_regional_params(const tfcfft_desc* d, const Geometry& g, const void* fake, const void* real, void* grad,
+                                   float* out, float* per_image, void* ws) {
+    tfcfft_desc d1 = *d;
+    d1.grid = 1;
+    Params p = make_params(&d1, g, fake, real, grad, out, per_image, ws);
+    p.tiles_per_image = g.cprime * RegCfg::BANDS;
+    p.tiles_total = (int)g.tiles_total;
+    // nn.L1Loss per band = mean over N * C' * 100 * 129 bins; the two bands are SUMMED (withregion_FFT.py:398-399)
+    p.norm = 1.0 / ((double)d->n * g.cprime * RegCfg::H * (RegCfg::W / 2 + 1));
+    if (d->flags & TFCFFT_NO_PHASE) {
+        p.sa = (float)((double)d->weight * p.norm);
+        p.sp = 0.f;
+    } else {
+        p.sa = p.sp = (float)(0.5 * (double)d->weight * p.norm);
+    }
+    return p;
 }
 
 // ---- patch triplet loss ------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@
 #include "sub_tile.cuh"
 #include "line_tile.cuh"
 #include "triplet.cuh"
+#include "regional.cuh"
 #include "spectral_core.cuh"
 
 namespace tfcfft {
@@ -435,6 +436,31 @@ __global__ void __launch_bounds__(256) grad_scale_kernel(T* __restrict__ dst, co
     }
     for (long long i = nvec * V + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride)
         dst[i] = (T)((float)src[i] * sc);
+}
+
+// ---- regional 100 x 256 FFT loss (regional.cuh): one CTA per (image, channel, band), tile resident in shared memory
+template <typename T, bool LUMA3>
+__global__ void __launch_bounds__(RegCfg::NT, 1) regional_kernel(const __grid_constant__ Params prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    float2* tw = s + RegCfg::H * RegCfg::LD;
+    float2* w100 = tw + RegCfg::W;
+    const BlockCtx ctx{(int)threadIdx.x, (int)blockDim.x};
+    fill_twiddles<RegCfg::W>(ctx, tw);
+    reg_fill_w100(ctx, w100);
+    ctx.sync();
+    pdl_wait();
+    for (int unit = blockIdx.x; unit < prm.tiles_total; unit += gridDim.x) {
+        float a = 0.f, p = 0.f;
+        regional_process<T, LUMA3>(ctx, prm, unit, s, tw, w100, a, p);
+        block_sum2(a, p);
+        if (threadIdx.x == 0) {
+            prm.partials[2 * unit] = a;
+            prm.partials[2 * unit + 1] = p;
+        }
+    }
+    pdl_release();
+    finish(prm, gridDim.x);
 }
 
 // ---- patch triplet loss (triplet.cuh): one lane group per patch row, persistent warps ------------------------

@@ -236,6 +236,17 @@ int launch_triplet(const TripletParams& tp, cudaStream_t st) {
     return 0;
 }
 
+template <typename T, bool LUMA3>
+int launch_regional(const Params& prm, cudaStream_t st) {
+    auto kernel = regional_kernel<T, LUMA3>;
+    if (int rc = set_smem(kernel, RegCfg::SMEM)) return rc;
+    const int sms = device_info().sms;
+    const int grid = prm.tiles_total < sms ? prm.tiles_total : sms;
+    if (cudaError_t e = launch_pdl(kernel, grid, RegCfg::NT, RegCfg::SMEM, st, prm)) return (int)e;
+    g_launches++;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -331,6 +342,32 @@ int tfcfft_loss(const tfcfft_desc* d, const void* fake, const void* real, float*
     prm.trace = g_trace.load();
     cudaStream_t st = (cudaStream_t)stream;
     return dispatch(prm, g, d->dtype, st);
+}
+
+size_t tfcfft_regional_workspace_bytes(const tfcfft_desc* d) {
+    Geometry g;
+    if (validate_regional(d, &g) != TFCFFT_OK) return 0;
+    return g.ws_bytes;
+}
+
+int tfcfft_regional_loss(const tfcfft_desc* d, const void* fake, const void* real, float* out, float* per_image, void* grad_fake,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    Geometry g;
+    int rc = validate_regional(d, &g);
+    if (rc) return rc;
+    if (!fake || !real || !out) return TFCFFT_ERR_NULL;
+    if ((rc = check_grad_args(d, grad_fake))) return rc;
+    if ((rc = check_alignment(d, fake, real, grad_fake))) return rc;
+    if (!workspace || workspace_bytes < g.ws_bytes || ((uintptr_t)workspace & 255)) return TFCFFT_ERR_WORKSPACE;
+    const Params prm = make_regional_params(d, g, fake, real, grad_fake, out, per_image, workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (d->dtype) {
+        case TFCFFT_F32: return g.luma3 ? launch_regional<float, true>(prm, st) : launch_regional<float, false>(prm, st);
+        case TFCFFT_F16: return g.luma3 ? launch_regional<__half, true>(prm, st) : launch_regional<__half, false>(prm, st);
+        case TFCFFT_BF16: return g.luma3 ? launch_regional<__nv_bfloat16, true>(prm, st) : launch_regional<__nv_bfloat16, false>(prm, st);
+        case TFCFFT_U8: return g.luma3 ? launch_regional<uint8_t, true>(prm, st) : launch_regional<uint8_t, false>(prm, st);
+    }
+    return TFCFFT_ERR_DTYPE;
 }
 
 size_t tfcfft_triplet_workspace_bytes(void) { return kTripletWsBytes; }

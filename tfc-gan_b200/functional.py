@@ -297,6 +297,73 @@ def spectral_components(x, *, channels: str = "luma", input_scale: float = 1.0, 
     return _SpectraFn.apply(x, cfg, bool(fftshift))
 
 
+# ---- regional FFT loss ------------------------------------------------------------------------
+def _launch_regional(fake, real, cfg: SpectralConfig, want_grad: bool):
+    lib = _lib.load()
+    dev = fake.device
+    with torch.cuda.device(dev):
+        stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        # rows 200..255 belong to no band: their gradient is zero
+        grad = torch.zeros(fake.shape, dtype=fake.dtype, device=dev) if want_grad else None
+        desc = _lib.make_desc(_DTYPES[fake.dtype], 1, cfg.flags(), fake.shape, fake.stride(), real.stride(),
+                              grad.stride() if want_grad else None, cfg.weight, cfg.input_scale)
+        nbytes = lib.tfcfft_regional_workspace_bytes(ctypes.byref(desc))
+        if nbytes == 0:
+            raise RuntimeError("tfcfft_regional_loss: unsupported configuration (needs [N, 1|3, 256, 256]; options: channels, "
+                               "use_phase, distance, quantize)")
+        ws = _workspace(dev, stream_ptr, nbytes)
+        rc = lib.tfcfft_regional_loss(ctypes.byref(desc), fake.data_ptr(), real.data_ptr(), out.data_ptr(), None,
+                                      grad.data_ptr() if want_grad else None, ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream_ptr))
+        if rc > 0:
+            _WORKSPACES.pop((dev.index, stream_ptr), None)
+        _lib.check(rc, "tfcfft_regional_loss")
+    return out, grad
+
+
+class _RegionalLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fake, real, cfg):
+        fake_p, real_p = _prep(fake.detach(), real.detach())
+        want_grad = ctx.needs_input_grad[0] and not cfg.quantize and fake_p.dtype != torch.uint8
+        out, grad = _launch_regional(fake_p, real_p, cfg, want_grad)
+        ctx.has_grad, ctx.in_dtype = want_grad, fake.dtype
+        if want_grad:
+            ctx.save_for_backward(grad)
+        terms = out[1:3]
+        ctx.mark_non_differentiable(terms)
+        return out[0], terms
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_loss, _grad_terms):
+        if not ctx.has_grad:
+            return None, None, None
+        (unit,) = ctx.saved_tensors
+        res = (unit.float() * grad_loss.detach().float()).to(ctx.in_dtype)
+        return res, None, None
+
+
+def regional_spectral_loss(fake, real, *, return_terms: bool = False, channels: str = "luma", use_phase: bool = True,
+                           distance: str = "l1", weight: float = 1.0, input_scale: float = 1.0, quantize: bool = False):
+    """The reference's ``regional_fft_loss`` (``TFCGAN_multigpu_patchFFT_withregion_FFT.py:353-402``) on the GPU, with a
+    gradient: FFT amplitude + phase L1 loss on the two 100 x 256 bands (rows 0..99 "hair", 100..199 "eyes"), the two
+    bands summed.  ``fake`` / ``real``: ``[N, 1|3, 256, 256]``."""
+    cfg = SpectralConfig(grid=1, channels=channels, use_phase=use_phase, distance=distance, weight=weight, input_scale=input_scale,
+                         quantize=quantize)
+    loss, terms = _RegionalLossFn.apply(fake, real, cfg)
+    return (loss, terms) if return_terms else loss
+
+
+@torch.no_grad()
+def regional_spectral_loss_and_grad(fake, real, **options):
+    """The fused pass without autograd: ``(loss, terms, d loss / d fake)``."""
+    cfg = SpectralConfig(grid=1, **options)
+    fake_p, real_p = _prep(fake, real)
+    out, grad = _launch_regional(fake_p, real_p, cfg, True)
+    return out[0], out[1:3], grad
+
+
 # ---- patch triplet loss (SURVEY.md §8f-1) ----------------------------------------------------------------------
 def _check_negatives(negatives, grid: int):
     neg = [int(k) for k in negatives]
