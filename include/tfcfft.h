@@ -130,6 +130,15 @@ size_t tfcfft_regional_workspace_bytes(const tfcfft_desc* d);
 int tfcfft_regional_loss(const tfcfft_desc* d, const void* fake, const void* real, float* out, float* per_image,
                          void* grad_fake, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Materialised spectra of the two bands -- the reference's inner reg_fft (withregion_FFT.py:358-371) -- and their
+ * backward, so that other criteria (e.g. the KLDivLoss variant, ..._withregion_FFT_KL.py:398-414) can be applied
+ * through autograd.  amp / pha: device float [N][C'][2 bands][100][129]; fftshift != 0 stores them fftshift-ed over
+ * both axes like the reference (:253).  Either output (or incoming gradient) may be NULL. */
+int tfcfft_regional_spectra(const tfcfft_desc* d, const void* x, float* amp, float* pha, int fftshift, void* workspace,
+                            size_t workspace_bytes, void* stream);
+int tfcfft_regional_spectra_bwd(const tfcfft_desc* d, const void* x, const float* grad_amp, const float* grad_pha,
+                                void* grad_x, int fftshift, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Patch triplet loss of the generator step, forward + backward in one streaming pass (the first "next" row of
  * the hot-path scope table).  Replaces, for all g*g patches at once,
  *     triplet_loss(fake_B_i, B_i, random_patches[k_i])      with nn.TripletMarginLoss(margin, p=2)

@@ -15,7 +15,7 @@ from inputs import make_pair
 from oracle import triplet as otri
 from oracle import temperature as otemp
 from oracle import regional as oreg
-from util import emulate_regional, emulate_temperature, emulate_triplet, l2rel
+from util import emulate_regional, emulate_regional_spectra, emulate_temperature, emulate_triplet, l2rel
 
 L = tfc._lib
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -263,3 +263,33 @@ def test_regional_single_channel_half_and_argument_checks():
     d = L.make_desc(L.F32, 1, 0, (2, 3, 256, 256), st, st, st, 1.0, 1.0)
     assert lib.tfcfft_regional_workspace_bytes(ctypes.byref(d)) >= 256
     assert lib.tfcfft_regional_loss(ctypes.byref(d), 256, 256, 256, None, None, None, 0, None) == -8
+
+
+def test_regional_spectra_emulated_match_reference_components_and_autograd():
+    from oracle.r0_literal import components_r0, gray_u8
+    f, _ = make_pair("unit", 91, (2, 3, 256, 256), "float32")
+    # as shipped (quantised, fftshift-ed): amplitudes against FFT_Components.make_components on each band
+    rc, amp, pha = emulate_regional_spectra(f, flags=L.QUANTIZE_U8, shift=True)
+    assert rc == 0
+    g = gray_u8(f)
+    for t in range(2):
+        for b, (lo, hi) in enumerate(((0, 100), (100, 200))):
+            a, p = components_r0(g[t, lo:hi])
+            assert np.abs(amp[t, 0, b] - a).max() <= 2e-6 * a.max()
+            big = a > 1e-3 * a.max()                                    # phases of negligible bins are noise
+            assert np.abs(np.angle(np.exp(1j * (pha[t, 0, b] - p))))[big].max() <= 1e-3
+    # differentiable variant: d/dx of sum(w_a * amp + w_p * pha) against torch autograd (fp64)
+    rs = np.random.RandomState(0)
+    wa = rs.normal(size=(2, 1, 2, 100, 129)).astype(np.float32)
+    wp = (1e-3 * rs.normal(size=(2, 1, 2, 100, 129))).astype(np.float32)
+    rc, gx = emulate_regional_spectra(f, input_scale=2.0, shift=False, grad_amp=wa, grad_pha=wp)
+    assert rc == 0
+    x = torch.from_numpy(f).double().requires_grad_(True)
+    w = torch.tensor([19595.0, 38470.0, 7471.0], dtype=torch.float64).view(1, 3, 1, 1) / 65536.0
+    lum = (x * 2.0 * w).sum(1)
+    tot = 0.0
+    for b, (lo, hi) in enumerate(((0, 100), (100, 200))):
+        F = torch.fft.rfft2(lum[:, lo:hi])
+        tot = tot + (torch.from_numpy(wa[:, 0, b]).double() * F.abs()).sum() + (torch.from_numpy(wp[:, 0, b]).double() * torch.angle(F)).sum()
+    tot.backward()
+    assert l2rel(gx.astype(np.float64), x.grad.numpy()) <= 1e-3

@@ -299,3 +299,32 @@ def test_regional_full_batch_properties():
         a, b = torch.fft.rfft2(lum(F)[:, lo:hi]), torch.fft.rfft2(lum(R)[:, lo:hi])
         ref = ref + (a.abs() - b.abs()).abs().mean() + (torch.angle(a) - torch.angle(b)).abs().mean()
     assert float(l1) == pytest.approx(0.01 * 0.5 * float(ref), rel=2e-4)
+
+
+def test_regional_components_differentiable_and_kl_variant_composes():
+    f, r = make_pair("unit", 93, (3, 3, 256, 256), "float32")
+    F, R = cu(f).requires_grad_(True), cu(r)
+    (Ah, Ph), (Ae, Pe) = tfc.compat.regional_components(F)
+    assert Ah.shape == (3, 1, 100, 129) and Pe.shape == (3, 1, 100, 129)
+    # the L1 loss rebuilt from the materialised spectra equals the fused kernel's
+    (Ahr, Phr), (Aer, Per) = tfc.compat.regional_components(R)
+    rebuilt = 0.5 * ((Ah - Ahr).abs().mean() + (Ae - Aer).abs().mean() + (Ph - Phr).abs().mean() + (Pe - Per).abs().mean())
+    fused = tfc.compat.regional_fft_loss(F, R)
+    assert float(rebuilt) == pytest.approx(float(fused), rel=1e-4)
+    # the KL variant's criterion (log_softmax over the batch + KLDivLoss, ..._withregion_FFT_KL.py:84, 401-413) through autograd
+    kl = torch.nn.KLDivLoss(reduction="mean", log_target=True)
+    ls = lambda t: torch.nn.functional.log_softmax(t, dim=0)
+    loss = kl(ls(Ah), ls(Ahr)) + kl(ls(Ae), ls(Aer))
+    loss.backward()
+    g = F.grad
+    assert torch.isfinite(g).all() and float(g.abs().sum()) > 0 and float(g[:, :, 200:].abs().max()) == 0.0
+    # against torch.fft autograd for the same criterion
+    X = cu(f).double().requires_grad_(True)
+    w = torch.tensor([19595.0, 38470.0, 7471.0], device="cuda", dtype=torch.float64).view(1, 3, 1, 1) / 65536.0
+    lumx, lumr = (X * 255.0 * w).sum(1, keepdim=True), (R.double() * 255.0 * w).sum(1, keepdim=True)
+    ref = 0.0
+    for lo, hi in ((0, 100), (100, 200)):
+        ref = ref + kl(ls(torch.fft.rfft2(lumx[:, :, lo:hi]).abs()), ls(torch.fft.rfft2(lumr[:, :, lo:hi]).abs()))
+    ref.backward()
+    assert float(loss) == pytest.approx(float(ref), rel=1e-3, abs=1e-9)
+    assert l2rel(g.double().cpu().numpy(), X.grad.cpu().numpy()) <= 5e-3

@@ -139,3 +139,24 @@ def emulate_regional(fake, real, flags=0, weight=1.0, input_scale=1.0, grad=True
     rc = lib.tfcfft_emulate_regional(ctypes.byref(d), fake.ctypes.data, real.ctypes.data, out.ctypes.data, per.ctypes.data,
                                      g.ctypes.data if grad else None)
     return rc, out, per, g
+
+
+def emulate_regional_spectra(x, flags=0, input_scale=1.0, shift=True, grad_amp=None, grad_pha=None):
+    """CPU twin of tfcfft_regional_spectra (no incoming gradients) / _bwd.  Returns (rc, amp, pha) or (rc, grad_x)."""
+    lib = emu_lib()
+    fn = lib.tfcfft_emulate_regional_spectra
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.POINTER(L.Desc)] + [ctypes.c_void_p] * 6 + [ctypes.c_int]
+    n, c = x.shape[:2]
+    cp = 3 if (flags & L.CHANNELS_RGB and c == 3) else 1
+    bwd = grad_amp is not None or grad_pha is not None
+    g = np.zeros_like(x) if bwd else None
+    d = L.make_desc(NP_DTYPES[str(x.dtype)], 1, flags, x.shape, _strides(x), _strides(x), _strides(g) if bwd else None, 1.0, input_scale)
+    if bwd:
+        rc = fn(ctypes.byref(d), x.ctypes.data, None, None, grad_amp.ctypes.data if grad_amp is not None else None,
+                grad_pha.ctypes.data if grad_pha is not None else None, g.ctypes.data, int(shift))
+        return rc, g
+    amp = np.zeros((n, cp, 2, 100, 129), np.float32)
+    pha = np.zeros_like(amp)
+    rc = fn(ctypes.byref(d), x.ctypes.data, amp.ctypes.data, pha.ctypes.data, None, None, None, int(shift))
+    return rc, amp, pha

@@ -43,6 +43,8 @@ EXPORTS = (
     "tfcfft_spectra_bwd",
     "tfcfft_regional_workspace_bytes",
     "tfcfft_regional_loss",
+    "tfcfft_regional_spectra",
+    "tfcfft_regional_spectra_bwd",
     "tfcfft_triplet_workspace_bytes",
     "tfcfft_patch_triplet",
     "tfcfft_temperature_triplet",
@@ -113,6 +115,10 @@ def bind(lib):
     lib.tfcfft_regional_workspace_bytes.argtypes = [dp]
     lib.tfcfft_regional_loss.restype = ctypes.c_int
     lib.tfcfft_regional_loss.argtypes = [dp, vp, vp, f32p, f32p, vp, vp, ctypes.c_size_t, vp]
+    lib.tfcfft_regional_spectra.restype = ctypes.c_int
+    lib.tfcfft_regional_spectra.argtypes = [dp, vp, f32p, f32p, ctypes.c_int, vp, ctypes.c_size_t, vp]
+    lib.tfcfft_regional_spectra_bwd.restype = ctypes.c_int
+    lib.tfcfft_regional_spectra_bwd.argtypes = [dp, vp, f32p, f32p, vp, ctypes.c_int, vp, ctypes.c_size_t, vp]
     lib.tfcfft_triplet_workspace_bytes.restype = ctypes.c_size_t
     lib.tfcfft_triplet_workspace_bytes.argtypes = []
     lib.tfcfft_patch_triplet.restype = ctypes.c_int

@@ -19,7 +19,7 @@ import torch
 
 import numpy as np
 
-from .functional import SpectralConfig, patch_triplet_loss, regional_spectral_loss, temperature_triplet_loss, vectorize_temps as _vectorize_temps, spectral_components, spectral_loss, spectral_terms_per_image
+from .functional import SpectralConfig, patch_triplet_loss, regional_components as _regional_components, regional_spectral_loss, temperature_triplet_loss, vectorize_temps as _vectorize_temps, spectral_components, spectral_loss, spectral_terms_per_image
 
 _MODE = {"mode": "r1", "input_scale": 255.0}
 
@@ -159,6 +159,16 @@ def regional_fft_loss(fake_B, real_B):
     if _MODE["mode"] == "r0":
         return regional_spectral_loss(fake_B, real_B, quantize=True)
     return regional_spectral_loss(fake_B, real_B, input_scale=_MODE["input_scale"])
+
+
+def regional_components(thermal_tensor):
+    """The four tensors ``reg_fft`` produces for one image batch in ``regional_fft_loss``
+    (``TFCGAN_multigpu_patchFFT_withregion_FFT.py:358-389``): ``((A_hair, P_hair), (A_eyes, P_eyes))``, each
+    ``[N,1,100,129]`` fp32 in the reference's fftshift-ed layout -- differentiable in ``"r1"`` mode, so the KL variant
+    (``..._withregion_FFT_KL.py:398-414``) or any other criterion can be applied with plain torch ops."""
+    kw = dict(quantize=True) if _MODE["mode"] == "r0" else dict(input_scale=_MODE["input_scale"])
+    amp, pha = _regional_components(thermal_tensor, **kw)
+    return (amp[:, :, 0], pha[:, :, 0]), (amp[:, :, 1], pha[:, :, 1])
 
 
 def global_fft_loss(fake_B, real_B):

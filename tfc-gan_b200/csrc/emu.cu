@@ -322,3 +322,29 @@ extern "C" int tfcfft_emulate_regional(const tfcfft_desc* d, const void* fake, c
     write_outputs(prm, sa, sp);
     return TFCFFT_OK;
 }
+
+// Host twins of tfcfft_regional_spectra / _bwd (mode 1: amp / pha out; mode 2: grad_amp / grad_pha in, grad_x out).
+extern "C" int tfcfft_emulate_regional_spectra(const tfcfft_desc* d, const void* x, float* amp, float* pha, const float* grad_amp,
+                                               const float* grad_pha, void* grad_x, int fftshift) {
+    Geometry g;
+    int rc = validate_regional(d, &g);
+    if (rc) return rc;
+    if (!x) return TFCFFT_ERR_NULL;
+    if ((rc = check_grad_args(d, grad_x))) return rc;
+    std::vector<char> ws(g.ws_bytes, 0);
+    float out[4];
+    Params prm = make_regional_params(d, g, x, x, grad_x, out, nullptr, ws.data());
+    prm.spec_mode = grad_x ? 2 : 1;
+    prm.spec_shift = fftshift != 0;
+    prm.spec_out[0] = amp;
+    prm.spec_out[1] = pha;
+    prm.spec_gin[0] = grad_amp;
+    prm.spec_gin[1] = grad_pha;
+    switch (d->dtype) {
+        case TFCFFT_F32: g.luma3 ? run_regional<float, true>(prm) : run_regional<float, false>(prm); break;
+        case TFCFFT_F16: g.luma3 ? run_regional<__half, true>(prm) : run_regional<__half, false>(prm); break;
+        case TFCFFT_BF16: g.luma3 ? run_regional<__nv_bfloat16, true>(prm) : run_regional<__nv_bfloat16, false>(prm); break;
+        case TFCFFT_U8: g.luma3 ? run_regional<uint8_t, true>(prm) : run_regional<uint8_t, false>(prm); break;
+    }
+    return TFCFFT_OK;
+}

@@ -127,17 +127,48 @@ TFC_HD void reg_rows(const Ctx& ctx, float2* s, const float2* tw) {
     fft_lines<256, INV>(ctx, s + 96 * LD, 1, LD, 2, tw);
 }
 
+// ---- materialised band spectra (the reference's reg_fft, withregion_FFT.py:358-371) and their backward ----------
+// layout [unit][100][129], unit = (n * C' + ch) * 2 + band; spec_shift = np.fft.fftshift over both axes (:253)
+TFC_HD long long reg_spec_index(const Params& prm, int unit, int ky, int kx) {
+    constexpr int H = RegCfg::H, WH = RegCfg::W / 2 + 1;
+    int r = ky, c = kx;
+    if (prm.spec_shift) {
+        r = (ky + H / 2) % H;
+        c = (kx + WH / 2) % WH;
+    }
+    return ((long long)unit * H + r) * WH + c;
+}
+TFC_HD void reg_bin_emit(const Params& prm, long long i, float2 zk, float2 zm) {
+    const float fx = zk.x + zm.x, fy = zk.y - zm.y;  // 2F
+    if (prm.spec_out[0]) prm.spec_out[0][i] = 0.5f * sqrtf(fx * fx + fy * fy);
+    if (prm.spec_out[1]) prm.spec_out[1][i] = atan2f(fy, fx);
+}
+TFC_HD float2 reg_bin_bwd(const Params& prm, long long i, float2 zk, float2 zm) {
+    const float fx = zk.x + zm.x, fy = zk.y - zm.y;
+    const float f2 = sqrtf(fx * fx + fy * fy);
+    const float finv = f2 > 0.f ? 1.0f / f2 : 0.f;
+    const float ga = prm.spec_gin[0] ? prm.spec_gin[0][i] : 0.f;
+    const float gp = prm.spec_gin[1] ? prm.spec_gin[1][i] : 0.f;
+    const float ca = ga * finv, cp = gp * 2.f * finv * finv;  // d|F|/dF = F2/|F2|, d angle/dF = 2 i F2/|F2|^2
+    return make_float2(ca * fx - cp * fy, ca * fy + cp * fx);
+}
+
 // loss + spectral gradient: every half-plane bin (ky, kx <= 128) is owned by exactly one item together with its mirror
 template <class Ctx>
-TFC_HD void reg_bins(const Ctx& ctx, const Params& prm, float2* s, float& accA, float& accP) {
+TFC_HD void reg_bins(const Ctx& ctx, const Params& prm, int unit, float2* s, float& accA, float& accP) {
     constexpr int LD = RegCfg::LD, H = RegCfg::H;
     const bool want_grad = prm.grad != nullptr;
+    const int mode = prm.spec_mode;  // 0 loss, 1 emit spectra, 2 backward of the spectra
     const float2 z0 = make_float2(0.f, 0.f);
     for (int it = ctx.tid; it < H * 127; it += ctx.nthreads) {  // kx = 1..127: the mirror lies outside the half plane
         const int ky = it % H, kx = 1 + it / H;
         float2* pk = s + reg_row_of_freq(ky) * LD + pos_of_freq<256>(kx);
         float2* pm = s + reg_row_of_freq((H - ky) % H) * LD + pos_of_freq<256>(256 - kx);
-        const float2 g = bin_eval(prm, *pk, *pm, 1.f, accA, accP);
+        if (mode == 1) {
+            reg_bin_emit(prm, reg_spec_index(prm, unit, ky, kx), *pk, *pm);
+            continue;
+        }
+        const float2 g = mode == 2 ? reg_bin_bwd(prm, reg_spec_index(prm, unit, ky, kx), *pk, *pm) : bin_eval(prm, *pk, *pm, 1.f, accA, accP);
         if (want_grad) {
             *pk = g;
             *pm = z0;
@@ -148,9 +179,14 @@ TFC_HD void reg_bins(const Ctx& ctx, const Params& prm, float2* s, float& accA, 
         float2* pk = s + reg_row_of_freq(ky) * LD + pos_of_freq<256>(kx);
         float2* pm = s + reg_row_of_freq(kym) * LD + pos_of_freq<256>(kx);
         const float2 zk = *pk, zm = *pm;
-        const float2 g = bin_eval(prm, zk, zm, 1.f, accA, accP);
+        if (mode == 1) {
+            reg_bin_emit(prm, reg_spec_index(prm, unit, ky, kx), zk, zm);
+            if (kym != ky) reg_bin_emit(prm, reg_spec_index(prm, unit, kym, kx), zm, zk);
+            continue;
+        }
+        const float2 g = mode == 2 ? reg_bin_bwd(prm, reg_spec_index(prm, unit, ky, kx), zk, zm) : bin_eval(prm, zk, zm, 1.f, accA, accP);
         if (kym != ky) {
-            const float2 g2 = bin_eval(prm, zm, zk, 1.f, accA, accP);
+            const float2 g2 = mode == 2 ? reg_bin_bwd(prm, reg_spec_index(prm, unit, kym, kx), zm, zk) : bin_eval(prm, zm, zk, 1.f, accA, accP);
             if (want_grad) *pm = g2;
         }
         if (want_grad) *pk = g;
@@ -176,9 +212,9 @@ TFC_HD void regional_process(const Ctx& ctx, const Params& prm, int unit, float2
     ctx.sync();
     reg_rows<false>(ctx, s, tw);
     reg_cols<false>(ctx, s, w100);
-    reg_bins(ctx, prm, s, accA, accP);
+    reg_bins(ctx, prm, unit, s, accA, accP);
     ctx.sync();
-    if (prm.grad != nullptr) {
+    if (prm.grad != nullptr && prm.spec_mode != 1) {
         reg_cols<true>(ctx, s, w100);
         reg_rows<true>(ctx, s, tw);
         T* gb = static_cast<T*>(prm.grad) + n * prm.gs[0] + ch * prm.gs[1] + (long long)(band * H) * prm.gs[2];

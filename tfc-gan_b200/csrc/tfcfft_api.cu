@@ -370,6 +370,50 @@ int tfcfft_regional_loss(const tfcfft_desc* d, const void* fake, const void* rea
     return TFCFFT_ERR_DTYPE;
 }
 
+static int regional_spectra_common(const tfcfft_desc* d, const void* x, void* grad, void* workspace, size_t workspace_bytes,
+                                   int mode, int fftshift, float* const* outs, const float* const* gins, cudaStream_t st) {
+    Geometry g;
+    int rc = validate_regional(d, &g);
+    if (rc) return rc;
+    if (d->flags & (TFCFFT_NO_PHASE | TFCFFT_DIST_MSE)) return TFCFFT_ERR_FLAGS;
+    if (!x) return TFCFFT_ERR_NULL;
+    if ((rc = check_grad_args(d, grad))) return rc;
+    if ((rc = check_alignment(d, x, x, grad))) return rc;
+    if (!workspace || workspace_bytes < g.ws_bytes || ((uintptr_t)workspace & 255)) return TFCFFT_ERR_WORKSPACE;
+    float* scratch_out = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 64);
+    Params prm = make_regional_params(d, g, x, x, grad, scratch_out, nullptr, workspace);
+    prm.spec_mode = mode;
+    prm.spec_shift = fftshift != 0;
+    if (outs) {
+        prm.spec_out[0] = outs[0];
+        prm.spec_out[1] = outs[1];
+    }
+    if (gins) {
+        prm.spec_gin[0] = gins[0];
+        prm.spec_gin[1] = gins[1];
+    }
+    switch (d->dtype) {
+        case TFCFFT_F32: return g.luma3 ? launch_regional<float, true>(prm, st) : launch_regional<float, false>(prm, st);
+        case TFCFFT_F16: return g.luma3 ? launch_regional<__half, true>(prm, st) : launch_regional<__half, false>(prm, st);
+        case TFCFFT_BF16: return g.luma3 ? launch_regional<__nv_bfloat16, true>(prm, st) : launch_regional<__nv_bfloat16, false>(prm, st);
+        case TFCFFT_U8: return g.luma3 ? launch_regional<uint8_t, true>(prm, st) : launch_regional<uint8_t, false>(prm, st);
+    }
+    return TFCFFT_ERR_DTYPE;
+}
+
+int tfcfft_regional_spectra(const tfcfft_desc* d, const void* x, float* amp, float* pha, int fftshift, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    float* outs[2] = {amp, pha};
+    return regional_spectra_common(d, x, nullptr, workspace, workspace_bytes, 1, fftshift, outs, nullptr, (cudaStream_t)stream);
+}
+
+int tfcfft_regional_spectra_bwd(const tfcfft_desc* d, const void* x, const float* grad_amp, const float* grad_pha, void* grad_x,
+                                int fftshift, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!grad_x) return TFCFFT_ERR_NULL;
+    const float* gins[2] = {grad_amp, grad_pha};
+    return regional_spectra_common(d, x, grad_x, workspace, workspace_bytes, 2, fftshift, nullptr, gins, (cudaStream_t)stream);
+}
+
 size_t tfcfft_triplet_workspace_bytes(void) { return kTripletWsBytes; }
 
 int tfcfft_patch_triplet(const tfcfft_desc* d, const void* fake, const void* real, const int32_t* negatives, float margin,

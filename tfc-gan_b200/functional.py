@@ -364,6 +364,63 @@ def regional_spectral_loss_and_grad(fake, real, **options):
     return out[0], out[1:3], grad
 
 
+class _RegionalSpectraFn(torch.autograd.Function):
+    """amp / phase of rfft2 of the two 100 x 256 bands of every image: differentiable ``reg_fft``."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, shift):
+        xp = _prep1(x.detach())
+        lib = _lib.load()
+        dev = xp.device
+        with torch.cuda.device(dev):
+            stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+            cp = 3 if (cfg.channels == "rgb" and xp.shape[1] == 3) else 1
+            shape = (xp.shape[0], cp, 2, 100, 129)
+            amp = torch.empty(shape, dtype=torch.float32, device=dev)
+            pha = torch.empty(shape, dtype=torch.float32, device=dev)
+            desc = _lib.make_desc(_DTYPES[xp.dtype], 1, cfg.flags(), xp.shape, xp.stride(), xp.stride(), None, 1.0, cfg.input_scale)
+            nbytes = lib.tfcfft_regional_workspace_bytes(ctypes.byref(desc))
+            if nbytes == 0:
+                raise RuntimeError("tfcfft_regional_spectra: needs [N, 1|3, 256, 256]")
+            ws = _workspace(dev, stream_ptr, nbytes)
+            _lib.check(lib.tfcfft_regional_spectra(ctypes.byref(desc), xp.data_ptr(), amp.data_ptr(), pha.data_ptr(), int(shift),
+                                                   ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream_ptr)), "tfcfft_regional_spectra")
+        ctx.cfg, ctx.shift, ctx.in_dtype = cfg, shift, x.dtype
+        ctx.differentiable = not cfg.quantize and xp.dtype != torch.uint8
+        if ctx.differentiable:
+            ctx.save_for_backward(xp)
+        return amp, pha
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_amp, g_pha):
+        if not ctx.differentiable or not ctx.needs_input_grad[0]:
+            return None, None, None
+        (xp,) = ctx.saved_tensors
+        lib = _lib.load()
+        dev = xp.device
+        with torch.cuda.device(dev):
+            stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+            g_amp, g_pha = g_amp.contiguous().float(), g_pha.contiguous().float()
+            grad = torch.zeros(xp.shape, dtype=xp.dtype, device=dev)  # rows 200..255 belong to no band
+            cfg = ctx.cfg
+            desc = _lib.make_desc(_DTYPES[xp.dtype], 1, cfg.flags(), xp.shape, xp.stride(), xp.stride(), grad.stride(), 1.0,
+                                  cfg.input_scale)
+            ws = _workspace(dev, stream_ptr, lib.tfcfft_regional_workspace_bytes(ctypes.byref(desc)))
+            _lib.check(lib.tfcfft_regional_spectra_bwd(ctypes.byref(desc), xp.data_ptr(), g_amp.data_ptr(), g_pha.data_ptr(),
+                                                       grad.data_ptr(), int(ctx.shift), ws.data_ptr(), ws.numel(),
+                                                       ctypes.c_void_p(stream_ptr)), "tfcfft_regional_spectra_bwd")
+        return (grad if grad.dtype == ctx.in_dtype else grad.to(ctx.in_dtype)), None, None
+
+
+def regional_components(x, *, channels: str = "luma", input_scale: float = 1.0, quantize: bool = False, fftshift: bool = True):
+    """``(AMP, PHA)`` of the two 100 x 256 bands of ``x`` ``[N, 1|3, 256, 256]``: fp32 ``[N, C', 2, 100, 129]`` (axis 2: hair
+    rows 0..99, eyes rows 100..199), optionally fftshift-ed like the reference's ``reg_fft``
+    (``TFCGAN_multigpu_patchFFT_withregion_FFT.py:358-371``).  Differentiable w.r.t. ``x``."""
+    cfg = SpectralConfig(grid=1, channels=channels, input_scale=input_scale, quantize=quantize)
+    return _RegionalSpectraFn.apply(x, cfg, bool(fftshift))
+
+
 # ---- patch triplet loss (SURVEY.md §8f-1) ----------------------------------------------------------------------
 def _check_negatives(negatives, grid: int):
     neg = [int(k) for k in negatives]
