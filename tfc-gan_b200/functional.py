@@ -145,6 +145,20 @@ def _launch(fake, real, cfg: SpectralConfig, want_grad: bool, want_per_image: bo
     return out, per, grad
 
 
+def _scale_saved_gradient(unit: torch.Tensor, grad_loss: torch.Tensor, in_dtype: torch.dtype) -> torch.Tensor:
+    """``unit * grad_loss`` (the saved d loss / d fake times autograd's incoming scalar: loss weight x GradScaler scale) in
+    one launch of the library's scaling kernel; the scalar stays on the device."""
+    lib = _lib.load()
+    dev = unit.device
+    with torch.cuda.device(dev):
+        stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+        go = grad_loss.detach().to(device=dev, dtype=torch.float32).contiguous()
+        res = torch.empty_like(unit)
+        _lib.check(lib.tfcfft_grad_scale(res.data_ptr(), unit.data_ptr(), _DTYPES[unit.dtype], unit.numel(), go.data_ptr(), 1.0,
+                                         ctypes.c_void_p(stream_ptr)), "tfcfft_grad_scale")
+    return res if res.dtype == in_dtype else res.to(in_dtype)
+
+
 class _SpectralLossFn(torch.autograd.Function):
     """forward: loss and the unit gradient in ONE pass over fake / real (3 tensor passes of HBM
     traffic); backward: one scaling launch by ``grad_output`` (weight x GradScaler scale)."""
@@ -168,20 +182,7 @@ class _SpectralLossFn(torch.autograd.Function):
         if not ctx.has_grad:
             return None, None, None
         (unit,) = ctx.saved_tensors
-        lib = _lib.load()
-        dev = unit.device
-        with torch.cuda.device(dev):
-            stream_ptr = torch.cuda.current_stream(dev).cuda_stream
-            go = grad_loss.detach().to(device=dev, dtype=torch.float32).contiguous()
-            res = torch.empty_like(unit)
-            _lib.check(
-                lib.tfcfft_grad_scale(res.data_ptr(), unit.data_ptr(), _DTYPES[unit.dtype], unit.numel(),
-                                      go.data_ptr(), 1.0, ctypes.c_void_p(stream_ptr)),
-                "tfcfft_grad_scale",
-            )
-        if res.dtype != ctx.in_dtype:
-            res = res.to(ctx.in_dtype)
-        return res, None, None
+        return _scale_saved_gradient(unit, grad_loss, ctx.in_dtype), None, None
 
 
 def spectral_loss(fake, real, *, return_terms: bool = False, config: SpectralConfig | None = None, **options):
@@ -340,8 +341,7 @@ class _RegionalLossFn(torch.autograd.Function):
         if not ctx.has_grad:
             return None, None, None
         (unit,) = ctx.saved_tensors
-        res = (unit.float() * grad_loss.detach().float()).to(ctx.in_dtype)
-        return res, None, None
+        return _scale_saved_gradient(unit, grad_loss, ctx.in_dtype), None, None
 
 
 def regional_spectral_loss(fake, real, *, return_terms: bool = False, channels: str = "luma", use_phase: bool = True,
@@ -472,17 +472,7 @@ class _PatchTripletFn(torch.autograd.Function):
         if not ctx.has_grad:
             return (None,) * 7
         (unit,) = ctx.saved_tensors
-        lib = _lib.load()
-        dev = unit.device
-        with torch.cuda.device(dev):
-            stream_ptr = torch.cuda.current_stream(dev).cuda_stream
-            go = grad_loss.detach().to(device=dev, dtype=torch.float32).contiguous()
-            res = torch.empty_like(unit)
-            _lib.check(lib.tfcfft_grad_scale(res.data_ptr(), unit.data_ptr(), _DTYPES[unit.dtype], unit.numel(), go.data_ptr(),
-                                             1.0, ctypes.c_void_p(stream_ptr)), "tfcfft_grad_scale")
-        if res.dtype != ctx.in_dtype:
-            res = res.to(ctx.in_dtype)
-        return (res,) + (None,) * 6
+        return (_scale_saved_gradient(unit, grad_loss, ctx.in_dtype),) + (None,) * 6
 
 
 def patch_triplet_loss(fake, real, negatives, *, grid: int = 4, margin: float = 1.0, eps: float = 1e-6, weight: float = 1.0):
@@ -598,8 +588,7 @@ class _TemperatureTripletFn(torch.autograd.Function):
         if not ctx.has_grad:
             return (None,) * 9
         (unit,) = ctx.saved_tensors
-        res = (unit.float() * grad_loss.detach().float()).to(ctx.in_dtype)
-        return (res,) + (None,) * 8
+        return (_scale_saved_gradient(unit, grad_loss, ctx.in_dtype),) + (None,) * 8
 
 
 def temperature_triplet_loss(fake, positive, negative, *, lut=None, quantize: bool = False, margin: float = 1.0, eps: float = 1e-6,
