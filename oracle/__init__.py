@@ -19,6 +19,11 @@ Two restatements of the reference (``/root/reference``, read-only):
   target of the CUDA kernels (loss rel <= 1e-4, gradient L2-rel <= 1e-3 against
   the fp64 evaluation).
 
+Three further restatements cover the "next" rows of the scope table, each with its own pin:
+``triplet`` (patch ``TripletMarginLoss`` block), ``temperature`` (``vectorize_temps`` + temperature triplet) and
+``regional`` (``regional_fft_loss`` on the 100 x 256 bands); their golden vectors come from
+``tests/golden/make_golden_triplet.py``, which executes the reference's own lines / functions.
+
 Parity pin: the reference ships no tests and no golden vectors,
 so the pin is "outputs of the reference itself run here":
 ``tests/golden/make_golden.py`` extracts the reference's own function bodies
