@@ -73,7 +73,25 @@ void run_sub(Params prm) {
     for (int base = 0; base < prm.tiles_total; base += prm.chunk_tiles) {
         prm.tile_base = base;
         prm.chunk_now = prm.tiles_total - base < prm.chunk_tiles ? prm.tiles_total - base : prm.chunk_tiles;
-        for (int u = 0; u < prm.chunk_now * npp; ++u) sub_fwd_process<T, LUMA3>(ctx, prm, u, s.data());
+        if (D == 4) {  // the cluster variant's load (sub_fwd_load_quad): both halves, both column pairs, then the transforms
+            std::vector<float2> s2((size_t)2 * 64 * SubCfg::LD);
+            for (int w = 0; w < prm.chunk_now * 4; ++w) {
+                const TileCoord tc = decode_tile(prm, base + (w >> 2));
+                for (int half = 0; half < 2; ++half) sub_fwd_load_quad<T, LUMA3>(ctx, prm, tc, w & 3, half, s.data(), s2.data());
+                for (int i = 0; i < 2; ++i) {
+                    SubUnit su;
+                    su.tile_local = w >> 2;
+                    su.p = w & 3;
+                    su.i = i;
+                    su.plane = su.p * 2 + i;
+                    float2* t = i ? s2.data() : s.data();
+                    sub_fwd_rows(ctx, t);
+                    sub_fwd_cols_store(ctx, prm, su, t);
+                }
+            }
+        } else {
+            for (int u = 0; u < prm.chunk_now * npp; ++u) sub_fwd_process<T, LUMA3>(ctx, prm, u, s.data());
+        }
         for (int lt = 0; lt < prm.chunk_now; ++lt) {
             float2* ws_tile = sub_plane(prm, lt, 0);
             for (int part = 0; part < kCombineParts; ++part) {

@@ -11,6 +11,8 @@
 //
 // Roofline / algorithmic bytes are documented in DESIGN.md.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "pair_tile.cuh"
 #include "sub_tile.cuh"
 #include "line_tile.cuh"
@@ -333,6 +335,39 @@ __global__ void __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd_kernel(const __grid
     }
     pdl_release();
 }
+// D = 4 forward launch as 2-CTA clusters: the two CTAs of a cluster own the two column pairs of one (tile, row phase),
+// load half of the rows each with full-sector 16-byte loads and hand the other CTA its half through distributed
+// shared memory (sub_fwd_load_quad).  Cluster barriers fence the hand-over in both directions.
+template <typename T, bool LUMA3>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd4_kernel(const __grid_constant__ Params prm) {
+    namespace cg = cooperative_groups;
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    float2* peer = cl.map_shared_rank(s, rank ^ 1);
+    float2* dst01 = rank == 0 ? s : peer;
+    float2* dst23 = rank == 0 ? peer : s;
+    BlockCtxT<SubCfg::NT_FWD> ctx{(int)threadIdx.x, nullptr};
+    const int npairs = prm.chunk_now * 4;  // (tile, row phase)
+    cl.sync();                             // the peer's shared memory exists from here on
+    for (int w = blockIdx.x >> 1; w < npairs; w += gridDim.x >> 1) {
+        SubUnit su;
+        su.tile_local = w >> 2;
+        su.p = w & 3;
+        su.i = rank;
+        su.plane = su.p * 2 + rank;
+        sub_fwd_load_quad<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, dst01, dst23);
+        cl.sync();
+        sub_fwd_rows(ctx, s);
+        ctx.sync();
+        sub_fwd_cols_store(ctx, prm, su, s);
+        cl.sync();  // the peer may refill my tiles only after my column pass has read them
+    }
+    pdl_release();
+}
+
 template <typename T, bool LUMA3>
 __global__ void __launch_bounds__(SubCfg::NT_INV, 6) sub_inv_kernel(const __grid_constant__ Params prm) {
     pdl_wait();

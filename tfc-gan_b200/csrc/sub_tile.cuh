@@ -94,6 +94,57 @@ TFC_HD void sub_fwd_load(const Ctx& ctx, const Params& prm, const TileCoord& tc,
         }
     }
 }
+// D = 4 variant for a 2-CTA cluster (one cluster = one row phase p of a tile = the two column pairs i = 0, 1): each
+// CTA reads HALF of the rows with full 16-byte loads (all four column phases q: every 32-byte sector is fetched
+// once instead of twice) and distributes the luma values: q = 0, 1 -> the work tiles of the i = 0 CTA (dst01),
+// q = 2, 3 -> those of the i = 1 CTA (dst23); one of the two destinations is the peer CTA's shared memory.
+template <typename T, bool LUMA3, class Ctx>
+TFC_HD void sub_fwd_load_quad(const Ctx& ctx, const Params& prm, const TileCoord& tc, int p, int half, float2* dst01, float2* dst23) {
+    constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1, NI = SubCfg::LOAD_NI, P = 256;
+    const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, P);
+    const T* rp = tile_ptr<T>(prm.real, prm.rs, tc, P);
+    const int fsh = (int)prm.fs[2], fsc = (int)prm.fs[1], rsh = (int)prm.rs[2], rsc = (int)prm.rs[1];
+    const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
+#pragma unroll 1
+    for (int it0 = ctx.tid; it0 < 2048; it0 += NI * ctx.nthreads) {
+        float raw[NI][2][NC][4];  // [item][fake|real][channel][q]
+#pragma unroll
+        for (int u = 0; u < NI; ++u) {
+            const int it = it0 + u * ctx.nthreads, b = it & 63, a = 32 * half + (it >> 6);
+            const int x = 4 * b, y = 4 * a + p;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                IO<T>::load4(fp + y * fsh + c * fsc + x, raw[u][0][c]);
+                IO<T>::load4(rp + y * rsh + c * rsc + x, raw[u][1][c]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NI; ++u) {
+            const int it = it0 + u * ctx.nthreads, b = it & 63, a = 32 * half + (it >> 6);
+            float z[2][4];  // [fake|real][q]
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (!quant) {
+                        float f = prm.lw[0] * raw[u][h][0][q];
+                        if constexpr (LUMA3) f = fmaf(prm.lw[2], raw[u][h][2][q], fmaf(prm.lw[1], raw[u][h][1][q], f));
+                        z[h][q] = f;
+                    } else if constexpr (LUMA3) {
+                        z[h][q] = (float)((19595 * IO<T>::quant(raw[u][h][0][q]) + 38470 * IO<T>::quant(raw[u][h][1][q]) +
+                                           7471 * IO<T>::quant(raw[u][h][2][q]) + 0x8000) >> 16);
+                    } else {
+                        z[h][q] = (float)IO<T>::quant(raw[u][h][0][q]);
+                    }
+                }
+            dst01[a * LD + b] = make_float2(z[0][0], z[1][0]);
+            dst01[64 * LD + a * LD + b] = make_float2(z[0][1], z[1][1]);
+            dst23[a * LD + b] = make_float2(z[0][2], z[1][2]);
+            dst23[64 * LD + a * LD + b] = make_float2(z[0][3], z[1][3]);
+        }
+    }
+}
+
 // rows of both work tiles, one thread per row
 template <class Ctx>
 TFC_HD void sub_fwd_rows(const Ctx& ctx, float2* s) {

@@ -131,7 +131,17 @@ int launch_sub(Params prm, cudaStream_t st) {
         const int units = prm.chunk_now * npp;
         const int grid_f = units < sms * per_sm_f ? units : sms * per_sm_f;
         const int grid_i = units < sms * per_sm_i ? units : sms * per_sm_i;
-        cudaError_t e = launch_pdl(kf, grid_f, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st, prm);
+        cudaError_t e;
+        static const bool no_cluster = getenv("TFCFFT_NO_CLUSTER") != nullptr;
+        if (D == 4 && !no_cluster) {  // 2-CTA clusters: full-sector loads, halves exchanged through DSMEM
+            auto kf4 = sub_fwd4_kernel<T, LUMA3>;
+            if (int rc = set_smem(kf4, SubCfg::SMEM_FWD)) return rc;
+            int g4 = units < sms * per_sm_f ? units : sms * per_sm_f;
+            g4 &= ~1;
+            e = launch_pdl(kf4, g4, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st, prm);
+        } else {
+            e = launch_pdl(kf, grid_f, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st, prm);
+        }
         if (e != cudaSuccess) return (int)e;
         g_launches++;
         e = D == 2 ? launch_pdl(combine_kernel<2>, prm.chunk_now * kCombineParts, kCombineThreads, 0, st, prm)
