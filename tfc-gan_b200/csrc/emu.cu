@@ -104,8 +104,25 @@ void run_sub(Params prm) {
                 prm.partials[2 * ((size_t)(base + lt) * kCombineParts + part) + 1] = p;
             }
         }
-        if (prm.grad)
+        if (prm.grad && D == 4) {  // the cluster variant's store (sub_inv_store_quad)
+            std::vector<float2> t0((size_t)64 * SubCfg::LD), t1((size_t)64 * SubCfg::LD);
+            for (int w = 0; w < prm.chunk_now * 4; ++w) {
+                for (int i = 0; i < 2; ++i) {
+                    SubUnit su;
+                    su.tile_local = w >> 2;
+                    su.p = w & 3;
+                    su.i = i;
+                    su.plane = su.p * 2 + i;
+                    float2* t = i ? t1.data() : t0.data();
+                    sub_inv_cols(ctx, prm, su, t);
+                    sub_inv_rows(ctx, t);
+                }
+                const TileCoord tc = decode_tile(prm, base + (w >> 2));
+                for (int half = 0; half < 2; ++half) sub_inv_store_quad<T, LUMA3>(ctx, prm, tc, w & 3, half, t0.data(), t1.data());
+            }
+        } else if (prm.grad) {
             for (int u = 0; u < prm.chunk_now * npp; ++u) sub_inv_process<T, LUMA3>(ctx, prm, u, s.data());
+        }
     }
 }
 

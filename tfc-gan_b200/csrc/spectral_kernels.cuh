@@ -384,6 +384,39 @@ __global__ void __launch_bounds__(SubCfg::NT_INV, 6) sub_inv_kernel(const __grid
     pdl_release();
 }
 
+// D = 4 inverse launch as 2-CTA clusters (the two packed planes i = 0, 1 of one (tile, row phase)): transforms as in
+// sub_inv_kernel, then each CTA stores half of the rows with full 16-byte stores, reading the other column pair from
+// the peer's shared memory (sub_inv_store_quad).
+template <typename T, bool LUMA3>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) sub_inv4_kernel(const __grid_constant__ Params prm) {
+    namespace cg = cooperative_groups;
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const float2* peer = cl.map_shared_rank(s, rank ^ 1);
+    const float2* s01 = rank == 0 ? s : peer;
+    const float2* s23 = rank == 0 ? peer : s;
+    BlockCtxT<SubCfg::NT_INV> ctx{(int)threadIdx.x, nullptr};
+    const int npairs = prm.chunk_now * 4;
+    cl.sync();
+    for (int w = blockIdx.x >> 1; w < npairs; w += gridDim.x >> 1) {
+        SubUnit su;
+        su.tile_local = w >> 2;
+        su.p = w & 3;
+        su.i = rank;
+        su.plane = su.p * 2 + rank;
+        sub_inv_cols(ctx, prm, su, s);
+        ctx.sync();
+        sub_inv_rows(ctx, s);
+        cl.sync();  // both column pairs are ready
+        sub_inv_store_quad<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, s01, s23);
+        cl.sync();  // the peer has read my tile
+    }
+    pdl_release();
+}
+
 // Sub-tile path, launch 2: per-position D x D butterflies, loss, spectral gradient (registers + L2 only).
 template <int D>
 __global__ void __launch_bounds__(kCombineThreads, 512 / kCombineThreads) combine_kernel(const __grid_constant__ Params prm) {

@@ -219,6 +219,28 @@ TFC_HD void sub_inv_store(const Ctx& ctx, const Params& prm, const TileCoord& tc
     }
 }
 
+// D = 4 variant for a 2-CTA cluster (mirror of sub_fwd_load_quad): the CTA writes HALF of the gradient rows of row
+// phase p with full 16-byte stores, taking pixels q = 0, 1 from the i = 0 CTA's tile (s01) and q = 2, 3 from the
+// i = 1 CTA's (s23); one of the two is the peer CTA's shared memory.
+template <typename T, bool LUMA3, class Ctx>
+TFC_HD void sub_inv_store_quad(const Ctx& ctx, const Params& prm, const TileCoord& tc, int p, int half, const float2* s01,
+                               const float2* s23) {
+    constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1, P = 256;
+    T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, P));
+    const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
+#pragma unroll 4
+    for (int it = ctx.tid; it < 2048; it += ctx.nthreads) {
+        const int b = it & 63, a = 32 * half + (it >> 6);
+        const float2 lo = s01[a * LD + b], hi = s23[a * LD + b];
+        const int x = 4 * b, y = 4 * a + p;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const float v[4] = {prm.gw[c] * lo.x, prm.gw[c] * lo.y, prm.gw[c] * hi.x, prm.gw[c] * hi.y};
+            IO<T>::store4(gp + y * sh + c * sc + x, v);
+        }
+    }
+}
+
 template <typename T, bool LUMA3, class Ctx>
 TFC_HD void sub_fwd_process(const Ctx& ctx, const Params& prm, int u, float2* s) {
     const SubUnit su = sub_unit(u, prm.sub_d);

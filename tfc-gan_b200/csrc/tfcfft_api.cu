@@ -149,7 +149,15 @@ int launch_sub(Params prm, cudaStream_t st) {
         if (e != cudaSuccess) return (int)e;
         g_launches++;
         if (prm.grad) {
-            e = launch_pdl(ki, grid_i, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
+            if (D == 4 && !no_cluster) {
+                auto ki4 = sub_inv4_kernel<T, LUMA3>;
+                if (int rc = set_smem(ki4, SubCfg::SMEM_INV)) return rc;
+                int g4 = units < sms * per_sm_i ? units : sms * per_sm_i;
+                g4 &= ~1;
+                e = launch_pdl(ki4, g4, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
+            } else {
+                e = launch_pdl(ki, grid_i, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
+            }
             if (e != cudaSuccess) return (int)e;
             g_launches++;
         }
