@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Stage timeline (global ns timer) of sub_fwd_kernel / sub_inv_kernel (debug aid).
 usage: python tools/trace_sub.py [n] [grid]"""
-import ctypes, sys
+import ctypes, os, sys
+os.environ.setdefault("TFCFFT_NO_CLUSTER", "1")  # the stage marks live in the plain (non-cluster) launches
 import numpy as np, torch
 sys.path.insert(0, ".")
 import tfc_gan_b200 as tfc
