@@ -96,7 +96,7 @@ void run_sub(Params prm) {
             float2* ws_tile = sub_plane(prm, lt, 0);
             for (int part = 0; part < kCombineParts; ++part) {
                 float a = 0.f, p = 0.f;
-                for (int item = part * kCombineThreads; item < (part + 1) * kCombineThreads && item < kCombineItems; ++item) {
+                for (int item = part * kCombineItemsPerPart; item < (part + 1) * kCombineItemsPerPart && item < kCombineItems; ++item) {
                     if (D == 2) combine_item<2>(prm, ws_tile, item, a, p);
                     else combine_item<4>(prm, ws_tile, item, a, p);
                 }

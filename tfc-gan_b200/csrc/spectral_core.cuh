@@ -62,8 +62,13 @@ constexpr int kCombineItems = 64 * 32 + 2 * 33;
 #ifndef TFCFFT_COMBINE_THREADS
 #define TFCFFT_COMBINE_THREADS 128
 #endif
-constexpr int kCombineThreads = TFCFFT_COMBINE_THREADS;  // one item per thread
-constexpr int kCombineParts = (kCombineItems + kCombineThreads - 1) / kCombineThreads;  // CTAs (= partial sums) per tile
+constexpr int kCombineThreads = TFCFFT_COMBINE_THREADS;
+#ifndef TFCFFT_COMBINE_REP
+#define TFCFFT_COMBINE_REP 2
+#endif
+constexpr int kCombineRep = TFCFFT_COMBINE_REP;  // items per thread (a rolled loop)
+constexpr int kCombineItemsPerPart = kCombineThreads * kCombineRep;
+constexpr int kCombineParts = (kCombineItems + kCombineItemsPerPart - 1) / kCombineItemsPerPart;  // CTAs (= partial sums) per tile
 
 template <typename T> struct IO;
 

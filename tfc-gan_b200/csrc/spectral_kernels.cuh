@@ -423,11 +423,12 @@ __global__ void __launch_bounds__(kCombineThreads, 512 / kCombineThreads) combin
     pdl_wait();
     constexpr int PARTS = kCombineParts;
     const int lt = blockIdx.x / PARTS, part = blockIdx.x % PARTS;
-    const int item = part * kCombineThreads + (int)threadIdx.x;
     float a = 0.f, p = 0.f;
-    if (item < kCombineItems) {
-        float2* ws_tile = sub_plane(prm, lt, 0);
-        combine_item<D>(prm, ws_tile, item, a, p);
+    float2* ws_tile = sub_plane(prm, lt, 0);
+#pragma unroll 1
+    for (int rep = 0; rep < kCombineRep; ++rep) {
+        const int item = part * kCombineItemsPerPart + rep * kCombineThreads + (int)threadIdx.x;
+        if (item < kCombineItems) combine_item<D>(prm, ws_tile, item, a, p);
     }
     block_sum2(a, p);
     if (threadIdx.x == 0) {
