@@ -11,7 +11,7 @@
 namespace tfcfft {
 
 constexpr size_t kWsHeader = 256;                      // ticket counter, padded
-constexpr size_t kWsChunkBytes = size_t(48) << 20;     // split path: spectrum workspace per chunk
+constexpr size_t kWsChunkBytes = (size_t)64 << 20;  // spectrum workspace per chunk: stays L2-resident (126 MB L2, pixel streams are evict-first)
 
 inline size_t elem_size(int dtype) {
     switch (dtype) {
@@ -83,6 +83,12 @@ inline int validate_desc(const tfcfft_desc* d, Geometry* geo, bool allow_sub = t
             const size_t per_tile = (size_t)p * p * sizeof(float2);
             long long ct = (long long)(kWsChunkBytes / per_tile);
             if (ct < 1) ct = 1;
+            if (geo->sub) {
+                // whole waves of the forward / inverse launches on a 148-SM part (3 resident 128-thread CTAs per SM = 444
+                // units per round): 222 tiles of 128 x 128 (2 units each), 111 tiles of 256 x 256 (8 units each, two rounds)
+                const long long wave = p == 128 ? 222 : 111;
+                if (ct >= wave) ct = (ct / wave) * wave;
+            }
             if (ct > geo->tiles_total) ct = geo->tiles_total;
             geo->chunk_tiles = ct;
             z = (size_t)ct * per_tile;
