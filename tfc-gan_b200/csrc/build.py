@@ -1,10 +1,11 @@
 """In-tree build of the native libraries (called by ``__graft_entry__.build()``).
 
-* ``libtfcfft.so``      -- the product: sm_100a kernels + C ABI (``include/tfcfft.h``).
+* ``libtfcfft.so``      -- the product: sm_100a kernels + C ABI (``include/tfcfft.h``), built from several translation
+                           units (``k_*.cu`` + ``tfcfft_api.cu``) compiled in parallel and linked with ``nvcc -shared``.
 * ``libtfcfft_emu.so``  -- test infrastructure: the same templates executed serially on the CPU.
 
 Explicit ``nvcc`` with ``-gencode arch=compute_100a,code=sm_100a -lineinfo``; nvcc cross-compiles
-without a GPU.  The built ``.so`` files are git-ignored but travel to the GPU box with the snapshot.
+without a GPU.  The built ``.so`` / ``.o`` files are git-ignored but travel to the GPU box with the snapshot.
 """
 
 from __future__ import annotations
@@ -13,50 +14,84 @@ import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(CSRC)
 ROOT = os.path.dirname(PKG)
+OBJ = os.path.join(CSRC, "_obj")
 
-COMMON = ["-std=c++17", "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-          "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", *ARCH, "-lineinfo"]
 
 TARGETS = {
-    "libtfcfft.so": dict(src=["tfcfft_api.cu"], opt=["-O3"]),
-    "libtfcfft_emu.so": dict(src=["emu.cu"], opt=["-O2"]),
+    # (source, extra defines): the FFT kernel families are compiled once per element type (-DTFC_DT=0..3)
+    "libtfcfft.so": dict(src=[("tfcfft_api.cu", None), ("k_misc.cu", None)] +
+                             [(f, dt) for f in ("k_line.cu", "k_sub.cu", "k_resident.cu", "k_split.cu") for dt in range(4)],
+                         opt=["-O3"]),
+    "libtfcfft_emu.so": dict(src=[("emu.cu", None)], opt=["-O2"]),
 }
 
 
-def _deps():
-    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+def _headers():
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     files.append(os.path.join(ROOT, "include", "tfcfft.h"))
     return files
 
 
-def _stale(out: str) -> bool:
-    if not os.path.exists(out):
+def _newer(path: str, deps) -> bool:
+    if not os.path.exists(path):
         return True
-    t = os.path.getmtime(out)
-    return any(os.path.getmtime(f) > t for f in _deps())
+    t = os.path.getmtime(path)
+    return any(os.path.getmtime(f) > t for f in deps)
 
 
-def build(force: bool = False, verbose: bool = False, extra=()):
+def _run(cmd, verbose):
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return p.returncode, p.stdout
+
+
+def build(force: bool = False, verbose: bool = False, extra=(), only=None):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    procs = []
+    os.makedirs(OBJ, exist_ok=True)
+    headers = _headers()
+    jobs = []  # (obj, cmd)
+    links = []
     for name, spec in TARGETS.items():
+        if only and name not in only:
+            continue
         out = os.path.join(PKG, name)
-        if not force and not _stale(out):
+        objs = []
+        for src, dt in spec["src"]:
+            tag = "" if dt is None else f"_dt{dt}"
+            obj = os.path.join(OBJ, name.replace(".so", "") + "__" + src.replace(".cu", tag + ".o"))
+            objs.append(obj)
+            defs = [] if dt is None else [f"-DTFC_DT={dt}"]
+            if force or _newer(obj, [os.path.join(CSRC, src), *headers]):
+                jobs.append((obj, [nvcc, *spec["opt"], *COMMON, *defs, *extra, "-c", "-o", obj, os.path.join(CSRC, src)]))
+        links.append((name, out, objs))
+    failed = []
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 4))) as ex:
+        for (obj, cmd), (rc, log) in zip(jobs, ex.map(lambda j: _run(j[1], verbose), jobs)):
+            if verbose and log.strip():
+                print(log, flush=True)
+            if rc != 0:
+                if os.path.exists(obj):
+                    os.remove(obj)
+                sys.stderr.write(log)
+                failed.append(obj)
+    if failed:
+        raise RuntimeError(f"nvcc failed for {', '.join(os.path.basename(f) for f in failed)}")
+    for name, out, objs in links:
+        if not force and not _newer(out, objs):
             continue
         tmp = out + ".tmp"
-        cmd = [nvcc, *spec["opt"], *COMMON, *extra, "-o", tmp, *[os.path.join(CSRC, s) for s in spec["src"]]]
-        if verbose:
-            print(" ".join(cmd), flush=True)
-        procs.append((name, out, tmp, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for name, out, tmp, p in procs:
-        log, _ = p.communicate()
-        if p.returncode != 0:
+        rc, log = _run([nvcc, "-shared", *ARCH, "-o", tmp, *objs], verbose)
+        if rc != 0:
             sys.stderr.write(log)
-            raise RuntimeError(f"nvcc failed for {name}")
+            raise RuntimeError(f"link failed for {name}")
         os.replace(tmp, out)
         if verbose:
             print(f"built {out}", flush=True)
@@ -64,4 +99,4 @@ def build(force: bool = False, verbose: bool = False, extra=()):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    build(force="--force" in sys.argv, verbose=True, extra=[a for a in sys.argv[1:] if a.startswith("-X")])

@@ -83,12 +83,7 @@ inline int validate_desc(const tfcfft_desc* d, Geometry* geo, bool allow_sub = t
             const size_t per_tile = (size_t)p * p * sizeof(float2);
             long long ct = (long long)(kWsChunkBytes / per_tile);
             if (ct < 1) ct = 1;
-            if (geo->sub) {
-                // whole waves of the forward / inverse launches on a 148-SM part (3 resident 128-thread CTAs per SM = 444
-                // units per round): 222 tiles of 128 x 128 (2 units each), 111 tiles of 256 x 256 (8 units each, two rounds)
-                const long long wave = p == 128 ? 222 : 111;
-                if (ct >= wave) ct = (ct / wave) * wave;
-            }
+            // (the launcher trims a chunk to whole waves of its launches from the device's occupancy: k_sub.cu)
             if (ct > geo->tiles_total) ct = geo->tiles_total;
             geo->chunk_tiles = ct;
             z = (size_t)ct * per_tile;

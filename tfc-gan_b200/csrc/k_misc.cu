@@ -1,0 +1,238 @@
+// k_misc.cu -- the streaming kernels next to the FFT path:
+//   triplet_kernel     patch triplet / temperature triplet loss, forward + backward in one pass (triplet.cuh)
+//   regional_kernel    100 x 256 "hair" / "eyes" band FFT loss (regional.cuh)
+//   temps_kernel       vectorize_temps: red channel -> uint8 -> table
+//   grad_scale_kernel  dst = src * scale (autograd's multiplication by grad_output when it is not folded)
+#include "launchers.h"
+
+namespace tfcfft {
+
+// dst = src * host_scale * (*dev_scale); 16-byte vectors, grid-stride.
+template <typename T>
+__global__ void __launch_bounds__(256) grad_scale_kernel(T* __restrict__ dst, const T* __restrict__ src, long long numel,
+                                                         const float* __restrict__ dev_scale, float host_scale) {
+    const float sc = host_scale * (dev_scale ? __ldg(dev_scale) : 1.0f);
+    constexpr int V = 16 / sizeof(T);
+    const long long nvec = numel / V;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        uint4 raw = reinterpret_cast<const uint4*>(src)[i];
+        T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+        for (int k = 0; k < V; ++k) e[k] = (T)((float)e[k] * sc);
+        reinterpret_cast<uint4*>(dst)[i] = raw;
+    }
+    for (long long i = nvec * V + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride)
+        dst[i] = (T)((float)src[i] * sc);
+}
+
+// ---- regional 100 x 256 FFT loss (regional.cuh): one CTA per (image, channel, band), tile resident in shared memory
+template <typename T, bool LUMA3>
+__global__ void __launch_bounds__(RegCfg::NT, 1) regional_kernel(const __grid_constant__ Params prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    float2* tw = s + RegCfg::H * RegCfg::LD;
+    float2* w100 = tw + RegCfg::W;
+    const BlockCtx ctx{(int)threadIdx.x, (int)blockDim.x};
+    fill_twiddles<RegCfg::W>(ctx, tw);
+    reg_fill_w100(ctx, w100);
+    ctx.sync();
+    pdl_wait();
+    for (int unit = blockIdx.x; unit < prm.tiles_total; unit += gridDim.x) {
+        float a = 0.f, p = 0.f;
+        regional_process<T, LUMA3>(ctx, prm, unit, s, tw, w100, a, p);
+        block_sum2(a, p);
+        if (threadIdx.x == 0) {
+            prm.partials[2 * unit] = a;
+            prm.partials[2 * unit + 1] = p;
+        }
+    }
+    pdl_release();
+    finish(prm, gridDim.x);
+}
+
+// ---- patch triplet loss (triplet.cuh): one lane group per patch row, persistent warps ------------------------
+struct ShflReduce {
+    int lpr;
+    __device__ __forceinline__ float operator()(float v) const {
+        for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+};
+template <typename T, int K>
+__global__ void __launch_bounds__(kTripletThreads) triplet_kernel(const __grid_constant__ TripletParams tp) {
+    const int lpr = tp.p / (4 * K), gpw = 32 / lpr;  // lanes per row, rows per warp pass (rows % gpw == 0 always)
+    const int lane = threadIdx.x & 31, sub = lane / lpr, l = lane - sub * lpr;
+    const long long nwarps = (long long)gridDim.x * (kTripletThreads / 32);
+    const long long warp = (long long)blockIdx.x * (kTripletThreads / 32) + (threadIdx.x >> 5);
+    const ShflReduce red{lpr};
+    float loss = 0.f, act = 0.f;
+    pdl_wait();
+    constexpr int R = kTripletRowsInFlight;
+    // a warp owns R * gpw CONSECUTIVE rows per pass (one contiguous window of the tensors is live at a time);
+    // whole warps are in or out of range because rows % gpw == 0
+    for (long long base = warp * gpw * R; base < tp.rows; base += nwarps * gpw * R) {
+        TripletRow<K> tr[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (base + r * gpw < tp.rows) triplet_row_load<T, K>(tp, base + r * gpw + sub, l, lpr, tr[r]);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (base + r * gpw < tp.rows) triplet_row_finish<T, K>(tp, tr[r], l, lpr, red, loss, act);
+    }
+    pdl_release();
+    block_sum2(loss, act);
+    if (threadIdx.x == 0) {
+        tp.partials[2 * blockIdx.x] = loss;
+        tp.partials[2 * blockIdx.x + 1] = act;
+    }
+    // last CTA: fixed-order sum of the per-CTA partials in double, ticket left at zero
+    __shared__ bool last;
+    __shared__ double dred[2][32];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(tp.counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+        a += (double)__ldcg(tp.partials + 2 * i);
+        b += (double)__ldcg(tp.partials + 2 * i + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+        dred[0][threadIdx.x >> 5] = a;
+        dred[1][threadIdx.x >> 5] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = 0.0;
+        b = 0.0;
+        for (int w = 0; w < kTripletThreads / 32; ++w) {
+            a += dred[0][w];
+            b += dred[1][w];
+        }
+        triplet_outputs(tp, a, b);
+        *tp.counter = 0u;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) temps_kernel(const __grid_constant__ TempsParams tp) {
+    const long long total4 = (long long)tp.n * tp.h * (tp.h / 4);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int x4 = (int)(i % (tp.h / 4));
+        const long long r = i / (tp.h / 4);
+        const int y = (int)(r % tp.h), n = (int)(r / tp.h);
+        float v[4];
+        IO<T>::load4(static_cast<const T*>(tp.x) + n * tp.xs[0] + (long long)y * tp.xs[2] + 4 * x4, v);
+        const float4 o = make_float4(tp.lut[IO<T>::quant(v[0])], tp.lut[IO<T>::quant(v[1])], tp.lut[IO<T>::quant(v[2])],
+                                     tp.lut[IO<T>::quant(v[3])]);
+        *reinterpret_cast<float4*>(tp.out + 4 * i) = o;
+    }
+}
+
+namespace {
+
+template <typename T>
+int launch_triplet(const TripletParams& tp, cudaStream_t st) {
+    // float4 per lane: 8 lanes per patch row up to 128-pixel rows (the per-row scalar work -- row decoding, shuffles,
+    // rsqrt -- is repeated by every lane of the group; ncu: 80 % issue-slot utilisation with 16 lanes x 1 float4)
+    const int K = tp.p >= 128 ? 4 : tp.p >= 64 ? 2 : 1;
+    const int gpw = 32 / (tp.p / (4 * K));
+    const long long warps_needed = (tp.rows + gpw - 1) / gpw;
+    long long blocks = (warps_needed + kTripletThreads / 32 - 1) / (kTripletThreads / 32);
+    void (*kernel)(TripletParams) = K == 1 ? triplet_kernel<T, 1> : K == 2 ? triplet_kernel<T, 2> : triplet_kernel<T, 4>;
+    static KernelFacts facts[3];
+    int per_sm = 1;
+    if (int rc = facts[K == 1 ? 0 : K == 2 ? 1 : 2].get(kernel, kTripletThreads, 0, &per_sm)) return rc;
+    // grid-stride warps over ~4 resident waves: measured 1.33 M img/s with exactly one wave, 1.45 M with three or more
+    // (the block scheduler evens out the skew between warps that a single persistent wave keeps to the end)
+    const long long cap = (long long)device_sms() * per_sm * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks > kTripletMaxBlocks) blocks = kTripletMaxBlocks;
+    if (cudaError_t e2 = launch_pdl(kernel, (int)blocks, kTripletThreads, 0, st, tp)) return (int)e2;
+    g_launches++;
+    return 0;
+}
+
+template <typename T, bool LUMA3>
+int launch_regional(const Params& prm, cudaStream_t st) {
+    auto kernel = regional_kernel<T, LUMA3>;
+    static KernelFacts facts;
+    if (int rc = facts.get(kernel, RegCfg::NT, RegCfg::SMEM, nullptr)) return rc;
+    const int sms = device_sms();
+    const int grid = prm.tiles_total < sms ? prm.tiles_total : sms;
+    if (cudaError_t e = launch_pdl(kernel, grid, RegCfg::NT, RegCfg::SMEM, st, prm)) return (int)e;
+    g_launches++;
+    return 0;
+}
+
+}  // namespace
+
+int launch_triplet_any(int dtype, const TripletParams& tp, cudaStream_t st) {
+    switch (dtype) {
+        case TFCFFT_F32: return launch_triplet<float>(tp, st);
+        case TFCFFT_F16: return launch_triplet<__half>(tp, st);
+        case TFCFFT_BF16: return launch_triplet<__nv_bfloat16>(tp, st);
+        case TFCFFT_U8: return launch_triplet<uint8_t>(tp, st);
+    }
+    return TFCFFT_ERR_DTYPE;
+}
+
+int launch_regional_any(int dtype, bool luma3, const Params& prm, cudaStream_t st) {
+#define TFC_CALL(T, L) launch_regional<T, L>(prm, st)
+    TFC_DISPATCH_T_L(dtype, luma3, TFC_CALL);
+#undef TFC_CALL
+}
+
+int launch_temps_any(int dtype, const TempsParams& tp, cudaStream_t st) {
+    const long long total4 = (long long)tp.n * tp.h * (tp.h / 4);
+    long long blocks = (total4 + 255) / 256;
+    const long long cap = (long long)device_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    switch (dtype) {
+        case TFCFFT_F32: temps_kernel<float><<<(int)blocks, 256, 0, st>>>(tp); break;
+        case TFCFFT_F16: temps_kernel<__half><<<(int)blocks, 256, 0, st>>>(tp); break;
+        case TFCFFT_BF16: temps_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>(tp); break;
+        case TFCFFT_U8: temps_kernel<uint8_t><<<(int)blocks, 256, 0, st>>>(tp); break;
+        default: return TFCFFT_ERR_DTYPE;
+    }
+    g_launches++;
+    TFC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_grad_scale_any(int dtype, void* dst, const void* src, long long numel, const float* dev_scale, float host_scale,
+                          cudaStream_t st) {
+    const size_t es = elem_size(dtype);
+    if (es == 0 || dtype == TFCFFT_U8) return TFCFFT_ERR_DTYPE;
+    const long long nvec = numel / (16 / (long long)es) + 1;
+    long long blocks = (nvec + 255) / 256;
+    const long long cap = (long long)device_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    switch (dtype) {
+        case TFCFFT_F32:
+            grad_scale_kernel<float><<<(int)blocks, 256, 0, st>>>((float*)dst, (const float*)src, numel, dev_scale, host_scale);
+            break;
+        case TFCFFT_F16:
+            grad_scale_kernel<__half><<<(int)blocks, 256, 0, st>>>((__half*)dst, (const __half*)src, numel, dev_scale, host_scale);
+            break;
+        case TFCFFT_BF16:
+            grad_scale_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)src, numel,
+                                                                          dev_scale, host_scale);
+            break;
+    }
+    g_launches++;
+    TFC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace tfcfft

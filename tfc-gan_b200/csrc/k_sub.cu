@@ -1,0 +1,206 @@
+// k_sub.cu -- sub-tile pipeline for P = 128 / 256 (sub_tile.cuh): three launches per workspace chunk
+//   sub_fwd_kernel / sub_fwd4_kernel   sub-images -> sub-spectra S_pq           (HBM read of fake / real)
+//   combine_kernel<D>                  S_pq -> Z -> loss, G -> packed planes   (L2 only)
+//   sub_inv_kernel / sub_inv4_kernel   packed planes -> gradient pixel pairs   (HBM write of grad)
+#include <cooperative_groups.h>
+
+#include "launchers.h"
+#include "sub_tile.cuh"
+
+namespace tfcfft {
+
+// Forward: one CTA = one sub-image PAIR (adjacent pixel columns, so the source rows are read as
+// 8-byte pairs), two 64-thread groups with a work tile each.  Inverse: one 64-thread CTA = one packed plane.
+template <typename T, bool LUMA3>
+__global__ void __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd_kernel(const __grid_constant__ Params prm) {
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    BlockCtxT<SubCfg::NT_FWD> ctx{(int)threadIdx.x, nullptr};
+    const int nunits = prm.chunk_now * (prm.sub_d * prm.sub_d / 2);
+    int iter = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++iter) {
+        ctx.trace = (prm.trace != nullptr && iter < 6) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
+        sub_fwd_process<T, LUMA3>(ctx, prm, u, s);
+        if (ctx.trace != nullptr && threadIdx.x == 0) ctx.trace[15] = 1;
+    }
+    pdl_release();
+}
+// D = 4 forward launch as 2-CTA clusters: the two CTAs of a cluster own the two column pairs of one (tile, row phase),
+// load half of the rows each with full-sector 16-byte loads and hand the other CTA its half through distributed
+// shared memory (sub_fwd_load_quad).  Cluster barriers fence the hand-over in both directions.
+template <typename T, bool LUMA3>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd4_kernel(const __grid_constant__ Params prm) {
+    namespace cg = cooperative_groups;
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    float2* peer = cl.map_shared_rank(s, rank ^ 1);
+    float2* dst01 = rank == 0 ? s : peer;
+    float2* dst23 = rank == 0 ? peer : s;
+    BlockCtxT<SubCfg::NT_FWD> ctx{(int)threadIdx.x, nullptr};
+    const int npairs = prm.chunk_now * 4;  // (tile, row phase)
+    cl.sync();                             // the peer's shared memory exists from here on
+    for (int w = blockIdx.x >> 1; w < npairs; w += gridDim.x >> 1) {
+        SubUnit su;
+        su.tile_local = w >> 2;
+        su.p = w & 3;
+        su.i = rank;
+        su.plane = su.p * 2 + rank;
+        sub_fwd_load_quad<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, dst01, dst23);
+        cl.sync();
+        sub_fwd_rows(ctx, s);
+        ctx.sync();
+        sub_fwd_cols_store(ctx, prm, su, s);
+        cl.sync();  // the peer may refill my tiles only after my column pass has read them
+    }
+    pdl_release();
+}
+
+template <typename T, bool LUMA3>
+__global__ void __launch_bounds__(SubCfg::NT_INV, 6) sub_inv_kernel(const __grid_constant__ Params prm) {
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    BlockCtxT<SubCfg::NT_INV> ctx{(int)threadIdx.x, nullptr};
+    const int nunits = prm.chunk_now * (prm.sub_d * prm.sub_d / 2);
+    int iter = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++iter) {
+        ctx.trace = (prm.trace != nullptr && iter < 6) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
+        sub_inv_process<T, LUMA3>(ctx, prm, u, s);
+        if (ctx.trace != nullptr && threadIdx.x == 0) ctx.trace[15] = 1;
+    }
+    pdl_release();
+}
+
+// D = 4 inverse launch as 2-CTA clusters (the two packed planes i = 0, 1 of one (tile, row phase)): transforms as in
+// sub_inv_kernel, then each CTA stores half of the rows with full 16-byte stores, reading the other column pair from
+// the peer's shared memory (sub_inv_store_quad).
+template <typename T, bool LUMA3>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) sub_inv4_kernel(const __grid_constant__ Params prm) {
+    namespace cg = cooperative_groups;
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const float2* peer = cl.map_shared_rank(s, rank ^ 1);
+    const float2* s01 = rank == 0 ? s : peer;
+    const float2* s23 = rank == 0 ? peer : s;
+    BlockCtxT<SubCfg::NT_INV> ctx{(int)threadIdx.x, nullptr};
+    const int npairs = prm.chunk_now * 4;
+    cl.sync();
+    for (int w = blockIdx.x >> 1; w < npairs; w += gridDim.x >> 1) {
+        SubUnit su;
+        su.tile_local = w >> 2;
+        su.p = w & 3;
+        su.i = rank;
+        su.plane = su.p * 2 + rank;
+        sub_inv_cols(ctx, prm, su, s);
+        ctx.sync();
+        sub_inv_rows(ctx, s);
+        cl.sync();  // both column pairs are ready
+        sub_inv_store_quad<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, s01, s23);
+        cl.sync();  // the peer has read my tile
+    }
+    pdl_release();
+}
+
+#if TFC_DT == 0
+// Launch 2: per-position D x D butterflies, loss, spectral gradient (registers + L2 only).
+template <int D>
+__global__ void __launch_bounds__(kCombineThreads, 512 / kCombineThreads) combine_kernel(const __grid_constant__ Params prm) {
+    pdl_wait();
+    constexpr int PARTS = kCombineParts;
+    const int lt = blockIdx.x / PARTS, part = blockIdx.x % PARTS;
+    float a = 0.f, p = 0.f;
+    float2* ws_tile = sub_plane(prm, lt, 0);
+#pragma unroll 1
+    for (int rep = 0; rep < kCombineRep; ++rep) {
+        const int item = part * kCombineItemsPerPart + rep * kCombineThreads + (int)threadIdx.x;
+        if (item < kCombineItems) combine_item<D>(prm, ws_tile, item, a, p);
+    }
+    block_sum2(a, p);
+    if (threadIdx.x == 0) {
+        const long long slot = (long long)(prm.tile_base + lt) * PARTS + part;
+        prm.partials[2 * slot] = a;
+        prm.partials[2 * slot + 1] = p;
+    }
+    pdl_release();
+    finish(prm, (unsigned)prm.tiles_total * PARTS);
+}
+cudaError_t launch_combine(int d, int grid, const Params& prm, cudaStream_t st) {
+    return d == 2 ? launch_pdl(combine_kernel<2>, grid, kCombineThreads, 0, st, prm)
+                  : launch_pdl(combine_kernel<4>, grid, kCombineThreads, 0, st, prm);
+}
+#endif
+
+namespace {
+
+template <typename T, bool LUMA3>
+int launch_sub(Params prm, cudaStream_t st) {
+    auto kf = sub_fwd_kernel<T, LUMA3>;
+    auto ki = sub_inv_kernel<T, LUMA3>;
+    auto kf4 = sub_fwd4_kernel<T, LUMA3>;
+    auto ki4 = sub_inv4_kernel<T, LUMA3>;
+    static KernelFacts ff, fi, ff4, fi4;
+    int per_sm_f = 1, per_sm_i = 1;
+    if (int rc = ff.get(kf, SubCfg::NT_FWD, SubCfg::SMEM_FWD, &per_sm_f)) return rc;
+    if (int rc = fi.get(ki, SubCfg::NT_INV, SubCfg::SMEM_INV, &per_sm_i)) return rc;
+    const int D = prm.sub_d, npp = D * D / 2;
+    static const bool no_cluster = getenv("TFCFFT_NO_CLUSTER") != nullptr;
+    const bool cluster = D == 4 && !no_cluster;
+    if (cluster) {
+        if (int rc = ff4.get(kf4, SubCfg::NT_FWD, SubCfg::SMEM_FWD, nullptr)) return rc;
+        if (int rc = fi4.get(ki4, SubCfg::NT_INV, SubCfg::SMEM_INV, nullptr)) return rc;
+    }
+    const int sms = device_sms();
+    // trim the workspace chunk to a whole number of waves of the forward launch on THIS device (smallest tile count
+    // whose units fill whole waves: 222 tiles of 128 x 128 / 111 tiles of 256 x 256 on a 148-SM part at 3 CTAs per SM)
+    int chunk = prm.chunk_tiles;
+    {
+        const int wave_units = sms * per_sm_f;
+        int a = wave_units, b = npp;
+        while (b) { const int t = a % b; a = b; b = t; }
+        const int wave_tiles = wave_units / a;
+        if (chunk >= wave_tiles) chunk = (chunk / wave_tiles) * wave_tiles;
+    }
+    for (int base = 0; base < prm.tiles_total; base += chunk) {
+        prm.tile_base = base;
+        prm.chunk_now = prm.tiles_total - base < chunk ? prm.tiles_total - base : chunk;
+        const int units = prm.chunk_now * npp;
+        const int grid_f = units < sms * per_sm_f ? units : sms * per_sm_f;
+        const int grid_i = units < sms * per_sm_i ? units : sms * per_sm_i;
+        cudaError_t e;
+        if (cluster) {  // 2-CTA clusters: full-sector loads, halves exchanged through DSMEM
+            e = launch_pdl(kf4, grid_f & ~1, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st, prm);
+        } else {
+            e = launch_pdl(kf, grid_f, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st, prm);
+        }
+        if (e != cudaSuccess) return (int)e;
+        g_launches++;
+        e = launch_combine(D, prm.chunk_now * kCombineParts, prm, st);
+        if (e != cudaSuccess) return (int)e;
+        g_launches++;
+        if (prm.grad) {
+            if (cluster) {
+                e = launch_pdl(ki4, grid_i & ~1, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
+            } else {
+                e = launch_pdl(ki, grid_i, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
+            }
+            if (e != cudaSuccess) return (int)e;
+            g_launches++;
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+int TFC_FN(launch_sub)(bool luma3, const Params& prm, cudaStream_t st) {
+    return luma3 ? launch_sub<TFC_T, true>(prm, st) : launch_sub<TFC_T, false>(prm, st);
+}
+
+}  // namespace tfcfft

@@ -1,0 +1,356 @@
+// line_ring.cuh -- 64 x 64 tiles: the thread-per-line transforms of line_tile.cuh fed by an ASYNCHRONOUS shared-memory
+// ring (sm_90+ bulk copies, mbarrier completion) instead of blocking per-thread loads.
+//
+// Why (profiles/r01_ncu_patch16_line_kernel_summary.txt): in line_kernel every CTA runs load -> transforms -> store
+// in sequence and the bytes it can keep in flight are bounded by its registers (24 KB per 64-thread CTA, four
+// dependent HBM round trips per tile); the memory phases and the transforms did not overlap (long_scoreboard was the
+// top stall, DRAM 38 % busy, issue slots 39 % busy).  Here ONE persistent CTA per SM holds
+//   * a producer warp that streams the raw pixel rows of the tiles (fake + real, all channels) into a ring of
+//     RING slots with `cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes` (SASS: UBLKCP) -- the bytes
+//     in flight are bounded by the ring (RING x 12 KB), not by registers, and never stall a compute warp;
+//   * G worker groups of 64 threads (one tile each, round robin): wait on a slot's `full` mbarrier, fold the slab to
+//     luma (`z = fake + i real`) into their work tile, release the slot (`empty` mbarrier), then run the register-
+//     resident 64-point line transforms, the loss stage and the inverse transforms of line_tile.cuh unchanged, and
+//     write the gradient tile with coalesced 128-bit streaming stores.
+// The slabs of consecutive tiles go to consecutive workers, so the workers' load phases are staggered by
+// construction and the transforms of G - 1 tiles overlap the HBM stream of the next one.
+#pragma once
+#include <string>
+
+#include "kernel_common.cuh"
+#include "line_tile.cuh"
+
+namespace tfcfft {
+
+#ifndef TFCFFT_RING_WORKERS
+#define TFCFFT_RING_WORKERS 5
+#endif
+#ifndef TFCFFT_RING_SLOTS
+#define TFCFFT_RING_SLOTS 4
+#endif
+
+constexpr int kRingSlotBytes = 12288;  // one slab: fake + real, NC channels, RPS rows of 64 pixels
+template <int G_, int RING_>
+struct RingCfgT {
+    static constexpr int G = G_;                       // worker groups (tiles in flight) per CTA
+    static constexpr int RING = RING_;                 // raw slabs in flight
+    static constexpr int SLOT_BYTES = kRingSlotBytes;
+    static constexpr int NT = 64 * G + 32;             // workers + producer warp
+    static constexpr int TILE_BYTES = (int)LineCfg::SMEM;  // 64 x 65 float2
+    static constexpr int BAR_BYTES = 256;              // full[RING], empty[RING] (8 bytes each)
+    static constexpr size_t SMEM = (size_t)G * TILE_BYTES + (size_t)RING * SLOT_BYTES + BAR_BYTES + 16 * G;
+    static_assert(2 * RING * 8 <= BAR_BYTES, "barrier area too small");
+    static_assert(SMEM + 2048 <= 227 * 1024, "ring configuration exceeds the shared memory of an SM");
+};
+using RingCfg = RingCfgT<TFCFFT_RING_WORKERS, TFCFFT_RING_SLOTS>;  // default configuration
+
+// rows per slab so that one slab fits a slot: 2 tensors x NC channels x RPS rows x 64 pixels
+template <typename T, int NC>
+struct RingSlab {
+    static constexpr int ROW_BYTES = 64 * (int)sizeof(T);
+    static constexpr int RPS_RAW = kRingSlotBytes / (2 * NC * ROW_BYTES);
+    static constexpr int RPS = RPS_RAW >= 64 ? 64 : RPS_RAW >= 32 ? 32 : RPS_RAW >= 16 ? 16 : 8;
+    static constexpr int SLABS = 64 / RPS;              // slabs per tile
+    static constexpr int COPIES = 2 * NC * RPS;         // row copies per slab
+    static constexpr int BYTES = COPIES * ROW_BYTES;
+    static_assert(BYTES <= kRingSlotBytes, "slab does not fit its slot");
+};
+
+// The bulk-copy engine needs 16-byte aligned global rows: base pointers and all strides in bytes multiples of 16
+// (always true for fp32 tensors that passed the C-ABI checks; fp16 / bf16 / uint8 views may miss it).
+template <typename T>
+inline bool ring_addressable(const Params& prm) {
+    auto ok = [](const void* p, const long long* st) {
+        if (reinterpret_cast<uintptr_t>(p) % 16) return false;
+        for (int i = 0; i < 3; ++i)
+            if ((st[i] * (long long)sizeof(T)) % 16) return false;
+        return true;
+    };
+    return ok(prm.fake, prm.fs) && ok(prm.real, prm.rs);
+}
+
+#ifdef __CUDACC__
+// ---- mbarrier / bulk-copy primitives (PTX ISA 8.x, sm_90+) -------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, completion counted in bytes on `bar`; L2 evict-first (the pixels are read once)
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar, unsigned long long policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+// plain (non-streaming) 4-pixel read of a slab row in shared memory
+template <typename T> struct SlabIO;
+template <> struct SlabIO<float> {
+    __device__ __forceinline__ static void load4(const unsigned char* p, float* v) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+};
+template <> struct SlabIO<__half> {
+    __device__ __forceinline__ static void load4(const unsigned char* p, float* v) {
+        const uint2 t = *reinterpret_cast<const uint2*>(p);
+        const __half2 a = *reinterpret_cast<const __half2*>(&t.x), b = *reinterpret_cast<const __half2*>(&t.y);
+        v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+    }
+};
+template <> struct SlabIO<__nv_bfloat16> {
+    __device__ __forceinline__ static void load4(const unsigned char* p, float* v) {
+        const uint2 t = *reinterpret_cast<const uint2*>(p);
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xFFFF0000u);
+        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xFFFF0000u);
+    }
+};
+template <> struct SlabIO<uint8_t> {
+    __device__ __forceinline__ static void load4(const unsigned char* p, float* v) {
+        const uchar4 t = *reinterpret_cast<const uchar4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+};
+
+// execution context of one 64-thread worker group: its own named barrier
+struct RingWorkerCtx {
+    int tid, bar;
+    static constexpr int nthreads = 64;
+    __device__ __forceinline__ void sync() const { bar_sync(bar, 64); }
+    __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
+    __device__ __forceinline__ void mark(int) const {}
+};
+
+// ---- worker: one slab (rows y0 .. y0 + RPS - 1 of the tile) -> luma -> work tile ---------------------------------
+// slab layout: [fake | real][channel][row][64 pixels]; work tile layout as line_load (line_slot permutation).
+// Returns false as soon as a fake pixel differs from the real pixel (after luma): the tile-level `fake == real` test.
+template <typename T, bool LUMA3>
+__device__ __forceinline__ bool ring_convert(const Params& prm, const unsigned char* slab, int y0, int tid, float2* s) {
+    constexpr int NC = LUMA3 ? 3 : 1, LD = LineCfg::LD;
+    using SL = RingSlab<T, NC>;
+    constexpr int RPS = SL::RPS, RB = SL::ROW_BYTES, PX4 = 4 * (int)sizeof(T);
+    const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
+    bool same = true;
+    constexpr int ITEMS = RPS * 16, PER = ITEMS / 64;  // 4-pixel items per thread
+    static_assert(ITEMS % 64 == 0, "slab items must divide over the group");
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int it = tid + 64 * u, x4 = it & 15, r = it >> 4;
+        float raw[2][NC][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) SlabIO<T>::load4(slab + ((h * NC + c) * RPS + r) * RB + x4 * PX4, raw[h][c]);
+        float2* row = s + (y0 + r) * LD + x4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float z[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (!quant) {
+                    float f = prm.lw[0] * raw[h][0][i];
+                    if constexpr (LUMA3) f = fmaf(prm.lw[2], raw[h][2][i], fmaf(prm.lw[1], raw[h][1][i], f));
+                    z[h] = f;
+                } else if constexpr (LUMA3) {
+                    z[h] = (float)((19595 * IO<T>::quant(raw[h][0][i]) + 38470 * IO<T>::quant(raw[h][1][i]) +
+                                    7471 * IO<T>::quant(raw[h][2][i]) + 0x8000) >> 16);
+                } else {
+                    z[h] = (float)IO<T>::quant(raw[h][0][i]);
+                }
+            }
+            same = same && (z[0] == z[1]);
+            row[16 * i] = make_float2(z[0], z[1]);  // == line_slot(4 * x4 + i)
+        }
+    }
+    return same;
+}
+
+// Gradient store of an all-zero tile (fake == real): the loss terms and their gradient vanish identically.
+template <typename T, bool LUMA3, class Ctx>
+__device__ __forceinline__ void ring_store_zero(const Ctx& ctx, const Params& prm, const TileCoord& tc) {
+    constexpr int NC = LUMA3 ? 3 : 1;
+    T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, 64));
+    const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
+    const float z[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int it = ctx.tid; it < 64 * 16; it += ctx.nthreads) {
+        const int x = (it & 15) * 4, y = it >> 4;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) IO<T>::store4(gp + y * sh + c * sc + x, z);
+    }
+}
+
+template <typename T, bool LUMA3, class RingCfg>
+__global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_constant__ Params prm) {
+    constexpr int G = RingCfg::G, RING = RingCfg::RING, NC = LUMA3 ? 3 : 1;
+    using SL = RingSlab<T, NC>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* ring = smem_raw;                                                   // RING slots
+    float2* tiles = reinterpret_cast<float2*>(smem_raw + RING * RingCfg::SLOT_BYTES);  // G work tiles
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + RING * RingCfg::SLOT_BYTES + G * RingCfg::TILE_BYTES);
+    float* scratch = reinterpret_cast<float*>(bars + RingCfg::BAR_BYTES / 8);          // [G][4]: cross-warp sums
+    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + RING);
+    const int tid = (int)threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < RING; ++i) {
+            mbar_init(full0 + 8 * i, 1);    // one arrive.expect_tx by the producer + the copies' bytes
+            mbar_init(empty0 + 8 * i, 64);  // every thread of the consuming group
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait();
+    // tiles of this CTA: blockIdx.x + k * gridDim.x, k = 0 .. ntiles - 1; tile k belongs to worker k % G
+    const int ntiles = ((int)prm.tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (tid >= 64 * G) {
+        // ---------------- producer warp: raw rows -> ring ----------------
+        const int lane = tid - 64 * G;
+        const unsigned long long pol = policy_evict_first();
+        unsigned c = 0;  // slab counter
+        for (int k = 0; k < ntiles; ++k) {
+            const TileCoord tc = decode_tile(prm, (int)blockIdx.x + k * (int)gridDim.x);
+            const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, 64);
+            const T* rp = tile_ptr<T>(prm.real, prm.rs, tc, 64);
+            for (int i = 0; i < SL::SLABS; ++i, ++c) {
+                const unsigned slot = c % RING, ph = (c / RING) & 1;
+                mbar_wait(empty0 + 8 * slot, ph ^ 1);  // the consumers of the previous round have released the slot
+                const unsigned fb = full0 + 8 * slot;
+                if (lane == 0) mbar_arrive_expect_tx(fb, SL::BYTES);
+                __syncwarp();
+                const unsigned dst0 = smem_u32(ring + slot * RingCfg::SLOT_BYTES);
+#pragma unroll
+                for (int q0 = 0; q0 < SL::COPIES; q0 += 32) {
+                    const int q = q0 + lane;  // copy index = ((h * NC + ch) * RPS + r)
+                    if (q < SL::COPIES) {
+                        const int r = q % SL::RPS, hc = q / SL::RPS, ch = hc % NC, h = hc / NC;
+                        const int y = i * SL::RPS + r;
+                        const T* src = h ? rp + (long long)y * prm.rs[2] + (long long)ch * prm.rs[1]
+                                         : fp + (long long)y * prm.fs[2] + (long long)ch * prm.fs[1];
+                        bulk_g2s(dst0 + q * SL::ROW_BYTES, src, SL::ROW_BYTES, fb, pol);
+                    }
+                }
+            }
+        }
+    } else {
+        // ---------------- worker groups ----------------
+        const int w = tid >> 6, gtid = tid & 63;
+        const RingWorkerCtx ctx{gtid, w + 1};  // named barrier id w + 1 (id 0 is __syncthreads)
+        float2* s = tiles + (size_t)w * (RingCfg::TILE_BYTES / sizeof(float2));
+        float* red = scratch + 4 * w;
+        const bool want_grad = prm.grad != nullptr;
+        for (int k = w; k < ntiles; k += G) {
+            const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+            const TileCoord tc = decode_tile(prm, tile);
+            bool same = true;
+            unsigned c = (unsigned)k * SL::SLABS;
+            for (int i = 0; i < SL::SLABS; ++i, ++c) {
+                const unsigned slot = c % RING, ph = (c / RING) & 1;
+                mbar_wait(full0 + 8 * slot, ph);
+                same = ring_convert<T, LUMA3>(prm, ring + slot * RingCfg::SLOT_BYTES, i * SL::RPS, gtid, s) && same;
+                mbar_arrive(empty0 + 8 * slot);
+            }
+            // group vote: is fake == real on the whole tile?  (the barrier also publishes the work tile)
+            int all_same;
+            asm volatile(
+                "{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbar.red.and.pred q, %2, 64, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+                : "=r"(all_same)
+                : "r"((int)same), "r"(w + 1)
+                : "memory");
+            float a = 0.f, p = 0.f;
+            if (all_same) {
+                // identical inputs: every loss term is exactly zero and so is the gradient (reference semantics of
+                // L1Loss / sign(0) = 0), independent of rounding in the packed transform
+                if (want_grad) ring_store_zero<T, LUMA3>(ctx, prm, tc);
+                ctx.sync();
+            } else {
+                line_rows_fwd(ctx, s);
+                ctx.sync();
+                line_cols_fwd(ctx, s);
+                ctx.sync();
+                line_bins(ctx, prm, s, a, p);
+                ctx.sync();
+                if (want_grad) {
+                    line_cols_inv(ctx, s);
+                    ctx.sync();
+                    line_rows_inv(ctx, s);
+                    ctx.sync();
+                    line_store<T, LUMA3>(ctx, prm, tc, s);
+                    ctx.sync();  // the next tile's slabs overwrite the work tile
+                }
+            }
+            // per-tile partial sums: warp shuffle, then the group's two warps through shared memory
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_down_sync(0xffffffffu, a, o);
+                p += __shfl_down_sync(0xffffffffu, p, o);
+            }
+            if ((gtid & 31) == 0) {
+                red[2 * (gtid >> 5)] = a;
+                red[2 * (gtid >> 5) + 1] = p;
+            }
+            ctx.sync();
+            if (gtid == 0) {
+                prm.partials[2 * tile] = red[0] + red[2];
+                prm.partials[2 * tile + 1] = red[1] + red[3];
+            }
+            ctx.sync();  // `red` is reused by the next tile
+        }
+    }
+    pdl_release();
+    finish(prm, gridDim.x);
+}
+
+template <typename T, bool LUMA3, class RingCfg>
+int launch_line_ring_cfg(const Params& prm, cudaStream_t st) {
+    auto kernel = line_ring_kernel<T, LUMA3, RingCfg>;
+    static KernelFacts facts;
+    if (int rc = facts.get(kernel, RingCfg::NT, RingCfg::SMEM, nullptr)) return rc;
+    const int sms = device_sms();
+    // one persistent CTA per SM; with few tiles use fewer CTAs so that every CTA keeps its G workers busy
+    long long want = ((long long)prm.tiles_total + RingCfg::G - 1) / RingCfg::G;
+    if (want < 1) want = 1;
+    const int grid = (int)(want < sms ? want : sms);
+    if (cudaError_t e = launch_pdl(kernel, grid, RingCfg::NT, RingCfg::SMEM, st, prm)) return (int)e;
+    g_launches++;
+    return 0;
+}
+
+// TFCFFT_RING=<workers>x<slots> selects one of the compiled ring configurations (A/B runs; fp32 objects only)
+template <typename T, bool LUMA3>
+int launch_line_ring(const Params& prm, cudaStream_t st) {
+#if defined(TFC_DT) && TFC_DT == 0
+    static const char* sel = getenv("TFCFFT_RING");
+    if (sel != nullptr) {
+        const std::string v(sel);
+        if (v == "4x7") return launch_line_ring_cfg<T, LUMA3, RingCfgT<4, 7>>(prm, st);
+        if (v == "6x2") return launch_line_ring_cfg<T, LUMA3, RingCfgT<6, 2>>(prm, st);
+        if (v == "5x3") return launch_line_ring_cfg<T, LUMA3, RingCfgT<5, 3>>(prm, st);
+        if (v == "3x8") return launch_line_ring_cfg<T, LUMA3, RingCfgT<3, 8>>(prm, st);
+    }
+#endif
+    return launch_line_ring_cfg<T, LUMA3, RingCfg>(prm, st);
+}
+#endif  // __CUDACC__
+
+}  // namespace tfcfft

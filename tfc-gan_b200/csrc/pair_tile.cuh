@@ -477,8 +477,5 @@ TFC_HD void pair_process(const Ctx& ctx, const Params& prm, int tile_a, int tile
     ctx.sync();
 }
 
-TFC_HD bool pair_supported(const Params& prm) {
-    return prm.p == 64 && prm.spec_mode == 0 && !(prm.flags & (TFCFFT_LOG_MAGNITUDE | TFCFFT_FULL_SPECTRUM | TFCFFT_FORCE_SPLIT | TFCFFT_FORCE_GENERIC));
-}
 
 }  // namespace tfcfft

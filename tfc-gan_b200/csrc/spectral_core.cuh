@@ -574,4 +574,9 @@ TFC_HD void write_outputs(const Params& prm, double suma, double sump) {
     prm.out[3] = (loss - loss == 0.0) ? 0.f : 1.f;  // 1 when the loss is inf / nan
 }
 
+// the packed / thread-per-line 64 x 64 engines implement the default loss modes only
+TFC_HD bool pair_supported(const Params& prm) {
+    return prm.p == 64 && prm.spec_mode == 0 && !(prm.flags & (TFCFFT_LOG_MAGNITUDE | TFCFFT_FULL_SPECTRUM | TFCFFT_FORCE_SPLIT | TFCFFT_FORCE_GENERIC));
+}
+
 }  // namespace tfcfft

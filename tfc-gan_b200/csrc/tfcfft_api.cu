@@ -2,267 +2,34 @@
 //
 // Host side only validates, builds the kernel parameter block and enqueues launches on the
 // caller's stream.  No device allocation, no host synchronisation, no fallback of any kind.
+// The kernels live in the k_*.cu translation units (launchers.h).
 #include <atomic>
 #include <cstdio>
 
-#include "host_common.h"
-#include "spectral_kernels.cuh"
+#include "launchers.h"
 
 using namespace tfcfft;
 
+namespace tfcfft {
+std::atomic<long long> g_launches{0};
+}
+
 namespace {
 
-std::atomic<long long> g_launches{0};
 std::atomic<long long*> g_trace{nullptr};  // debug only (tfcfft_debug_trace)
 
-struct DeviceInfo {
-    int sms = 0;
-};
-DeviceInfo device_info() {
-    // queried per call: cheap (cached by the runtime) and keeps the library free of global state
-    DeviceInfo di;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev);
-    return di;
-}
-
-#define TFC_LAUNCH_CHECK()                       \
-    do {                                         \
-        cudaError_t e__ = cudaGetLastError();    \
-        if (e__ != cudaSuccess) return (int)e__; \
-    } while (0)
-
-template <typename K>
-int set_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e != cudaSuccess) return (int)e;
+// Which engine runs a validated descriptor
+int dispatch(const Params& prm, const Geometry& g, int dtype, cudaStream_t st) {
+    if (prm.sub_d > 1) return launch_sub_any(dtype, g.luma3, prm, st);
+    if (g.split) return launch_split_any(g.p, dtype, g.luma3, prm, st);
+    if (g.p == 64 && pair_supported(prm)) {
+        // measured (profiles/): the thread-per-line engine wins on both luma and single-channel tiles; the packed
+        // pair kernel stays selectable for A/B runs
+        if (prm.flags & TFCFFT_USE_PAIR) return launch_pair_any(dtype, g.luma3, prm, st);
+        return launch_line_any(dtype, g.luma3, prm, st);
     }
-    return 0;
-}
-
-template <int P, typename T, bool LUMA3>
-int launch_resident(const Params& prm, cudaStream_t st) {
-    auto kernel = resident_kernel<P, T, LUMA3>;
-    constexpr size_t smem = ResidentCfg<P>::SMEM;
-    constexpr int nt = ResidentCfg<P>::NT;
-    if (int rc = set_smem(kernel, smem)) return rc;
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem);
-    if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) per_sm = 1;
-    const long long cap = (long long)device_info().sms * per_sm;  // persistent: one wave
-    const int grid = (int)(prm.tiles_total < cap ? prm.tiles_total : cap);
-    kernel<<<grid, nt, smem, st>>>(prm);
-    g_launches++;
-    TFC_LAUNCH_CHECK();
-    return 0;
-}
-
-template <int P, typename T, bool LUMA3>
-int launch_pair(const Params& prm, cudaStream_t st) {
-    auto kernel = pair_kernel<P, T, LUMA3>;
-    constexpr size_t smem = PairCfg<P>::SMEM;
-    constexpr int nt = PairCfg<P>::NT;
-    if (int rc = set_smem(kernel, smem)) return rc;
-    const long long npairs = ((long long)prm.tiles_total + 1) / 2;
-    const long long cap = device_info().sms;  // persistent, warp-specialised: one CTA per SM
-    const int grid = (int)(npairs < cap ? npairs : cap);
-    kernel<<<grid, nt, smem, st>>>(prm);
-    g_launches++;
-    TFC_LAUNCH_CHECK();
-    return 0;
-}
-
-// launch with the programmatic-stream-serialization attribute (spectral_kernels.cuh: pdl_wait / pdl_release)
-template <class K, class P>
-cudaError_t launch_pdl(K kernel, int grid, int block, size_t smem, cudaStream_t st, const P& prm) {
-    static const bool off = getenv("TFCFFT_NO_PDL") != nullptr;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)block);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = off ? 0 : 1;
-    return cudaLaunchKernelEx(&cfg, kernel, prm);
-}
-
-template <typename T, bool LUMA3>
-int launch_line(const Params& prm, cudaStream_t st) {
-    auto kernel = line_kernel<T, LUMA3>;
-    constexpr size_t smem = LineCfg::SMEM;
-    if (int rc = set_smem(kernel, smem)) return rc;
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, LineCfg::NT, smem);
-    if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) per_sm = 1;
-    const long long cap = (long long)device_info().sms * per_sm;
-    const int grid = (int)(prm.tiles_total < cap ? prm.tiles_total : cap);
-    if (cudaError_t e2 = launch_pdl(kernel, grid, LineCfg::NT, smem, st, prm)) return (int)e2;
-    g_launches++;
-    return 0;
-}
-
-template <typename T, bool LUMA3>
-int launch_sub(Params prm, cudaStream_t st) {
-    auto kf = sub_fwd_kernel<T, LUMA3>;
-    auto ki = sub_inv_kernel<T, LUMA3>;
-    if (int rc = set_smem(kf, SubCfg::SMEM_FWD)) return rc;
-    if (int rc = set_smem(ki, SubCfg::SMEM_INV)) return rc;
-    static int per_sm_f = 0, per_sm_i = 0;
-    if (!per_sm_f) {
-        int f = 0, i = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f, kf, SubCfg::NT_FWD, SubCfg::SMEM_FWD);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&i, ki, SubCfg::NT_INV, SubCfg::SMEM_INV);
-        if (e != cudaSuccess) return (int)e;
-        per_sm_i = i < 1 ? 1 : i;
-        per_sm_f = f < 1 ? 1 : f;
-    }
-    const int D = prm.sub_d, npp = D * D / 2;
-    const int sms = device_info().sms;
-    for (int base = 0; base < prm.tiles_total; base += prm.chunk_tiles) {
-        prm.tile_base = base;
-        prm.chunk_now = prm.tiles_total - base < prm.chunk_tiles ? prm.tiles_total - base : prm.chunk_tiles;
-        const int units = prm.chunk_now * npp;
-        const int grid_f = units < sms * per_sm_f ? units : sms * per_sm_f;
-        const int grid_i = units < sms * per_sm_i ? units : sms * per_sm_i;
-        cudaError_t e;
-        static const bool no_cluster = getenv("TFCFFT_NO_CLUSTER") != nullptr;
-        if (D == 4 && !no_cluster) {  // 2-CTA clusters: full-sector loads, halves exchanged through DSMEM
-            auto kf4 = sub_fwd4_kernel<T, LUMA3>;
-            if (int rc = set_smem(kf4, SubCfg::SMEM_FWD)) return rc;
-            int g4 = units < sms * per_sm_f ? units : sms * per_sm_f;
-            g4 &= ~1;
-            e = launch_pdl(kf4, g4, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st, prm);
-        } else {
-            e = launch_pdl(kf, grid_f, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st, prm);
-        }
-        if (e != cudaSuccess) return (int)e;
-        g_launches++;
-        e = D == 2 ? launch_pdl(combine_kernel<2>, prm.chunk_now * kCombineParts, kCombineThreads, 0, st, prm)
-                   : launch_pdl(combine_kernel<4>, prm.chunk_now * kCombineParts, kCombineThreads, 0, st, prm);
-        if (e != cudaSuccess) return (int)e;
-        g_launches++;
-        if (prm.grad) {
-            if (D == 4 && !no_cluster) {
-                auto ki4 = sub_inv4_kernel<T, LUMA3>;
-                if (int rc = set_smem(ki4, SubCfg::SMEM_INV)) return rc;
-                int g4 = units < sms * per_sm_i ? units : sms * per_sm_i;
-                g4 &= ~1;
-                e = launch_pdl(ki4, g4, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
-            } else {
-                e = launch_pdl(ki, grid_i, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
-            }
-            if (e != cudaSuccess) return (int)e;
-            g_launches++;
-        }
-    }
-    return 0;
-}
-
-template <int P, typename T, bool LUMA3>
-int launch_split(Params prm, cudaStream_t st) {
-    if constexpr (P >= 64) {
-        using Sp = Split<P>;
-        auto k1 = split_rows_fwd_kernel<P, T, LUMA3>;
-        auto k2 = split_cols_kernel<P>;
-        auto k3 = split_rows_inv_kernel<P, T, LUMA3>;
-        if (int rc = set_smem(k1, SplitCfg<P>::SMEM_ROWS)) return rc;
-        if (int rc = set_smem(k2, SplitCfg<P>::SMEM_COLS)) return rc;
-        if (int rc = set_smem(k3, SplitCfg<P>::SMEM_ROWS)) return rc;
-        for (int base = 0; base < prm.tiles_total; base += prm.chunk_tiles) {
-            prm.tile_base = base;
-            const int nt = prm.tiles_total - base < prm.chunk_tiles ? prm.tiles_total - base : prm.chunk_tiles;
-            if (cudaError_t e = launch_pdl(k1, nt * Sp::ROW_SLABS, SplitCfg<P>::NT, SplitCfg<P>::SMEM_ROWS, st, prm)) return (int)e;
-            g_launches++;
-            if (cudaError_t e = launch_pdl(k2, nt * Sp::PARTS, SplitCfg<P>::NT, SplitCfg<P>::SMEM_COLS, st, prm)) return (int)e;
-            g_launches++;
-            if (prm.grad) {
-                if (cudaError_t e = launch_pdl(k3, nt * Sp::ROW_SLABS, SplitCfg<P>::NT, SplitCfg<P>::SMEM_ROWS, st, prm)) return (int)e;
-                g_launches++;
-            }
-        }
-        return 0;
-    } else {
-        return TFCFFT_ERR_SHAPE;
-    }
-}
-
-template <int P, typename T, bool LUMA3>
-int launch(const Params& prm, bool split, cudaStream_t st) {
-    if constexpr (P == 128 || P == 256) {
-        if (prm.sub_d > 1) return launch_sub<T, LUMA3>(prm, st);
-    }
-    if (split) return launch_split<P, T, LUMA3>(prm, st);
-    if constexpr (P <= 128) {
-        if constexpr (P == 64) {
-            if (pair_supported(prm)) {
-                // measured (profiles/): the thread-per-line kernel wins on both luma (1.45 M vs 1.39 M img/s) and
-                // single-channel tiles (0.80 M vs 0.60 M); the packed pair kernel stays selectable for A/B runs
-                const bool line = !(prm.flags & TFCFFT_USE_PAIR);
-                if (line) return launch_line<T, LUMA3>(prm, st);
-                return launch_pair<P, T, LUMA3>(prm, st);
-            }
-        }
-        return launch_resident<P, T, LUMA3>(prm, st);
-    } else {
-        return TFCFFT_ERR_SHAPE;
-    }
-}
-
-template <int P, typename T>
-int launch_l(const Params& prm, bool split, bool luma3, cudaStream_t st) {
-    return luma3 ? launch<P, T, true>(prm, split, st) : launch<P, T, false>(prm, split, st);
-}
-
-template <int P>
-int launch_t(const Params& prm, bool split, bool luma3, int dtype, cudaStream_t st) {
-    switch (dtype) {
-        case TFCFFT_F32: return launch_l<P, float>(prm, split, luma3, st);
-        case TFCFFT_F16: return launch_l<P, __half>(prm, split, luma3, st);
-        case TFCFFT_BF16: return launch_l<P, __nv_bfloat16>(prm, split, luma3, st);
-        case TFCFFT_U8: return launch_l<P, uint8_t>(prm, split, luma3, st);
-    }
-    return TFCFFT_ERR_DTYPE;
-}
-
-template <typename T>
-int launch_triplet(const TripletParams& tp, cudaStream_t st) {
-    // float4 per lane: 8 lanes per patch row up to 128-pixel rows (the per-row scalar work -- row decoding, shuffles,
-    // rsqrt -- is repeated by every lane of the group; ncu: 80 % issue-slot utilisation with 16 lanes x 1 float4)
-    const int K = tp.p >= 128 ? 4 : tp.p >= 64 ? 2 : 1;
-    const int gpw = 32 / (tp.p / (4 * K));
-    const long long warps_needed = (tp.rows + gpw - 1) / gpw;
-    long long blocks = (warps_needed + kTripletThreads / 32 - 1) / (kTripletThreads / 32);
-    void (*kernel)(TripletParams) = K == 1 ? triplet_kernel<T, 1> : K == 2 ? triplet_kernel<T, 2> : triplet_kernel<T, 4>;
-    if (K != 1 && K != 2 && K != 4) return TFCFFT_ERR_SHAPE;
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTripletThreads, 0);
-    if (e != cudaSuccess) return (int)e;
-    // grid-stride warps over ~4 resident waves: measured 1.33 M img/s with exactly one wave, 1.45 M with three or more
-    // (the block scheduler evens out the skew between warps that a single persistent wave keeps to the end)
-    const long long cap = (long long)device_info().sms * (per_sm < 1 ? 1 : per_sm) * 4;
-    if (blocks > cap) blocks = cap;
-    if (blocks > kTripletMaxBlocks) blocks = kTripletMaxBlocks;
-    if (cudaError_t e2 = launch_pdl(kernel, (int)blocks, kTripletThreads, 0, st, tp)) return (int)e2;
-    g_launches++;
-    return 0;
-}
-
-template <typename T, bool LUMA3>
-int launch_regional(const Params& prm, cudaStream_t st) {
-    auto kernel = regional_kernel<T, LUMA3>;
-    if (int rc = set_smem(kernel, RegCfg::SMEM)) return rc;
-    const int sms = device_info().sms;
-    const int grid = prm.tiles_total < sms ? prm.tiles_total : sms;
-    if (cudaError_t e = launch_pdl(kernel, grid, RegCfg::NT, RegCfg::SMEM, st, prm)) return (int)e;
-    g_launches++;
-    return 0;
+    if (g.p <= 128) return launch_resident_any(g.p, dtype, g.luma3, prm, st);
+    return TFCFFT_ERR_SHAPE;
 }
 
 }  // namespace
@@ -289,18 +56,6 @@ int tfcfft_workspace_init(void* workspace, size_t workspace_bytes, void* stream)
     if (!workspace || workspace_bytes < kWsHeader || ((uintptr_t)workspace & 255)) return TFCFFT_ERR_WORKSPACE;
     cudaError_t e = cudaMemsetAsync(workspace, 0, kWsHeader, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : (int)e;
-}
-
-static int dispatch(const Params& prm, const Geometry& g, int dtype, cudaStream_t st) {
-    switch (g.p) {
-        case 16: return launch_t<16>(prm, g.split, g.luma3, dtype, st);
-        case 32: return launch_t<32>(prm, g.split, g.luma3, dtype, st);
-        case 64: return launch_t<64>(prm, g.split, g.luma3, dtype, st);
-        case 128: return launch_t<128>(prm, g.split, g.luma3, dtype, st);
-        case 256: return launch_t<256>(prm, g.split, g.luma3, dtype, st);
-        case 512: return launch_t<512>(prm, g.split, g.luma3, dtype, st);
-    }
-    return TFCFFT_ERR_SHAPE;
 }
 
 // shared argument checks of the two spectra entry points; the scalar outputs of the reduction tail land in
@@ -379,13 +134,7 @@ int tfcfft_regional_loss(const tfcfft_desc* d, const void* fake, const void* rea
     if (!workspace || workspace_bytes < g.ws_bytes || ((uintptr_t)workspace & 255)) return TFCFFT_ERR_WORKSPACE;
     const Params prm = make_regional_params(d, g, fake, real, grad_fake, out, per_image, workspace);
     cudaStream_t st = (cudaStream_t)stream;
-    switch (d->dtype) {
-        case TFCFFT_F32: return g.luma3 ? launch_regional<float, true>(prm, st) : launch_regional<float, false>(prm, st);
-        case TFCFFT_F16: return g.luma3 ? launch_regional<__half, true>(prm, st) : launch_regional<__half, false>(prm, st);
-        case TFCFFT_BF16: return g.luma3 ? launch_regional<__nv_bfloat16, true>(prm, st) : launch_regional<__nv_bfloat16, false>(prm, st);
-        case TFCFFT_U8: return g.luma3 ? launch_regional<uint8_t, true>(prm, st) : launch_regional<uint8_t, false>(prm, st);
-    }
-    return TFCFFT_ERR_DTYPE;
+    return launch_regional_any(d->dtype, g.luma3, prm, st);
 }
 
 static int regional_spectra_common(const tfcfft_desc* d, const void* x, void* grad, void* workspace, size_t workspace_bytes,
@@ -410,13 +159,7 @@ static int regional_spectra_common(const tfcfft_desc* d, const void* x, void* gr
         prm.spec_gin[0] = gins[0];
         prm.spec_gin[1] = gins[1];
     }
-    switch (d->dtype) {
-        case TFCFFT_F32: return g.luma3 ? launch_regional<float, true>(prm, st) : launch_regional<float, false>(prm, st);
-        case TFCFFT_F16: return g.luma3 ? launch_regional<__half, true>(prm, st) : launch_regional<__half, false>(prm, st);
-        case TFCFFT_BF16: return g.luma3 ? launch_regional<__nv_bfloat16, true>(prm, st) : launch_regional<__nv_bfloat16, false>(prm, st);
-        case TFCFFT_U8: return g.luma3 ? launch_regional<uint8_t, true>(prm, st) : launch_regional<uint8_t, false>(prm, st);
-    }
-    return TFCFFT_ERR_DTYPE;
+    return launch_regional_any(d->dtype, g.luma3, prm, st);
 }
 
 int tfcfft_regional_spectra(const tfcfft_desc* d, const void* x, float* amp, float* pha, int fftshift, void* workspace,
@@ -444,13 +187,7 @@ int tfcfft_patch_triplet(const tfcfft_desc* d, const void* fake, const void* rea
     if (!workspace || workspace_bytes < kTripletWsBytes || ((uintptr_t)workspace & 255)) return TFCFFT_ERR_WORKSPACE;
     const TripletParams tp = make_triplet_params(d, fake, real, negatives, margin, eps, out, grad_fake, workspace);
     cudaStream_t st = (cudaStream_t)stream;
-    switch (d->dtype) {
-        case TFCFFT_F32: return launch_triplet<float>(tp, st);
-        case TFCFFT_F16: return launch_triplet<__half>(tp, st);
-        case TFCFFT_BF16: return launch_triplet<__nv_bfloat16>(tp, st);
-        case TFCFFT_U8: return launch_triplet<uint8_t>(tp, st);
-    }
-    return TFCFFT_ERR_DTYPE;
+    return launch_triplet_any(d->dtype, tp, st);
 }
 
 int tfcfft_temperature_triplet(const tfcfft_desc* d, const void* fake, const void* positive, const void* negative,
@@ -466,13 +203,7 @@ int tfcfft_temperature_triplet(const tfcfft_desc* d, const void* fake, const voi
     if (!workspace || workspace_bytes < kTripletWsBytes || ((uintptr_t)workspace & 255)) return TFCFFT_ERR_WORKSPACE;
     const TripletParams tp = make_temperature_params(d, fake, positive, negative, neg_stride, lut, margin, eps, out, grad_fake, workspace);
     cudaStream_t st = (cudaStream_t)stream;
-    switch (d->dtype) {
-        case TFCFFT_F32: return launch_triplet<float>(tp, st);
-        case TFCFFT_F16: return launch_triplet<__half>(tp, st);
-        case TFCFFT_BF16: return launch_triplet<__nv_bfloat16>(tp, st);
-        case TFCFFT_U8: return launch_triplet<uint8_t>(tp, st);
-    }
-    return TFCFFT_ERR_DTYPE;
+    return launch_triplet_any(d->dtype, tp, st);
 }
 
 int tfcfft_vectorize_temps(const tfcfft_desc* d, const void* x, const float* lut, float* out, void* stream) {
@@ -488,21 +219,7 @@ int tfcfft_vectorize_temps(const tfcfft_desc* d, const void* x, const float* lut
     tp.h = (int)d->h;
     tp.out = out;
     for (int i = 0; i < 256; ++i) tp.lut[i] = lut[i];
-    const long long total4 = (long long)d->n * d->h * (d->h / 4);
-    long long blocks = (total4 + 255) / 256;
-    const long long cap = (long long)device_info().sms * 16;
-    if (blocks > cap) blocks = cap;
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (d->dtype) {
-        case TFCFFT_F32: temps_kernel<float><<<(int)blocks, 256, 0, st>>>(tp); break;
-        case TFCFFT_F16: temps_kernel<__half><<<(int)blocks, 256, 0, st>>>(tp); break;
-        case TFCFFT_BF16: temps_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>(tp); break;
-        case TFCFFT_U8: temps_kernel<uint8_t><<<(int)blocks, 256, 0, st>>>(tp); break;
-        default: return TFCFFT_ERR_DTYPE;
-    }
-    g_launches++;
-    TFC_LAUNCH_CHECK();
-    return 0;
+    return launch_temps_any(d->dtype, tp, (cudaStream_t)stream);
 }
 
 int tfcfft_grad_scale(void* dst, const void* src, int32_t dtype, int64_t numel, const float* dev_scale, float host_scale,
@@ -513,24 +230,7 @@ int tfcfft_grad_scale(void* dst, const void* src, int32_t dtype, int64_t numel, 
     cudaStream_t st = (cudaStream_t)stream;
     const size_t es = elem_size(dtype);
     if (es == 0 || dtype == TFCFFT_U8) return TFCFFT_ERR_DTYPE;
-    const long long nvec = numel / (16 / (long long)es) + 1;
-    long long blocks = (nvec + 255) / 256;
-    const long long cap = (long long)device_info().sms * 16;
-    if (blocks > cap) blocks = cap;
-    switch (dtype) {
-        case TFCFFT_F32:
-            grad_scale_kernel<float><<<(int)blocks, 256, 0, st>>>((float*)dst, (const float*)src, numel, dev_scale, host_scale);
-            break;
-        case TFCFFT_F16:
-            grad_scale_kernel<__half><<<(int)blocks, 256, 0, st>>>((__half*)dst, (const __half*)src, numel, dev_scale, host_scale);
-            break;
-        case TFCFFT_BF16:
-            grad_scale_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)src, numel, dev_scale, host_scale);
-            break;
-    }
-    g_launches++;
-    TFC_LAUNCH_CHECK();
-    return 0;
+    return launch_grad_scale_any(dtype, dst, src, numel, dev_scale, host_scale, st);
 }
 
 void tfcfft_debug_trace(void* device_buffer) { g_trace.store((long long*)device_buffer); }
