@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TFCFFT_VERSION 100 /* major*100 + minor */
+#define TFCFFT_VERSION 200 /* major*100 + minor */
 
 /* element type of fake / real / grad_fake */
 enum tfcfft_dtype { TFCFFT_F32 = 0, TFCFFT_F16 = 1, TFCFFT_BF16 = 2, TFCFFT_U8 = 3 };
@@ -49,7 +49,8 @@ enum tfcfft_dtype { TFCFFT_F32 = 0, TFCFFT_F16 = 1, TFCFFT_BF16 = 2, TFCFFT_U8 =
 #define TFCFFT_FULL_SPECTRUM (1u << 5) /* mean over the full P x P plane (fft2) not P x (P/2+1)   */
 #define TFCFFT_QUANTIZE_U8   (1u << 6) /* reference-as-shipped input path: uint8 wrap + integer
                                           luma (patchFFT_16P.py:300); forward only               */
-#define TFCFFT_GRAD_ACCUMULATE (1u << 8) /* tfcfft_patch_triplet only: grad_fake += instead of grad_fake =   */
+#define TFCFFT_GRAD_ACCUMULATE (1u << 8) /* grad_fake += instead of grad_fake = (all loss entry points): lets several
+                                            loss terms share one gradient buffer without an extra add pass    */
 #define TFCFFT_TEMPS_POSITIVE (1u << 9) /* tfcfft_temperature_triplet only: `positive` is an fp32 tensor of
                                            temperatures (the loader's T_B), not an image                  */
 #define TFCFFT_USE_PAIR      (1u << 28) /* testing: 64x64 tiles through the packed pair kernel            */
@@ -82,6 +83,14 @@ typedef struct tfcfft_desc {
     int64_t grad_stride[4];  /* ignored when grad_fake == NULL */
     float weight;            /* multiplies the loss and the gradient (1/100 at patchFFT_16P.py:607) */
     float input_scale;       /* x' = input_scale * x before the transform (ignored with QUANTIZE_U8) */
+    /* Gradient-only scale: grad_fake = (d loss / d fake) * grad_scale_host * (*grad_scale_dev).  This is the factor
+     * autograd would apply afterwards for scaler.scale(loss_G).backward() (patchFFT_16P.py:607-610): folding it into
+     * the producing launch saves the separate scaling pass (2 of 5 tensor passes) and keeps fp16 gradients in range.
+     * grad_scale_host == 0 is read as 1; grad_scale_dev may be NULL (a device float otherwise, read at kernel time:
+     * no host synchronisation).  Neither touches the loss value. */
+    float grad_scale_host;
+    uint32_t reserved;       /* must be 0 */
+    const float* grad_scale_dev;
 } tfcfft_desc;
 
 int tfcfft_version(void);
@@ -92,6 +101,8 @@ int tfcfft_validate(const tfcfft_desc* d);
 
 /* Bytes of caller-owned device scratch tfcfft_loss needs for `d` (0 if `d` is invalid). */
 size_t tfcfft_workspace_bytes(const tfcfft_desc* d);
+/* Same for tfcfft_spectra / tfcfft_spectra_bwd (they run on a different kernel geometry at P >= 128). */
+size_t tfcfft_spectra_workspace_bytes(const tfcfft_desc* d);
 
 /* Zeroes the workspace header.  Call once after allocating a workspace (and after any call that
  * returned a CUDA error); calls leave the header zeroed for the next call.  A workspace must not be
@@ -99,13 +110,22 @@ size_t tfcfft_workspace_bytes(const tfcfft_desc* d);
 int tfcfft_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 
 /* Loss (and, when grad_fake != NULL, d loss / d fake) in one pass over the inputs.
- *   out        device float[4]: weight * 1/2 (amp + pha)  [weight * amp with NO_PHASE], amp, pha,
- *              non-finite flag
+ *   out        device float[8]: weight * 1/2 (amp + pha)  [weight * amp with NO_PHASE], amp, pha,
+ *              non-finite flag, the gradient scale that was applied (grad_scale_host * *grad_scale_dev; this
+ *              element is what tfcfft_grad_rescale takes as `applied_dev`), 3 reserved
  *   per_image  device float[2*N] or NULL: per-image (amp, pha) terms; their mean over N is amp/pha
  *   grad_fake  device buffer of d->dtype laid out by grad_stride, or NULL for forward only
  * The reduction order is fixed: the loss is bit-stable from run to run. */
 int tfcfft_loss(const tfcfft_desc* d, const void* fake, const void* real, float* out, float* per_image,
                 void* grad_fake, void* workspace, size_t workspace_bytes, void* stream);
+
+/* tfcfft_loss for the reference's 4-patch call convention, where the real quadrants arrive from the data loader as
+ * four SEPARATE tensors: fft_loss(fake_B, B1, B2, B3, B4) (TFCGAN_multigpu_patchFFT_experiment.py:317-339; quadrants
+ * B1..B4 = top-left, top-right, bottom-left, bottom-right: datasets_temp.py:76-118; same convention inline at
+ * TFCGAN_multigpu_patchFFT.py:498-511).  d->grid must be 2; real_quadrants[i] is a [N, C, H/2, W/2] tensor of d->dtype
+ * whose strides are d->real_stride (all four alike).  No concatenation copy is made. */
+int tfcfft_loss_quads(const tfcfft_desc* d, const void* fake, const void* const real_quadrants[4], float* out,
+                      float* per_image, void* grad_fake, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Materialised spectra: the differentiable counterpart of the reference's fft_components
  * (TFCGAN_multigpu_patchFFT_16P.py:293-319; global variant TFCGAN_multigpu_globalFFT.py:266-284) and of
@@ -184,6 +204,14 @@ int tfcfft_vectorize_temps(const tfcfft_desc* d, const void* x, const float* lut
  * numel elements of `dtype`, both 16-byte aligned. */
 int tfcfft_grad_scale(void* dst, const void* src, int32_t dtype, int64_t numel, const float* dev_scale,
                       float host_scale, void* stream);
+
+/* In-place correction of a gradient that was produced with an expected scale folded in (grad_scale_host /
+ * grad_scale_dev above) once autograd's actual grad_output is known: grad *= (*grad_output_dev) / (*applied_dev), after
+ * which *applied_dev = *grad_output_dev (so a repeated backward pass stays correct).  When the two scalars are equal
+ * -- the normal case -- the kernel exits after reading them: no pass over the tensor.  `applied_dev` is a caller-owned
+ * device float that the caller initialised with grad_scale_host * (*grad_scale_dev). */
+int tfcfft_grad_rescale(void* grad, int32_t dtype, int64_t numel, const float* grad_output_dev, float* applied_dev,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* DEBUG / profiling aid, not part of the stable surface: while `device_buffer` is non-NULL the 64x64 line kernel
  * and the sub-tile launches record the global nanosecond timer at their stage boundaries for the first 6 work

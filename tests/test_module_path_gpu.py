@@ -1,0 +1,150 @@
+"""GPU tests of the drop-in module path (``-m gpu``): the expected ``grad_output`` folded into the producing launch,
+arbitrary ``grad_output`` still honoured, gradient accumulation into a shared buffer, the loader-quadrant pointer
+path, and the spectra workspace sizing."""
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import tfc_gan_b200 as tfc
+from tfc_gan_b200 import compat
+from util import l2rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(n, side=256, seed=3, dtype=torch.float32):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    f = torch.empty(n, 3, side, side, device="cuda").uniform_(-1, 1, generator=g).to(dtype)
+    r = torch.empty(n, 3, side, side, device="cuda").uniform_(-1, 1, generator=g).to(dtype)
+    return f, r
+
+
+@pytest.mark.parametrize("grid", [4, 2, 1])
+def test_folded_grad_scale_equals_plain_backward(grid):
+    """``SpectralLoss(grad_scaler=..., loss_multiplier=...)`` produces ``unit * scale * multiplier`` directly and the
+    backward pass launches only the scalar check (no pass over the tensor); the values equal the unfolded path."""
+    f, r = _pair(6, seed=grid)
+    scaler = torch.amp.GradScaler("cuda", init_scale=4096.0)
+    plain = tfc.SpectralLoss(grid=grid, input_scale=255.0)
+    fa = f.clone().requires_grad_(True)
+    scaler.scale(0.01 * plain(fa, r)).backward()
+    folded = tfc.SpectralLoss(grid=grid, input_scale=255.0, grad_scaler=scaler, loss_multiplier=0.01)
+    fb = f.clone().requires_grad_(True)
+    loss = folded(fb, r)
+    tfc.reset_launch_count()
+    scaler.scale(0.01 * loss).backward()
+    assert tfc.launch_count() == 1  # tfcfft_grad_rescale: compares two scalars and exits
+    assert l2rel(fb.grad.cpu().numpy(), fa.grad.cpu().numpy()) <= 2e-6
+    # and the unit gradient against the oracle
+    l, _, _, g = oracle.spectral_loss_and_grad_r1(f.cpu().numpy(), r.cpu().numpy(), grid=grid, input_scale=255.0)
+    assert loss.item() == pytest.approx(l, rel=1e-4)
+    assert l2rel(fb.grad.cpu().numpy() / (4096.0 * 0.01), g) <= 1e-3
+
+
+def test_arbitrary_grad_output_and_retained_graph():
+    f, r = _pair(4, seed=11)
+    want = tfc.spectral_loss_and_grad(f, r, grid=4, input_scale=255.0)[2]
+    for expected in (None, 7.0):  # nothing folded / a wrong guess folded: both must give grad_output * unit
+        fa = f.clone().requires_grad_(True)
+        loss = tfc.spectral_loss(fa, r, grid=4, input_scale=255.0, grad_scale=expected)
+        (loss * 3.5).backward(retain_graph=True)
+        assert l2rel(fa.grad.cpu().numpy(), 3.5 * want.cpu().numpy()) <= 2e-6
+        fa.grad = None
+        (loss * -2.0).backward()  # second pass through the retained graph: the buffer is produced again
+        assert l2rel(fa.grad.cpu().numpy(), -2.0 * want.cpu().numpy()) <= 2e-6
+
+
+def test_non_leaf_input_and_gradient_flow():
+    """fake is a generator output in the training script: the returned buffer feeds the previous node."""
+    f, r = _pair(3, seed=12)
+    w = torch.full((1,), 0.5, device="cuda", requires_grad=True)
+    loss = tfc.spectral_loss(f * w, r, grid=4, input_scale=255.0)
+    loss.backward()
+    unit = tfc.spectral_loss_and_grad(f * 0.5, r, grid=4, input_scale=255.0)[2]
+    assert w.grad.item() == pytest.approx(float((unit * f).sum()), rel=1e-4)
+
+
+@pytest.mark.parametrize("grid", [4, 2, 1])
+def test_accumulate_into_shared_gradient_buffer(grid):
+    f, r = _pair(5, seed=20 + grid)
+    a = tfc.spectral_loss_and_grad(f, r, grid=grid, input_scale=255.0)[2]
+    base = torch.randn_like(f)
+    acc = base.clone()
+    tfc.spectral_loss_and_grad(f, r, grid=grid, input_scale=255.0, accumulate_into=acc)
+    assert l2rel((acc - base).cpu().numpy(), a.cpu().numpy()) <= 1e-5
+    with pytest.raises(ValueError):
+        tfc.spectral_loss_and_grad(f, r, grid=grid, accumulate_into=acc[:2])
+
+
+def test_loader_quadrants_take_the_pointer_path(monkeypatch):
+    """``fft_loss(fake_B, B1..B4)`` with separately allocated quadrants (``datasets_temp.py:76-118``): four base
+    pointers, no concatenation kernel -- value and gradient equal the single-tensor call."""
+    f, r = _pair(7, seed=31)
+    quads = [r[:, :, y:y + 128, x:x + 128].contiguous() for y in (0, 128) for x in (0, 128)]
+    fa = f.clone().requires_grad_(True)
+    la = tfc.spectral_loss(fa, r, grid=2, patch_reduce="sum", input_scale=255.0)
+    la.backward()
+    fb = f.clone().requires_grad_(True)
+
+    def no_cat(*a, **k):
+        raise AssertionError("the quadrant path must not concatenate")
+
+    monkeypatch.setattr(torch, "cat", no_cat)
+    lb = compat.fft_loss(fb, *quads)
+    mean4 = compat.patch4_fft_loss(f, *quads).item()
+    monkeypatch.undo()
+    lb.backward()
+    assert lb.item() == la.item()
+    assert torch.equal(fa.grad, fb.grad)
+    # mean convention (TFCGAN_multigpu_patchFFT.py:498-511)
+    assert mean4 == pytest.approx(la.item() / 4, rel=1e-6)
+
+
+def test_spectra_workspace_is_sized_for_its_own_geometry():
+    """fft_components on more than 111 images of 256 x 256 failed with a fresh workspace."""
+    from tfc_gan_b200 import functional as F
+
+    F._WORKSPACES.clear()
+    x = torch.empty(120, 3, 256, 256, device="cuda").uniform_(-1, 1)
+    amp, pha = compat.fft_components(x)
+    assert amp.shape == (120, 1, 256, 129) and torch.isfinite(amp).all()
+    F._WORKSPACES.clear()
+    xr = x[:40].clone().requires_grad_(True)
+    a, p = tfc.spectral_components(xr, channels="rgb", input_scale=255.0)  # 120 tiles of 256 x 256
+    (a.sum() + p.sum()).backward()
+    assert torch.isfinite(xr.grad).all()
+    ref = torch.fft.rfft2(x[:2].double().mul(torch.tensor(oracle.LUMA_WEIGHTS, device="cuda").view(1, 3, 1, 1)).sum(1) * 255.0)
+    got = torch.fft.ifftshift(amp[:2, 0].double(), dim=(-2, -1))
+    assert l2rel(got.cpu().numpy(), ref.abs().cpu().numpy()) <= 1e-5
+
+
+def test_temperature_accumulate_into_is_validated():
+    f, r = _pair(2, seed=41)
+    n = torch.rand_like(f)
+    with pytest.raises(ValueError):
+        tfc.temperature_triplet_loss_and_grad(f, r, n, accumulate_into=torch.zeros(1, 3, 256, 256, device="cuda"))
+    with pytest.raises(ValueError):
+        tfc.temperature_triplet_loss_and_grad(f, r, n, accumulate_into=torch.zeros_like(f, dtype=torch.float16))
+    # 1-channel images with precomputed temperatures: say so explicitly
+    f1, n1 = f[:, :1].contiguous(), n[:, :1].contiguous()
+    tb = tfc.vectorize_temps(r)
+    out_a, _ = tfc.temperature_triplet_loss_and_grad(f1, tb, n1, positive_is_temperatures=True, input_scale=255.0)
+    out_b, _ = tfc.temperature_triplet_loss_and_grad(f1, tb[:, 0], n1, input_scale=255.0)  # [N,H,W]: temperatures by shape
+    assert out_a[0].item() == out_b[0].item()
+
+
+def test_fake_equals_real_gives_exact_zero():
+    """Known answer: identical inputs -> loss 0 and gradient EXACTLY 0 (sign(0) = 0 in the reference's
+    L1Loss); the 64 x 64 engine detects the tile-level equality while it folds the pixels to luma."""
+    f, _ = _pair(9, seed=51)
+    loss, terms, grad = tfc.spectral_loss_and_grad(f, f.clone(), grid=4, weight=0.01, input_scale=255.0)
+    assert loss.item() == 0.0 and float(terms.abs().max()) == 0.0
+    assert float(grad.abs().max()) == 0.0
+    # mixed batch: only the identical images get the exact zero
+    r = f.clone()
+    r[::2] = torch.rand_like(r[::2])
+    loss, _, grad = tfc.spectral_loss_and_grad(f, r, grid=4, weight=0.01, input_scale=255.0)
+    assert loss.item() > 0
+    assert float(grad[1::2].abs().max()) == 0.0 and float(grad[::2].abs().max()) > 0.0

@@ -9,6 +9,8 @@ from . import compat, dist  # noqa: F401
 from .functional import (  # noqa: F401
     SpectralConfig,
     launch_count,
+    multi_grid_loss,
+    multi_grid_loss_and_grad,
     patch_triplet_loss,
     regional_components,
     regional_spectral_loss,
@@ -27,5 +29,5 @@ from .modules import PatchTripletLoss, SpectralLoss  # noqa: F401
 
 __all__ = [
     "SpectralConfig", "SpectralLoss", "spectral_loss", "spectral_components", "spectral_loss_and_grad", "spectral_terms_per_image",
-    "PatchTripletLoss", "patch_triplet_loss", "regional_components", "regional_spectral_loss", "regional_spectral_loss_and_grad", "temperature_triplet_loss", "temperature_triplet_loss_and_grad", "vectorize_temps", "patch_triplet_loss_and_grad", "launch_count", "reset_launch_count", "compat", "dist",
+    "PatchTripletLoss", "patch_triplet_loss", "regional_components", "regional_spectral_loss", "regional_spectral_loss_and_grad", "temperature_triplet_loss", "temperature_triplet_loss_and_grad", "vectorize_temps", "patch_triplet_loss_and_grad", "launch_count", "reset_launch_count", "multi_grid_loss", "multi_grid_loss_and_grad", "compat", "dist",
 ]

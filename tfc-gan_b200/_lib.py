@@ -37,8 +37,10 @@ EXPORTS = (
     "tfcfft_strerror",
     "tfcfft_validate",
     "tfcfft_workspace_bytes",
+    "tfcfft_spectra_workspace_bytes",
     "tfcfft_workspace_init",
     "tfcfft_loss",
+    "tfcfft_loss_quads",
     "tfcfft_spectra",
     "tfcfft_spectra_bwd",
     "tfcfft_regional_workspace_bytes",
@@ -50,6 +52,7 @@ EXPORTS = (
     "tfcfft_temperature_triplet",
     "tfcfft_vectorize_temps",
     "tfcfft_grad_scale",
+    "tfcfft_grad_rescale",
     "tfcfft_debug_trace",
     "tfcfft_launch_count",
     "tfcfft_launch_count_reset",
@@ -73,10 +76,14 @@ class Desc(ctypes.Structure):
         ("grad_stride", ctypes.c_int64 * 4),
         ("weight", ctypes.c_float),
         ("input_scale", ctypes.c_float),
+        ("grad_scale_host", ctypes.c_float),
+        ("reserved", ctypes.c_uint32),
+        ("grad_scale_dev", ctypes.c_void_p),
     ]
 
 
-def make_desc(dtype, grid, flags, shape, fake_stride, real_stride, grad_stride=None, weight=1.0, input_scale=1.0):
+def make_desc(dtype, grid, flags, shape, fake_stride, real_stride, grad_stride=None, weight=1.0, input_scale=1.0,
+              grad_scale_host=1.0, grad_scale_dev=None):
     d = Desc()
     d.struct_size = ctypes.sizeof(Desc)
     d.dtype = dtype
@@ -88,6 +95,9 @@ def make_desc(dtype, grid, flags, shape, fake_stride, real_stride, grad_stride=N
     d.grad_stride = (ctypes.c_int64 * 4)(*[int(v) for v in (grad_stride or (0, 0, 0, 0))])
     d.weight = float(weight)
     d.input_scale = float(input_scale)
+    d.grad_scale_host = float(grad_scale_host)
+    d.reserved = 0
+    d.grad_scale_dev = grad_scale_dev  # device address (int) or None
     return d
 
 
@@ -103,10 +113,14 @@ def bind(lib):
     lib.tfcfft_validate.argtypes = [dp]
     lib.tfcfft_workspace_bytes.restype = ctypes.c_size_t
     lib.tfcfft_workspace_bytes.argtypes = [dp]
+    lib.tfcfft_spectra_workspace_bytes.restype = ctypes.c_size_t
+    lib.tfcfft_spectra_workspace_bytes.argtypes = [dp]
     lib.tfcfft_workspace_init.restype = ctypes.c_int
     lib.tfcfft_workspace_init.argtypes = [vp, ctypes.c_size_t, vp]
     lib.tfcfft_loss.restype = ctypes.c_int
     lib.tfcfft_loss.argtypes = [dp, vp, vp, f32p, f32p, vp, vp, ctypes.c_size_t, vp]
+    lib.tfcfft_loss_quads.restype = ctypes.c_int
+    lib.tfcfft_loss_quads.argtypes = [dp, vp, ctypes.POINTER(ctypes.c_void_p), f32p, f32p, vp, vp, ctypes.c_size_t, vp]
     lib.tfcfft_spectra.restype = ctypes.c_int
     lib.tfcfft_spectra.argtypes = [dp, vp, vp, f32p, f32p, f32p, f32p, ctypes.c_int, vp, ctypes.c_size_t, vp]
     lib.tfcfft_spectra_bwd.restype = ctypes.c_int
@@ -131,6 +145,8 @@ def bind(lib):
     lib.tfcfft_vectorize_temps.argtypes = [dp, vp, ctypes.POINTER(ctypes.c_float), f32p, vp]
     lib.tfcfft_grad_scale.restype = ctypes.c_int
     lib.tfcfft_grad_scale.argtypes = [vp, vp, ctypes.c_int32, ctypes.c_int64, f32p, ctypes.c_float, vp]
+    lib.tfcfft_grad_rescale.restype = ctypes.c_int
+    lib.tfcfft_grad_rescale.argtypes = [vp, ctypes.c_int32, ctypes.c_int64, f32p, f32p, vp, ctypes.c_size_t, vp]
     lib.tfcfft_debug_trace.restype = None
     lib.tfcfft_debug_trace.argtypes = [vp]
     lib.tfcfft_launch_count.restype = ctypes.c_int64

@@ -30,6 +30,20 @@ def set_mode(mode: str = "r1", input_scale: float = 255.0) -> None:
     _MODE["mode"], _MODE["input_scale"] = mode, float(input_scale)
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def reference_mode():
+    """``with compat.reference_mode():`` -- the reference as shipped (``"r0"``) inside the block."""
+    old = dict(_MODE)
+    set_mode("r0")
+    try:
+        yield
+    finally:
+        _MODE.update(old)
+
+
 def _cfg(grid, patch_reduce="mean", weight=1.0):
     if _MODE["mode"] == "r0":
         return SpectralConfig(grid=grid, patch_reduce=patch_reduce, weight=weight, quantize=True)
@@ -103,18 +117,25 @@ def calculate_ffts(*patches):
     return spectral_loss(fake, real, config=_cfg(4))
 
 
+def _loss_quadrants(fake_B, quads, reduce):
+    """4-patch loss on the loader's quadrant tensors: views of one tensor go to the plain launch, separately allocated
+    quadrants are handed to the kernels as four base pointers (``tfcfft_loss_quads``) -- no concatenation copy."""
+    b = _common_base(quads, 2)
+    if b is not None:
+        return spectral_loss(fake_B, b, config=_cfg(2, reduce))
+    return spectral_loss(fake_B, quads[0], config=_cfg(2, reduce), real_quadrants=quads)
+
+
 def fft_loss(fake_B, B1, B2, B3, B4):
     """``fft_loss`` (``TFCGAN_multigpu_patchFFT_experiment.py:317-339``): 4-patch loss with the patch
     terms SUMMED; the real quadrants arrive as separate tensors from the loader
     (``datasets_temp.py:76-118``)."""
-    real = _assemble((B1, B2, B3, B4), 2)
-    return spectral_loss(fake_B, real, config=_cfg(2, "sum"))
+    return _loss_quadrants(fake_B, (B1, B2, B3, B4), "sum")
 
 
 def patch4_fft_loss(fake_B, B1, B2, B3, B4):
     """The inline 4-patch block of ``TFCGAN_multigpu_patchFFT.py:498-511`` (patch terms averaged)."""
-    real = _assemble((B1, B2, B3, B4), 2)
-    return spectral_loss(fake_B, real, config=_cfg(2, "mean"))
+    return _loss_quadrants(fake_B, (B1, B2, B3, B4), "mean")
 
 
 def draw_negatives(patch_num: int):

@@ -29,7 +29,7 @@ TARGETS = {
     "libtfcfft.so": dict(src=[("tfcfft_api.cu", None), ("k_misc.cu", None)] +
                              [(f, dt) for f in ("k_line.cu", "k_sub.cu", "k_resident.cu", "k_split.cu") for dt in range(4)],
                          opt=["-O3"]),
-    "libtfcfft_emu.so": dict(src=[("emu.cu", None)], opt=["-O2"]),
+    "libtfcfft_emu.so": dict(src=[("emu.cu", None)] + [("emu_fft.cu", dt) for dt in range(4)], opt=["-O2"]),
 }
 
 

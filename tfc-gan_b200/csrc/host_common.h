@@ -57,11 +57,12 @@ inline int validate_desc(const tfcfft_desc* d, Geometry* geo, bool allow_sub = t
     if (p != 16 && p != 32 && p != 64 && p != 128 && p != 256 && p != 512) return TFCFFT_ERR_SHAPE;
     const unsigned known = TFCFFT_CHANNELS_RGB | TFCFFT_NO_PHASE | TFCFFT_DIST_MSE | TFCFFT_PATCH_SUM |
                            TFCFFT_LOG_MAGNITUDE | TFCFFT_FULL_SPECTRUM | TFCFFT_QUANTIZE_U8 | TFCFFT_FORCE_SPLIT |
-                           TFCFFT_FORCE_GENERIC | TFCFFT_USE_LINE | TFCFFT_USE_PAIR;
+                           TFCFFT_FORCE_GENERIC | TFCFFT_USE_LINE | TFCFFT_USE_PAIR | TFCFFT_GRAD_ACCUMULATE;
     if (d->flags & ~known) return TFCFFT_ERR_FLAGS;
     // the reference quantises to a single grey channel; a per-channel quantised variant does not exist
     if ((d->flags & TFCFFT_QUANTIZE_U8) && (d->flags & TFCFFT_CHANNELS_RGB) && d->c == 3) return TFCFFT_ERR_FLAGS;
     if ((d->flags & TFCFFT_FORCE_SPLIT) && p < 64) return TFCFFT_ERR_FLAGS;
+    if (d->reserved != 0 || !(d->grad_scale_host == d->grad_scale_host)) return TFCFFT_ERR_FLAGS;
     for (int t = 0; t < 2; ++t) {
         const int64_t* st = t ? d->real_stride : d->fake_stride;
         if (st[3] != 1) return TFCFFT_ERR_STRIDE;
@@ -130,10 +131,13 @@ inline Params make_params(const tfcfft_desc* d, const Geometry& g, const void* f
     p.tiles_total = (int)g.tiles_total;
     p.flags = d->flags;
     const float sc = (d->flags & TFCFFT_QUANTIZE_U8) ? 1.0f : d->input_scale;
+    const float gsh = d->grad_scale_host == 0.f ? 1.f : d->grad_scale_host;
     for (int i = 0; i < 3; ++i) {
         p.lw[i] = g.luma3 ? kLuma[i] * sc : sc;
-        p.gw[i] = p.lw[i];
+        p.gw[i] = p.lw[i] * gsh;
     }
+    p.gscale_dev = d->grad_scale_dev;
+    p.gscale_host = gsh;
     const double kbins = (d->flags & TFCFFT_FULL_SPECTRUM) ? (double)g.p * g.p : (double)g.p * (g.p / 2 + 1);
     const double red = (d->flags & TFCFFT_PATCH_SUM) ? (double)d->grid * d->grid : 1.0;
     p.norm = red / ((double)d->n * g.cprime * d->grid * d->grid * kbins);
@@ -183,7 +187,8 @@ inline int validate_regional(const tfcfft_desc* d, Geometry* geo) {
     if (d->n < 0 || d->n > (1 << 22)) return TFCFFT_ERR_SHAPE;
     if (d->c != 1 && d->c != 3) return TFCFFT_ERR_SHAPE;
     if (d->h != 256 || d->w != 256) return TFCFFT_ERR_SHAPE;  // the reference's bands: rows 0..99 and 100..199 of 256
-    if (d->flags & ~(TFCFFT_CHANNELS_RGB | TFCFFT_NO_PHASE | TFCFFT_DIST_MSE | TFCFFT_QUANTIZE_U8)) return TFCFFT_ERR_FLAGS;
+    if (d->flags & ~(TFCFFT_CHANNELS_RGB | TFCFFT_NO_PHASE | TFCFFT_DIST_MSE | TFCFFT_QUANTIZE_U8 | TFCFFT_GRAD_ACCUMULATE))
+        return TFCFFT_ERR_FLAGS;
     if ((d->flags & TFCFFT_QUANTIZE_U8) && (d->flags & TFCFFT_CHANNELS_RGB) && d->c == 3) return TFCFFT_ERR_FLAGS;
     for (int t = 0; t < 2; ++t) {
         const int64_t* st = t ? d->real_stride : d->fake_stride;

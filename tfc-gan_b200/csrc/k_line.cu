@@ -53,7 +53,10 @@ int launch_line_v1(const Params& prm, cudaStream_t st) {
 template <typename T, bool LUMA3>
 int launch_line(const Params& prm, cudaStream_t st) {
     static const bool v1 = getenv("TFCFFT_LINE_V1") != nullptr;
-    if (!v1 && ring_addressable<T>(prm)) return launch_line_ring<T, LUMA3>(prm, st);
+    if (!v1 && ring_addressable<T>(prm)) {
+        const int rc = launch_line_ring<T, LUMA3>(prm, st);
+        if (rc != TFCFFT_ERR_STRIDE) return rc;  // no tensor map for these inputs: blocking-load kernel below
+    }
     return launch_line_v1<T, LUMA3>(prm, st);
 }
 

@@ -55,6 +55,8 @@ int launch_regional_any(int dtype, bool luma3, const Params& prm, cudaStream_t s
 int launch_temps_any(int dtype, const TempsParams& tp, cudaStream_t st);                    // k_misc.cu
 int launch_grad_scale_any(int dtype, void* dst, const void* src, long long numel, const float* dev_scale, float host_scale,
                           cudaStream_t st);                                                 // k_misc.cu
+int launch_grad_rescale_any(int dtype, void* grad, long long numel, const float* go_dev, float* applied_dev, unsigned* ticket,
+                            cudaStream_t st);                                               // k_misc.cu
 
 // element type of the object being compiled
 #ifdef TFC_DT

@@ -5,9 +5,12 @@
 // in sequence and the bytes it can keep in flight are bounded by its registers (24 KB per 64-thread CTA, four
 // dependent HBM round trips per tile); the memory phases and the transforms did not overlap (long_scoreboard was the
 // top stall, DRAM 38 % busy, issue slots 39 % busy).  Here ONE persistent CTA per SM holds
-//   * a producer warp that streams the raw pixel rows of the tiles (fake + real, all channels) into a ring of
-//     RING slots with `cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes` (SASS: UBLKCP) -- the bytes
-//     in flight are bounded by the ring (RING x 12 KB), not by registers, and never stall a compute warp;
+//   * a producer warp whose elected lane streams raw row slabs of the tiles (fake + real, all channels) into a ring
+//     of RING slots with TMA tensor copies (`cp.async.bulk.tensor.4d...mbarrier::complete_tx::bytes` over a rank-4
+//     tensor map of the NCHW input, box [1, C, rows, 64]; SASS: UTMALDG) -- the bytes in flight are bounded by the
+//     ring (RING x 12 KB), not by registers, and never stall a compute warp.  (A first version issued one 256-byte
+//     `cp.async.bulk` per pixel row, 384 per tile: the copy issue rate, ~65 cycles each, capped the kernel at
+//     0.71 M img/s whatever the ring shape -- profiles/r02_ring_ab.txt.)
 //   * G worker groups of 64 threads (one tile each, round robin): wait on a slot's `full` mbarrier, fold the slab to
 //     luma (`z = fake + i real`) into their work tile, release the slot (`empty` mbarrier), then run the register-
 //     resident 64-point line transforms, the loss stage and the inverse transforms of line_tile.cuh unchanged, and
@@ -15,6 +18,8 @@
 // The slabs of consecutive tiles go to consecutive workers, so the workers' load phases are staggered by
 // construction and the transforms of G - 1 tiles overlap the HBM stream of the next one.
 #pragma once
+#include <cuda.h>
+
 #include <string>
 
 #include "kernel_common.cuh"
@@ -23,10 +28,13 @@
 namespace tfcfft {
 
 #ifndef TFCFFT_RING_WORKERS
-#define TFCFFT_RING_WORKERS 5
+#define TFCFFT_RING_WORKERS 4
 #endif
 #ifndef TFCFFT_RING_SLOTS
-#define TFCFFT_RING_SLOTS 4
+#define TFCFFT_RING_SLOTS 7
+#endif
+#ifndef TFCFFT_RING_PREFETCH
+#define TFCFFT_RING_PREFETCH 0  // tiles of L2 look-ahead per CTA
 #endif
 
 constexpr int kRingSlotBytes = 12288;  // one slab: fake + real, NC channels, RPS rows of 64 pixels
@@ -39,7 +47,7 @@ struct RingCfgT {
     static constexpr int TILE_BYTES = (int)LineCfg::SMEM;  // 64 x 65 float2
     static constexpr int BAR_BYTES = 256;              // full[RING], empty[RING] (8 bytes each)
     static constexpr size_t SMEM = (size_t)G * TILE_BYTES + (size_t)RING * SLOT_BYTES + BAR_BYTES + 16 * G;
-    static_assert(2 * RING * 8 <= BAR_BYTES, "barrier area too small");
+    static_assert(2 * RING * 8 + 8 <= BAR_BYTES, "barrier area too small");
     static_assert(SMEM + 2048 <= 227 * 1024, "ring configuration exceeds the shared memory of an SM");
 };
 using RingCfg = RingCfgT<TFCFFT_RING_WORKERS, TFCFFT_RING_SLOTS>;  // default configuration
@@ -66,7 +74,7 @@ inline bool ring_addressable(const Params& prm) {
             if ((st[i] * (long long)sizeof(T)) % 16) return false;
         return true;
     };
-    return ok(prm.fake, prm.fs) && ok(prm.real, prm.rs);
+    return prm.real_q[0] == nullptr && ok(prm.fake, prm.fs) && ok(prm.real, prm.rs);
 }
 
 #ifdef __CUDACC__
@@ -92,12 +100,20 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         "r"(parity)
         : "memory");
 }
-// global -> shared bulk copy, completion counted in bytes on `bar`; L2 evict-first (the pixels are read once)
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar, unsigned long long policy) {
+// TMA tensor copy global -> shared: box of the rank-4 map at (x, y, c, n), completion counted in bytes on `bar`;
+// L2 evict-first (the pixels are read once)
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map, int x, int y, int c, int n, unsigned bar,
+                                            unsigned long long policy) {
     asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;" ::"r"(dst),
+        "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(c), "r"(n), "r"(bar), "l"(policy)
         : "memory");
+}
+// TMA prefetch of the same box into L2 only
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int x, int y, int c, int n) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<unsigned long long>(map)),
+                 "r"(x), "r"(y), "r"(c), "r"(n)
+                 : "memory");
 }
 __device__ __forceinline__ unsigned long long policy_evict_first() {
     unsigned long long p;
@@ -193,6 +209,7 @@ __device__ __forceinline__ void ring_store_zero(const Ctx& ctx, const Params& pr
     constexpr int NC = LUMA3 ? 3 : 1;
     T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, 64));
     const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
+    if (prm.flags & TFCFFT_GRAD_ACCUMULATE) return;  // adding zero
     const float z[4] = {0.f, 0.f, 0.f, 0.f};
     for (int it = ctx.tid; it < 64 * 16; it += ctx.nthreads) {
         const int x = (it & 15) * 4, y = it >> 4;
@@ -202,7 +219,9 @@ __device__ __forceinline__ void ring_store_zero(const Ctx& ctx, const Params& pr
 }
 
 template <typename T, bool LUMA3, class RingCfg>
-__global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_constant__ Params prm) {
+__global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_constant__ Params prm,
+                                                                    const __grid_constant__ CUtensorMap map_fake,
+                                                                    const __grid_constant__ CUtensorMap map_real) {
     constexpr int G = RingCfg::G, RING = RingCfg::RING, NC = LUMA3 ? 3 : 1;
     using SL = RingSlab<T, NC>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -210,6 +229,10 @@ __global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_
     float2* tiles = reinterpret_cast<float2*>(smem_raw + RING * RingCfg::SLOT_BYTES);  // G work tiles
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + RING * RingCfg::SLOT_BYTES + G * RingCfg::TILE_BYTES);
     float* scratch = reinterpret_cast<float*>(bars + RingCfg::BAR_BYTES / 8);          // [G][4]: cross-warp sums
+    // tile of this CTA whose worker may take slabs off the ring.  The mbarrier waits below only carry ONE bit of
+    // phase, so a worker must not start waiting for its first slab while the ring is still several rounds behind
+    // (it would wake up on an earlier round of the same slot): workers take turns in tile order.
+    volatile unsigned* turn = reinterpret_cast<volatile unsigned*>(bars + 2 * RING);
     const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + RING);
     const int tid = (int)threadIdx.x;
     if (tid == 0) {
@@ -218,37 +241,47 @@ __global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_
             mbar_init(empty0 + 8 * i, 64);  // every thread of the consuming group
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        *turn = 0u;
     }
     __syncthreads();
     pdl_wait();
     // tiles of this CTA: blockIdx.x + k * gridDim.x, k = 0 .. ntiles - 1; tile k belongs to worker k % G
     const int ntiles = ((int)prm.tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if (tid >= 64 * G) {
-        // ---------------- producer warp: raw rows -> ring ----------------
-        const int lane = tid - 64 * G;
-        const unsigned long long pol = policy_evict_first();
-        unsigned c = 0;  // slab counter
-        for (int k = 0; k < ntiles; ++k) {
-            const TileCoord tc = decode_tile(prm, (int)blockIdx.x + k * (int)gridDim.x);
-            const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, 64);
-            const T* rp = tile_ptr<T>(prm.real, prm.rs, tc, 64);
-            for (int i = 0; i < SL::SLABS; ++i, ++c) {
-                const unsigned slot = c % RING, ph = (c / RING) & 1;
-                mbar_wait(empty0 + 8 * slot, ph ^ 1);  // the consumers of the previous round have released the slot
-                const unsigned fb = full0 + 8 * slot;
-                if (lane == 0) mbar_arrive_expect_tx(fb, SL::BYTES);
-                __syncwarp();
-                const unsigned dst0 = smem_u32(ring + slot * RingCfg::SLOT_BYTES);
-#pragma unroll
-                for (int q0 = 0; q0 < SL::COPIES; q0 += 32) {
-                    const int q = q0 + lane;  // copy index = ((h * NC + ch) * RPS + r)
-                    if (q < SL::COPIES) {
-                        const int r = q % SL::RPS, hc = q / SL::RPS, ch = hc % NC, h = hc / NC;
-                        const int y = i * SL::RPS + r;
-                        const T* src = h ? rp + (long long)y * prm.rs[2] + (long long)ch * prm.rs[1]
-                                         : fp + (long long)y * prm.fs[2] + (long long)ch * prm.fs[1];
-                        bulk_g2s(dst0 + q * SL::ROW_BYTES, src, SL::ROW_BYTES, fb, pol);
+        // ---------------- producer warp: raw row slabs -> ring (one elected lane issues the TMA copies) --------
+        if (tid == 64 * G) {
+            const unsigned long long pol = policy_evict_first();
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&map_fake)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&map_real)) : "memory");
+            unsigned c = 0;  // slab counter
+            // L2 look-ahead: the tiles PF ahead of the one being staged are pulled from HBM into L2 with TMA prefetches,
+            // so the ring itself only has to cover the L2 -> shared-memory latency (a deep HBM pipeline at no
+            // shared-memory cost)
+            const int PF = prm.ring_prefetch;
+            for (int k = 0; k < PF && k < ntiles; ++k) {
+                const TileCoord tp = decode_tile(prm, (int)blockIdx.x + k * (int)gridDim.x);
+                for (int i = 0; i < SL::SLABS; ++i) {
+                    tma_prefetch_4d(&map_fake, tp.px * 64, tp.py * 64 + i * SL::RPS, tp.ch, tp.n);
+                    tma_prefetch_4d(&map_real, tp.px * 64, tp.py * 64 + i * SL::RPS, tp.ch, tp.n);
+                }
+            }
+            for (int k = 0; k < ntiles; ++k) {
+                const TileCoord tc = decode_tile(prm, (int)blockIdx.x + k * (int)gridDim.x);
+                const bool pf = PF > 0 && k + PF < ntiles;
+                const TileCoord tp = decode_tile(prm, (int)blockIdx.x + (pf ? k + PF : k) * (int)gridDim.x);
+                for (int i = 0; i < SL::SLABS; ++i, ++c) {
+                    if (pf) {
+                        tma_prefetch_4d(&map_fake, tp.px * 64, tp.py * 64 + i * SL::RPS, tp.ch, tp.n);
+                        tma_prefetch_4d(&map_real, tp.px * 64, tp.py * 64 + i * SL::RPS, tp.ch, tp.n);
                     }
+                    const unsigned slot = c % RING, ph = (c / RING) & 1;
+                    mbar_wait(empty0 + 8 * slot, ph ^ 1);  // the consumers of the previous round have released the slot
+                    const unsigned fb = full0 + 8 * slot;
+                    mbar_arrive_expect_tx(fb, SL::BYTES);
+                    const unsigned dst0 = smem_u32(ring + slot * RingCfg::SLOT_BYTES);
+                    const int x = tc.px * 64, y = tc.py * 64 + i * SL::RPS;
+                    tma_load_4d(dst0, &map_fake, x, y, tc.ch, tc.n, fb, pol);                   // [channel][row][64 px]
+                    tma_load_4d(dst0 + SL::BYTES / 2, &map_real, x, y, tc.ch, tc.n, fb, pol);
                 }
             }
         }
@@ -264,9 +297,14 @@ __global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_
             const TileCoord tc = decode_tile(prm, tile);
             bool same = true;
             unsigned c = (unsigned)k * SL::SLABS;
+            if (gtid == 0) {
+                while (*turn != (unsigned)k) __nanosleep(64);
+            }
+            ctx.sync();  // my turn: every slab before tile k's has been taken
             for (int i = 0; i < SL::SLABS; ++i, ++c) {
                 const unsigned slot = c % RING, ph = (c / RING) & 1;
                 mbar_wait(full0 + 8 * slot, ph);
+                if (i == SL::SLABS - 1 && gtid == 0) *turn = (unsigned)k + 1u;  // the next worker may start waiting
                 same = ring_convert<T, LUMA3>(prm, ring + slot * RingCfg::SLOT_BYTES, i * SL::RPS, gtid, s) && same;
                 mbar_arrive(empty0 + 8 * slot);
             }
@@ -321,17 +359,81 @@ __global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_
     finish(prm, gridDim.x);
 }
 
+// ---- host: rank-4 tensor maps of the NCHW inputs (driver entry point fetched through the runtime: no libcuda link) --
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+template <typename T> struct TmaType;
+template <> struct TmaType<float> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; };
+template <> struct TmaType<__half> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT16; };
+template <> struct TmaType<__nv_bfloat16> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; };
+template <> struct TmaType<uint8_t> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_UINT8; };
+
+// box [1][NC][RPS][64] over [N][C][H][W] with the tensor's own strides (views are fine: strides are multiples of 16 bytes)
+template <typename T>
+inline bool make_tile_map(CUtensorMap* map, const void* base, const long long* st, const Params& prm, int nc, int rps) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t es = sizeof(T);
+    const cuuint64_t dims[4] = {(cuuint64_t)prm.w, (cuuint64_t)prm.h, (cuuint64_t)prm.c, (cuuint64_t)prm.n};
+    auto stride = [&](long long s, cuuint64_t lower) {  // a size-1 dimension may carry any stride: give the encoder a valid one
+        cuuint64_t b = (cuuint64_t)s * es;
+        return b < lower ? lower : b;
+    };
+    const cuuint64_t row = stride(st[2], dims[0] * es);
+    const cuuint64_t chan = stride(st[1], row);
+    const cuuint64_t img = stride(st[0], chan);
+    const cuuint64_t strides[3] = {row, chan, img};
+    const cuuint32_t box[4] = {64u, (cuuint32_t)rps, (cuuint32_t)nc, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    return enc(map, TmaType<T>::v, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// returns TFCFFT_ERR_STRIDE when the inputs cannot be described by a tensor map (the caller falls back to line_kernel)
 template <typename T, bool LUMA3, class RingCfg>
 int launch_line_ring_cfg(const Params& prm, cudaStream_t st) {
+    constexpr int NC = LUMA3 ? 3 : 1;
+    using SL = RingSlab<T, NC>;
     auto kernel = line_ring_kernel<T, LUMA3, RingCfg>;
     static KernelFacts facts;
     if (int rc = facts.get(kernel, RingCfg::NT, RingCfg::SMEM, nullptr)) return rc;
+    static const int pf_env = getenv("TFCFFT_RING_PF") ? atoi(getenv("TFCFFT_RING_PF")) : TFCFFT_RING_PREFETCH;
+    Params prm2 = prm;
+    prm2.ring_prefetch = pf_env;
+    alignas(64) CUtensorMap mf, mr;
+    if (!make_tile_map<T>(&mf, prm.fake, prm.fs, prm, NC, SL::RPS) || !make_tile_map<T>(&mr, prm.real, prm.rs, prm, NC, SL::RPS))
+        return TFCFFT_ERR_STRIDE;
     const int sms = device_sms();
     // one persistent CTA per SM; with few tiles use fewer CTAs so that every CTA keeps its G workers busy
     long long want = ((long long)prm.tiles_total + RingCfg::G - 1) / RingCfg::G;
     if (want < 1) want = 1;
     const int grid = (int)(want < sms ? want : sms);
-    if (cudaError_t e = launch_pdl(kernel, grid, RingCfg::NT, RingCfg::SMEM, st, prm)) return (int)e;
+    {
+        static const bool off = getenv("TFCFFT_NO_PDL") != nullptr;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)RingCfg::NT);
+        cfg.dynamicSmemBytes = RingCfg::SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = off ? 0 : 1;
+        if (cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, prm2, mf, mr)) return (int)e;
+    }
     g_launches++;
     return 0;
 }
@@ -347,6 +449,8 @@ int launch_line_ring(const Params& prm, cudaStream_t st) {
         if (v == "6x2") return launch_line_ring_cfg<T, LUMA3, RingCfgT<6, 2>>(prm, st);
         if (v == "5x3") return launch_line_ring_cfg<T, LUMA3, RingCfgT<5, 3>>(prm, st);
         if (v == "3x8") return launch_line_ring_cfg<T, LUMA3, RingCfgT<3, 8>>(prm, st);
+        if (v == "5x4") return launch_line_ring_cfg<T, LUMA3, RingCfgT<5, 4>>(prm, st);
+        if (v == "4x6") return launch_line_ring_cfg<T, LUMA3, RingCfgT<4, 6>>(prm, st);
     }
 #endif
     return launch_line_ring_cfg<T, LUMA3, RingCfg>(prm, st);

@@ -107,7 +107,7 @@ template <typename T, bool LUMA3, class Ctx>
 TFC_HD void line_load(const Ctx& ctx, const Params& prm, const TileCoord& tc, float2* s) {
     constexpr int LD = LineCfg::LD, NC = LUMA3 ? 3 : 1;
     const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, 64);
-    const T* rp = tile_ptr<T>(prm.real, prm.rs, tc, 64);
+    const T* rp = real_tile_ptr<T>(prm, tc, 64);
     const int fsh = (int)prm.fs[2], fsc = (int)prm.fs[1], rsh = (int)prm.rs[2], rsc = (int)prm.rs[1];
     const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
     constexpr int NI = 4;  // items in flight per thread: 2*NC*NI 128-bit loads (the FFT registers are idle here)
@@ -312,6 +312,7 @@ TFC_HD void line_store(const Ctx& ctx, const Params& prm, const TileCoord& tc, c
     constexpr int LD = LineCfg::LD, NC = LUMA3 ? 3 : 1;
     T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, 64));
     const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
+    const GradOut go = grad_out(prm);
 #pragma unroll 2
     for (int it = ctx.tid; it < 64 * 16; it += ctx.nthreads) {
         const int x = (it & 15) * 4, y = it >> 4;
@@ -319,8 +320,8 @@ TFC_HD void line_store(const Ctx& ctx, const Params& prm, const TileCoord& tc, c
         const float2 lo = *reinterpret_cast<const float2*>(g), hi = *reinterpret_cast<const float2*>(g + 2);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            const float v[4] = {prm.gw[c] * lo.x, prm.gw[c] * lo.y, prm.gw[c] * hi.x, prm.gw[c] * hi.y};
-            IO<T>::store4(gp + y * sh + c * sc + x, v);
+            float v[4] = {go.w[c] * lo.x, go.w[c] * lo.y, go.w[c] * hi.x, go.w[c] * hi.y};
+            grad_store4<T>(go, gp + y * sh + c * sc + x, v);
         }
     }
 }
@@ -332,7 +333,7 @@ TFC_HD void line_prefetch_l2(const Ctx& ctx, const Params& prm, const TileCoord&
 #ifdef __CUDA_ARCH__
     constexpr int NC = LUMA3 ? 3 : 1, EPL = 128 / (int)sizeof(T), LPR = (64 + EPL - 1) / EPL;
     const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, 64);
-    const T* rp = tile_ptr<T>(prm.real, prm.rs, tc, 64);
+    const T* rp = real_tile_ptr<T>(prm, tc, 64);
     for (int it = ctx.tid; it < 2 * NC * 64 * LPR; it += ctx.nthreads) {
         const int l = it % LPR, y = (it / LPR) & 63, hc = it / (LPR * 64);
         const int h = hc & 1, c = hc >> 1;

@@ -172,9 +172,9 @@ template <int P, typename T>
 TFC_HD PairSrc<T> pair_src(const Params& prm, const TileCoord& ta, const TileCoord& tb) {
     PairSrc<T> r;
     r.p[0] = tile_ptr<T>(prm.fake, prm.fs, ta, P);
-    r.p[1] = tile_ptr<T>(prm.real, prm.rs, ta, P);
+    r.p[1] = real_tile_ptr<T>(prm, ta, P);
     r.p[2] = tile_ptr<T>(prm.fake, prm.fs, tb, P);
-    r.p[3] = tile_ptr<T>(prm.real, prm.rs, tb, P);
+    r.p[3] = real_tile_ptr<T>(prm, tb, P);
     r.sh[0] = r.sh[2] = (int)prm.fs[2];
     r.sh[1] = r.sh[3] = (int)prm.rs[2];
     r.sc[0] = r.sc[2] = (int)prm.fs[1];
@@ -401,6 +401,7 @@ TFC_HD void pair_store(const Ctx& ctx, const Params& prm, const TileCoord& ta, c
     T* ga = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, ta, P));
     T* gb = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tb, P));
     const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
+    const GradOut go = grad_out(prm);
     for (int it = ctx.tid; it < P * XV; it += ctx.nthreads) {
         const int x = (it % XV) * 4, y = it / XV;
         const float4* row = s + y * LD;
@@ -416,11 +417,11 @@ TFC_HD void pair_store(const Ctx& ctx, const Params& prm, const TileCoord& ta, c
             float va[4], vb[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                va[i] = prm.gw[c] * a[i];
-                vb[i] = prm.gw[c] * b[i];
+                va[i] = go.w[c] * a[i];
+                vb[i] = go.w[c] * b[i];
             }
-            IO<T>::store4(ga + y * sh + c * sc + x, va);
-            if (b_valid) IO<T>::store4(gb + y * sh + c * sc + x, vb);
+            grad_store4<T>(go, ga + y * sh + c * sc + x, va);
+            if (b_valid) grad_store4<T>(go, gb + y * sh + c * sc + x, vb);
         }
     }
 }

@@ -219,14 +219,15 @@ TFC_HD void regional_process(const Ctx& ctx, const Params& prm, int unit, float2
         reg_rows<true>(ctx, s, tw);
         T* gb = static_cast<T*>(prm.grad) + n * prm.gs[0] + ch * prm.gs[1] + (long long)(band * H) * prm.gs[2];
         constexpr int NC = LUMA3 ? 3 : 1;
+        const GradOut go = grad_out(prm);
         for (int it = ctx.tid; it < H * XV; it += ctx.nthreads) {
             const int x = (it % XV) * 4, y = it / XV;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 float v[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = prm.gw[c] * s[y * LD + x + i].x;
-                IO<T>::store4(gb + (long long)y * prm.gs[2] + c * prm.gs[1] + x, v);
+                for (int i = 0; i < 4; ++i) v[i] = go.w[c] * s[y * LD + x + i].x;
+                grad_store4<T>(go, gb + (long long)y * prm.gs[2] + c * prm.gs[1] + x, v);
             }
         }
         ctx.sync();

@@ -38,7 +38,7 @@ struct Params {
     float* partials;       // [tiles_total * parts][2] (amp, pha) raw sums
     int parts;             // partial sums per tile (1 resident, #column-group pairs split)
     unsigned* counter;     // self-resetting ticket for the last-block finalise
-    float* out;            // [4]: loss, amp, pha, non-finite flag
+    float* out;            // [8]: loss, amp, pha, non-finite flag, gradient scale applied, 3 reserved
     float* per_image;      // [N][2] or nullptr
     float2* zws;           // split path: spectrum workspace [chunk_tiles][P][P]
     int tile_base;         // split path: first tile of this chunk
@@ -52,6 +52,13 @@ struct Params {
     int spec_shift;        // outputs (and incoming gradients) in np.fft.fftshift order over both axes
     float* spec_out[4];    // emit: amp(fake), pha(fake), amp(real), pha(real); [tiles][P][W]; may be null
     const float* spec_gin[2];  // backward: d loss / d amp, d loss / d pha of `fake`; may be null
+    // gradient epilogue: d loss / d fake is multiplied by *gscale_dev (GradScaler's device scale; may be null) on the
+    // way out -- gw[] already holds the host-side factors -- and added to the buffer with TFCFFT_GRAD_ACCUMULATE
+    const float* gscale_dev;
+    int ring_prefetch;     // line_ring_kernel: tiles of L2 look-ahead (set by its launcher)
+    float gscale_host;     // already folded into gw[]; reported in out[4] together with *gscale_dev
+    // loader quadrants (tfcfft_loss_quads): `real` given as 4 separate [N,C,P,P] tensors (grid == 2); else all null
+    const void* real_q[4];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -239,11 +246,61 @@ TFC_HD const T* tile_ptr(const void* base, const long long* st, const TileCoord&
     return reinterpret_cast<const T*>(base) + t.n * st[0] + t.ch * st[1] + (long long)t.py * p * st[2] + (long long)t.px * p;
 }
 
+// `real` tile: a window of the full tensor, or -- loader quadrants B1..B4 = TL, TR, BL, BR (datasets_temp.py:76-118,
+// fft_loss(fake_B, B1, B2, B3, B4) at TFCGAN_multigpu_patchFFT_experiment.py:317-339) -- a whole separate tensor
+template <typename T>
+TFC_HD const T* real_tile_ptr(const Params& prm, const TileCoord& t, int p) {
+    if (prm.real_q[0] == nullptr) return tile_ptr<T>(prm.real, prm.rs, t, p);
+    return reinterpret_cast<const T*>(prm.real_q[t.py * prm.grid + t.px]) + t.n * prm.rs[0] + t.ch * prm.rs[1];
+}
+
+// Gradient epilogue shared by every kernel: per-channel weights on the way out (luma coefficient x input_scale x
+// host gradient scale, times the optional device scalar) and plain or accumulating 4-pixel stores.
+struct GradOut {
+    float w[3];
+    bool acc;
+};
+TFC_HD GradOut grad_out(const Params& prm) {
+    GradOut g;
+    float sc = 1.f;
+    if (prm.gscale_dev != nullptr) {
+#ifdef __CUDA_ARCH__
+        sc = __ldg(prm.gscale_dev);
+#else
+        sc = *prm.gscale_dev;
+#endif
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g.w[c] = prm.gw[c] * sc;
+    g.acc = (prm.flags & TFCFFT_GRAD_ACCUMULATE) != 0;
+    return g;
+}
+template <typename T>
+TFC_HD void grad_store4(const GradOut& go, T* p, float* v) {
+    if (go.acc) {
+        float o[4];
+        IO<T>::load4(p, o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] += o[i];
+    }
+    IO<T>::store4(p, v);
+}
+template <typename T>
+TFC_HD void grad_store2(const GradOut& go, T* p, float a, float b) {
+    if (go.acc) {
+        float o[2];
+        IO<T>::load2(p, o);
+        a += o[0];
+        b += o[1];
+    }
+    IO<T>::store2(p, a, b);
+}
+
 // Packs rows [row0, row0+nrows) of a tile into s[(r-row0)*ld + x] = (f, r).
 template <int P, typename T, bool LUMA3, class Ctx>
 TFC_HD void load_rows(const Ctx& ctx, const Params& prm, const TileCoord& tc, int row0, int nrows, float2* s, int ld) {
     const T* fb = tile_ptr<T>(prm.fake, prm.fs, tc, P);
-    const T* rb = tile_ptr<T>(prm.real, prm.rs, tc, P);
+    const T* rb = real_tile_ptr<T>(prm, tc, P);
     constexpr int XV = P / 4;
     for (int it = ctx.tid; it < nrows * XV; it += ctx.nthreads) {
         const int x = (it % XV) * 4, y = it / XV;
@@ -261,6 +318,7 @@ template <int P, typename T, bool LUMA3, class Ctx>
 TFC_HD void store_rows(const Ctx& ctx, const Params& prm, const TileCoord& tc, int row0, int nrows, const float2* s, int ld) {
     T* gb = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, P));
     constexpr int XV = P / 4;
+    const GradOut go = grad_out(prm);
     for (int it = ctx.tid; it < nrows * XV; it += ctx.nthreads) {
         const int x = (it % XV) * 4, y = it / XV;
         const float2* d = s + y * ld + x;
@@ -270,8 +328,8 @@ TFC_HD void store_rows(const Ctx& ctx, const Params& prm, const TileCoord& tc, i
         for (int c = 0; c < NC; ++c) {
             float v[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = prm.gw[c] * d[i].x;
-            IO<T>::store4(p0 + c * prm.gs[1], v);
+            for (int i = 0; i < 4; ++i) v[i] = go.w[c] * d[i].x;
+            grad_store4<T>(go, p0 + c * prm.gs[1], v);
         }
     }
 }
@@ -572,6 +630,10 @@ TFC_HD void write_outputs(const Params& prm, double suma, double sump) {
     prm.out[1] = (float)amp;
     prm.out[2] = (float)pha;
     prm.out[3] = (loss - loss == 0.0) ? 0.f : 1.f;  // 1 when the loss is inf / nan
+    // the factor folded into the gradient on top of d loss / d fake (tfcfft_grad_rescale's `applied` scalar)
+    float sc = prm.gscale_host;
+    if (prm.gscale_dev != nullptr) sc *= *prm.gscale_dev;
+    prm.out[4] = sc;
 }
 
 // the packed / thread-per-line 64 x 64 engines implement the default loss modes only

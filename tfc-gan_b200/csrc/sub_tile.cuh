@@ -52,7 +52,7 @@ TFC_HD void sub_fwd_load(const Ctx& ctx, const Params& prm, const TileCoord& tc,
     constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1, NI = SubCfg::LOAD_NI;
     const int D = prm.sub_d, P = 64 * D;
     const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, P);
-    const T* rp = tile_ptr<T>(prm.real, prm.rs, tc, P);
+    const T* rp = real_tile_ptr<T>(prm, tc, P);
     const int fsh = (int)prm.fs[2], fsc = (int)prm.fs[1], rsh = (int)prm.rs[2], rsc = (int)prm.rs[1];
     const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
     // one sub-image column b per lane (consecutive lanes -> consecutive 8-byte pixel pairs of the source row),
@@ -102,7 +102,7 @@ template <typename T, bool LUMA3, class Ctx>
 TFC_HD void sub_fwd_load_quad(const Ctx& ctx, const Params& prm, const TileCoord& tc, int p, int half, float2* dst01, float2* dst23) {
     constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1, NI = SubCfg::LOAD_NI, P = 256;
     const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, P);
-    const T* rp = tile_ptr<T>(prm.real, prm.rs, tc, P);
+    const T* rp = real_tile_ptr<T>(prm, tc, P);
     const int fsh = (int)prm.fs[2], fsc = (int)prm.fs[1], rsh = (int)prm.rs[2], rsc = (int)prm.rs[1];
     const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
 #pragma unroll 1
@@ -209,13 +209,14 @@ TFC_HD void sub_inv_store(const Ctx& ctx, const Params& prm, const TileCoord& tc
     const int D = prm.sub_d, P = 64 * D;
     T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, P));
     const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
+    const GradOut go = grad_out(prm);
 #pragma unroll 4
     for (int it = ctx.tid; it < 4096; it += ctx.nthreads) {
         const int b = it & 63, a = it >> 6;  // consecutive lanes: consecutive 8-byte pairs of the gradient row
         const int x = D * b + 2 * su.i, y = D * a + su.p;
         const float2 g = s[a * LD + b];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) IO<T>::store2(gp + y * sh + c * sc + x, prm.gw[c] * g.x, prm.gw[c] * g.y);
+        for (int c = 0; c < NC; ++c) grad_store2<T>(go, gp + y * sh + c * sc + x, go.w[c] * g.x, go.w[c] * g.y);
     }
 }
 
@@ -228,6 +229,7 @@ TFC_HD void sub_inv_store_quad(const Ctx& ctx, const Params& prm, const TileCoor
     constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1, P = 256;
     T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, P));
     const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
+    const GradOut go = grad_out(prm);
 #pragma unroll 4
     for (int it = ctx.tid; it < 2048; it += ctx.nthreads) {
         const int b = it & 63, a = 32 * half + (it >> 6);
@@ -235,8 +237,8 @@ TFC_HD void sub_inv_store_quad(const Ctx& ctx, const Params& prm, const TileCoor
         const int x = 4 * b, y = 4 * a + p;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            const float v[4] = {prm.gw[c] * lo.x, prm.gw[c] * lo.y, prm.gw[c] * hi.x, prm.gw[c] * hi.y};
-            IO<T>::store4(gp + y * sh + c * sc + x, v);
+            float v[4] = {go.w[c] * lo.x, go.w[c] * lo.y, go.w[c] * hi.x, go.w[c] * hi.y};
+            grad_store4<T>(go, gp + y * sh + c * sc + x, v);
         }
     }
 }

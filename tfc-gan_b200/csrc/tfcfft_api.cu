@@ -52,6 +52,12 @@ size_t tfcfft_workspace_bytes(const tfcfft_desc* d) {
     return g.ws_bytes;
 }
 
+size_t tfcfft_spectra_workspace_bytes(const tfcfft_desc* d) {
+    Geometry g;
+    if (validate_desc(d, &g, /*allow_sub=*/false) != TFCFFT_OK) return 0;
+    return g.ws_bytes;
+}
+
 int tfcfft_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
     if (!workspace || workspace_bytes < kWsHeader || ((uintptr_t)workspace & 255)) return TFCFFT_ERR_WORKSPACE;
     cudaError_t e = cudaMemsetAsync(workspace, 0, kWsHeader, (cudaStream_t)stream);
@@ -102,8 +108,8 @@ int tfcfft_spectra_bwd(const tfcfft_desc* d, const void* x, const float* grad_am
     return dispatch(prm, g, d->dtype, (cudaStream_t)stream);
 }
 
-int tfcfft_loss(const tfcfft_desc* d, const void* fake, const void* real, float* out, float* per_image, void* grad_fake,
-                void* workspace, size_t workspace_bytes, void* stream) {
+static int loss_common(const tfcfft_desc* d, const void* fake, const void* real, const void* const* quads, float* out,
+                       float* per_image, void* grad_fake, void* workspace, size_t workspace_bytes, void* stream) {
     Geometry g;
     int rc = validate_desc(d, &g);
     if (rc) return rc;
@@ -112,9 +118,28 @@ int tfcfft_loss(const tfcfft_desc* d, const void* fake, const void* real, float*
     if ((rc = check_alignment(d, fake, real, grad_fake))) return rc;
     if (!workspace || workspace_bytes < g.ws_bytes || ((uintptr_t)workspace & 255)) return TFCFFT_ERR_WORKSPACE;
     Params prm = make_params(d, g, fake, real, grad_fake, out, per_image, workspace);
+    if (quads) {
+        if (d->grid != 2) return TFCFFT_ERR_SHAPE;
+        for (int i = 0; i < 4; ++i) {
+            if (!quads[i]) return TFCFFT_ERR_NULL;
+            if ((uintptr_t)quads[i] % (4 * elem_size(d->dtype))) return TFCFFT_ERR_ALIGNMENT;
+            prm.real_q[i] = quads[i];
+        }
+    }
     prm.trace = g_trace.load();
     cudaStream_t st = (cudaStream_t)stream;
     return dispatch(prm, g, d->dtype, st);
+}
+
+int tfcfft_loss(const tfcfft_desc* d, const void* fake, const void* real, float* out, float* per_image, void* grad_fake,
+                void* workspace, size_t workspace_bytes, void* stream) {
+    return loss_common(d, fake, real, nullptr, out, per_image, grad_fake, workspace, workspace_bytes, stream);
+}
+
+int tfcfft_loss_quads(const tfcfft_desc* d, const void* fake, const void* const real_quadrants[4], float* out, float* per_image,
+                      void* grad_fake, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!real_quadrants) return TFCFFT_ERR_NULL;
+    return loss_common(d, fake, real_quadrants[0], real_quadrants, out, per_image, grad_fake, workspace, workspace_bytes, stream);
 }
 
 size_t tfcfft_regional_workspace_bytes(const tfcfft_desc* d) {
@@ -231,6 +256,18 @@ int tfcfft_grad_scale(void* dst, const void* src, int32_t dtype, int64_t numel, 
     const size_t es = elem_size(dtype);
     if (es == 0 || dtype == TFCFFT_U8) return TFCFFT_ERR_DTYPE;
     return launch_grad_scale_any(dtype, dst, src, numel, dev_scale, host_scale, st);
+}
+
+int tfcfft_grad_rescale(void* grad, int32_t dtype, int64_t numel, const float* grad_output_dev, float* applied_dev, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    if (!grad || !grad_output_dev || !applied_dev) return TFCFFT_ERR_NULL;
+    if (numel <= 0) return numel == 0 ? 0 : TFCFFT_ERR_SHAPE;
+    if ((uintptr_t)grad & 15) return TFCFFT_ERR_ALIGNMENT;
+    if (!workspace || workspace_bytes < kWsHeader || ((uintptr_t)workspace & 255)) return TFCFFT_ERR_WORKSPACE;
+    if (elem_size(dtype) == 0 || dtype == TFCFFT_U8) return TFCFFT_ERR_DTYPE;
+    // the ticket of the rescale launch lives at byte 128 of the workspace header (the loss launches use byte 0)
+    unsigned* ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) + 128);
+    return launch_grad_rescale_any(dtype, grad, numel, grad_output_dev, applied_dev, ticket, (cudaStream_t)stream);
 }
 
 void tfcfft_debug_trace(void* device_buffer) { g_trace.store((long long*)device_buffer); }

@@ -118,27 +118,103 @@ def _prep(fake: torch.Tensor, real: torch.Tensor):
     return fake, real
 
 
-def _launch(fake, real, cfg: SpectralConfig, want_grad: bool, want_per_image: bool):
+def _fp16_prescale(cfg: "SpectralConfig", shape) -> float:
+    """Power-of-two factor folded into an fp16 gradient when the caller does not name the real ``grad_output`` (a
+    GradScaler): the 1 / (N g^2 K) normalised gradient of a batch of 32+ images is fp16-SUBNORMAL (round-1 advisor
+    finding), an MSE gradient on 8-bit-scale spectra can exceed fp16's maximum.  The factor brings the estimated rms
+    of the stored values to ~2^-3 (the estimate only has to be right within 2^+-15); ``backward`` divides it out again
+    together with autograd's ``grad_output``."""
+    import math
+
+    n, c, h, _ = shape
+    p = h // cfg.grid
+    k = p * (p if cfg.spectrum == "full" else p // 2 + 1)
+    cp = 3 if (cfg.channels == "rgb" and c == 3) else 1
+    per_bin = abs(cfg.weight) * (1.0 if not cfg.use_phase else 0.5) / (n * cp * cfg.grid ** 2 * k)
+    if cfg.patch_reduce == "sum":
+        per_bin *= cfg.grid ** 2
+    amp = 0.4 * abs(cfg.input_scale) * p  # typical |F| of a [-1, 1] image
+    if cfg.distance == "mse":
+        per_bin *= 2.0 * (1.0 if cfg.log_magnitude else amp)
+    if cfg.log_magnitude:
+        per_bin /= amp
+    rms = per_bin * math.sqrt(2.0 * k) * abs(cfg.input_scale) * (0.6 if cp == 1 and c == 3 else 1.0)
+    if not (rms > 0.0) or not math.isfinite(rms):
+        return 1.0
+    e = round(math.log2(0.125 / rms))
+    return float(2.0 ** max(-24, min(30, e)))
+
+
+def _resolve_grad_scale(grad_scale, dtype, dev, cfg=None, shape=None):
+    """``grad_scale`` -> (host factor, device scalar tensor or None).  Accepts None, a float, a 0-dim / 1-element
+    CUDA tensor, a ``torch.amp.GradScaler`` (its device-side scale is read at kernel time: no sync), or a tuple
+    ``(GradScaler | tensor, float)`` whose float is the factor applied to the returned loss before ``backward``."""
+    host, dev_t = 1.0, None
+    items = grad_scale if isinstance(grad_scale, (tuple, list)) else (grad_scale,)
+    for it in items:
+        if it is None:
+            continue
+        if isinstance(it, (int, float)):
+            host *= float(it)
+        elif isinstance(it, torch.Tensor):
+            if it.numel() != 1 or not it.is_cuda:
+                raise ValueError("grad_scale tensor must be a 1-element CUDA tensor")
+            dev_t = it.detach().reshape(()).to(device=dev, dtype=torch.float32)
+        elif hasattr(it, "_scale") and hasattr(it, "is_enabled"):  # torch.amp.GradScaler
+            if it.is_enabled():
+                if it._scale is None:
+                    it._lazy_init_scale_growth_tracker(dev)
+                dev_t = it._scale.detach().reshape(()).to(device=dev, dtype=torch.float32)
+        else:
+            raise TypeError(f"unsupported grad_scale item {type(it).__name__}")
+    if grad_scale is None and dtype == torch.float16 and cfg is not None:
+        host = _fp16_prescale(cfg, shape)
+    return host, dev_t
+
+
+def _launch(fake, real, cfg: SpectralConfig, want_grad: bool, want_per_image: bool, *, gs_host: float = 1.0, gs_dev=None,
+            accumulate_into=None, real_quads=None, grad_buffer=None):
     lib = _lib.load()
     dev = fake.device
     with torch.cuda.device(dev):
         stream_ptr = torch.cuda.current_stream(dev).cuda_stream
-        out = torch.empty(4, dtype=torch.float32, device=dev)
+        out = torch.empty(8, dtype=torch.float32, device=dev)
         per = torch.empty((fake.shape[0], 2), dtype=torch.float32, device=dev) if want_per_image else None
-        grad = torch.empty(fake.shape, dtype=fake.dtype, device=dev) if want_grad else None
+        flags = cfg.flags()
+        if accumulate_into is not None:
+            if accumulate_into.shape != fake.shape or accumulate_into.dtype != fake.dtype or accumulate_into.device != dev \
+                    or not _acceptable(accumulate_into):
+                raise ValueError("accumulate_into must match fake in shape / dtype / device and have 16-byte friendly strides")
+            grad, flags = accumulate_into, flags | _lib.GRAD_ACCUMULATE
+        elif grad_buffer is not None:  # caller-owned destination, overwritten
+            if grad_buffer.shape != fake.shape or grad_buffer.dtype != fake.dtype or grad_buffer.device != dev \
+                    or not _acceptable(grad_buffer):
+                raise ValueError("grad_buffer must match fake in shape / dtype / device and have 16-byte friendly strides")
+            grad = grad_buffer
+        else:
+            grad = torch.empty(fake.shape, dtype=fake.dtype, device=dev) if want_grad else None
         desc = _lib.make_desc(
-            _DTYPES[fake.dtype], cfg.grid, cfg.flags(), fake.shape, fake.stride(), real.stride(),
-            grad.stride() if want_grad else None, cfg.weight, cfg.input_scale,
+            _DTYPES[fake.dtype], cfg.grid, flags, fake.shape, fake.stride(), real.stride(),
+            grad.stride() if grad is not None else None, cfg.weight, cfg.input_scale,
+            grad_scale_host=gs_host, grad_scale_dev=gs_dev.data_ptr() if gs_dev is not None else None,
         )
         nbytes = lib.tfcfft_workspace_bytes(ctypes.byref(desc))
         if nbytes == 0:
             _lib.check(lib.tfcfft_validate(ctypes.byref(desc)), "tfcfft_validate")
         ws = _workspace(dev, stream_ptr, nbytes)
-        rc = lib.tfcfft_loss(
-            ctypes.byref(desc), fake.data_ptr(), real.data_ptr(), out.data_ptr(),
-            per.data_ptr() if want_per_image else None, grad.data_ptr() if want_grad else None,
-            ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream_ptr),
-        )
+        if real_quads is None:
+            rc = lib.tfcfft_loss(
+                ctypes.byref(desc), fake.data_ptr(), real.data_ptr(), out.data_ptr(),
+                per.data_ptr() if want_per_image else None, grad.data_ptr() if grad is not None else None,
+                ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream_ptr),
+            )
+        else:
+            qp = (ctypes.c_void_p * 4)(*[q.data_ptr() for q in real_quads])
+            rc = lib.tfcfft_loss_quads(
+                ctypes.byref(desc), fake.data_ptr(), qp, out.data_ptr(),
+                per.data_ptr() if want_per_image else None, grad.data_ptr() if grad is not None else None,
+                ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream_ptr),
+            )
         if rc > 0:  # a CUDA error may have left the ticket header dirty
             _WORKSPACES.pop((dev.index, stream_ptr), None)
         _lib.check(rc, "tfcfft_loss")
@@ -147,7 +223,8 @@ def _launch(fake, real, cfg: SpectralConfig, want_grad: bool, want_per_image: bo
 
 def _scale_saved_gradient(unit: torch.Tensor, grad_loss: torch.Tensor, in_dtype: torch.dtype) -> torch.Tensor:
     """``unit * grad_loss`` (the saved d loss / d fake times autograd's incoming scalar: loss weight x GradScaler scale) in
-    one launch of the library's scaling kernel; the scalar stays on the device."""
+    one launch of the library's scaling kernel; the scalar stays on the device.  Used by the auxiliary losses; the FFT
+    loss folds the expected scale into its producing launch instead (``_rescale_in_place``)."""
     lib = _lib.load()
     dev = unit.device
     with torch.cuda.device(dev):
@@ -159,19 +236,58 @@ def _scale_saved_gradient(unit: torch.Tensor, grad_loss: torch.Tensor, in_dtype:
     return res if res.dtype == in_dtype else res.to(in_dtype)
 
 
+def _rescale_in_place(buf: torch.Tensor, out: torch.Tensor, grad_loss: torch.Tensor) -> None:
+    """``buf *= grad_loss / applied`` on the device, where ``applied`` (``out[4]``) is the scale the producing launch
+    already folded in.  Equal scalars -- the expected case -- cost one tiny launch and no pass over ``buf``."""
+    lib = _lib.load()
+    dev = buf.device
+    with torch.cuda.device(dev):
+        stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+        go = grad_loss.detach().to(device=dev, dtype=torch.float32).reshape(())
+        ws = _workspace(dev, stream_ptr, 256)
+        _lib.check(lib.tfcfft_grad_rescale(buf.data_ptr(), _DTYPES[buf.dtype], buf.numel(), go.data_ptr(),
+                                           out.data_ptr() + 16, ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream_ptr)),
+                   "tfcfft_grad_rescale")
+
+
+def _common_quads(quads, fake):
+    """The loader's four real quadrants as pointer-array arguments: same dtype / shape / strides, else None."""
+    q0 = quads[0]
+    n, c, h, w = fake.shape
+    for q in quads:
+        if q.dtype != fake.dtype or q.device != fake.device or tuple(q.shape) != (n, c, h // 2, w // 2) \
+                or q.stride() != q0.stride() or not _acceptable(q):
+            return None
+    return quads
+
+
 class _SpectralLossFn(torch.autograd.Function):
-    """forward: loss and the unit gradient in ONE pass over fake / real (3 tensor passes of HBM
-    traffic); backward: one scaling launch by ``grad_output`` (weight x GradScaler scale)."""
+    """forward: loss and d loss / d fake -- with the expected ``grad_output`` already folded in -- in ONE pass over
+    fake / real (3 tensor passes of HBM traffic); backward: a scalar comparison on the device; the tensor is touched
+    again (in place, no allocation) only when autograd's ``grad_output`` differs from the expected one."""
 
     @staticmethod
-    def forward(ctx, fake, real, cfg):
-        fake_p, real_p = _prep(fake.detach(), real.detach())
+    def forward(ctx, fake, real, cfg, grad_scale, quads):
+        if quads is not None:
+            fake_p, _ = _prep(fake.detach(), fake.detach())
+            qs = _common_quads([q.detach() for q in quads], fake_p)
+            if qs is None:  # mixed layouts: one concatenation copy (the reference's tensors are always alike)
+                top = torch.cat((quads[0], quads[1]), dim=3)
+                bot = torch.cat((quads[2], quads[3]), dim=3)
+                fake_p, real_p = _prep(fake.detach(), torch.cat((top, bot), dim=2).detach())
+            else:
+                real_p = qs[0]
+        else:
+            fake_p, real_p = _prep(fake.detach(), real.detach())
+            qs = None
         want_grad = ctx.needs_input_grad[0] and not cfg.quantize and fake_p.dtype != torch.uint8
-        out, _, grad = _launch(fake_p, real_p, cfg, want_grad, False)
+        gs_host, gs_dev = _resolve_grad_scale(grad_scale, fake_p.dtype, fake_p.device, cfg, fake_p.shape) if want_grad else (1.0, None)
+        out, _, grad = _launch(fake_p, real_p, cfg, want_grad, False, gs_host=gs_host, gs_dev=gs_dev, real_quads=qs)
         ctx.has_grad = want_grad
         ctx.in_dtype = fake.dtype
         if want_grad:
-            ctx.save_for_backward(grad)
+            ctx.buf, ctx.out = grad, out
+            ctx.regen = (fake_p, real_p, cfg, gs_host, gs_dev, qs)
         terms = out[1:3]
         ctx.mark_non_differentiable(terms)
         return out[0], terms
@@ -180,30 +296,116 @@ class _SpectralLossFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_loss, _grad_terms):
         if not ctx.has_grad:
-            return None, None, None
-        (unit,) = ctx.saved_tensors
-        return _scale_saved_gradient(unit, grad_loss, ctx.in_dtype), None, None
+            return None, None, None, None, None
+        buf = ctx.buf
+        if buf is None:  # a second backward through a retained graph: the buffer was handed out, produce it again
+            fake_p, real_p, cfg, gs_host, gs_dev, qs = ctx.regen
+            ctx.out, _, buf = _launch(fake_p, real_p, cfg, True, False, gs_host=gs_host, gs_dev=gs_dev, real_quads=qs)
+        _rescale_in_place(buf, ctx.out, grad_loss)
+        ctx.buf = None  # autograd now owns the only reference: no defensive copy when it accumulates into .grad
+        return (buf if buf.dtype == ctx.in_dtype else buf.to(ctx.in_dtype)), None, None, None, None
 
 
-def spectral_loss(fake, real, *, return_terms: bool = False, config: SpectralConfig | None = None, **options):
+def spectral_loss(fake, real, *, return_terms: bool = False, config: SpectralConfig | None = None, grad_scale=None,
+                  real_quadrants=None, **options):
     """Differentiable frequency-domain loss.  ``options`` are the fields of :class:`SpectralConfig`.
 
     Returns a 0-dim fp32 CUDA tensor (``weight * 1/2 (amp + pha)``); with ``return_terms`` also a
     detached ``[2]`` tensor ``(amp, pha)`` for logging.  Gradient flows to ``fake`` only -- ``real``
     is data in every reference call site.
+
+    ``grad_scale`` names the ``grad_output`` autograd will hand back (``scaler.scale(loss_G).backward()``,
+    ``TFCGAN_multigpu_patchFFT_16P.py:607-610``): a ``GradScaler``, a device scalar, a float, or a tuple of them.  It
+    is folded into the gradient in the producing launch, so ``backward`` does not touch the tensor again (3 passes
+    of HBM traffic instead of 5); any other ``grad_output`` is still honoured (one in-place rescale).
+    ``real_quadrants``: the loader's four separate real quadrant tensors (``grid=2``; ``real`` is then ignored).
     """
     cfg = config if config is not None else SpectralConfig(**options)
-    loss, terms = _SpectralLossFn.apply(fake, real, cfg)
+    if real_quadrants is not None and cfg.grid != 2:
+        raise ValueError("real_quadrants needs grid=2")
+    loss, terms = _SpectralLossFn.apply(fake, real, cfg, grad_scale,
+                                        tuple(real_quadrants) if real_quadrants is not None else None)
     return (loss, terms) if return_terms else loss
 
 
 @torch.no_grad()
-def spectral_loss_and_grad(fake, real, *, config: SpectralConfig | None = None, **options):
-    """The fused hot path without autograd: ``(loss, terms, d loss / d fake)`` in one launch."""
+def spectral_loss_and_grad(fake, real, *, config: SpectralConfig | None = None, grad_scale=None, accumulate_into=None,
+                           **options):
+    """The fused hot path without autograd: ``(loss, terms, d loss / d fake)`` in one launch.  ``grad_scale`` (float /
+    device scalar / GradScaler) multiplies the gradient only; with ``accumulate_into`` the gradient is ADDED to that
+    tensor (several loss terms share one buffer without an add pass)."""
     cfg = config if config is not None else SpectralConfig(**options)
     fake_p, real_p = _prep(fake, real)
-    out, _, grad = _launch(fake_p, real_p, cfg, True, False)
+    gs_host, gs_dev = (1.0, None) if grad_scale is None else _resolve_grad_scale(grad_scale, fake_p.dtype, fake_p.device)
+    out, _, grad = _launch(fake_p, real_p, cfg, True, False, gs_host=gs_host, gs_dev=gs_dev, accumulate_into=accumulate_into)
     return out[0], out[1:3], grad
+
+
+def _multi_launch(fake_p, real_p, cfgs, chunk, gs_host, gs_dev):
+    """Several loss configurations on the same tensors, one summed gradient: per L2-sized chunk of the batch the first
+    configuration writes the chunk's gradient and the others add into it (``TFCFFT_GRAD_ACCUMULATE``) while fake / real /
+    the gradient chunk are still L2-resident.  Chunk losses are means over their own images: weighted by chunk size."""
+    import dataclasses
+
+    n = fake_p.shape[0]
+    grad = torch.empty(fake_p.shape, dtype=fake_p.dtype, device=fake_p.device)
+    total, terms, out = None, [], None
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        w = (hi - lo) / n
+        for j, cfg in enumerate(cfgs):
+            c = dataclasses.replace(cfg, weight=cfg.weight * w)
+            out, _, _ = _launch(fake_p[lo:hi], real_p[lo:hi], c, True, False, gs_host=gs_host, gs_dev=gs_dev,
+                                accumulate_into=grad[lo:hi] if j else None, grad_buffer=None if j else grad[lo:hi])
+            total = out[0] if total is None else total + out[0]
+            terms.append(out[1:3] * w)
+    k = len(cfgs)
+    per_cfg = torch.stack([torch.stack(terms[j::k]).sum(0) for j in range(k)])  # [len(cfgs), 2]: (amp, pha) of each grid
+    return total, per_cfg, grad, out
+
+
+class _MultiGridLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fake, real, cfgs, chunk, grad_scale):
+        fake_p, real_p = _prep(fake.detach(), real.detach())
+        gs_host, gs_dev = _resolve_grad_scale(grad_scale, fake_p.dtype, fake_p.device)
+        total, per_cfg, grad, out = _multi_launch(fake_p, real_p, cfgs, chunk, gs_host, gs_dev)
+        ctx.buf, ctx.out, ctx.in_dtype = grad, out, fake.dtype
+        ctx.regen = (fake_p, real_p, cfgs, chunk, gs_host, gs_dev)
+        ctx.mark_non_differentiable(per_cfg)
+        return total, per_cfg
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_loss, _g):
+        buf = ctx.buf
+        if buf is None:
+            _, _, buf, ctx.out = _multi_launch(*ctx.regen)
+        _rescale_in_place(buf, ctx.out, grad_loss)
+        ctx.buf = None
+        return (buf if buf.dtype == ctx.in_dtype else buf.to(ctx.in_dtype)), None, None, None, None
+
+
+def _grid_configs(grids, options):
+    return tuple(SpectralConfig(grid=int(g), **options) for g in grids)
+
+
+def multi_grid_loss(fake, real, *, grids=(4, 1), chunk: int = 8, return_terms: bool = False, grad_scale=None, **options):
+    """Sum of the FFT losses of several grids on the SAME tensors -- BASELINE config 5's "patch-FFT-16 + global-FFT
+    combined loss" -- with ONE gradient tensor.  Differentiable w.r.t. ``fake``; ``options`` as for
+    :func:`spectral_loss` (each grid's loss carries ``weight``).  ``chunk`` images are processed per step so that the
+    second grid finds fake / real / the gradient chunk in L2 (8 images of 512 x 512 = 75 MB of the 126 MB L2)."""
+    total, per_cfg = _MultiGridLossFn.apply(fake, real, _grid_configs(grids, options), int(chunk), grad_scale)
+    return (total, per_cfg) if return_terms else total
+
+
+@torch.no_grad()
+def multi_grid_loss_and_grad(fake, real, *, grids=(4, 1), chunk: int = 8, grad_scale=None, **options):
+    """The fused hot path of :func:`multi_grid_loss` without autograd: ``(loss, per-grid (amp, pha), d loss / d fake)``."""
+    fake_p, real_p = _prep(fake, real)
+    gs_host, gs_dev = (1.0, None) if grad_scale is None else _resolve_grad_scale(grad_scale, fake_p.dtype, fake_p.device)
+    total, per_cfg, grad, _ = _multi_launch(fake_p, real_p, _grid_configs(grids, options), int(chunk), gs_host, gs_dev)
+    return total, per_cfg, grad
 
 
 @torch.no_grad()
@@ -252,7 +454,7 @@ class _SpectraFn(torch.autograd.Function):
             amp = torch.empty(shape, dtype=torch.float32, device=dev)
             pha = torch.empty(shape, dtype=torch.float32, device=dev)
             desc = _spectra_desc(xp, cfg)
-            nbytes = lib.tfcfft_workspace_bytes(ctypes.byref(desc))
+            nbytes = lib.tfcfft_spectra_workspace_bytes(ctypes.byref(desc))
             if nbytes == 0:
                 _lib.check(lib.tfcfft_validate(ctypes.byref(desc)), "tfcfft_validate")
             ws = _workspace(dev, stream_ptr, nbytes)
@@ -279,7 +481,7 @@ class _SpectraFn(torch.autograd.Function):
             g_pha = g_pha.contiguous().float()
             grad = torch.empty(xp.shape, dtype=xp.dtype, device=dev)
             desc = _spectra_desc(xp, ctx.cfg, grad)
-            nbytes = lib.tfcfft_workspace_bytes(ctypes.byref(desc))
+            nbytes = lib.tfcfft_spectra_workspace_bytes(ctypes.byref(desc))
             ws = _workspace(dev, stream_ptr, nbytes)
             _lib.check(lib.tfcfft_spectra_bwd(ctypes.byref(desc), xp.data_ptr(), g_amp.data_ptr(), g_pha.data_ptr(),
                                               grad.data_ptr(), int(ctx.shift), ws.data_ptr(), ws.numel(),
@@ -304,7 +506,7 @@ def _launch_regional(fake, real, cfg: SpectralConfig, want_grad: bool):
     dev = fake.device
     with torch.cuda.device(dev):
         stream_ptr = torch.cuda.current_stream(dev).cuda_stream
-        out = torch.empty(4, dtype=torch.float32, device=dev)
+        out = torch.empty(8, dtype=torch.float32, device=dev)
         # rows 200..255 belong to no band: their gradient is zero
         grad = torch.zeros(fake.shape, dtype=fake.dtype, device=dev) if want_grad else None
         desc = _lib.make_desc(_DTYPES[fake.dtype], 1, cfg.flags(), fake.shape, fake.stride(), real.stride(),
@@ -530,16 +732,21 @@ def vectorize_temps(x, lut=None):
     return out
 
 
-def _launch_temperature(fake, positive, negative, lut, quantize, margin, eps, weight, input_scale, want_grad, accumulate_into=None):
+def _launch_temperature(fake, positive, negative, lut, quantize, margin, eps, weight, input_scale, want_grad, accumulate_into=None,
+                        positive_is_temps=None):
     lib = _lib.load()
     dev = fake.device
-    positive_is_temps = positive.shape[1] == 1 and positive.dtype == torch.float32 and fake.shape[1] != 1
+    if positive_is_temps is None:  # heuristic kept for 3-channel images; 1-channel callers say which one they pass
+        positive_is_temps = positive.shape[1] == 1 and positive.dtype == torch.float32 and fake.shape[1] != 1
     flags = (_lib.QUANTIZE_U8 if quantize else 0) | (_lib.TEMPS_POSITIVE if positive_is_temps else 0)
     with torch.cuda.device(dev):
         stream_ptr = torch.cuda.current_stream(dev).cuda_stream
         out = torch.empty(4, dtype=torch.float32, device=dev)
         grad = None
         if accumulate_into is not None:
+            if accumulate_into.shape != fake.shape or accumulate_into.dtype != fake.dtype or accumulate_into.device != dev \
+                    or not _acceptable(accumulate_into):
+                raise ValueError("accumulate_into must match fake in shape / dtype / device and have 16-byte friendly strides")
             grad, flags = accumulate_into, flags | _lib.GRAD_ACCUMULATE
         elif want_grad:
             grad = torch.zeros(fake.shape, dtype=fake.dtype, device=dev)  # only channel 0 receives a gradient
@@ -556,27 +763,34 @@ def _launch_temperature(fake, positive, negative, lut, quantize, margin, eps, we
     return out, grad
 
 
-def _prep_temperature(fake, positive, negative):
+def _prep_temperature(fake, positive, negative, positive_is_temps=None):
+    """Returns (fake, positive, negative, positive_is_temps).  ``positive`` holds temperatures (the loader's ``T_B``) when
+    the caller says so, when it is 3-D ``[N,H,W]`` (the reference's shape, ``...patchFFT_16P.py:593``), or -- for
+    multi-channel images -- when it is a 1-channel fp32 tensor."""
     fake = _prep_img(fake)
     negative = _prep_img(negative, like=fake)
+    if positive_is_temps is None:
+        positive_is_temps = positive.dim() == 3 or (positive.shape[1] == 1 and fake.shape[1] != 1 and positive.dtype == torch.float32)
     if positive.dim() == 3:
         positive = positive.reshape(positive.shape[0], 1, positive.shape[1], positive.shape[2])  # the reference's reshape (:593)
-    if positive.shape[1] == 1 and fake.shape[1] != 1:
+    if positive_is_temps:
+        if positive.shape[1] != 1:
+            raise ValueError("temperatures must be [N,H,W] or [N,1,H,W]")
         positive = positive.float()
         positive = positive if _acceptable(positive) else positive.contiguous()
     else:
         positive = _prep_img(positive, like=fake)
     if negative.shape != fake.shape or positive.shape[0] != fake.shape[0] or positive.shape[2:] != fake.shape[2:]:
         raise ValueError("fake, positive and negative must agree in batch and image size")
-    return fake, positive, negative
+    return fake, positive, negative, bool(positive_is_temps)
 
 
 class _TemperatureTripletFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, fake, positive, negative, lut, quantize, margin, eps, weight, input_scale):
-        f, p, n = _prep_temperature(fake.detach(), positive.detach(), negative.detach())
+    def forward(ctx, fake, positive, negative, lut, quantize, margin, eps, weight, input_scale, positive_is_temps):
+        f, p, n, pit = _prep_temperature(fake.detach(), positive.detach(), negative.detach(), positive_is_temps)
         want_grad = ctx.needs_input_grad[0] and not quantize and f.dtype != torch.uint8
-        out, grad = _launch_temperature(f, p, n, lut, quantize, margin, eps, weight, input_scale, want_grad)
+        out, grad = _launch_temperature(f, p, n, lut, quantize, margin, eps, weight, input_scale, want_grad, positive_is_temps=pit)
         ctx.has_grad, ctx.in_dtype = want_grad, fake.dtype
         if want_grad:
             ctx.save_for_backward(grad)
@@ -586,28 +800,31 @@ class _TemperatureTripletFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_loss):
         if not ctx.has_grad:
-            return (None,) * 9
+            return (None,) * 10
         (unit,) = ctx.saved_tensors
-        return (_scale_saved_gradient(unit, grad_loss, ctx.in_dtype),) + (None,) * 8
+        return (_scale_saved_gradient(unit, grad_loss, ctx.in_dtype),) + (None,) * 9
 
 
 def temperature_triplet_loss(fake, positive, negative, *, lut=None, quantize: bool = False, margin: float = 1.0, eps: float = 1e-6,
-                             weight: float = 1.0, input_scale: float = 255.0):
+                             weight: float = 1.0, input_scale: float = 255.0, positive_is_temperatures=None):
     """``weight * TripletMarginLoss(margin, p=2)(temps(fake), temps(positive), temps(negative))`` in one fused pass
     (``TFCGAN_multigpu_patchFFT_16P.py:585-595``; ``weight`` is the reference's ``lambda_t``).  ``positive`` is either an
     image batch or the loader's precomputed temperatures ``T_B`` (fp32 ``[N,H,W]`` / ``[N,1,H,W]``).  ``quantize=True``
     is the reference as shipped (uint8 + table, no gradient); the default is the differentiable linear variant on
-    ``input_scale * x``."""
+    ``input_scale * x``.  ``positive_is_temperatures`` states explicitly whether ``positive`` already holds temperatures
+    (needed for 1-channel images, where the shapes alone cannot tell)."""
     return _TemperatureTripletFn.apply(fake, positive, negative, None if lut is None else tuple(lut), bool(quantize), float(margin),
-                                       float(eps), float(weight), float(input_scale))
+                                       float(eps), float(weight), float(input_scale), positive_is_temperatures)
 
 
 @torch.no_grad()
 def temperature_triplet_loss_and_grad(fake, positive, negative, *, lut=None, quantize: bool = False, margin: float = 1.0,
-                                      eps: float = 1e-6, weight: float = 1.0, input_scale: float = 255.0, accumulate_into=None):
+                                      eps: float = 1e-6, weight: float = 1.0, input_scale: float = 255.0, accumulate_into=None,
+                                      positive_is_temperatures=None):
     """The fused pass without autograd: ``(out[4], grad_or_None)``."""
-    f, p, n = _prep_temperature(fake, positive, negative)
-    return _launch_temperature(f, p, n, lut, quantize, margin, eps, weight, input_scale, not quantize, accumulate_into)
+    f, p, n, pit = _prep_temperature(fake, positive, negative, positive_is_temperatures)
+    return _launch_temperature(f, p, n, lut, quantize, margin, eps, weight, input_scale, not quantize, accumulate_into,
+                               positive_is_temps=pit)
 
 
 def launch_count() -> int:

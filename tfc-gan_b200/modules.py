@@ -17,12 +17,20 @@ class SpectralLoss(nn.Module):
     (``TFCGAN_multigpu_globalFFT.py:494-499``).  ``weight`` folds the call-site factor (``1/100`` at
     ``...patchFFT_16P.py:607``) into the kernel.  After each call ``last_terms`` holds the detached
     ``(amp, pha)`` terms for logging (the reference logs ``loss_FFT.item()`` every step, ``:664``).
+
+    ``grad_scaler`` (the script's ``torch.amp.GradScaler``, ``:518``) and ``loss_multiplier`` (the factor the script
+    applies to the returned loss before ``backward``, e.g. ``1/100`` if ``weight`` is left at 1) name the
+    ``grad_output`` that ``scaler.scale(loss_G).backward()`` (``:610``) will send back: it is folded into the gradient
+    while it is produced, so the backward pass does not touch the tensor again.  Any other ``grad_output`` still
+    gives the right gradient (one in-place rescale).
     """
 
     def __init__(self, grid: int = 4, channels: str = "luma", use_phase: bool = True, distance: str = "l1",
                  patch_reduce: str = "mean", log_magnitude: bool = False, spectrum: str = "half",
-                 weight: float = 1.0, input_scale: float = 1.0, quantize: bool = False):
+                 weight: float = 1.0, input_scale: float = 1.0, quantize: bool = False, grad_scaler=None,
+                 loss_multiplier: float = 1.0):
         super().__init__()
+        self.grad_scaler, self.loss_multiplier = grad_scaler, float(loss_multiplier)
         self.config = SpectralConfig(grid=grid, channels=channels, use_phase=use_phase, distance=distance,
                                      patch_reduce=patch_reduce, log_magnitude=log_magnitude, spectrum=spectrum,
                                      weight=weight, input_scale=input_scale, quantize=quantize)
@@ -30,7 +38,10 @@ class SpectralLoss(nn.Module):
         self.last_terms = None
 
     def forward(self, fake: torch.Tensor, real: torch.Tensor) -> torch.Tensor:
-        loss, terms = spectral_loss(fake, real, config=self.config, return_terms=True)
+        gs = None
+        if self.grad_scaler is not None or self.loss_multiplier != 1.0:
+            gs = (self.grad_scaler, self.loss_multiplier)
+        loss, terms = spectral_loss(fake, real, config=self.config, return_terms=True, grad_scale=gs)
         self.last_terms = terms
         return loss
 

@@ -8,8 +8,14 @@ VARS=${3:-"|TFCFFT_LINE_V1=1"}
 STEPS=${4:-300}
 OUT=gpurun_out
 mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -q --timeout 300 -p no:cacheprovider -x > $OUT/pytest_$TAG.log 2>&1
+timeout 120 python tools/ring_check.py > $OUT/ringcheck_$TAG.log 2>&1
+RC=$?
+cat $OUT/ringcheck_$TAG.log | tail -n 12
+if [ $RC -ne 0 ]; then echo "ring_check failed or hung (exit $RC): stopping"; exit 1; fi
+if [ "${SKIP_PYTEST:-0}" != "1" ]; then
+timeout 600 python -m pytest tests -m gpu -q --timeout 120 -p no:cacheprovider -x > $OUT/pytest_$TAG.log 2>&1
 echo "pytest exit $?"; tail -n 6 $OUT/pytest_$TAG.log
+fi
 IFS='|' read -ra VV <<< "$VARS"
 [ ${#VV[@]} -eq 0 ] && VV=("")
 for WL in $WLS; do
