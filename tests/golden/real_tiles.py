@@ -37,4 +37,4 @@ def load_pairs(dtype="float32"):
         for i, j in PAIRS:
             fakes.append((tiles[i] - 0.5) / 0.5)
             reals.append((tiles[j] - 0.5) / 0.5)
-    return np.stack(fakes).astype(dtype), np.stack(reals).astype(dtype)
+    return np.ascontiguousarray(np.stack(fakes), dtype=dtype), np.ascontiguousarray(np.stack(reals), dtype=dtype)

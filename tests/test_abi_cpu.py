@@ -29,12 +29,13 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(L.LIB_PATH)
     for name in header_functions():
         assert hasattr(lib, name), name
-    assert L.load().tfcfft_version() == 100
+    assert L.load().tfcfft_version() == 200
 
 
 def test_struct_layout_matches_header():
-    # 4x4 + 4x8 + 3x4x8 + 2x4 = 152 bytes, no padding surprises
-    assert ctypes.sizeof(L.Desc) == 152
+    # 4x4 + 4x8 + 3x4x8 + 2x4 (weight, input_scale) + 2x4 (grad_scale_host, reserved) + 8 (grad_scale_dev) = 168 bytes
+    assert ctypes.sizeof(L.Desc) == 168
+    assert L.Desc.grad_scale_dev.offset == 160
 
 
 def desc(**kw):

@@ -11,7 +11,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtfcfft.so")
+# TFCFFT_LIB selects another build of the SAME library (A/B runs of kernel variants, tools/gpu_ab.sh)
+LIB_PATH = os.environ.get("TFCFFT_LIB") or os.path.join(HERE, "libtfcfft.so")
 
 # enum tfcfft_dtype
 F32, F16, BF16, U8 = 0, 1, 2, 3

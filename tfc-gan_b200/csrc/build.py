@@ -98,5 +98,37 @@ def build(force: bool = False, verbose: bool = False, extra=(), only=None):
     return [os.path.join(PKG, n) for n in TARGETS]
 
 
+def build_variant(tag: str, defines, units=("k_line.cu",), verbose: bool = False):
+    """A/B build: ``libtfcfft_<tag>.so`` = the product library with ``units`` recompiled under extra ``defines``
+    (e.g. ``["-DTFCFFT_LINE_BIN_EVALS=2"]``); every other object is shared with the main build.  Select it at run
+    time with ``TFCFFT_LIB=<path>``.  Not part of ``build()``: variants are experiments, not the product."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    build(only=["libtfcfft.so"], verbose=verbose)
+    spec = TARGETS["libtfcfft.so"]
+    objs, jobs = [], []
+    for src, dt in spec["src"]:
+        tagd = "" if dt is None else f"_dt{dt}"
+        base = os.path.join(OBJ, "libtfcfft__" + src.replace(".cu", tagd + ".o"))
+        if src in units:
+            obj = base.replace(".o", f"__{tag}.o")
+            defs = ([] if dt is None else [f"-DTFC_DT={dt}"]) + list(defines)
+            if _newer(obj, [os.path.join(CSRC, src), *_headers()]):
+                jobs.append((obj, [nvcc, *spec["opt"], *COMMON, *defs, "-c", "-o", obj, os.path.join(CSRC, src)]))
+            objs.append(obj)
+        else:
+            objs.append(base)
+    with ThreadPoolExecutor(max_workers=max(1, len(jobs))) as ex:
+        for (obj, cmd), (rc, log) in zip(jobs, ex.map(lambda j: _run(j[1], verbose), jobs)):
+            if rc != 0:
+                sys.stderr.write(log)
+                raise RuntimeError(f"nvcc failed for {obj}")
+    out = os.path.join(PKG, f"libtfcfft_{tag}.so")
+    rc, log = _run([nvcc, "-shared", *ARCH, "-o", out, *objs], verbose)
+    if rc != 0:
+        sys.stderr.write(log)
+        raise RuntimeError("link failed")
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True, extra=[a for a in sys.argv[1:] if a.startswith("-X")])

@@ -33,9 +33,7 @@ namespace tfcfft {
 #ifndef TFCFFT_RING_SLOTS
 #define TFCFFT_RING_SLOTS 7
 #endif
-#ifndef TFCFFT_RING_PREFETCH
-#define TFCFFT_RING_PREFETCH 0  // tiles of L2 look-ahead per CTA
-#endif
+// (an L2 look-ahead with TMA prefetches, 1-2 tiles per CTA, was measured and lost 1-4 %: the ring already covers HBM latency)
 
 constexpr int kRingSlotBytes = 12288;  // one slab: fake + real, NC channels, RPS rows of 64 pixels
 template <int G_, int RING_>
@@ -109,12 +107,6 @@ __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map
         "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(c), "r"(n), "r"(bar), "l"(policy)
         : "memory");
 }
-// TMA prefetch of the same box into L2 only
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int x, int y, int c, int n) {
-    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<unsigned long long>(map)),
-                 "r"(x), "r"(y), "r"(c), "r"(n)
-                 : "memory");
-}
 __device__ __forceinline__ unsigned long long policy_evict_first() {
     unsigned long long p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -180,24 +172,40 @@ __device__ __forceinline__ bool ring_convert(const Params& prm, const unsigned c
 #pragma unroll
             for (int c = 0; c < NC; ++c) SlabIO<T>::load4(slab + ((h * NC + c) * RPS + r) * RB + x4 * PX4, raw[h][c]);
         float2* row = s + (y0 + r) * LD + x4;
+        if (!quant) {
+            // luma of two pixels per packed instruction: (w0 * r + w1 * g + w2 * b) on (pixel i, pixel i + 1) lanes
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float z[2];
+            for (int i = 0; i < 4; i += 2) {
+                float2 z[2];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (!quant) {
-                    float f = prm.lw[0] * raw[h][0][i];
-                    if constexpr (LUMA3) f = fmaf(prm.lw[2], raw[h][2][i], fmaf(prm.lw[1], raw[h][1][i], f));
+                for (int h = 0; h < 2; ++h) {
+                    float2 f = p_mul(p_dup(prm.lw[0]), make_float2(raw[h][0][i], raw[h][0][i + 1]));
+                    if constexpr (LUMA3) {
+                        f = p_fma(p_dup(prm.lw[1]), make_float2(raw[h][1][i], raw[h][1][i + 1]), f);
+                        f = p_fma(p_dup(prm.lw[2]), make_float2(raw[h][2][i], raw[h][2][i + 1]), f);
+                    }
                     z[h] = f;
-                } else if constexpr (LUMA3) {
-                    z[h] = (float)((19595 * IO<T>::quant(raw[h][0][i]) + 38470 * IO<T>::quant(raw[h][1][i]) +
-                                    7471 * IO<T>::quant(raw[h][2][i]) + 0x8000) >> 16);
-                } else {
-                    z[h] = (float)IO<T>::quant(raw[h][0][i]);
                 }
+                same = same && (z[0].x == z[1].x) && (z[0].y == z[1].y);
+                row[16 * i] = make_float2(z[0].x, z[1].x);  // == line_slot(4 * x4 + i)
+                row[16 * (i + 1)] = make_float2(z[0].y, z[1].y);
             }
-            same = same && (z[0] == z[1]);
-            row[16 * i] = make_float2(z[0], z[1]);  // == line_slot(4 * x4 + i)
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float z[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if constexpr (LUMA3) {
+                        z[h] = (float)((19595 * IO<T>::quant(raw[h][0][i]) + 38470 * IO<T>::quant(raw[h][1][i]) +
+                                        7471 * IO<T>::quant(raw[h][2][i]) + 0x8000) >> 16);
+                    } else {
+                        z[h] = (float)IO<T>::quant(raw[h][0][i]);
+                    }
+                }
+                same = same && (z[0] == z[1]);
+                row[16 * i] = make_float2(z[0], z[1]);
+            }
         }
     }
     return same;
@@ -254,26 +262,9 @@ __global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&map_fake)) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&map_real)) : "memory");
             unsigned c = 0;  // slab counter
-            // L2 look-ahead: the tiles PF ahead of the one being staged are pulled from HBM into L2 with TMA prefetches,
-            // so the ring itself only has to cover the L2 -> shared-memory latency (a deep HBM pipeline at no
-            // shared-memory cost)
-            const int PF = prm.ring_prefetch;
-            for (int k = 0; k < PF && k < ntiles; ++k) {
-                const TileCoord tp = decode_tile(prm, (int)blockIdx.x + k * (int)gridDim.x);
-                for (int i = 0; i < SL::SLABS; ++i) {
-                    tma_prefetch_4d(&map_fake, tp.px * 64, tp.py * 64 + i * SL::RPS, tp.ch, tp.n);
-                    tma_prefetch_4d(&map_real, tp.px * 64, tp.py * 64 + i * SL::RPS, tp.ch, tp.n);
-                }
-            }
             for (int k = 0; k < ntiles; ++k) {
                 const TileCoord tc = decode_tile(prm, (int)blockIdx.x + k * (int)gridDim.x);
-                const bool pf = PF > 0 && k + PF < ntiles;
-                const TileCoord tp = decode_tile(prm, (int)blockIdx.x + (pf ? k + PF : k) * (int)gridDim.x);
                 for (int i = 0; i < SL::SLABS; ++i, ++c) {
-                    if (pf) {
-                        tma_prefetch_4d(&map_fake, tp.px * 64, tp.py * 64 + i * SL::RPS, tp.ch, tp.n);
-                        tma_prefetch_4d(&map_real, tp.px * 64, tp.py * 64 + i * SL::RPS, tp.ch, tp.n);
-                    }
                     const unsigned slot = c % RING, ph = (c / RING) & 1;
                     mbar_wait(empty0 + 8 * slot, ph ^ 1);  // the consumers of the previous round have released the slot
                     const unsigned fb = full0 + 8 * slot;
@@ -322,17 +313,17 @@ __global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_
                 if (want_grad) ring_store_zero<T, LUMA3>(ctx, prm, tc);
                 ctx.sync();
             } else {
-                line_rows_fwd(ctx, s);
-                ctx.sync();
-                line_cols_fwd(ctx, s);
-                ctx.sync();
-                line_bins(ctx, prm, s, a, p);
-                ctx.sync();
+                const int npass = want_grad ? 4 : 2;
+#pragma unroll 1
+                for (int pass = 0; pass < npass; ++pass) {  // rolled: ONE copy of the 64-point core (line_fft_pass)
+                    line_fft_pass(ctx, s, pass);
+                    ctx.sync();
+                    if (pass == 1) {
+                        line_bins(ctx, prm, s, a, p);
+                        ctx.sync();
+                    }
+                }
                 if (want_grad) {
-                    line_cols_inv(ctx, s);
-                    ctx.sync();
-                    line_rows_inv(ctx, s);
-                    ctx.sync();
                     line_store<T, LUMA3>(ctx, prm, tc, s);
                     ctx.sync();  // the next tile's slabs overwrite the work tile
                 }
@@ -409,9 +400,6 @@ int launch_line_ring_cfg(const Params& prm, cudaStream_t st) {
     auto kernel = line_ring_kernel<T, LUMA3, RingCfg>;
     static KernelFacts facts;
     if (int rc = facts.get(kernel, RingCfg::NT, RingCfg::SMEM, nullptr)) return rc;
-    static const int pf_env = getenv("TFCFFT_RING_PF") ? atoi(getenv("TFCFFT_RING_PF")) : TFCFFT_RING_PREFETCH;
-    Params prm2 = prm;
-    prm2.ring_prefetch = pf_env;
     alignas(64) CUtensorMap mf, mr;
     if (!make_tile_map<T>(&mf, prm.fake, prm.fs, prm, NC, SL::RPS) || !make_tile_map<T>(&mr, prm.real, prm.rs, prm, NC, SL::RPS))
         return TFCFFT_ERR_STRIDE;
@@ -432,7 +420,7 @@ int launch_line_ring_cfg(const Params& prm, cudaStream_t st) {
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = off ? 0 : 1;
-        if (cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, prm2, mf, mr)) return (int)e;
+        if (cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, prm, mf, mr)) return (int)e;
     }
     g_launches++;
     return 0;

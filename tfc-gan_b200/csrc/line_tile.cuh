@@ -179,7 +179,7 @@ TFC_HD void line_cols_fwd(const Ctx& ctx, float2* s) {
 // ---- loss + spectral gradient over the half plane (natural frequency order) ------------------------
 template <class Ctx>
 TFC_HD void line_bins(const Ctx& ctx, const Params& prm, float2* s, float& accA, float& accP) {
-    constexpr int LD = LineCfg::LD, NREG = 64 * 31;
+    constexpr int LD = LineCfg::LD;
     const bool mse = (prm.flags & TFCFFT_DIST_MSE) != 0, phase = !(prm.flags & TFCFFT_NO_PHASE);
     const bool want_grad = prm.grad != nullptr;
     const float2 z0 = make_float2(0.f, 0.f);
@@ -188,46 +188,47 @@ TFC_HD void line_bins(const Ctx& ctx, const Params& prm, float2* s, float& accA,
     // polynomial dependency chains interleave).  Kept as a real loop: the kernel is instruction-fetch sensitive
     // (straight-line 64-point transforms), the loss code should not be replicated 16 times
     constexpr int NE = LineCfg::BIN_EVALS;
+    // a thread owns spectrum row ky and walks the columns kx = 1..31 (Z(k) at rk[kx], Z(-k) at rm[-kx]): two pointers,
+    // no per-bin index arithmetic; consecutive threads = consecutive rows (odd pitch: conflict-free both ways)
+    for (int ky = ctx.tid; ky < 64; ky += ctx.nthreads) {
+        float2* rk = s + ky * LD;
+        float2* rm = s + ((64 - ky) & 63) * LD + 64;
 #pragma unroll 1
-    for (int it0 = ctx.tid; it0 < NREG; it0 += 2 * NE * ctx.nthreads) {
-        float2* pk[NE][2];
-        float2* pm[NE][2];
-        float2 zk[NE][2], zm[NE][2];
-        bool live[NE][2];
+        for (int kx0 = 1; kx0 < 32; kx0 += 2 * NE) {
+            float2 zk[NE][2], zm[NE][2];
+            bool live[NE][2];
 #pragma unroll
-        for (int e = 0; e < NE; ++e)
+            for (int e = 0; e < NE; ++e)
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int it = it0 + (2 * e + u) * ctx.nthreads;
-                live[e][u] = it < NREG;
-                const int iq = live[e][u] ? it : 0;
-                const int ky = iq & 63, kx = 1 + (iq >> 6);  // consecutive threads: consecutive rows
-                pk[e][u] = s + ky * LD + kx;
-                pm[e][u] = s + ((64 - ky) & 63) * LD + (64 - kx);
-                zk[e][u] = live[e][u] ? *pk[e][u] : z0;
-                zm[e][u] = live[e][u] ? *pm[e][u] : z0;
-            }
-        c2 g[NE];
-        float2 qA[NE], qP[NE];
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            qA[e] = z0;
-            qP[e] = z0;
-            g[e] = bin_eval_pair(prm, mse, phase, make_c2(make_float2(zk[e][0].x, zk[e][1].x), make_float2(zk[e][0].y, zk[e][1].y)),
-                                 make_c2(make_float2(zm[e][0].x, zm[e][1].x), make_float2(zm[e][0].y, zm[e][1].y)), qA[e], qP[e]);
-        }
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            pA = p_add(pA, qA[e]);
-            pP = p_add(pP, qP[e]);
-            if (want_grad) {
-                if (live[e][0]) {
-                    *pk[e][0] = make_float2(g[e].re.x, g[e].im.x);
-                    *pm[e][0] = z0;
+                for (int u = 0; u < 2; ++u) {
+                    const int kx = kx0 + 2 * e + u;
+                    live[e][u] = kx < 32;
+                    zk[e][u] = live[e][u] ? rk[kx] : z0;
+                    zm[e][u] = live[e][u] ? rm[-kx] : z0;
                 }
-                if (live[e][1]) {
-                    *pk[e][1] = make_float2(g[e].re.y, g[e].im.y);
-                    *pm[e][1] = z0;
+            c2 g[NE];
+            float2 qA[NE], qP[NE];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                qA[e] = z0;
+                qP[e] = z0;
+                g[e] = bin_eval_pair(prm, mse, phase, make_c2(make_float2(zk[e][0].x, zk[e][1].x), make_float2(zk[e][0].y, zk[e][1].y)),
+                                     make_c2(make_float2(zm[e][0].x, zm[e][1].x), make_float2(zm[e][0].y, zm[e][1].y)), qA[e], qP[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                pA = p_add(pA, qA[e]);
+                pP = p_add(pP, qP[e]);
+                if (want_grad) {
+                    const int kx = kx0 + 2 * e;
+                    if (live[e][0]) {
+                        rk[kx] = make_float2(g[e].re.x, g[e].im.x);
+                        rm[-kx] = z0;
+                    }
+                    if (live[e][1]) {
+                        rk[kx + 1] = make_float2(g[e].re.y, g[e].im.y);
+                        rm[-kx - 1] = z0;
+                    }
                 }
             }
         }
@@ -306,24 +307,111 @@ TFC_HD void line_rows_inv(const Ctx& ctx, float2* s) {
     }
 }
 
+// ---- all four transform passes on ONE copy of the 64-point core ---------------------------------------------------
+// pass 0: forward rows, 1: forward columns, 2: inverse columns (32 lines: kx = 1..31 and the packed pair {0, 32}),
+// 3: inverse rows (real part -> floats).  The unnormalised inverse is the forward transform read backwards,
+//     IDFT(x)[n] = DFT(x)[(64 - n) mod 64],
+// so every pass runs the SAME straight-line `fft64<false>` code and differs only in where it loads and stores.  The
+// caller keeps the pass loop rolled (`#pragma unroll 1`): the kernel then holds one ~9 KB copy of the core instead of
+// four specialised ones (~52 KB), which is what the instruction cache of an SM can keep hot while several tiles are in
+// different passes (ncu, profiles/r02_ncu_ring_4x7_summary.txt: `no_instruction` was the top stall, 55 % of it inside
+// the forward transforms).  Cost: the zero-pruned / real-output shortcuts of the specialised inverse rows are gone
+// (+2.5 % executed instructions).
+template <class Ctx>
+TFC_HD void line_fft_pass(const Ctx& ctx, float2* s, int pass) {
+    constexpr int LD = LineCfg::LD;
+    const int nlines = pass == 2 ? 32 : 64;
+    for (int l = ctx.tid; l < nlines; l += ctx.nthreads) {
+        float2 v[64];
+        float2* row = s + l * LD;
+        float2* col = s + l;
+        if (pass == 0) {
+#pragma unroll
+            for (int x = 0; x < 64; ++x) v[x] = row[line_slot(x)];
+        } else if (pass == 3) {
+            // columns 33..63 hold exact zeros and column 0 holds (u_0(y), u_32(y)), the real inverse transforms of
+            // columns 0 and 32 (line_bins)
+#pragma unroll
+            for (int k = 0; k < 64; ++k) v[k] = (k >= 1 && k < 32) ? row[k] : make_float2(0.f, 0.f);
+            const float2 u = row[0];
+            v[0] = make_float2(u.x, 0.f);
+            v[32] = make_float2(u.y, 0.f);
+        } else {
+#pragma unroll
+            for (int y = 0; y < 64; ++y) v[y] = col[y * LD];
+        }
+        fft64<false>(v);
+        if (pass == 0) {
+#pragma unroll
+            for (int sl = 0; sl < 64; ++sl) row[fft64_freq(sl)] = v[sl];
+        } else if (pass == 1) {
+#pragma unroll
+            for (int sl = 0; sl < 64; ++sl) col[fft64_freq(sl) * LD] = v[sl];
+        } else if (pass == 2) {
+#pragma unroll
+            for (int sl = 0; sl < 64; ++sl) col[((64 - fft64_freq(sl)) & 63) * LD] = v[sl];
+        } else {
+            // gradient row as floats g[x] at float index x (the row is reused as a float array): pixel x is the
+            // real part of frequency (64 - x) mod 64, which lives in slot (f >> 3) + 8 * (f & 7)
+            float* g = reinterpret_cast<float*>(row);
+#pragma unroll
+            for (int m = 0; m < 32; ++m) {
+                const int f0 = (64 - 2 * m) & 63, f1 = (64 - (2 * m + 1)) & 63;
+                const float a = v[(f0 >> 3) + 8 * (f0 & 7)].x, b = v[(f1 >> 3) + 8 * (f1 & 7)].x;
+                *reinterpret_cast<float2*>(g + 2 * m) = make_float2(a, b);
+            }
+        }
+    }
+}
+
 // ---- gradient store: rows of floats -> global, 128-bit stores ----------------------------------------
+template <typename T, bool LUMA3, bool ACC, class Ctx>
+TFC_HD void line_store_rows(const Ctx& ctx, const GradOut& go, T* gp, int sh, int sc, const float2* s) {
+    constexpr int LD = LineCfg::LD, NC = LUMA3 ? 3 : 1;
+    if (ctx.nthreads == 64) {
+        // a thread keeps its 4-pixel column and walks down the rows: one pointer bump per row, no index arithmetic
+        const int x = (ctx.tid & 15) * 4, y0 = ctx.tid >> 4;
+        T* p = gp + y0 * sh + x;
+        const float* g = reinterpret_cast<const float*>(s + y0 * LD) + x;
+#pragma unroll 4
+        for (int j = 0; j < 16; ++j) {
+            const float2 lo = *reinterpret_cast<const float2*>(g), hi = *reinterpret_cast<const float2*>(g + 2);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                float v[4] = {go.w[c] * lo.x, go.w[c] * lo.y, go.w[c] * hi.x, go.w[c] * hi.y};
+                if constexpr (ACC) {
+                    float o[4];
+                    IO<T>::load4(p + c * sc, o);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] += o[i];
+                }
+                IO<T>::store4(p + c * sc, v);
+            }
+            p += 4 * sh;
+            g += 4 * LD * 2;
+        }
+    } else {
+        for (int it = ctx.tid; it < 64 * 16; it += ctx.nthreads) {
+            const int x = (it & 15) * 4, y = it >> 4;
+            const float* g = reinterpret_cast<const float*>(s + y * LD) + x;
+            const float2 lo = *reinterpret_cast<const float2*>(g), hi = *reinterpret_cast<const float2*>(g + 2);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                float v[4] = {go.w[c] * lo.x, go.w[c] * lo.y, go.w[c] * hi.x, go.w[c] * hi.y};
+                GradOut g1 = go;
+                g1.acc = ACC;
+                grad_store4<T>(g1, gp + y * sh + c * sc + x, v);
+            }
+        }
+    }
+}
 template <typename T, bool LUMA3, class Ctx>
 TFC_HD void line_store(const Ctx& ctx, const Params& prm, const TileCoord& tc, const float2* s) {
-    constexpr int LD = LineCfg::LD, NC = LUMA3 ? 3 : 1;
     T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, 64));
     const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
     const GradOut go = grad_out(prm);
-#pragma unroll 2
-    for (int it = ctx.tid; it < 64 * 16; it += ctx.nthreads) {
-        const int x = (it & 15) * 4, y = it >> 4;
-        const float* g = reinterpret_cast<const float*>(s + y * LD) + x;
-        const float2 lo = *reinterpret_cast<const float2*>(g), hi = *reinterpret_cast<const float2*>(g + 2);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            float v[4] = {go.w[c] * lo.x, go.w[c] * lo.y, go.w[c] * hi.x, go.w[c] * hi.y};
-            grad_store4<T>(go, gp + y * sh + c * sc + x, v);
-        }
-    }
+    if (go.acc) line_store_rows<T, LUMA3, true>(ctx, go, gp, sh, sc, s);
+    else line_store_rows<T, LUMA3, false>(ctx, go, gp, sh, sc, s);
 }
 
 // Pull the next tile's source lines into L2 shortly before they are needed (late enough to survive in L2, early
@@ -352,22 +440,21 @@ TFC_HD void line_process(const Ctx& ctx, const Params& prm, int tile, float2* s,
     line_load<T, LUMA3>(ctx, prm, tc, s);
     ctx.sync();
     ctx.mark(1);
-    line_rows_fwd(ctx, s);
-    ctx.sync();
-    ctx.mark(2);
-    line_cols_fwd(ctx, s);
-    ctx.sync();
-    ctx.mark(3);
-    line_bins(ctx, prm, s, accA, accP);
-    ctx.sync();
-    ctx.mark(4);
-    if (prm.grad != nullptr) {
-        line_cols_inv(ctx, s);
-        if (next_tile >= 0) line_prefetch_l2<T, LUMA3>(ctx, prm, decode_tile(prm, next_tile));
+    const bool want_grad = prm.grad != nullptr;
+    const int npass = want_grad ? 4 : 2;
+#pragma unroll 1
+    for (int pass = 0; pass < npass; ++pass) {  // rolled: ONE copy of the 64-point core in the kernel
+        line_fft_pass(ctx, s, pass);
+        if (pass == 2 && next_tile >= 0) line_prefetch_l2<T, LUMA3>(ctx, prm, decode_tile(prm, next_tile));
         ctx.sync();
-        ctx.mark(5);
-        line_rows_inv(ctx, s);
-        ctx.sync();
+        ctx.mark(pass < 2 ? 2 + pass : 3 + pass);
+        if (pass == 1) {
+            line_bins(ctx, prm, s, accA, accP);
+            ctx.sync();
+            ctx.mark(4);
+        }
+    }
+    if (want_grad) {
         ctx.mark(6);
         line_store<T, LUMA3>(ctx, prm, tc, s);
         ctx.sync();

@@ -55,7 +55,6 @@ struct Params {
     // gradient epilogue: d loss / d fake is multiplied by *gscale_dev (GradScaler's device scale; may be null) on the
     // way out -- gw[] already holds the host-side factors -- and added to the buffer with TFCFFT_GRAD_ACCUMULATE
     const float* gscale_dev;
-    int ring_prefetch;     // line_ring_kernel: tiles of L2 look-ahead (set by its launcher)
     float gscale_host;     // already folded into gw[]; reported in out[4] together with *gscale_dev
     // loader quadrants (tfcfft_loss_quads): `real` given as 4 separate [N,C,P,P] tensors (grid == 2); else all null
     const void* real_q[4];
