@@ -193,3 +193,21 @@ def test_thread_per_line_path_matches_oracle_and_pair_path(opt):
     assert l2rel(g1, gr) <= 1e-3
     np.testing.assert_allclose(o1[:3], o2[:3], rtol=2e-6)
     assert l2rel(g1, g2) <= 2e-5
+
+
+@pytest.mark.parametrize("cf,cr", [(-0.5, 0.5), (0.5, -0.5), (-0.5, -0.25), (0.5, 0.25)])
+@pytest.mark.parametrize("grid", [4, 1])
+def test_real_axis_phase_signs(cf, cr, grid):
+    """Self-conjugate bins are exactly real: the phase difference there is 0 or +-pi and its sign decides the sign of
+    the gradient.  Constant images of either sign plus a little noise exercise every (F, R) sign combination of the
+    single-arctangent phase difference (pair_tile.cuh: phase_delta) at the DC / Nyquist bins."""
+    rs = np.random.RandomState(5)
+    shape = (2, 3, 64 * grid if grid == 4 else 64, 64 * grid if grid == 4 else 64)
+    fake = (cf + 0.05 * rs.uniform(-1, 1, shape)).astype(np.float32)
+    real = (cr + 0.05 * rs.uniform(-1, 1, shape)).astype(np.float32)
+    rc, out, _, g = emulate(fake, real, grid, 0, weight=1.0, input_scale=255.0)
+    assert rc == 0
+    l, a, p, go = oracle.spectral_loss_and_grad_r1(fake, real, grid=grid, weight=1.0, input_scale=255.0)
+    assert out[0] == pytest.approx(l, rel=1e-4)
+    assert out[2] == pytest.approx(p, rel=1e-4)
+    assert l2rel(g, go) <= 1e-3

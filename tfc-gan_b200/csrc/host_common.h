@@ -10,7 +10,13 @@
 
 namespace tfcfft {
 
-constexpr size_t kWsHeader = 256;                      // ticket counter, padded
+// workspace header (zeroed by tfcfft_workspace_init, left zeroed by every call):
+//   [0]    finalise ticket          [64..95] scratch outputs of the spectra entry points     [128] rescale ticket
+//   [256]  scheduler of the pipelined sub-tile kernel: 3 queue heads + exit ticket (kSchedHeads)
+//   [512]  forward-done counters, one per chunk tile (kSchedMaxTiles)     [512 + 4096] combine-done counters
+constexpr size_t kWsHeader = 512 + 2 * 4096;
+constexpr size_t kSchedHeads = 256, kSchedFwdDone = 512, kSchedCmbDone = 512 + 4096;
+constexpr int kSchedMaxTiles = 1024;
 constexpr size_t kWsChunkBytes = (size_t)64 << 20;  // spectrum workspace per chunk: stays L2-resident (126 MB L2, pixel streams are evict-first)
 
 inline size_t elem_size(int dtype) {
@@ -85,6 +91,7 @@ inline int validate_desc(const tfcfft_desc* d, Geometry* geo, bool allow_sub = t
             long long ct = (long long)(kWsChunkBytes / per_tile);
             if (ct < 1) ct = 1;
             // (the launcher trims a chunk to whole waves of its launches from the device's occupancy: k_sub.cu)
+            if (ct > kSchedMaxTiles) ct = kSchedMaxTiles;
             if (ct > geo->tiles_total) ct = geo->tiles_total;
             geo->chunk_tiles = ct;
             z = (size_t)ct * per_tile;
@@ -155,6 +162,7 @@ inline Params make_params(const tfcfft_desc* d, const Geometry& g, const void* f
     p.out = out;
     p.per_image = per_image;
     p.zws = (g.split || g.sub) ? reinterpret_cast<float2*>(w + kWsHeader + g.partial_bytes) : nullptr;
+    p.sched = reinterpret_cast<unsigned*>(w + kSchedHeads);
     p.sub_d = g.sub ? g.p / 64 : 0;
     p.tile_base = 0;
     p.chunk_tiles = (int)g.chunk_tiles;

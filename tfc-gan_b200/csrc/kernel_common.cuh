@@ -133,18 +133,9 @@ __device__ __forceinline__ void block_sum2(float& a, float& b) {
     __syncthreads();
 }
 
-// Last block to arrive sums all partials in a fixed order (double) and writes the outputs;
-// the ticket counter is left at zero for the next call.
-__device__ __forceinline__ void finish(const Params& prm, unsigned total_blocks) {
-    __shared__ bool last;
+// Fixed-order sum of all partials in double by ONE block; writes the outputs.  Every partial must be visible.
+__device__ __forceinline__ void finalize_sums(const Params& prm) {
     __shared__ double dred[2][32];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        last = (atomicAdd(prm.counter, 1u) == total_blocks - 1);
-    }
-    __syncthreads();
-    if (!last) return;
     __threadfence();
     double a = 0.0, p = 0.0;
     const double img_norm = prm.norm * (double)prm.n;
@@ -181,8 +172,22 @@ __device__ __forceinline__ void finish(const Params& prm, unsigned total_blocks)
             p += dred[1][w];
         }
         write_outputs(prm, a, p);
-        *prm.counter = 0u;
     }
+}
+
+// Last block to arrive sums all partials in a fixed order (double) and writes the outputs;
+// the ticket counter is left at zero for the next call.
+__device__ __forceinline__ void finish(const Params& prm, unsigned total_blocks) {
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(prm.counter, 1u) == total_blocks - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    finalize_sums(prm);
+    if (threadIdx.x == 0) *prm.counter = 0u;
 }
 
 // ---- named barriers (bar.sync / bar.arrive with explicit participant counts) ---------------------

@@ -84,6 +84,72 @@ TFC_HD float2 atan2_pair(float2 y, float2 x) {
     return r;
 }
 
+// unsigned angle of two lanes: atan2(|s|, c) in [0, pi] (same polynomial as atan2_pair, no final sign fix-up)
+TFC_HD float2 atan2_abs_pair(float2 sn, float2 cs) {
+    const float ax0 = fabsf(cs.x), ay0 = fabsf(sn.x), ax1 = fabsf(cs.y), ay1 = fabsf(sn.y);
+    const float mx0 = fmaxf(ax0, ay0), mn0 = fminf(ax0, ay0);
+    const float mx1 = fmaxf(ax1, ay1), mn1 = fminf(ax1, ay1);
+    float2 t;
+    t.x = mx0 > 1e-30f ? mn0 * fast_rcp(mx0) : 0.f;
+    t.y = mx1 > 1e-30f ? mn1 * fast_rcp(mx1) : 0.f;
+    const float2 s = p_mul(t, t);
+    float2 p = p_dup(-4.0545672114e-03f);
+    p = p_fma(p, s, p_dup(2.1862957868e-02f));
+    p = p_fma(p, s, p_dup(-5.5912326758e-02f));
+    p = p_fma(p, s, p_dup(9.6421973272e-02f));
+    p = p_fma(p, s, p_dup(-1.3908629550e-01f));
+    p = p_fma(p, s, p_dup(1.9946565651e-01f));
+    p = p_fma(p, s, p_dup(-3.3329860784e-01f));
+    p = p_fma(p, s, p_dup(9.9999933558e-01f));
+    float2 r = p_mul(p, t);
+    constexpr float kPi = 3.14159265358979f, kHalfPi = 1.57079632679490f;
+    if (ay0 > ax0) r.x = kHalfPi - r.x;
+    if (ay1 > ax1) r.y = kHalfPi - r.y;
+    if (cs.x < 0.f) r.x = kPi - r.x;
+    if (cs.y < 0.f) r.y = kPi - r.y;
+    return r;
+}
+
+TFC_HD int f_bits(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_int(f);
+#else
+    int i;
+    memcpy(&i, &f, 4);
+    return i;
+#endif
+}
+TFC_HD float bits_f(int i) {
+#ifdef __CUDA_ARCH__
+    return __int_as_float(i);
+#else
+    float f;
+    memcpy(&f, &i, 4);
+    return f;
+#endif
+}
+
+// Phase difference d = angle(F) - angle(R) in (-2 pi, 2 pi) -- the reference subtracts two arctan2 values without
+// re-wrapping -- from ONE arctangent: a = atan2(|Im(F conj R)|, Re(F conj R)) is the unsigned angle between F and R,
+// and the half planes of F and R (the sign bits of their imaginary parts) say which multiple of 2 pi separates d
+// from the wrapped angle:
+//   same half plane:       d = sign(Im(F conj R)) * a
+//   F upper, R lower:      d in (0, 2 pi):   d = a if Im(F conj R) >= 0 else 2 pi - a          (and mirrored)
+// The decisions only read sign bits; where such a sign is decided by cancellation (d near 0 / +-pi in the same half
+// plane, d near pi across) the two candidate values coincide, and at the real axis the signed zeros of the fused
+// multiply-add give the IEEE answers (atan2(+0, x < 0) = +pi).  Returns |d| in `absd` and the sign bit of d in the
+// top bit of `sgn` (per lane).
+TFC_HD void phase_delta(float fx, float fy, float rx, float ry, float sn, float a, float& absd, int& sgn) {
+    constexpr float kTwoPi = 6.28318530717958648f;
+    const int bf = f_bits(fy), br = f_bits(ry), bs = f_bits(sn);
+    const int opp = bf ^ br;              // top bit: F and R in different half planes
+    sgn = opp < 0 ? bf : bs;
+    const int wrap = (bs ^ bf) & opp;     // top bit: different half planes and the short way round is the wrong way
+    absd = wrap < 0 ? kTwoPi - a : a;
+    (void)fx;
+    (void)rx;
+}
+
 TFC_HD float sign_of(float d) {  // copysign(1, d): the sign(0) = 0 case only matters when F == 0, where the
                                  // gradient is already zeroed through 1/|F| := 0
 #if defined(__CUDA_ARCH__)
@@ -117,15 +183,21 @@ TFC_HD c2 bin_eval_pair(const Params& prm, bool mse, bool phase, c2 zk, c2 zm, f
     const float2 ca = p_mul(p_mul(ga, finv), p_dup(prm.sa));
     c2 g = make_c2(p_mul(ca, fx), p_mul(ca, fy));
     if (phase) {
-        const float2 dp = p_sub(atan2_pair(fy, fx), atan2_pair(ry, rx));
+        const float2 cs = p_fma(fx, rx, p_mul(fy, ry));          // Re(F conj R)
+        const float2 sn = p_fma(fy, rx, p_neg(p_mul(fx, ry)));   // Im(F conj R)
+        const float2 a = atan2_abs_pair(sn, cs);
+        float2 ad;
+        int s0, s1;
+        phase_delta(fx.x, fy.x, rx.x, ry.x, sn.x, a.x, ad.x, s0);
+        phase_delta(fx.y, fy.y, rx.y, ry.y, sn.y, a.y, ad.y, s1);
         float2 gp;
         if (mse) {
-            accP = p_fma(dp, dp, accP);
-            gp = p_add(dp, dp);
+            accP = p_fma(ad, ad, accP);
+            gp = make_float2(bits_f((s0 & 0x80000000) | (f_bits(ad.x + ad.x) & 0x7fffffff)),
+                             bits_f((s1 & 0x80000000) | (f_bits(ad.y + ad.y) & 0x7fffffff)));
         } else {
-            accP.x += fabsf(dp.x);
-            accP.y += fabsf(dp.y);
-            gp = make_float2(sign_of(dp.x), sign_of(dp.y));
+            accP = p_add(accP, ad);
+            gp = make_float2(bits_f((s0 & 0x80000000) | 0x3f800000), bits_f((s1 & 0x80000000) | 0x3f800000));
         }
         const float2 cp = p_mul(p_mul(gp, p_mul(finv, finv)), p_dup(2.f * prm.sp));
         g.re = p_fma(p_neg(cp), fy, g.re);

@@ -46,6 +46,16 @@ TFC_HD float2* sub_plane(const Params& prm, int tile_local, int plane) {
     return reinterpret_cast<float2*>(prm.zws) + ((long long)tile_local * (prm.sub_d * prm.sub_d) + plane) * 4096;
 }
 
+// Workspace planes are written by one CTA and read by another within ONE launch of the pipelined kernel (and
+// rewritten in between): reads bypass L1 (ld.global.cg), which may hold a stale copy of a line this SM read earlier.
+TFC_HD float2 ws_load(const float2* p) {
+#ifdef __CUDA_ARCH__
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+
 // ---- forward launch: sub-image pair (columns q = 2i, 2i+1 of row phase p) -> two complex work tiles ------
 template <typename T, bool LUMA3, class Ctx>
 TFC_HD void sub_fwd_load(const Ctx& ctx, const Params& prm, const TileCoord& tc, const SubUnit& su, float2* s) {
@@ -184,7 +194,7 @@ TFC_HD void sub_inv_cols(const Ctx& ctx, const Params& prm, const SubUnit& su, f
         const float2* plane = sub_plane(prm, su.tile_local, su.plane) + x;
         float2 v[64];
 #pragma unroll
-        for (int y = 0; y < 64; ++y) v[y] = plane[y * 64];
+        for (int y = 0; y < 64; ++y) v[y] = ws_load(plane + y * 64);
         fft64<true>(v);
 #pragma unroll
         for (int sl = 0; sl < 64; ++sl) s[fft64_freq(sl) * LD + x] = v[sl];
@@ -426,8 +436,8 @@ TFC_HD void combine_item(const Params& prm, float2* ws_tile, int item, float& ac
     for (int p = 0; p < D; ++p)
 #pragma unroll
         for (int q = 0; q < D; ++q) {
-            za[p][q] = ws_tile[(p * D + q) * 4096 + offA];
-            zb[p][q] = ws_tile[(p * D + q) * 4096 + offB];
+            za[p][q] = ws_load(ws_tile + (p * D + q) * 4096 + offA);
+            zb[p][q] = ws_load(ws_tile + (p * D + q) * 4096 + offB);
         }
     {
         c2 z2[D][D];

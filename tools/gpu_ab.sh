@@ -13,8 +13,8 @@ RC=$?
 cat $OUT/ringcheck_$TAG.log | tail -n 12
 if [ $RC -ne 0 ]; then echo "ring_check failed or hung (exit $RC): stopping"; exit 1; fi
 if [ "${SKIP_PYTEST:-0}" != "1" ]; then
-timeout 600 python -m pytest tests -m gpu -q --timeout 120 -p no:cacheprovider -x > $OUT/pytest_$TAG.log 2>&1
-echo "pytest exit $?"; tail -n 6 $OUT/pytest_$TAG.log
+timeout 700 python -m pytest tests -m gpu -q --timeout 200 -p no:cacheprovider > $OUT/pytest_$TAG.log 2>&1
+echo "pytest exit $?"; grep -E "^(FAILED|ERROR)|passed|failed" $OUT/pytest_$TAG.log | head -20
 fi
 IFS='|' read -ra VV <<< "$VARS"
 [ ${#VV[@]} -eq 0 ] && VV=("")
