@@ -51,9 +51,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
         su.plane = su.p * 2 + rank;
         sub_fwd_load_quad<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, dst01, dst23);
         cl.sync();
-        sub_fwd_rows(ctx, s);
-        ctx.sync();
-        sub_fwd_cols_store(ctx, prm, su, s);
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the 64-point core
+            sub_fwd_pass(ctx, prm, su, s, pass);
+            if (pass == 0) ctx.sync();
+        }
         cl.sync();  // the peer may refill my tiles only after my column pass has read them
     }
     pdl_release();
@@ -98,9 +100,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) s
         su.p = w & 3;
         su.i = rank;
         su.plane = su.p * 2 + rank;
-        sub_inv_cols(ctx, prm, su, s);
-        ctx.sync();
-        sub_inv_rows(ctx, s);
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the 64-point core
+            sub_inv_pass(ctx, prm, su, s, pass);
+            if (pass == 0) ctx.sync();
+        }
         cl.sync();  // both column pairs are ready
         sub_inv_store_quad<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, s01, s23);
         cl.sync();  // the peer has read my tile
@@ -137,6 +141,139 @@ cudaError_t launch_combine(int d, int grid, const Params& prm, cudaStream_t st) 
 }
 #endif
 
+// ---------------------------------------------------------------------------------------------------------------
+// Pipelined variant: ONE persistent launch per workspace chunk instead of three.  The three launches above are each
+// about one wave deep at batch 64 (1.15 / 1 / 1.15 waves): three wave tails, no overlap between the HBM-bound loads of
+// launch 1, the L2 / issue-bound combine and the HBM-bound stores of launch 3.  Here every CTA pulls work items from
+// three statically partitioned queues -- inverse (gradient store), combine, forward (pixel load) -- and a tile's combine items
+// become ready when its D*D/2 forward items have signalled, its inverse items when its 9 combine parts have: tile
+// j's loads overlap tile i's combine and tile h's stores on the same SM, and the only tail is the last tile's.
+//   * items run the SAME device functions as the three launches (sub_fwd_process, combine_item, sub_inv_process):
+//     results are bit-identical to the 3-launch path (tests compare them);
+//   * no deadlock: forward items wait for nothing, a combine / inverse item is only CLAIMED when its dependencies
+//     have completed, and all CTAs are co-resident (grid = SMs x occupancy);
+//   * scheduler state (per-tile done counters, exit ticket) lives in the zero-initialised workspace header and is
+//     reset by the last CTA to leave, like the finalise ticket.
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct PipeCfg {
+    static constexpr int NT = 128;
+    static constexpr size_t SMEM = SubCfg::SMEM_FWD;  // two work tiles: a forward pair, or two inverse planes
+};
+
+template <typename T, bool LUMA3>
+__global__ void __launch_bounds__(PipeCfg::NT, 3) sub_pipe_kernel(const __grid_constant__ Params prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    __shared__ int s_type, s_idx;
+    const int tid = (int)threadIdx.x;
+    const int D = prm.sub_d, npp = D * D / 2, T_ = prm.chunk_now;
+    const int n_fwd = T_ * npp, n_cmb = T_ * kCombineParts;
+    const int inv_per_tile = npp / 2;  // a CTA runs two inverse planes at once (two 64-thread groups)
+    const int n_inv = prm.grad != nullptr ? T_ * inv_per_tile : 0;
+    unsigned* heads = prm.sched;                  // [0] fwd, [1] cmb, [2] inv, [3] exit ticket
+    unsigned* fwd_done = prm.sched + (kSchedFwdDone - kSchedHeads) / 4;
+    unsigned* cmb_done = prm.sched + (kSchedCmbDone - kSchedHeads) / 4;
+    pdl_wait();
+    // Items are OWNED statically (item i of a queue belongs to CTA i mod gridDim): no claim traffic -- a first version
+    // with three shared atomic queue heads spent ~0.45 us per claim serialising 444 CTAs on three L2 addresses (5 x
+    // slower than the three launches).  A CTA only decides WHICH of its own next items to run: inverse if that tile's
+    // combine parts are done, else combine if that tile's forward items are done, else its next forward item (never
+    // waits), else it polls (only per-tile counters, read by a handful of CTAs each).
+    const int G_ = (int)gridDim.x, b_ = (int)blockIdx.x;
+    int nf = b_, nc = b_, ni = b_;  // this CTA's next forward / combine / inverse item
+    for (;;) {
+        if (tid == 0) {
+            int type = 0, idx = 0;  // 0 retry, 1 fwd, 2 cmb, 3 inv, 4 exit
+            if (ni < n_inv && ld_acquire(cmb_done + ni / inv_per_tile) == (unsigned)kCombineParts) {
+                type = 3;
+                idx = ni;
+                ni += G_;
+            } else if (nc < n_cmb && ld_acquire(fwd_done + nc / kCombineParts) == (unsigned)npp) {
+                type = 2;
+                idx = nc;
+                nc += G_;
+            } else if (nf < n_fwd) {
+                type = 1;
+                idx = nf;
+                nf += G_;
+            } else if (ni >= n_inv && nc >= n_cmb) {
+                type = 4;
+            } else {
+                __nanosleep(100);
+            }
+            s_type = type;
+            s_idx = idx;
+        }
+        __syncthreads();
+        const int type = s_type, idx = s_idx;
+        __syncthreads();  // s_type / s_idx may be rewritten by thread 0 from here on
+        if (type == 4) break;
+        if (type == 0) continue;
+        if (type == 1) {
+            const BlockCtxT<PipeCfg::NT> ctx{tid, nullptr};
+            sub_fwd_process<T, LUMA3>(ctx, prm, idx, s);  // ends with a block barrier
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) red_release_add(fwd_done + idx / npp, 1u);
+        } else if (type == 2) {
+            const int lt = idx / kCombineParts, part = idx % kCombineParts;
+            float a = 0.f, p = 0.f;
+            float2* ws_tile = sub_plane(prm, lt, 0);
+#pragma unroll 1
+            for (int rep = 0; rep < kCombineRep; ++rep) {
+                const int item = part * kCombineItemsPerPart + rep * kCombineThreads + tid;
+                if (item < kCombineItems) {
+                    if (D == 2) combine_item<2>(prm, ws_tile, item, a, p);
+                    else combine_item<4>(prm, ws_tile, item, a, p);
+                }
+            }
+            block_sum2(a, p);
+            if (tid == 0) {
+                const long long slot = (long long)(prm.tile_base + lt) * kCombineParts + part;
+                prm.partials[2 * slot] = a;
+                prm.partials[2 * slot + 1] = p;
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) red_release_add(cmb_done + lt, 1u);
+        } else {
+            // two packed planes of one tile, one per 64-thread group (named barriers 1 and 2)
+            const int g = tid >> 6;
+            const GroupCtx<64, 1> c0{tid & 63, nullptr};
+            const GroupCtx<64, 2> c1{tid & 63, nullptr};
+            const int u = (idx / inv_per_tile) * npp + (idx % inv_per_tile) * 2 + g;
+            if (g == 0) sub_inv_process<T, LUMA3>(c0, prm, u, s);
+            else sub_inv_process<T, LUMA3>(c1, prm, u, s + 64 * SubCfg::LD);
+            __syncthreads();
+        }
+    }
+    pdl_release();
+    // last CTA to leave: final reduction (after the last chunk) and scheduler reset for the next launch
+    __shared__ bool last;
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        last = (atomicAdd(heads + 3, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    if (prm.tile_base + T_ >= prm.tiles_total) finalize_sums(prm);
+    __syncthreads();
+    for (int i = tid; i < T_; i += PipeCfg::NT) {
+        fwd_done[i] = 0u;
+        cmb_done[i] = 0u;
+    }
+    if (tid < 4) heads[tid] = 0u;
+}
+
 namespace {
 
 template <typename T, bool LUMA3>
@@ -155,6 +292,27 @@ int launch_sub(Params prm, cudaStream_t st) {
     if (cluster) {
         if (int rc = ff4.get(kf4, SubCfg::NT_FWD, SubCfg::SMEM_FWD, nullptr)) return rc;
         if (int rc = fi4.get(ki4, SubCfg::NT_INV, SubCfg::SMEM_INV, nullptr)) return rc;
+    }
+    // measured (profiles/r02_sub_pipe_ab.txt): the pipelined kernel is bit-identical but SLOWER than the three launches
+    // (global 256^2 b64: 118 vs 73 us; 4-patch b256: 372 vs 248 us) -- one kernel that holds the forward, combine and
+    // inverse code of both decimations thrashes the instruction cache, runs the combine at 12 instead of 16 warps per
+    // SM and loses the 2-CTA cluster loads -- so it is opt-in (TFCFFT_SUB_PIPE=1) and the three launches stay.
+    static const bool pipe = getenv("TFCFFT_SUB_PIPE") != nullptr;
+    if (pipe) {
+        auto kp = sub_pipe_kernel<T, LUMA3>;
+        static KernelFacts fp;
+        int per_sm = 1;
+        if (int rc = fp.get(kp, PipeCfg::NT, PipeCfg::SMEM, &per_sm)) return rc;
+        const int cap = device_sms() * per_sm;  // every CTA must be resident: items wait on each other
+        for (int base = 0; base < prm.tiles_total; base += prm.chunk_tiles) {
+            prm.tile_base = base;
+            prm.chunk_now = prm.tiles_total - base < prm.chunk_tiles ? prm.tiles_total - base : prm.chunk_tiles;
+            const int items = prm.chunk_now * npp;
+            const int grid = items < cap ? items : cap;
+            if (cudaError_t e = launch_pdl(kp, grid, PipeCfg::NT, PipeCfg::SMEM, st, prm)) return (int)e;
+            g_launches++;
+        }
+        return 0;
     }
     const int sms = device_sms();
     // trim the workspace chunk to a whole number of waves of the forward launch on THIS device (smallest tile count

@@ -155,63 +155,79 @@ TFC_HD void sub_fwd_load_quad(const Ctx& ctx, const Params& prm, const TileCoord
     }
 }
 
-// rows of both work tiles, one thread per row
+// Forward passes of both work tiles on ONE copy of the 64-point core (callers keep the pass loop rolled, like
+// line_fft_pass): pass 0 = rows (one thread per row, in place), pass 1 = columns, written straight to the workspace
+// planes (coalesced across the column index).
 template <class Ctx>
-TFC_HD void sub_fwd_rows(const Ctx& ctx, float2* s) {
-    constexpr int LD = SubCfg::LD;
-    for (int l = ctx.tid; l < 128; l += ctx.nthreads) {
-        float2* row = s + l * LD;  // tile (l >> 6), row (l & 63): the two tiles are contiguous
-        float2 v[64];
-#pragma unroll
-        for (int x = 0; x < 64; ++x) v[x] = row[x];
-        fft64<false>(v);
-#pragma unroll
-        for (int sl = 0; sl < 64; ++sl) row[fft64_freq(sl)] = v[sl];
-    }
-}
-// columns, one thread per column, written straight to the workspace planes (coalesced across the column index)
-template <class Ctx>
-TFC_HD void sub_fwd_cols_store(const Ctx& ctx, const Params& prm, const SubUnit& su, const float2* s) {
+TFC_HD void sub_fwd_pass(const Ctx& ctx, const Params& prm, const SubUnit& su, float2* s, int pass) {
     constexpr int LD = SubCfg::LD;
     for (int l = ctx.tid; l < 128; l += ctx.nthreads) {
         const int t = l >> 6, x = l & 63;
+        float2* row = s + l * LD;  // tile (l >> 6), row (l & 63): the two tiles are contiguous
         const float2* col = s + t * 64 * LD + x;
         float2 v[64];
+        if (pass == 0) {
 #pragma unroll
-        for (int y = 0; y < 64; ++y) v[y] = col[y * LD];
+            for (int i = 0; i < 64; ++i) v[i] = row[i];
+        } else {
+#pragma unroll
+            for (int y = 0; y < 64; ++y) v[y] = col[y * LD];
+        }
         fft64<false>(v);
-        float2* plane = sub_plane(prm, su.tile_local, su.p * prm.sub_d + 2 * su.i + t) + x;
+        if (pass == 0) {
 #pragma unroll
-        for (int sl = 0; sl < 64; ++sl) plane[fft64_freq(sl) * 64] = v[sl];
+            for (int sl = 0; sl < 64; ++sl) row[fft64_freq(sl)] = v[sl];
+        } else {
+            float2* plane = sub_plane(prm, su.tile_local, su.p * prm.sub_d + 2 * su.i + t) + x;
+#pragma unroll
+            for (int sl = 0; sl < 64; ++sl) plane[fft64_freq(sl) * 64] = v[sl];
+        }
     }
+}
+template <class Ctx>
+TFC_HD void sub_fwd_rows(const Ctx& ctx, float2* s) {
+    sub_fwd_pass(ctx, Params{}, SubUnit{}, s, 0);
+}
+template <class Ctx>
+TFC_HD void sub_fwd_cols_store(const Ctx& ctx, const Params& prm, const SubUnit& su, float2* s) {
+    sub_fwd_pass(ctx, prm, su, s, 1);
 }
 
 // ---- inverse launch: packed plane C_pi -> gradients of the sub-image pair ----------------------------
+// Inverse passes on ONE copy of the forward core: IDFT(x)[n] = DFT(x)[(64 - n) mod 64], so the results are stored at
+// the mirrored index.  pass 0 = columns straight from the workspace plane (64 independent 8-byte loads in flight per
+// thread), pass 1 = rows in shared memory (real / imaginary parts = gradients of two horizontally adjacent pixels).
 template <class Ctx>
-TFC_HD void sub_inv_cols(const Ctx& ctx, const Params& prm, const SubUnit& su, float2* s) {
+TFC_HD void sub_inv_pass(const Ctx& ctx, const Params& prm, const SubUnit& su, float2* s, int pass) {
     constexpr int LD = SubCfg::LD;
-    for (int x = ctx.tid; x < 64; x += ctx.nthreads) {
-        const float2* plane = sub_plane(prm, su.tile_local, su.plane) + x;
+    for (int l = ctx.tid; l < 64; l += ctx.nthreads) {
+        float2* row = s + l * LD;
         float2 v[64];
+        if (pass == 0) {
+            const float2* plane = sub_plane(prm, su.tile_local, su.plane) + l;
 #pragma unroll
-        for (int y = 0; y < 64; ++y) v[y] = ws_load(plane + y * 64);
-        fft64<true>(v);
+            for (int y = 0; y < 64; ++y) v[y] = ws_load(plane + y * 64);
+        } else {
 #pragma unroll
-        for (int sl = 0; sl < 64; ++sl) s[fft64_freq(sl) * LD + x] = v[sl];
+            for (int k = 0; k < 64; ++k) v[k] = row[k];
+        }
+        fft64<false>(v);
+        if (pass == 0) {
+#pragma unroll
+            for (int sl = 0; sl < 64; ++sl) s[((64 - fft64_freq(sl)) & 63) * LD + l] = v[sl];
+        } else {
+#pragma unroll
+            for (int sl = 0; sl < 64; ++sl) row[(64 - fft64_freq(sl)) & 63] = v[sl];  // (grad of pixel 2i, grad of pixel 2i+1)
+        }
     }
 }
 template <class Ctx>
+TFC_HD void sub_inv_cols(const Ctx& ctx, const Params& prm, const SubUnit& su, float2* s) {
+    sub_inv_pass(ctx, prm, su, s, 0);
+}
+template <class Ctx>
 TFC_HD void sub_inv_rows(const Ctx& ctx, float2* s) {
-    constexpr int LD = SubCfg::LD;
-    for (int a = ctx.tid; a < 64; a += ctx.nthreads) {
-        float2* row = s + a * LD;
-        float2 v[64];
-#pragma unroll
-        for (int k = 0; k < 64; ++k) v[k] = row[k];
-        fft64<true>(v);
-#pragma unroll
-        for (int sl = 0; sl < 64; ++sl) row[fft64_freq(sl)] = v[sl];  // (grad of pixel 2i, grad of pixel 2i+1)
-    }
+    sub_inv_pass(ctx, Params{}, SubUnit{}, s, 1);
 }
 template <typename T, bool LUMA3, class Ctx>
 TFC_HD void sub_inv_store(const Ctx& ctx, const Params& prm, const TileCoord& tc, const SubUnit& su, const float2* s) {
@@ -260,23 +276,23 @@ TFC_HD void sub_fwd_process(const Ctx& ctx, const Params& prm, int u, float2* s)
     sub_fwd_load<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
     ctx.sync();
     ctx.mark(1);
-    sub_fwd_rows(ctx, s);
-    ctx.sync();
-    ctx.mark(2);
-    sub_fwd_cols_store(ctx, prm, su, s);
-    ctx.sync();
-    ctx.mark(3);
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the 64-point core
+        sub_fwd_pass(ctx, prm, su, s, pass);
+        ctx.sync();
+        ctx.mark(2 + pass);
+    }
 }
 template <typename T, bool LUMA3, class Ctx>
 TFC_HD void sub_inv_process(const Ctx& ctx, const Params& prm, int u, float2* s) {
     const SubUnit su = sub_unit(u, prm.sub_d);
     ctx.mark(0);
-    sub_inv_cols(ctx, prm, su, s);
-    ctx.sync();
-    ctx.mark(1);
-    sub_inv_rows(ctx, s);
-    ctx.sync();
-    ctx.mark(2);
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the 64-point core
+        sub_inv_pass(ctx, prm, su, s, pass);
+        ctx.sync();
+        ctx.mark(1 + pass);
+    }
     sub_inv_store<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
     ctx.sync();
     ctx.mark(3);

@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""GPU self-check of the pipelined sub-tile kernel: its loss / gradient must equal the three-launch path BIT FOR BIT
+(same device functions, different scheduling).  Each path runs in its own process (the switch is read once)."""
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+CASES = [(1, 256, 3, "luma"), (1, 256, 64, "luma"), (2, 256, 37, "luma"), (2, 256, 256, "luma"), (1, 256, 20, "rgb"),
+         (4, 512, 9, "luma"), (2, 256, 600, "luma"), (1, 256, 130, "luma")]
+
+
+def worker(path):
+    import tfc_gan_b200 as tfc
+
+    out = []
+    for grid, side, n, ch in CASES:
+        g = torch.Generator(device="cuda").manual_seed(n + grid)
+        f = torch.empty(n, 3, side, side, device="cuda").uniform_(-1, 1, generator=g)
+        r = torch.empty(n, 3, side, side, device="cuda").uniform_(-1, 1, generator=g)
+        for rep in range(2):  # twice: the scheduler state must come back to zero
+            l, t, gr = tfc.spectral_loss_and_grad(f, r, grid=grid, channels=ch, weight=0.01, input_scale=255.0)
+        lf = tfc.spectral_loss(f, r, grid=grid, channels=ch, weight=0.01, input_scale=255.0)  # forward only
+        torch.cuda.synchronize()
+        out.append((l.cpu(), t.cpu(), gr.cpu(), lf.detach().cpu()))
+        print("done", grid, side, n, ch, float(l), flush=True)
+    torch.save(out, path)
+
+
+def main():
+    if len(sys.argv) > 1:
+        return worker(sys.argv[1])
+    res = {}
+    for name, env in (("pipe", {"TFCFFT_SUB_PIPE": "1"}), ("three", {})):
+        path = f"/tmp/pipe_check_{name}.pt"
+        p = subprocess.run([sys.executable, __file__, path], env={**os.environ, **env}, timeout=100)
+        if p.returncode != 0:
+            print("pipe_check", name, "FAILED rc", p.returncode)
+            sys.exit(1)
+        res[name] = torch.load(path)
+    ok = True
+    for c, a, b in zip(CASES, res["pipe"], res["three"]):
+        same = all(torch.equal(x, y) for x, y in zip(a, b))
+        ok &= same
+        print(c, "bit-identical" if same else f"MISMATCH loss {float(a[0])} vs {float(b[0])} grad rel {float((a[2] - b[2]).norm() / b[2].norm()):.2e}")
+    print("pipe_check", "PASS" if ok else "FAIL")
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
