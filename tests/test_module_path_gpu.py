@@ -148,3 +148,28 @@ def test_fake_equals_real_gives_exact_zero():
     loss, _, grad = tfc.spectral_loss_and_grad(f, r, grid=4, weight=0.01, input_scale=255.0)
     assert loss.item() > 0
     assert float(grad[1::2].abs().max()) == 0.0 and float(grad[::2].abs().max()) > 0.0
+
+
+def test_triplet_on_spectra_variant():
+    """``triplet_patches`` of ``..._debiased_V5.py:386-443``: TripletMarginLoss on amplitude / phase spectra of the
+    quadrants + the pixel-space patch triplet, against the same composition on the fp64 oracle spectra."""
+    f, r = _pair(3, seed=61)
+    quads = [r[:, :, y:y + 128, x:x + 128].contiguous() for y in (0, 128) for x in (0, 128)]
+    neg = [2, 0, 3, 3]
+    fa = f.clone().requires_grad_(True)
+    amp, pha, patch = compat.triplet_patches(fa, *quads, negatives=neg)
+    (amp + pha + patch).backward()
+    fo = f.double().cpu().requires_grad_(True)
+    crit = torch.nn.TripletMarginLoss(margin=1.0, p=2)
+    fq = [fo[:, :, y:y + 128, x:x + 128] for y in (0, 128) for x in (0, 128)]
+    rq = [q.double().cpu() for q in quads]
+    sf = [oracle.fft_components_r1(q, input_scale=255.0) for q in fq]
+    sr = [oracle.fft_components_r1(q, input_scale=255.0) for q in rq]
+    a = sum(crit(sf[i][0], sr[i][0], sr[neg[i]][0]) for i in range(4)) / 4
+    p = sum(crit(sf[i][1], sr[i][1], sr[neg[i]][1]) for i in range(4)) / 4
+    t = sum(crit(fq[i], rq[i], rq[neg[i]]) for i in range(4)) / 4
+    (a + p + t).backward()
+    assert amp.item() == pytest.approx(a.item(), rel=1e-4)
+    assert pha.item() == pytest.approx(p.item(), rel=1e-4)
+    assert patch.item() == pytest.approx(t.item(), rel=1e-4)
+    assert l2rel(fa.grad.cpu().numpy(), fo.grad.numpy()) <= 2e-3

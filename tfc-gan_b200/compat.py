@@ -160,6 +160,26 @@ def patch_triplet(fake_patches, real_patches, negatives=None, margin: float = 1.
     return patch_triplet_loss(_assemble(tuple(fake_patches), g), _assemble(tuple(real_patches), g), negatives, grid=g, margin=margin)
 
 
+def triplet_patches(fake_B, B1, B2, B3, B4, negatives=None, margin: float = 1.0):
+    """``triplet_patches(fake_B, B1, B2, B3, B4) -> (Amp_loss, Pha_loss, Patch_loss)``
+    (``TFC-GAN-FFT/TFCGAN_multigpu_patchFFT_debiased_V5.py:386-443``): ``nn.TripletMarginLoss(margin=1, p=2)`` on the
+    AMPLITUDE and on the PHASE spectra of the four quadrants (``criterion_amp``, ``:93-94``; anchor = fake quadrant,
+    positive = real quadrant, negative = a randomly drawn real quadrant ``K_i``) plus the pixel-space patch triplet with the
+    same negatives.  The spectra come from the differentiable :func:`fft_components` (upstream they are detached), the
+    pixel term from the fused patch-triplet kernel; ``negatives`` defaults to the reference's four NumPy draws."""
+    if negatives is None:
+        negatives = draw_negatives(4)
+    fq = make_4_patches(fake_B)
+    rq = (B1, B2, B3, B4)
+    crit = torch.nn.TripletMarginLoss(margin=margin, p=2)
+    sf = [fft_components(q) for q in fq]
+    sr = [fft_components(q) for q in rq]  # K_i is one of B1..B4: its spectra are already here
+    amp = sum(crit(sf[i][0], sr[i][0], sr[negatives[i]][0]) for i in range(4)) / 4
+    pha = sum(crit(sf[i][1], sr[i][1], sr[negatives[i]][1]) for i in range(4)) / 4
+    patch = patch_triplet(fq, rq, negatives, margin=margin)
+    return amp, pha, patch
+
+
 def vectorize_temps(fake_B):
     """``vectorize_temps`` (``...patchFFT_16P.py:260-268``): ``[N,1,H,W]`` fp32 temperatures of the red channel."""
     return _vectorize_temps(fake_B)

@@ -2,7 +2,7 @@
 # ncu launch list (per-kernel device times) for a workload. usage: bash tools/gpu_list.sh TAG WORKLOAD
 set -u
 TAG=$1; WL=$2; OUT=gpurun_out; mkdir -p $OUT
-CMD="python bench.py --workload $WL --steps 5 --warmup 3 --no-variants --no-cpu-baseline"
+CMD="python bench.py --workload $WL --steps 5 --warmup 3 --no-variants --no-cpu-baseline --no-graph"
 timeout 300 $CMD > $OUT/plain_${WL}_$TAG.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_${WL}_$TAG.csv $CMD > $OUT/ncu_list_${WL}_$TAG.log 2>&1
 echo "ncu list $WL exit $?"
