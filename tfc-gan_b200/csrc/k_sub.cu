@@ -9,22 +9,79 @@
 
 namespace tfcfft {
 
+// ---- tile-granular dependencies between the three launches --------------------------------------------------------
+// The launches are chained with programmatic dependent launch, but `griddepcontrol.wait` is a whole-grid barrier: at
+// batch 64 the forward launch is 1.15 waves deep and 85 % of the SMs idle through its 15 us tail, then the same
+// again after the combine launch.  Instead every launch releases its dependents at START (all launches are
+// persistent, one wave: a waiting dependent CTA never takes a slot a primary CTA still needs), and a combine /
+// inverse CTA waits only for ITS TILE: forward CTAs count finished units per tile (`fwd_done`), combine CTAs count
+// finished parts (`cmb_done`), both in the workspace header with release / acquire semantics.  Combine CTAs of the
+// tiles of the first wave run on the SMs the forward tail leaves idle, inverse CTAs start as tiles complete.  Only the
+// FORWARD launch still waits for the whole previous grid (it overwrites the workspace the previous call's inverse
+// launch reads).  NEGATIVE RESULT (profiles/r02_sub_pipe_ab.txt): bit-identical, but 10 % slower than whole-grid
+// waits on every workload, so this mode is opt-in (TFCFFT_FINE_DEPS=1) and whole-grid waits are the default.
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned* sched_fwd_done(const Params& prm) { return prm.sched + (kSchedFwdDone - kSchedHeads) / 4; }
+__device__ __forceinline__ unsigned* sched_cmb_done(const Params& prm) { return prm.sched + (kSchedCmbDone - kSchedHeads) / 4; }
+// all threads of the CTA: publish this CTA's global stores, then count one finished item
+__device__ __forceinline__ void sched_signal(unsigned* counter) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) red_release_add(counter, 1u);
+}
+// all threads of the CTA: wait until `counter` reaches `target` (thread 0 polls)
+__device__ __forceinline__ void sched_wait(const unsigned* counter, unsigned target) {
+    if (threadIdx.x == 0) {
+        while (ld_acquire(counter) < target) __nanosleep(100);
+    }
+    __syncthreads();
+}
+// last CTA of the LAST launch of a chunk: final reduction after the last chunk, counters back to zero
+__device__ __forceinline__ void sched_finish(const Params& prm, bool reduce) {
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(prm.sched + 3, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    if (reduce && prm.tile_base + prm.chunk_now >= prm.tiles_total) finalize_sums(prm);
+    __syncthreads();
+    unsigned* fd = sched_fwd_done(prm);
+    unsigned* cd = sched_cmb_done(prm);
+    for (int i = (int)threadIdx.x; i < prm.chunk_now; i += (int)blockDim.x) {
+        fd[i] = 0u;
+        cd[i] = 0u;
+    }
+    if (threadIdx.x == 0) prm.sched[3] = 0u;
+}
+
 // Forward: one CTA = one sub-image PAIR (adjacent pixel columns, so the source rows are read as
 // 8-byte pairs), two 64-thread groups with a work tile each.  Inverse: one 64-thread CTA = one packed plane.
 template <typename T, bool LUMA3>
 __global__ void __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd_kernel(const __grid_constant__ Params prm) {
-    pdl_wait();
+    pdl_wait();  // whole previous grid: this launch overwrites the workspace planes
+    if (prm.fine_deps) pdl_release();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
     BlockCtxT<SubCfg::NT_FWD> ctx{(int)threadIdx.x, nullptr};
-    const int nunits = prm.chunk_now * (prm.sub_d * prm.sub_d / 2);
+    const int npp = prm.sub_d * prm.sub_d / 2, nunits = prm.chunk_now * npp;
     int iter = 0;
     for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++iter) {
         ctx.trace = (prm.trace != nullptr && iter < 6) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
         sub_fwd_process<T, LUMA3>(ctx, prm, u, s);
         if (ctx.trace != nullptr && threadIdx.x == 0) ctx.trace[15] = 1;
+        if (prm.fine_deps) sched_signal(sched_fwd_done(prm) + u / npp);
     }
-    pdl_release();
+    if (!prm.fine_deps) pdl_release();
 }
 // D = 4 forward launch as 2-CTA clusters: the two CTAs of a cluster own the two column pairs of one (tile, row phase),
 // load half of the rows each with full-sector 16-byte loads and hand the other CTA its half through distributed
@@ -32,7 +89,8 @@ __global__ void __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd_kernel(const __grid
 template <typename T, bool LUMA3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd4_kernel(const __grid_constant__ Params prm) {
     namespace cg = cooperative_groups;
-    pdl_wait();
+    pdl_wait();  // whole previous grid: this launch overwrites the workspace planes
+    if (prm.fine_deps) pdl_release();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
     cg::cluster_group cl = cg::this_cluster();
@@ -56,25 +114,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
             sub_fwd_pass(ctx, prm, su, s, pass);
             if (pass == 0) ctx.sync();
         }
+        if (prm.fine_deps) sched_signal(sched_fwd_done(prm) + su.tile_local);  // this CTA's two planes are out
         cl.sync();  // the peer may refill my tiles only after my column pass has read them
     }
-    pdl_release();
+    if (!prm.fine_deps) pdl_release();
 }
 
 template <typename T, bool LUMA3>
 __global__ void __launch_bounds__(SubCfg::NT_INV, 6) sub_inv_kernel(const __grid_constant__ Params prm) {
-    pdl_wait();
+    if (prm.fine_deps) pdl_release();
+    else pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
     BlockCtxT<SubCfg::NT_INV> ctx{(int)threadIdx.x, nullptr};
-    const int nunits = prm.chunk_now * (prm.sub_d * prm.sub_d / 2);
+    const int npp = prm.sub_d * prm.sub_d / 2, nunits = prm.chunk_now * npp;
     int iter = 0;
     for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++iter) {
         ctx.trace = (prm.trace != nullptr && iter < 6) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
+        if (prm.fine_deps) sched_wait(sched_cmb_done(prm) + u / npp, (unsigned)kCombineParts);
         sub_inv_process<T, LUMA3>(ctx, prm, u, s);
         if (ctx.trace != nullptr && threadIdx.x == 0) ctx.trace[15] = 1;
     }
-    pdl_release();
+    if (prm.fine_deps) sched_finish(prm, true);
+    else pdl_release();
 }
 
 // D = 4 inverse launch as 2-CTA clusters (the two packed planes i = 0, 1 of one (tile, row phase)): transforms as in
@@ -83,7 +145,8 @@ __global__ void __launch_bounds__(SubCfg::NT_INV, 6) sub_inv_kernel(const __grid
 template <typename T, bool LUMA3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) sub_inv4_kernel(const __grid_constant__ Params prm) {
     namespace cg = cooperative_groups;
-    pdl_wait();
+    if (prm.fine_deps) pdl_release();
+    else pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
     cg::cluster_group cl = cg::this_cluster();
@@ -100,6 +163,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) s
         su.p = w & 3;
         su.i = rank;
         su.plane = su.p * 2 + rank;
+        if (prm.fine_deps) sched_wait(sched_cmb_done(prm) + su.tile_local, (unsigned)kCombineParts);
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the 64-point core
             sub_inv_pass(ctx, prm, su, s, pass);
@@ -109,16 +173,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) s
         sub_inv_store_quad<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, s01, s23);
         cl.sync();  // the peer has read my tile
     }
-    pdl_release();
+    if (prm.fine_deps) sched_finish(prm, true);
+    else pdl_release();
 }
 
 #if TFC_DT == 0
 // Launch 2: per-position D x D butterflies, loss, spectral gradient (registers + L2 only).
 template <int D>
 __global__ void __launch_bounds__(kCombineThreads, 512 / kCombineThreads) combine_kernel(const __grid_constant__ Params prm) {
-    pdl_wait();
     constexpr int PARTS = kCombineParts;
     const int lt = blockIdx.x / PARTS, part = blockIdx.x % PARTS;
+    if (prm.fine_deps) {
+        pdl_release();
+        sched_wait(sched_fwd_done(prm) + lt, (unsigned)(D * D / 2));
+    } else {
+        pdl_wait();
+    }
     float a = 0.f, p = 0.f;
     float2* ws_tile = sub_plane(prm, lt, 0);
 #pragma unroll 1
@@ -132,8 +202,14 @@ __global__ void __launch_bounds__(kCombineThreads, 512 / kCombineThreads) combin
         prm.partials[2 * slot] = a;
         prm.partials[2 * slot + 1] = p;
     }
-    pdl_release();
-    finish(prm, (unsigned)prm.tiles_total * PARTS);
+    if (prm.fine_deps) {
+        sched_signal(sched_cmb_done(prm) + lt);
+        // with a gradient the inverse launch is the last one of the chunk: it reduces and resets (sched_finish)
+        if (prm.grad == nullptr) sched_finish(prm, true);
+    } else {
+        pdl_release();
+        finish(prm, (unsigned)prm.tiles_total * PARTS);
+    }
 }
 cudaError_t launch_combine(int d, int grid, const Params& prm, cudaStream_t st) {
     return d == 2 ? launch_pdl(combine_kernel<2>, grid, kCombineThreads, 0, st, prm)
@@ -154,15 +230,6 @@ cudaError_t launch_combine(int d, int grid, const Params& prm, cudaStream_t st) 
 //     have completed, and all CTAs are co-resident (grid = SMs x occupancy);
 //   * scheduler state (per-tile done counters, exit ticket) lives in the zero-initialised workspace header and is
 //     reset by the last CTA to leave, like the finalise ticket.
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 struct PipeCfg {
     static constexpr int NT = 128;
     static constexpr size_t SMEM = SubCfg::SMEM_FWD;  // two work tiles: a forward pair, or two inverse planes
@@ -314,6 +381,11 @@ int launch_sub(Params prm, cudaStream_t st) {
         }
         return 0;
     }
+    // measured: tile-granular dependencies (below) are bit-identical but 10 % SLOWER than whole-grid waits on every
+    // sub-tile workload (global 256^2 b64: 83 vs 75 us) -- dependent CTAs that become resident early spin on their tile's
+    // counter next to the CTAs that do the work -- so they are opt-in (TFCFFT_FINE_DEPS=1)
+    static const bool fine = getenv("TFCFFT_FINE_DEPS") != nullptr && getenv("TFCFFT_NO_PDL") == nullptr;
+    prm.fine_deps = fine ? 1 : 0;
     const int sms = device_sms();
     // trim the workspace chunk to a whole number of waves of the forward launch on THIS device (smallest tile count
     // whose units fill whole waves: 222 tiles of 128 x 128 / 111 tiles of 256 x 256 on a 148-SM part at 3 CTAs per SM)

@@ -38,6 +38,7 @@ struct Params {
     float* partials;       // [tiles_total * parts][2] (amp, pha) raw sums
     int parts;             // partial sums per tile (1 resident, #column-group pairs split)
     unsigned* counter;     // self-resetting ticket for the last-block finalise
+    int fine_deps;         // sub-tile launches: tile-granular dependencies through `sched` instead of whole-grid waits
     unsigned* sched;       // pipelined sub-tile kernel: queue heads, exit ticket, per-tile done counters (workspace header)
     float* out;            // [8]: loss, amp, pha, non-finite flag, gradient scale applied, 3 reserved
     float* per_image;      // [N][2] or nullptr

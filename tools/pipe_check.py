@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""GPU self-check of the pipelined sub-tile kernel: its loss / gradient must equal the three-launch path BIT FOR BIT
-(same device functions, different scheduling).  Each path runs in its own process (the switch is read once)."""
+"""GPU self-check of the sub-tile path's scheduling variants: tile-granular dependencies between the three launches
+(TFCFFT_FINE_DEPS=1), whole-grid waits (default) and the pipelined single kernel (TFCFFT_SUB_PIPE=1) must give the
+same loss / gradient BIT FOR BIT (same device functions, different scheduling).  Each variant runs in its own process
+(the switches are read once)."""
 import os
 import subprocess
 import sys
@@ -34,7 +36,7 @@ def main():
     if len(sys.argv) > 1:
         return worker(sys.argv[1])
     res = {}
-    for name, env in (("pipe", {"TFCFFT_SUB_PIPE": "1"}), ("three", {})):
+    for name, env in (("fine", {"TFCFFT_FINE_DEPS": "1"}), ("pipe", {"TFCFFT_SUB_PIPE": "1"}), ("three", {})):
         path = f"/tmp/pipe_check_{name}.pt"
         p = subprocess.run([sys.executable, __file__, path], env={**os.environ, **env}, timeout=100)
         if p.returncode != 0:
@@ -42,10 +44,11 @@ def main():
             sys.exit(1)
         res[name] = torch.load(path)
     ok = True
-    for c, a, b in zip(CASES, res["pipe"], res["three"]):
-        same = all(torch.equal(x, y) for x, y in zip(a, b))
-        ok &= same
-        print(c, "bit-identical" if same else f"MISMATCH loss {float(a[0])} vs {float(b[0])} grad rel {float((a[2] - b[2]).norm() / b[2].norm()):.2e}")
+    for name in ("fine", "pipe"):
+        for c, a, b in zip(CASES, res[name], res["three"]):
+            same = all(torch.equal(x, y) for x, y in zip(a, b))
+            ok &= same
+            print(name, c, "bit-identical" if same else f"MISMATCH loss {float(a[0])} vs {float(b[0])} grad rel {float((a[2] - b[2]).norm() / b[2].norm()):.2e}")
     print("pipe_check", "PASS" if ok else "FAIL")
     sys.exit(0 if ok else 1)
 
