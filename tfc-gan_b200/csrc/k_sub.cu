@@ -6,6 +6,7 @@
 
 #include "launchers.h"
 #include "sub_tile.cuh"
+#include "sub_ring.cuh"
 
 namespace tfcfft {
 
@@ -404,7 +405,18 @@ int launch_sub(Params prm, cudaStream_t st) {
         const int grid_f = units < sms * per_sm_f ? units : sms * per_sm_f;
         const int grid_i = units < sms * per_sm_i ? units : sms * per_sm_i;
         cudaError_t e;
-        if (cluster) {  // 2-CTA clusters: full-sector loads, halves exchanged through DSMEM
+        // ring-fed forward launch (sub_ring.cuh): bit-identical, 32.4 vs 35.7 us alone under ncu, but the STEP is 4 %
+        // slower (77.0 vs 74.1 us; rgb 190 vs 153 us) -- its 207 KB CTA cannot become resident while the previous
+        // call's inverse CTAs drain, and 72 KB of ring is not enough bytes in flight per SM -- so it is opt-in
+        static const bool use_ring = getenv("TFCFFT_SUB_FWD_RING") != nullptr;
+        int ring_rc = TFCFFT_ERR_STRIDE;
+        if (D == 4 && use_ring && !prm.fine_deps && ring_addressable<T>(prm)) ring_rc = launch_sub_fwd_ring<T, LUMA3>(prm, st);
+        if (ring_rc == 0) {
+            e = cudaSuccess;
+            g_launches--;  // counted by the ring launcher; the common increment follows below
+        } else if (ring_rc != TFCFFT_ERR_STRIDE) {
+            return ring_rc;
+        } else if (cluster) {  // 2-CTA clusters: full-sector loads, halves exchanged through DSMEM
             e = launch_pdl(kf4, grid_f & ~1, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st, prm);
         } else {
             e = launch_pdl(kf, grid_f, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st, prm);

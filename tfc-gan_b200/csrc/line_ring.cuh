@@ -373,7 +373,8 @@ template <> struct TmaType<uint8_t> { static constexpr CUtensorMapDataType v = C
 
 // box [1][NC][RPS][64] over [N][C][H][W] with the tensor's own strides (views are fine: strides are multiples of 16 bytes)
 template <typename T>
-inline bool make_tile_map(CUtensorMap* map, const void* base, const long long* st, const Params& prm, int nc, int rps) {
+inline bool make_tile_map(CUtensorMap* map, const void* base, const long long* st, const Params& prm, int nc, int rps,
+                          int box_w = 64, int row_step = 1) {
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return false;
     const cuuint64_t es = sizeof(T);
@@ -386,8 +387,9 @@ inline bool make_tile_map(CUtensorMap* map, const void* base, const long long* s
     const cuuint64_t chan = stride(st[1], row);
     const cuuint64_t img = stride(st[0], chan);
     const cuuint64_t strides[3] = {row, chan, img};
-    const cuuint32_t box[4] = {64u, (cuuint32_t)rps, (cuuint32_t)nc, 1u};
-    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    // a traversal stride s along H loads every s-th row: the box then spans rps * s rows of the tensor
+    const cuuint32_t box[4] = {(cuuint32_t)box_w, (cuuint32_t)(rps * row_step), (cuuint32_t)nc, 1u};
+    const cuuint32_t estr[4] = {1u, (cuuint32_t)row_step, 1u, 1u};
     return enc(map, TmaType<T>::v, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }

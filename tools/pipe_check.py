@@ -11,7 +11,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-CASES = [(1, 256, 3, "luma"), (1, 256, 64, "luma"), (2, 256, 37, "luma"), (2, 256, 256, "luma"), (1, 256, 20, "rgb"),
+CASES = [(1, 256, 1, "luma"), (2, 512, 5, "luma"), (1, 256, 3, "luma"), (1, 256, 64, "luma"), (2, 256, 37, "luma"), (2, 256, 256, "luma"), (1, 256, 20, "rgb"),
          (4, 512, 9, "luma"), (2, 256, 600, "luma"), (1, 256, 130, "luma")]
 
 
@@ -36,15 +36,16 @@ def main():
     if len(sys.argv) > 1:
         return worker(sys.argv[1])
     res = {}
-    for name, env in (("fine", {"TFCFFT_FINE_DEPS": "1"}), ("pipe", {"TFCFFT_SUB_PIPE": "1"}), ("three", {})):
+    for name, env in (("ring", {"TFCFFT_SUB_FWD_RING": "1"}), ("fine", {"TFCFFT_FINE_DEPS": "1"}),
+                      ("pipe", {"TFCFFT_SUB_PIPE": "1"}), ("three", {})):
         path = f"/tmp/pipe_check_{name}.pt"
-        p = subprocess.run([sys.executable, __file__, path], env={**os.environ, **env}, timeout=100)
+        p = subprocess.run([sys.executable, __file__, path], env={**os.environ, **env}, timeout=100, stdout=subprocess.DEVNULL)
         if p.returncode != 0:
             print("pipe_check", name, "FAILED rc", p.returncode)
             sys.exit(1)
         res[name] = torch.load(path)
     ok = True
-    for name in ("fine", "pipe"):
+    for name in ("ring", "fine", "pipe"):
         for c, a, b in zip(CASES, res[name], res["three"]):
             same = all(torch.equal(x, y) for x, y in zip(a, b))
             ok &= same
