@@ -121,7 +121,11 @@ def test_half_precision_io(dtype, grid):
                                                   grid=grid, input_scale=255.0)
     assert loss.item() == pytest.approx(l, rel=LOSS_TOL)
     assert f.grad.dtype == dtype
-    # the gradient is rounded to the 16-bit storage type on the way out
+    # the gradient is rounded to the 16-bit storage type on the way out: against the oracle gradient ROUNDED THE SAME
+    # WAY the contract tolerance (1e-3) holds -- the kernel's only extra error is that one rounding (fp16 gradients are
+    # stored with a power-of-two prescale that backward divides out, so they do not go subnormal)
+    want = torch.from_numpy(g).to(dtype).float().numpy()
+    assert l2rel(f.grad.float().cpu().numpy(), want) <= 1e-3
     assert l2rel(f.grad.float().cpu().numpy(), g) <= (2e-3 if dtype == torch.float16 else 1e-2)
 
 

@@ -190,11 +190,16 @@ TFC_HD void line_bins(const Ctx& ctx, const Params& prm, float2* s, float& accA,
     constexpr int NE = LineCfg::BIN_EVALS;
     // a thread owns spectrum row ky and walks the columns kx = 1..31 (Z(k) at rk[kx], Z(-k) at rm[-kx]): two pointers,
     // no per-bin index arithmetic; consecutive threads = consecutive rows (odd pitch: conflict-free both ways)
-    for (int ky = ctx.tid; ky < 64; ky += ctx.nthreads) {
+    // work item t = spectrum row ky (t & 63) x part of the column range: groups of 64 threads take all of kx = 1..31,
+    // groups of 128 split it 1..16 | 17..31
+    const int parts = ctx.nthreads >= 128 ? 2 : 1;
+    for (int t = ctx.tid; t < 64 * parts; t += ctx.nthreads) {
+        const int ky = t & 63, part = t >> 6;
         float2* rk = s + ky * LD;
         float2* rm = s + ((64 - ky) & 63) * LD + 64;
+        const int kx_lo = 1 + 16 * part, kx_hi = parts == 2 ? (part ? 32 : 17) : 32;
 #pragma unroll 1
-        for (int kx0 = 1; kx0 < 32; kx0 += 2 * NE) {
+        for (int kx0 = kx_lo; kx0 < kx_hi; kx0 += 2 * NE) {
             float2 zk[NE][2], zm[NE][2];
             bool live[NE][2];
 #pragma unroll
@@ -202,7 +207,7 @@ TFC_HD void line_bins(const Ctx& ctx, const Params& prm, float2* s, float& accA,
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int kx = kx0 + 2 * e + u;
-                    live[e][u] = kx < 32;
+                    live[e][u] = kx < kx_hi;
                     zk[e][u] = live[e][u] ? rk[kx] : z0;
                     zm[e][u] = live[e][u] ? rm[-kx] : z0;
                 }
@@ -364,17 +369,140 @@ TFC_HD void line_fft_pass(const Ctx& ctx, float2* s, int pass) {
     }
 }
 
+// ================================================================================================================
+// Half-line engine: TWO threads per transform line (128 threads per tile).
+//
+// The thread-per-line engine holds 64 complex values per thread (~160 registers): a tile gets two warps and an SM
+// whose shared memory holds four tiles runs eight compute warps -- ncu shows the fixed-latency `wait` stall on top and
+// issue slots 43 % busy (profiles/r02_ncu_patch16_line_ring_final_summary.txt).  Here a line is split with one
+// decimation-in-frequency radix-2 step across two threads (in different warps, no shuffles):
+//     h = 0:  a[n] = x[n] + x[n+32]                 ->  X[2m]   = DFT32(a)[m]
+//     h = 1:  b[n] = (x[n] - x[n+32]) * W64^n       ->  X[2m+1] = DFT32(b)[m]
+// Each thread reads the whole line (smem bandwidth has head room: 23 % busy), keeps 32 complex values (~100
+// registers) and writes its 32 outputs, so a tile gets FOUR warps at the same shared memory: twice the resident
+// warps per SM to hide the fixed latencies.  All passes share one rolled copy of the 32-point core (`fft32<false>`;
+// inverse passes store at mirrored indices, as in line_fft_pass); the half-zero input of the inverse rows halves its
+// loads for free (x[n+32] = 0 for n >= 1).
+// ================================================================================================================
+template <bool INV, int N1, int K2>
+TFC_HD void fft32_twiddle_row(float2* v) {  // v[N1 + 4*k2] *= W32^{N1*k2} for k2 = K2 .. 7
+    if constexpr (K2 < 8) {
+        v[N1 + 4 * K2] = mul_w<32, N1 * K2, INV>(v[N1 + 4 * K2]);
+        fft32_twiddle_row<INV, N1, K2 + 1>(v);
+    }
+}
+// In-register 32-point DFT = 4 x 8.  Input natural order v[n]; output X[k2 + 8*k1] is left in slot k1 + 4*k2.
+template <bool INV>
+TFC_HD void fft32(float2* v) {
+#pragma unroll
+    for (int n1 = 0; n1 < 4; ++n1) {
+        float2 u[8];
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) u[n2] = v[n1 + 4 * n2];
+        Dft<8, INV>::run(u);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) v[n1 + 4 * k2] = u[k2];
+    }
+    fft32_twiddle_row<INV, 1, 1>(v);
+    fft32_twiddle_row<INV, 2, 1>(v);
+    fft32_twiddle_row<INV, 3, 1>(v);
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) Dft<4, INV>::run(v + 4 * k2);
+}
+TFC_HD constexpr int fft32_freq(int slot) { return (slot >> 2) + 8 * (slot & 3); }
+
+template <int N>
+TFC_HD float2 half_in(float2 xl, float2 xh, int h) {  // radix-2 DIF input of half h
+    return h ? mul_w64<N, false>(csub(xl, xh)) : cadd(xl, xh);
+}
+template <int N, int END, class Load>
+TFC_HD void half_load(float2* a, int h, const Load& ld) {
+    if constexpr (N < END) {
+        a[N] = half_in<N>(ld(N), ld(N + 32), h);
+        half_load<N + 1, END>(a, h, ld);
+    }
+}
+template <int N, int END, class Load>
+TFC_HD void half_load_lo(float2* a, int h, const Load& ld) {  // x[n + 32] == 0
+    if constexpr (N < END) {
+        a[N] = h ? mul_w64<N, false>(ld(N)) : ld(N);
+        half_load_lo<N + 1, END>(a, h, ld);
+    }
+}
+
+// One half-line: load + radix-2 step + 32-point core.  a[sl] = X[2 * fft32_freq(sl) + h] of the line's 64-point DFT.
+TFC_HD void half_line_compute(float2* s, int pass, int l, int h, float2* a) {
+    constexpr int LD = LineCfg::LD;
+    const float2* row = s + l * LD;
+    const float2* col = s + l;
+    if (pass == 0) {
+        half_load<0, 32>(a, h, [&](int n) { return row[line_slot(n)]; });
+    } else if (pass == 3) {
+        // row[0] = (u_0(y), u_32(y)): real inverse transforms of columns 0 and 32; columns 33..63 are exact zeros
+        const float2 u = row[0];
+        a[0] = h ? make_float2(u.x - u.y, 0.f) : make_float2(u.x + u.y, 0.f);
+        half_load_lo<1, 32>(a, h, [&](int n) { return row[n]; });
+    } else {
+        half_load<0, 32>(a, h, [&](int n) { return col[n * LD]; });
+    }
+    fft32<false>(a);
+}
+// position of frequency f = 2 F + h of a MIRRORED store (inverse passes): (64 - f) mod 64
+TFC_HD int half_mirror(int F, int h) { return F == 0 ? (h ? 63 : 0) : 64 - 2 * F - h; }
+TFC_HD void half_line_store(float2* s, int pass, int l, int h, const float2* a) {
+    constexpr int LD = LineCfg::LD;
+    float2* row = s + l * LD;
+    float2* col = s + l;
+    if (pass == 0) {
+#pragma unroll
+        for (int sl = 0; sl < 32; ++sl) row[2 * fft32_freq(sl) + h] = a[sl];
+    } else if (pass == 1) {
+#pragma unroll
+        for (int sl = 0; sl < 32; ++sl) col[(2 * fft32_freq(sl) + h) * LD] = a[sl];
+    } else if (pass == 2) {
+#pragma unroll
+        for (int sl = 0; sl < 32; ++sl) col[half_mirror(fft32_freq(sl), h) * LD] = a[sl];
+    } else {
+        float* g = reinterpret_cast<float*>(row);  // gradient row as floats, pixel x at float index x
+#pragma unroll
+        for (int sl = 0; sl < 32; ++sl) g[half_mirror(fft32_freq(sl), h)] = a[sl].x;
+    }
+}
+// All four passes, 128 threads per tile (thread = line + 64 * half); ends with the data stored but NOT yet
+// synchronised (the caller's barrier follows, as for line_fft_pass).  Both halves of a line read the whole line and
+// write into it: a barrier separates the loads from the stores.
+template <class Ctx>
+TFC_HD void line2_fft_pass(const Ctx& ctx, float2* s, int pass) {
+    const int nlines = pass == 2 ? 32 : 64;
+    if (ctx.nthreads == 128) {
+        const int l = ctx.tid & 63, h = ctx.tid >> 6;
+        float2 a[32];
+        if (l < nlines) half_line_compute(s, pass, l, h, a);
+        ctx.sync();
+        if (l < nlines) half_line_store(s, pass, l, h, a);
+    } else {  // serial emulation: a line at a time, both halves before either store
+        for (int l = ctx.tid; l < nlines; l += ctx.nthreads) {
+            float2 a0[32], a1[32];
+            half_line_compute(s, pass, l, 0, a0);
+            half_line_compute(s, pass, l, 1, a1);
+            half_line_store(s, pass, l, 0, a0);
+            half_line_store(s, pass, l, 1, a1);
+        }
+    }
+}
+
 // ---- gradient store: rows of floats -> global, 128-bit stores ----------------------------------------
 template <typename T, bool LUMA3, bool ACC, class Ctx>
 TFC_HD void line_store_rows(const Ctx& ctx, const GradOut& go, T* gp, int sh, int sc, const float2* s) {
     constexpr int LD = LineCfg::LD, NC = LUMA3 ? 3 : 1;
-    if (ctx.nthreads == 64) {
+    if (ctx.nthreads == 64 || ctx.nthreads == 128) {
         // a thread keeps its 4-pixel column and walks down the rows: one pointer bump per row, no index arithmetic
         const int x = (ctx.tid & 15) * 4, y0 = ctx.tid >> 4;
+        const int rstep = ctx.nthreads / 16;  // rows per sweep of the group: 4 or 8
         T* p = gp + y0 * sh + x;
         const float* g = reinterpret_cast<const float*>(s + y0 * LD) + x;
 #pragma unroll 4
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 64 / rstep; ++j) {
             const float2 lo = *reinterpret_cast<const float2*>(g), hi = *reinterpret_cast<const float2*>(g + 2);
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
@@ -387,8 +515,8 @@ TFC_HD void line_store_rows(const Ctx& ctx, const GradOut& go, T* gp, int sh, in
                 }
                 IO<T>::store4(p + c * sc, v);
             }
-            p += 4 * sh;
-            g += 4 * LD * 2;
+            p += rstep * sh;
+            g += rstep * LD * 2;
         }
     } else {
         for (int it = ctx.tid; it < 64 * 16; it += ctx.nthreads) {
