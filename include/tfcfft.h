@@ -53,6 +53,7 @@ enum tfcfft_dtype { TFCFFT_F32 = 0, TFCFFT_F16 = 1, TFCFFT_BF16 = 2, TFCFFT_U8 =
                                             loss terms share one gradient buffer without an extra add pass    */
 #define TFCFFT_TEMPS_POSITIVE (1u << 9) /* tfcfft_temperature_triplet only: `positive` is an fp32 tensor of
                                            temperatures (the loader's T_B), not an image                  */
+#define TFCFFT_USE_HALFLINE  (1u << 27) /* testing / A-B: 64x64 tiles on the half-line engine (two threads per line) */
 #define TFCFFT_USE_PAIR      (1u << 28) /* testing: 64x64 tiles through the packed pair kernel            */
 #define TFCFFT_USE_LINE      (1u << 29) /* testing: 64x64 tiles through the thread-per-line kernel        */
 #define TFCFFT_FORCE_GENERIC (1u << 30) /* testing: bypass the packed 64x64 fast path                */

@@ -211,3 +211,21 @@ def test_real_axis_phase_signs(cf, cr, grid):
     assert out[0] == pytest.approx(l, rel=1e-4)
     assert out[2] == pytest.approx(p, rel=1e-4)
     assert l2rel(g, go) <= 1e-3
+
+
+@pytest.mark.parametrize("opt", [dict(), dict(channels="rgb"), dict(distance="mse"), dict(use_phase=False)],
+                         ids=["default", "rgb", "mse", "amp-only"])
+def test_half_line_engine_matches_oracle(opt):
+    """The half-line engine (two threads per line, 32-point core, line_tile.cuh: line2_fft_pass) executed serially:
+    same loss and gradient as the fp64 oracle, and the thread-per-line engine to rounding."""
+    fake, real = make_pair("tanh", 321, (2, 3, 256, 256), "float32")
+    base = flags_of(**opt)
+    rc, out_h, _, g_h = emulate(fake, real, 4, base | L.USE_HALFLINE, weight=0.01, input_scale=255.0)
+    assert rc == 0
+    rc, out_l, _, g_l = emulate(fake, real, 4, base, weight=0.01, input_scale=255.0)
+    assert rc == 0
+    l, a, p, g = oracle.spectral_loss_and_grad_r1(fake, real, grid=4, weight=0.01, input_scale=255.0, **opt)
+    assert out_h[0] == pytest.approx(l, rel=1e-4)
+    assert l2rel(g_h, g) <= 1e-3
+    assert out_h[0] == pytest.approx(out_l[0], rel=2e-6)
+    assert l2rel(g_h, g_l) <= 1e-4

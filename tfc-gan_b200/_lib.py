@@ -27,6 +27,7 @@ FULL_SPECTRUM = 1 << 5
 QUANTIZE_U8 = 1 << 6
 GRAD_ACCUMULATE = 1 << 8
 TEMPS_POSITIVE = 1 << 9
+USE_HALFLINE = 1 << 27
 USE_PAIR = 1 << 28
 USE_LINE = 1 << 29
 FORCE_GENERIC = 1 << 30

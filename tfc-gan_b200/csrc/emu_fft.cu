@@ -31,7 +31,7 @@ void run_line(Params prm) {
     std::vector<float2> s((size_t)64 * LineCfg::LD);
     for (int tile = 0; tile < prm.tiles_total; ++tile) {
         float a = 0.f, p = 0.f;
-        line_process<T, LUMA3>(ctx, prm, tile, s.data(), a, p);
+        line_process<T, LUMA3>(ctx, prm, tile, s.data(), a, p, -1, (prm.flags & TFCFFT_USE_HALFLINE) != 0);
         prm.partials[2 * tile] = a;
         prm.partials[2 * tile + 1] = p;
     }

@@ -63,7 +63,7 @@ inline int validate_desc(const tfcfft_desc* d, Geometry* geo, bool allow_sub = t
     if (p != 16 && p != 32 && p != 64 && p != 128 && p != 256 && p != 512) return TFCFFT_ERR_SHAPE;
     const unsigned known = TFCFFT_CHANNELS_RGB | TFCFFT_NO_PHASE | TFCFFT_DIST_MSE | TFCFFT_PATCH_SUM |
                            TFCFFT_LOG_MAGNITUDE | TFCFFT_FULL_SPECTRUM | TFCFFT_QUANTIZE_U8 | TFCFFT_FORCE_SPLIT |
-                           TFCFFT_FORCE_GENERIC | TFCFFT_USE_LINE | TFCFFT_USE_PAIR | TFCFFT_GRAD_ACCUMULATE;
+                           TFCFFT_FORCE_GENERIC | TFCFFT_USE_LINE | TFCFFT_USE_PAIR | TFCFFT_GRAD_ACCUMULATE | TFCFFT_USE_HALFLINE;
     if (d->flags & ~known) return TFCFFT_ERR_FLAGS;
     // the reference quantises to a single grey channel; a per-channel quantised variant does not exist
     if ((d->flags & TFCFFT_QUANTIZE_U8) && (d->flags & TFCFFT_CHANNELS_RGB) && d->c == 3) return TFCFFT_ERR_FLAGS;

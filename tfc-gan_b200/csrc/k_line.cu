@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(LineCfg::NT, 6) line_kernel(const __grid_const
         float a = 0.f, p = 0.f;
         ctx.trace = (prm.trace != nullptr && iter < 6) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
         const int nt = tile + (int)gridDim.x;
-        line_process<T, LUMA3>(ctx, prm, tile, s, a, p, nt < prm.tiles_total ? nt : -1);
+        line_process<T, LUMA3>(ctx, prm, tile, s, a, p, nt < prm.tiles_total ? nt : -1, false);
         block_sum2(a, p);
         if (threadIdx.x == 0) {
             prm.partials[2 * tile] = a;

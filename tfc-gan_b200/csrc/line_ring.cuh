@@ -36,15 +36,16 @@ namespace tfcfft {
 // (an L2 look-ahead with TMA prefetches, 1-2 tiles per CTA, was measured and lost 1-4 %: the ring already covers HBM latency)
 
 constexpr int kRingSlotBytes = 12288;  // one slab: fake + real, NC channels, RPS rows of 64 pixels
-template <int G_, int RING_>
+template <int G_, int RING_, int NTG_ = 64>
 struct RingCfgT {
     static constexpr int G = G_;                       // worker groups (tiles in flight) per CTA
     static constexpr int RING = RING_;                 // raw slabs in flight
+    static constexpr int NTG = NTG_;                   // threads per worker group: 64 = thread per line, 128 = half-line engine
     static constexpr int SLOT_BYTES = kRingSlotBytes;
-    static constexpr int NT = 64 * G + 32;             // workers + producer warp
+    static constexpr int NT = NTG * G + 32;            // workers + producer warp
     static constexpr int TILE_BYTES = (int)LineCfg::SMEM;  // 64 x 65 float2
     static constexpr int BAR_BYTES = 256;              // full[RING], empty[RING] (8 bytes each)
-    static constexpr size_t SMEM = (size_t)G * TILE_BYTES + (size_t)RING * SLOT_BYTES + BAR_BYTES + 16 * G;
+    static constexpr size_t SMEM = (size_t)G * TILE_BYTES + (size_t)RING * SLOT_BYTES + BAR_BYTES + 32 * G;
     static_assert(2 * RING * 8 + 8 <= BAR_BYTES, "barrier area too small");
     static_assert(SMEM + 2048 <= 227 * 1024, "ring configuration exceeds the shared memory of an SM");
 };
@@ -143,29 +144,31 @@ template <> struct SlabIO<uint8_t> {
 };
 
 // execution context of one 64-thread worker group: its own named barrier
-struct RingWorkerCtx {
+template <int NTG>
+struct RingWorkerCtxT {
     int tid, bar;
-    static constexpr int nthreads = 64;
-    __device__ __forceinline__ void sync() const { bar_sync(bar, 64); }
+    static constexpr int nthreads = NTG;
+    __device__ __forceinline__ void sync() const { bar_sync(bar, NTG); }
     __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
     __device__ __forceinline__ void mark(int) const {}
 };
+using RingWorkerCtx = RingWorkerCtxT<64>;
 
 // ---- worker: one slab (rows y0 .. y0 + RPS - 1 of the tile) -> luma -> work tile ---------------------------------
 // slab layout: [fake | real][channel][row][64 pixels]; work tile layout as line_load (line_slot permutation).
 // Returns false as soon as a fake pixel differs from the real pixel (after luma): the tile-level `fake == real` test.
-template <typename T, bool LUMA3>
+template <typename T, bool LUMA3, int NTG = 64>
 __device__ __forceinline__ bool ring_convert(const Params& prm, const unsigned char* slab, int y0, int tid, float2* s) {
     constexpr int NC = LUMA3 ? 3 : 1, LD = LineCfg::LD;
     using SL = RingSlab<T, NC>;
     constexpr int RPS = SL::RPS, RB = SL::ROW_BYTES, PX4 = 4 * (int)sizeof(T);
     const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
     bool same = true;
-    constexpr int ITEMS = RPS * 16, PER = ITEMS / 64;  // 4-pixel items per thread
-    static_assert(ITEMS % 64 == 0, "slab items must divide over the group");
+    constexpr int ITEMS = RPS * 16, PER = ITEMS / NTG;  // 4-pixel items per thread
+    static_assert(ITEMS % NTG == 0, "slab items must divide over the group");
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
-        const int it = tid + 64 * u, x4 = it & 15, r = it >> 4;
+        const int it = tid + NTG * u, x4 = it & 15, r = it >> 4;
         float raw[2][NC][4];
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -230,7 +233,7 @@ template <typename T, bool LUMA3, class RingCfg>
 __global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_constant__ Params prm,
                                                                     const __grid_constant__ CUtensorMap map_fake,
                                                                     const __grid_constant__ CUtensorMap map_real) {
-    constexpr int G = RingCfg::G, RING = RingCfg::RING, NC = LUMA3 ? 3 : 1;
+    constexpr int G = RingCfg::G, RING = RingCfg::RING, NC = LUMA3 ? 3 : 1, NTG = RingCfg::NTG;
     using SL = RingSlab<T, NC>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* ring = smem_raw;                                                   // RING slots
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_
     if (tid == 0) {
         for (int i = 0; i < RING; ++i) {
             mbar_init(full0 + 8 * i, 1);    // one arrive.expect_tx by the producer + the copies' bytes
-            mbar_init(empty0 + 8 * i, 64);  // every thread of the consuming group
+            mbar_init(empty0 + 8 * i, NTG);  // every thread of the consuming group
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         *turn = 0u;
@@ -255,9 +258,9 @@ __global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_
     pdl_wait();
     // tiles of this CTA: blockIdx.x + k * gridDim.x, k = 0 .. ntiles - 1; tile k belongs to worker k % G
     const int ntiles = ((int)prm.tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    if (tid >= 64 * G) {
+    if (tid >= NTG * G) {
         // ---------------- producer warp: raw row slabs -> ring (one elected lane issues the TMA copies) --------
-        if (tid == 64 * G) {
+        if (tid == NTG * G) {
             const unsigned long long pol = policy_evict_first();
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&map_fake)) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&map_real)) : "memory");
@@ -278,10 +281,10 @@ __global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_
         }
     } else {
         // ---------------- worker groups ----------------
-        const int w = tid >> 6, gtid = tid & 63;
-        const RingWorkerCtx ctx{gtid, w + 1};  // named barrier id w + 1 (id 0 is __syncthreads)
+        const int w = tid / NTG, gtid = tid % NTG;
+        const RingWorkerCtxT<NTG> ctx{gtid, w + 1};  // named barrier id w + 1 (id 0 is __syncthreads)
         float2* s = tiles + (size_t)w * (RingCfg::TILE_BYTES / sizeof(float2));
-        float* red = scratch + 4 * w;
+        float* red = scratch + 8 * w;
         const bool want_grad = prm.grad != nullptr;
         for (int k = w; k < ntiles; k += G) {
             const int tile = (int)blockIdx.x + k * (int)gridDim.x;
@@ -296,15 +299,15 @@ __global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_
                 const unsigned slot = c % RING, ph = (c / RING) & 1;
                 mbar_wait(full0 + 8 * slot, ph);
                 if (i == SL::SLABS - 1 && gtid == 0) *turn = (unsigned)k + 1u;  // the next worker may start waiting
-                same = ring_convert<T, LUMA3>(prm, ring + slot * RingCfg::SLOT_BYTES, i * SL::RPS, gtid, s) && same;
+                same = ring_convert<T, LUMA3, NTG>(prm, ring + slot * RingCfg::SLOT_BYTES, i * SL::RPS, gtid, s) && same;
                 mbar_arrive(empty0 + 8 * slot);
             }
             // group vote: is fake == real on the whole tile?  (the barrier also publishes the work tile)
             int all_same;
             asm volatile(
-                "{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbar.red.and.pred q, %2, 64, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+                "{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbar.red.and.pred q, %2, %3, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
                 : "=r"(all_same)
-                : "r"((int)same), "r"(w + 1)
+                : "r"((int)same), "r"(w + 1), "r"(NTG)
                 : "memory");
             float a = 0.f, p = 0.f;
             if (all_same) {
@@ -315,8 +318,9 @@ __global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_
             } else {
                 const int npass = want_grad ? 4 : 2;
 #pragma unroll 1
-                for (int pass = 0; pass < npass; ++pass) {  // rolled: ONE copy of the 64-point core (line_fft_pass)
-                    line_fft_pass(ctx, s, pass);
+                for (int pass = 0; pass < npass; ++pass) {  // rolled: ONE copy of the transform core
+                    if constexpr (NTG == 128) line2_fft_pass(ctx, s, pass);  // two threads per line, 32-point core
+                    else line_fft_pass(ctx, s, pass);
                     ctx.sync();
                     if (pass == 1) {
                         line_bins(ctx, prm, s, a, p);
@@ -340,8 +344,14 @@ __global__ void __launch_bounds__(RingCfg::NT, 1) line_ring_kernel(const __grid_
             }
             ctx.sync();
             if (gtid == 0) {
-                prm.partials[2 * tile] = red[0] + red[2];
-                prm.partials[2 * tile + 1] = red[1] + red[3];
+                float sa = 0.f, sp = 0.f;
+#pragma unroll
+                for (int i = 0; i < NTG / 32; ++i) {
+                    sa += red[2 * i];
+                    sp += red[2 * i + 1];
+                }
+                prm.partials[2 * tile] = sa;
+                prm.partials[2 * tile + 1] = sp;
             }
             ctx.sync();  // `red` is reused by the next tile
         }
@@ -436,13 +446,16 @@ int launch_line_ring(const Params& prm, cudaStream_t st) {
     if (sel != nullptr) {
         const std::string v(sel);
         if (v == "4x7") return launch_line_ring_cfg<T, LUMA3, RingCfgT<4, 7>>(prm, st);
-        if (v == "6x2") return launch_line_ring_cfg<T, LUMA3, RingCfgT<6, 2>>(prm, st);
         if (v == "5x3") return launch_line_ring_cfg<T, LUMA3, RingCfgT<5, 3>>(prm, st);
-        if (v == "3x8") return launch_line_ring_cfg<T, LUMA3, RingCfgT<3, 8>>(prm, st);
         if (v == "5x4") return launch_line_ring_cfg<T, LUMA3, RingCfgT<5, 4>>(prm, st);
         if (v == "4x6") return launch_line_ring_cfg<T, LUMA3, RingCfgT<4, 6>>(prm, st);
+        if (v == "4x7") return launch_line_ring_cfg<T, LUMA3, RingCfgT<4, 7>>(prm, st);
+        if (v == "h4x7") return launch_line_ring_cfg<T, LUMA3, RingCfgT<4, 7, 128>>(prm, st);
+        if (v == "h3x8") return launch_line_ring_cfg<T, LUMA3, RingCfgT<3, 8, 128>>(prm, st);
+        if (v == "h4x6") return launch_line_ring_cfg<T, LUMA3, RingCfgT<4, 6, 128>>(prm, st);
     }
 #endif
+    if (prm.flags & TFCFFT_USE_HALFLINE) return launch_line_ring_cfg<T, LUMA3, RingCfgT<4, 7, 128>>(prm, st);
     // single-channel tiles (per-channel rgb mode, grey inputs): three times the transforms per byte, so the ring can be
     // shallower and a fifth worker pays (measured 0.820 vs 0.786 M img/s on patch-16 rgb b256)
     if constexpr (!LUMA3) return launch_line_ring_cfg<T, LUMA3, RingCfgT<5, 4>>(prm, st);

@@ -562,7 +562,7 @@ TFC_HD void line_prefetch_l2(const Ctx& ctx, const Params& prm, const TileCoord&
 // ---- one tile ---------------------------------------------------------------------------------------
 template <typename T, bool LUMA3, class Ctx>
 TFC_HD void line_process(const Ctx& ctx, const Params& prm, int tile, float2* s, float& accA, float& accP,
-                         int next_tile = -1) {
+                         int next_tile = -1, bool halfline = false) {
     const TileCoord tc = decode_tile(prm, tile);
     ctx.mark(0);
     line_load<T, LUMA3>(ctx, prm, tc, s);
@@ -572,7 +572,8 @@ TFC_HD void line_process(const Ctx& ctx, const Params& prm, int tile, float2* s,
     const int npass = want_grad ? 4 : 2;
 #pragma unroll 1
     for (int pass = 0; pass < npass; ++pass) {  // rolled: ONE copy of the 64-point core in the kernel
-        line_fft_pass(ctx, s, pass);
+        if (halfline) line2_fft_pass(ctx, s, pass);  // CPU emulation of the half-line engine (TFCFFT_USE_HALFLINE)
+        else line_fft_pass(ctx, s, pass);
         if (pass == 2 && next_tile >= 0) line_prefetch_l2<T, LUMA3>(ctx, prm, decode_tile(prm, next_tile));
         ctx.sync();
         ctx.mark(pass < 2 ? 2 + pass : 3 + pass);

@@ -39,6 +39,7 @@ class SpectralConfig:
     force_generic: bool = False  # testing: bypass the packed 64x64 fast path
     use_line: bool = False       # testing: 64x64 tiles through the thread-per-line kernel
     use_pair: bool = False       # testing: 64x64 tiles through the packed pair kernel
+    use_halfline: bool = False   # testing / A-B: 64x64 tiles on the half-line engine (two threads per line)
 
     def flags(self) -> int:
         if self.channels not in ("luma", "rgb"):
@@ -72,6 +73,8 @@ class SpectralConfig:
             f |= _lib.USE_LINE
         if self.use_pair:
             f |= _lib.USE_PAIR
+        if self.use_halfline:
+            f |= _lib.USE_HALFLINE
         return f
 
 

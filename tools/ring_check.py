@@ -20,14 +20,15 @@ def main():
         g = torch.Generator(device="cuda").manual_seed(n)
         f = torch.empty(n, 3, 256, 256, device="cuda").uniform_(-1, 1, generator=g).to(dt)
         r = torch.empty(n, 3, 256, 256, device="cuda").uniform_(-1, 1, generator=g).to(dt)
-        la, ta, ga = tfc.spectral_loss_and_grad(f, r, grid=4, channels=ch, weight=0.01, input_scale=255.0)
         lb, tb, gb = tfc.spectral_loss_and_grad(f, r, grid=4, channels=ch, weight=0.01, input_scale=255.0, force_generic=True)
-        torch.cuda.synchronize()
-        dl = abs(la.item() - lb.item()) / abs(lb.item())
-        dg = ((ga.float() - gb.float()).norm() / gb.float().norm()).item()
-        good = dl < 2e-5 and dg < 3e-3  # one marginal L1 sign flip between two fp32 kernels moves this by ~1e-3
-        ok &= good
-        print(f"n={n:4d} {ch:4s} {str(dt):15s} loss {la.item():.6f} vs {lb.item():.6f} (rel {dl:.1e})  grad rel {dg:.1e}  {'ok' if good else 'MISMATCH'}", flush=True)
+        for half in (False, True):  # thread-per-line and half-line ring kernels
+            la, ta, ga = tfc.spectral_loss_and_grad(f, r, grid=4, channels=ch, weight=0.01, input_scale=255.0, use_halfline=half)
+            torch.cuda.synchronize()
+            dl = abs(la.item() - lb.item()) / abs(lb.item())
+            dg = ((ga.float() - gb.float()).norm() / gb.float().norm()).item()
+            good = dl < 2e-5 and dg < 3e-3  # one marginal L1 sign flip between two fp32 kernels moves this by ~1e-3
+            ok &= good
+            print(f"n={n:4d} {ch:4s} {str(dt):15s} half={int(half)} loss {la.item():.6f} vs {lb.item():.6f} (rel {dl:.1e})  grad rel {dg:.1e}  {'ok' if good else 'MISMATCH'}", flush=True)
     # identical inputs: exact zeros
     f = torch.empty(5, 3, 256, 256, device="cuda").uniform_(-1, 1)
     l, t, g = tfc.spectral_loss_and_grad(f, f.clone(), grid=4, weight=0.01, input_scale=255.0)
