@@ -29,6 +29,9 @@ CASES = [
     (256, 1, dict()),
     (256, 1, dict(channels="rgb", use_phase=False, log_magnitude=True, spectrum="full", distance="mse")),
     (512, 1, dict()),
+    (512, 1, dict(distance="mse", use_phase=False)),
+    (512, 1, dict(spectrum="full", log_magnitude=True)),
+    (512, 1, dict(force_split=True)),
     (256, 4, dict(force_split=True)),
     (256, 2, dict(force_split=True, channels="rgb")),
     (256, 1, dict(force_split=True)),

@@ -6,6 +6,7 @@
 #include "launchers.h"
 #include "pair_tile.cuh"
 #include "sub_tile.cuh"
+#include "combine8.cuh"
 #include "line_tile.cuh"
 
 using namespace tfcfft;
@@ -83,10 +84,37 @@ void run_sub(Params prm) {
                     sub_fwd_cols_store(ctx, prm, su, t);
                 }
             }
+        } else if (D == 8) {  // the 4-CTA cluster variant's load (sub_fwd_load_oct): four quarters, four column pairs
+            std::vector<float2> tb[4];
+            for (auto& t : tb) t.resize((size_t)2 * 64 * SubCfg::LD);
+            float2* const dst[4] = {tb[0].data(), tb[1].data(), tb[2].data(), tb[3].data()};
+            for (int w = 0; w < prm.chunk_now * 8; ++w) {
+                const TileCoord tc = decode_tile(prm, base + (w >> 3));
+                for (int quarter = 0; quarter < 4; ++quarter) sub_fwd_load_oct<T, LUMA3>(ctx, prm, tc, w & 7, quarter, dst);
+                for (int i = 0; i < 4; ++i) {
+                    SubUnit su;
+                    su.tile_local = w >> 3;
+                    su.p = w & 7;
+                    su.i = i;
+                    su.plane = su.p * 4 + i;
+                    sub_fwd_rows(ctx, dst[i]);
+                    sub_fwd_cols_store(ctx, prm, su, dst[i]);
+                }
+            }
         } else {
             for (int u = 0; u < prm.chunk_now * npp; ++u) sub_fwd_process<T, LUMA3>(ctx, prm, u, s.data());
         }
-        for (int lt = 0; lt < prm.chunk_now; ++lt) {
+        if (D == 8) {
+            std::vector<float2> sm(Combine8Cfg::SMEM / sizeof(float2));
+            for (int lt = 0; lt < prm.chunk_now; ++lt)
+                for (int row = 0; row < kCombine8Parts; ++row) {
+                    float a = 0.f, p = 0.f;
+                    combine8_rows(ctx, prm, sub_plane(prm, lt, 0), row, sm.data(), a, p);
+                    prm.partials[2 * ((size_t)(base + lt) * kCombine8Parts + row)] = a;
+                    prm.partials[2 * ((size_t)(base + lt) * kCombine8Parts + row) + 1] = p;
+                }
+        }
+        for (int lt = 0; lt < prm.chunk_now && D != 8; ++lt) {
             float2* ws_tile = sub_plane(prm, lt, 0);
             for (int part = 0; part < kCombineParts; ++part) {
                 float a = 0.f, p = 0.f;
@@ -113,6 +141,23 @@ void run_sub(Params prm) {
                 }
                 const TileCoord tc = decode_tile(prm, base + (w >> 2));
                 for (int half = 0; half < 2; ++half) sub_inv_store_quad<T, LUMA3>(ctx, prm, tc, w & 3, half, t0.data(), t1.data());
+            }
+        } else if (prm.grad && D == 8) {  // the 4-CTA cluster variant's store (sub_inv_store_oct)
+            std::vector<float2> tb[4];
+            for (auto& t : tb) t.resize((size_t)64 * SubCfg::LD);
+            const float2* const src[4] = {tb[0].data(), tb[1].data(), tb[2].data(), tb[3].data()};
+            for (int w = 0; w < prm.chunk_now * 8; ++w) {
+                for (int i = 0; i < 4; ++i) {
+                    SubUnit su;
+                    su.tile_local = w >> 3;
+                    su.p = w & 7;
+                    su.i = i;
+                    su.plane = su.p * 4 + i;
+                    sub_inv_cols(ctx, prm, su, tb[i].data());
+                    sub_inv_rows(ctx, tb[i].data());
+                }
+                const TileCoord tc = decode_tile(prm, base + (w >> 3));
+                for (int quarter = 0; quarter < 4; ++quarter) sub_inv_store_oct<T, LUMA3>(ctx, prm, tc, w & 7, quarter, src);
             }
         } else if (prm.grad) {
             for (int u = 0; u < prm.chunk_now * npp; ++u) sub_inv_process<T, LUMA3>(ctx, prm, u, s.data());
@@ -148,7 +193,7 @@ void run_split(Params prm) {
 
 template <int P, typename T, bool LUMA3>
 void run(const Params& prm, bool split) {
-    if ((P == 128 || P == 256) && prm.sub_d > 1) run_sub<T, LUMA3>(prm);
+    if ((P == 128 || P == 256 || P == 512) && prm.sub_d > 1) run_sub<T, LUMA3>(prm);
     else if (split) run_split<P, T, LUMA3>(prm);
     else if (P == 64 && pair_supported(prm) && !(prm.flags & TFCFFT_USE_PAIR)) run_line<T, LUMA3>(prm);
     else if (P == 64 && pair_supported(prm)) run_pair<P, T, LUMA3>(prm);

@@ -1,6 +1,7 @@
 // host_common.h -- argument validation, workspace layout and Params construction shared by the
 // C-ABI library (tfcfft_api.cu) and the CPU emulation library (emu.cu).
 #pragma once
+#include <cstdlib>
 #include <cstddef>
 #include <cstdint>
 
@@ -79,9 +80,10 @@ inline int validate_desc(const tfcfft_desc* d, Geometry* geo, bool allow_sub = t
         geo->p = (int)p;
         geo->luma3 = (d->c == 3) && !(d->flags & TFCFFT_CHANNELS_RGB);
         geo->cprime = (d->c == 3 && !geo->luma3) ? 3 : 1;
-        geo->sub = allow_sub && (p == 128 || p == 256) && !(d->flags & (TFCFFT_FORCE_SPLIT | TFCFFT_FORCE_GENERIC));
+        static const bool no_d8 = getenv("TFCFFT_NO_D8") != nullptr;  // A/B switch: 512 x 512 tiles back on the split kernels
+        geo->sub = allow_sub && (p == 128 || p == 256 || (p == 512 && !no_d8)) && !(d->flags & (TFCFFT_FORCE_SPLIT | TFCFFT_FORCE_GENERIC));
         geo->split = !geo->sub && ((p >= 256) || (d->flags & TFCFFT_FORCE_SPLIT));
-        geo->parts = geo->sub ? kCombineParts : geo->split ? split_parts((int)p) : 1;
+        geo->parts = geo->sub ? (p == 512 ? kCombine8Parts : kCombineParts) : geo->split ? split_parts((int)p) : 1;
         geo->tiles_total = (long long)d->n * geo->cprime * d->grid * d->grid;
         geo->partial_bytes = align_up((size_t)geo->tiles_total * geo->parts * 2 * sizeof(float), 256);
         geo->chunk_tiles = 0;

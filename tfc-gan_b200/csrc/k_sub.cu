@@ -6,6 +6,7 @@
 
 #include "launchers.h"
 #include "sub_tile.cuh"
+#include "combine8.cuh"
 #include "sub_ring.cuh"
 
 namespace tfcfft {
@@ -121,6 +122,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
     if (!prm.fine_deps) pdl_release();
 }
 
+// D = 8 forward launch as 4-CTA clusters: the four CTAs of a cluster own the four column pairs of one (tile, row
+// phase), load a quarter of the rows each with full-sector loads and hand the other CTAs their columns through
+// distributed shared memory (sub_fwd_load_oct).
+template <typename T, bool LUMA3>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd8_kernel(const __grid_constant__ Params prm) {
+    namespace cg = cooperative_groups;
+    pdl_wait();  // whole previous grid: this launch overwrites the workspace planes
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    float2* const dst[4] = {cl.map_shared_rank(s, 0), cl.map_shared_rank(s, 1), cl.map_shared_rank(s, 2), cl.map_shared_rank(s, 3)};
+    BlockCtxT<SubCfg::NT_FWD> ctx{(int)threadIdx.x, nullptr};
+    const int nrows = prm.chunk_now * 8;  // (tile, row phase)
+    cl.sync();                            // the peers' shared memory exists from here on
+    for (int w = blockIdx.x >> 2; w < nrows; w += gridDim.x >> 2) {
+        SubUnit su;
+        su.tile_local = w >> 3;
+        su.p = w & 7;
+        su.i = rank;
+        su.plane = su.p * 4 + rank;
+        sub_fwd_load_oct<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, dst);
+        cl.sync();
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the 64-point core
+            sub_fwd_pass(ctx, prm, su, s, pass);
+            if (pass == 0) ctx.sync();
+        }
+        cl.sync();  // the peers may refill my tiles only after my column pass has read them
+    }
+    pdl_release();
+}
+
 template <typename T, bool LUMA3>
 __global__ void __launch_bounds__(SubCfg::NT_INV, 6) sub_inv_kernel(const __grid_constant__ Params prm) {
     if (prm.fine_deps) pdl_release();
@@ -178,6 +212,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) s
     else pdl_release();
 }
 
+// D = 8 inverse launch as 4-CTA clusters (the four packed planes i = 0..3 of one (tile, row phase)): transforms as
+// in sub_inv_kernel, then each CTA stores a quarter of the rows with full-sector stores, reading the other column
+// pairs from the peers' shared memory (sub_inv_store_oct).
+template <typename T, bool LUMA3>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) sub_inv8_kernel(const __grid_constant__ Params prm) {
+    namespace cg = cooperative_groups;
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const float2* const src[4] = {cl.map_shared_rank(s, 0), cl.map_shared_rank(s, 1), cl.map_shared_rank(s, 2), cl.map_shared_rank(s, 3)};
+    BlockCtxT<SubCfg::NT_INV> ctx{(int)threadIdx.x, nullptr};
+    const int nrows = prm.chunk_now * 8;
+    cl.sync();
+    for (int w = blockIdx.x >> 2; w < nrows; w += gridDim.x >> 2) {
+        SubUnit su;
+        su.tile_local = w >> 3;
+        su.p = w & 7;
+        su.i = rank;
+        su.plane = su.p * 4 + rank;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the 64-point core
+            sub_inv_pass(ctx, prm, su, s, pass);
+            if (pass == 0) ctx.sync();
+        }
+        cl.sync();  // all four column pairs are ready
+        sub_inv_store_oct<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, src);
+        cl.sync();  // the peers have read my tile
+    }
+    pdl_release();
+}
+
 #if TFC_DT == 0
 // Launch 2: per-position D x D butterflies, loss, spectral gradient (registers + L2 only).
 template <int D>
@@ -212,7 +279,48 @@ __global__ void __launch_bounds__(kCombineThreads, 512 / kCombineThreads) combin
         finish(prm, (unsigned)prm.tiles_total * PARTS);
     }
 }
+#ifndef TFC_C8_MINB
+#define TFC_C8_MINB 2
+#endif
+// Launch 2 for 512 x 512 tiles: one CTA per (tile, row of the position grid), staged in shared memory (combine8.cuh).
+__global__ void __launch_bounds__(Combine8Cfg::NT, TFC_C8_MINB) combine8_kernel(const __grid_constant__ Params prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* sm = reinterpret_cast<float2*>(smem_raw);
+    constexpr int PARTS = kCombine8Parts;
+    const int lt = blockIdx.x / PARTS, row = blockIdx.x % PARTS;
+    pdl_wait();
+    float a = 0.f, p = 0.f;
+    const BlockCtx ctx{(int)threadIdx.x, Combine8Cfg::NT};
+    combine8_rows(ctx, prm, sub_plane(prm, lt, 0), row, sm, a, p);
+    pdl_release();
+    block_sum2(a, p);
+    if (threadIdx.x == 0) {
+        const long long slot = (long long)(prm.tile_base + lt) * PARTS + row;
+        prm.partials[2 * slot] = a;
+        prm.partials[2 * slot + 1] = p;
+    }
+    finish(prm, (unsigned)prm.tiles_total * PARTS);
+}
+// auxiliary stream + fork / join events of the two-lane schedule (launch_sub), one set per device, created on first use
+Lanes* lanes_get() {
+    static Lanes table[kMaxDevices];
+    static std::atomic<int> ready[kMaxDevices];
+    static std::mutex mu;
+    const int dev = current_device();
+    if (!ready[dev].load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!ready[dev].load(std::memory_order_relaxed)) {
+            Lanes& l = table[dev];
+            if (cudaStreamCreateWithFlags(&l.aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            ready[dev].store(1, std::memory_order_release);
+        }
+    }
+    return &table[dev];
+}
 cudaError_t launch_combine(int d, int grid, const Params& prm, cudaStream_t st) {
+    if (d == 8) return launch_pdl(combine8_kernel, grid, Combine8Cfg::NT, Combine8Cfg::SMEM, st, prm);
     return d == 2 ? launch_pdl(combine_kernel<2>, grid, kCombineThreads, 0, st, prm)
                   : launch_pdl(combine_kernel<4>, grid, kCombineThreads, 0, st, prm);
 }
@@ -350,13 +458,20 @@ int launch_sub(Params prm, cudaStream_t st) {
     auto ki = sub_inv_kernel<T, LUMA3>;
     auto kf4 = sub_fwd4_kernel<T, LUMA3>;
     auto ki4 = sub_inv4_kernel<T, LUMA3>;
-    static KernelFacts ff, fi, ff4, fi4;
+    auto kf8 = sub_fwd8_kernel<T, LUMA3>;
+    auto ki8 = sub_inv8_kernel<T, LUMA3>;
+    static KernelFacts ff, fi, ff4, fi4, ff8, fi8;
     int per_sm_f = 1, per_sm_i = 1;
     if (int rc = ff.get(kf, SubCfg::NT_FWD, SubCfg::SMEM_FWD, &per_sm_f)) return rc;
     if (int rc = fi.get(ki, SubCfg::NT_INV, SubCfg::SMEM_INV, &per_sm_i)) return rc;
     const int D = prm.sub_d, npp = D * D / 2;
     static const bool no_cluster = getenv("TFCFFT_NO_CLUSTER") != nullptr;
     const bool cluster = D == 4 && !no_cluster;
+    const bool cluster8 = D == 8 && !no_cluster;
+    if (cluster8) {
+        if (int rc = ff8.get(kf8, SubCfg::NT_FWD, SubCfg::SMEM_FWD, nullptr)) return rc;
+        if (int rc = fi8.get(ki8, SubCfg::NT_INV, SubCfg::SMEM_INV, nullptr)) return rc;
+    }
     if (cluster) {
         if (int rc = ff4.get(kf4, SubCfg::NT_FWD, SubCfg::SMEM_FWD, nullptr)) return rc;
         if (int rc = fi4.get(ki4, SubCfg::NT_INV, SubCfg::SMEM_INV, nullptr)) return rc;
@@ -366,7 +481,7 @@ int launch_sub(Params prm, cudaStream_t st) {
     // inverse code of both decimations thrashes the instruction cache, runs the combine at 12 instead of 16 warps per
     // SM and loses the 2-CTA cluster loads -- so it is opt-in (TFCFFT_SUB_PIPE=1) and the three launches stay.
     static const bool pipe = getenv("TFCFFT_SUB_PIPE") != nullptr;
-    if (pipe) {
+    if (pipe && D != 8) {
         auto kp = sub_pipe_kernel<T, LUMA3>;
         static KernelFacts fp;
         int per_sm = 1;
@@ -386,7 +501,7 @@ int launch_sub(Params prm, cudaStream_t st) {
     // sub-tile workload (global 256^2 b64: 83 vs 75 us) -- dependent CTAs that become resident early spin on their tile's
     // counter next to the CTAs that do the work -- so they are opt-in (TFCFFT_FINE_DEPS=1)
     static const bool fine = getenv("TFCFFT_FINE_DEPS") != nullptr && getenv("TFCFFT_NO_PDL") == nullptr;
-    prm.fine_deps = fine ? 1 : 0;
+    prm.fine_deps = (fine && D != 8) ? 1 : 0;
     const int sms = device_sms();
     // trim the workspace chunk to a whole number of waves of the forward launch on THIS device (smallest tile count
     // whose units fill whole waves: 222 tiles of 128 x 128 / 111 tiles of 256 x 256 on a 148-SM part at 3 CTAs per SM)
@@ -398,9 +513,48 @@ int launch_sub(Params prm, cudaStream_t st) {
         const int wave_tiles = wave_units / a;
         if (chunk >= wave_tiles) chunk = (chunk / wave_tiles) * wave_tiles;
     }
-    for (int base = 0; base < prm.tiles_total; base += chunk) {
+    // Two lanes: when the batch is more than one wave of the forward launch, chunks of ONE wave alternate between the
+    // caller's stream and an auxiliary stream of this library (fork / join with events), each lane owning one half of
+    // the workspace.  Each launch is still bounded by the critical path of one CTA, but the ragged last wave of a lane
+    // (15 us of a 36 us forward launch at batch 64, where 85 % of the SMs idle) now runs under the other lane's
+    // combine / inverse launches instead of in front of them.
+    Lanes* lanes = nullptr;
+    int lane_tiles = 0;
+    {
+        static const int mode = getenv("TFCFFT_SUB_LANES") ? atoi(getenv("TFCFFT_SUB_LANES")) : 1;
+        static const int waves = getenv("TFCFFT_SUB_WAVES") ? atoi(getenv("TFCFFT_SUB_WAVES")) : 1;
+        const int wave_tiles = (sms * per_sm_f / npp) * (waves < 1 ? 1 : waves);  // whole tiles that fit the wave(s)
+        // every tile has its own workspace slot when the batch fits one workspace chunk; otherwise the lanes take
+        // one half of the workspace each
+        const int half = prm.tiles_total <= prm.chunk_tiles ? prm.tiles_total : prm.chunk_tiles / 2;
+        if (mode >= 2 && !prm.fine_deps && wave_tiles >= 1 && prm.tiles_total > wave_tiles && half >= 1) {
+            lane_tiles = wave_tiles < half ? wave_tiles : half;
+            lanes = lanes_get();
+            if (lanes == nullptr) return (int)cudaErrorUnknown;
+            chunk = lane_tiles;
+        }
+    }
+    // one call at a time enqueues on the shared auxiliary stream / events
+    std::unique_lock<std::mutex> lane_lock;
+    if (lanes != nullptr) lane_lock = std::unique_lock<std::mutex>(lanes->mu);
+    const bool ws_per_tile = prm.tiles_total <= prm.chunk_tiles;
+    float2* const zws0 = prm.zws;
+    cudaStream_t const st0 = st;
+    bool forked = false;
+    int nchunk = 0;
+    for (int base = 0; base < prm.tiles_total; base += chunk, ++nchunk) {
         prm.tile_base = base;
         prm.chunk_now = prm.tiles_total - base < chunk ? prm.tiles_total - base : chunk;
+        if (lanes != nullptr) {
+            const int lane = nchunk & 1;
+            st = lane ? lanes->aux : st0;
+            prm.zws = zws0 + (long long)(ws_per_tile ? base : lane * (prm.chunk_tiles / 2)) * (D * D) * 4096;
+            if (lane && !forked) {  // fork: the auxiliary lane starts after everything already queued on the caller's stream
+                if (cudaError_t e = cudaEventRecord(lanes->fork, st0)) return (int)e;
+                if (cudaError_t e = cudaStreamWaitEvent(lanes->aux, lanes->fork, 0)) return (int)e;
+                forked = true;
+            }
+        }
         const int units = prm.chunk_now * npp;
         const int grid_f = units < sms * per_sm_f ? units : sms * per_sm_f;
         const int grid_i = units < sms * per_sm_i ? units : sms * per_sm_i;
@@ -416,6 +570,8 @@ int launch_sub(Params prm, cudaStream_t st) {
             g_launches--;  // counted by the ring launcher; the common increment follows below
         } else if (ring_rc != TFCFFT_ERR_STRIDE) {
             return ring_rc;
+        } else if (cluster8) {  // 4-CTA clusters
+            e = launch_pdl(kf8, grid_f & ~3, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st, prm);
         } else if (cluster) {  // 2-CTA clusters: full-sector loads, halves exchanged through DSMEM
             e = launch_pdl(kf4, grid_f & ~1, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st, prm);
         } else {
@@ -423,11 +579,13 @@ int launch_sub(Params prm, cudaStream_t st) {
         }
         if (e != cudaSuccess) return (int)e;
         g_launches++;
-        e = launch_combine(D, prm.chunk_now * kCombineParts, prm, st);
+        e = launch_combine(D, prm.chunk_now * (D == 8 ? kCombine8Parts : kCombineParts), prm, st);
         if (e != cudaSuccess) return (int)e;
         g_launches++;
         if (prm.grad) {
-            if (cluster) {
+            if (cluster8) {
+                e = launch_pdl(ki8, grid_i & ~3, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
+            } else if (cluster) {
                 e = launch_pdl(ki4, grid_i & ~1, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
             } else {
                 e = launch_pdl(ki, grid_i, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
@@ -435,6 +593,10 @@ int launch_sub(Params prm, cudaStream_t st) {
             if (e != cudaSuccess) return (int)e;
             g_launches++;
         }
+    }
+    if (forked) {  // join: the caller's stream continues after the auxiliary lane
+        if (cudaError_t e = cudaEventRecord(lanes->join, lanes->aux)) return (int)e;
+        if (cudaError_t e = cudaStreamWaitEvent(st0, lanes->join, 0)) return (int)e;
     }
     return 0;
 }

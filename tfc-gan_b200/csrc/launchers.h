@@ -2,6 +2,7 @@
 // Every function validates nothing: arguments were checked by the C-ABI layer.  Return 0, a negative
 // TFCFFT_ERR_* or a positive cudaError_t.
 #pragma once
+#include <mutex>
 #include "host_common.h"
 #include "kernel_common.cuh"
 
@@ -47,6 +48,12 @@ TFC_ANY(split, (int p, int dtype, bool luma3, const Params& prm, cudaStream_t st
 
 // dtype-independent launches of the multi-launch pipelines (defined in the TFC_DT == 0 object of their unit)
 cudaError_t launch_combine(int d, int grid, const Params& prm, cudaStream_t st);            // k_sub.cu
+struct Lanes {  // auxiliary stream + fork / join events of the two-lane chunk schedule (k_sub.cu), one per device
+    cudaStream_t aux;
+    cudaEvent_t fork, join;
+    std::mutex mu;
+};
+Lanes* lanes_get();                                                                          // k_sub.cu
 int split_cols_facts(int p);                                                                 // k_split.cu
 cudaError_t launch_split_cols(int p, int grid, const Params& prm, cudaStream_t st);          // k_split.cu
 

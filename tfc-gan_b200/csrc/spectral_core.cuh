@@ -47,7 +47,7 @@ struct Params {
     int chunk_tiles;
     long long* trace;      // debug: per-CTA stage timestamps (tfcfft_debug_trace), normally nullptr
     // sub-tile path (P = 128 / 256): the tile is decimated into D x D interleaved 64 x 64 sub-images
-    int sub_d;             // 0 / 1: not used; 2 or 4
+    int sub_d;             // 0 / 1: not used; 2, 4 or 8
     int chunk_now;         // tiles in the chunk being processed by this launch
     // spectra materialisation (fft_components / make_spectra): grid == 1, tile = n * C' + ch
     int spec_mode;         // 0 loss, 1 emit amp / phase of both inputs, 2 backward from d/d(amp, phase)
@@ -77,6 +77,7 @@ constexpr int kCombineThreads = TFCFFT_COMBINE_THREADS;
 constexpr int kCombineRep = TFCFFT_COMBINE_REP;  // items per thread (a rolled loop)
 constexpr int kCombineItemsPerPart = kCombineThreads * kCombineRep;
 constexpr int kCombineParts = (kCombineItems + kCombineItemsPerPart - 1) / kCombineItemsPerPart;  // CTAs (= partial sums) per tile
+constexpr int kCombine8Parts = 64;  // 512 x 512 tiles (combine8.cuh): one CTA per row of the 64 x 64 position grid
 
 template <typename T> struct IO;
 

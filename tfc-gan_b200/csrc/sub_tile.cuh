@@ -1,6 +1,6 @@
-// sub_tile.cuh -- 128 x 128 and 256 x 256 tiles on top of the thread-per-line 64 x 64 machinery.
+// sub_tile.cuh -- 128 x 128, 256 x 256 and 512 x 512 tiles on top of the thread-per-line 64 x 64 machinery.
 //
-// A P x P tile (P = 64 D, D = 2 or 4) is decimated in both dimensions into D x D interleaved sub-images
+// A P x P tile (P = 64 D, D = 2, 4 or 8; the D = 8 cross-sub-image step is combine8.cuh) is decimated in both dimensions into D x D interleaved sub-images
 // s_pq[a, b] = x[D a + p, D b + q].  The 2-D DFT factors exactly (decimation in time):
 //     Z[ky' + 64 al, kx' + 64 be] = sum_{p,q} W_D^{p al + q be} * W_P^{p ky' + q kx'} * S_pq[ky', kx']
 // so the heavy work -- D^2 independent 64 x 64 complex transforms -- runs on the register-resident 64-point
@@ -155,6 +155,60 @@ TFC_HD void sub_fwd_load_quad(const Ctx& ctx, const Params& prm, const TileCoord
     }
 }
 
+// D = 8 variant for a 4-CTA cluster (one cluster = one row phase p of a 512 x 512 tile = the four column pairs
+// i = 0..3): each CTA reads a QUARTER of the rows with two 16-byte loads per pixel octet (all eight column phases q:
+// every 32-byte sector is fetched once instead of four times) and distributes the luma values: q = 2i, 2i+1 -> the
+// work tiles of CTA i (dst[i]); three of the four destinations are peer CTAs' shared memory.
+template <typename T, bool LUMA3, class Ctx>
+TFC_HD void sub_fwd_load_oct(const Ctx& ctx, const Params& prm, const TileCoord& tc, int p, int quarter, float2* const (&dst)[4]) {
+    constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1, NI = 2, P = 512;
+    const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, P);
+    const T* rp = real_tile_ptr<T>(prm, tc, P);
+    const int fsh = (int)prm.fs[2], fsc = (int)prm.fs[1], rsh = (int)prm.rs[2], rsc = (int)prm.rs[1];
+    const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
+#pragma unroll 1
+    for (int it0 = ctx.tid; it0 < 1024; it0 += NI * ctx.nthreads) {
+        float raw[NI][2][NC][8];  // [item][fake|real][channel][q]
+#pragma unroll
+        for (int u = 0; u < NI; ++u) {
+            const int it = it0 + u * ctx.nthreads, b = it & 63, a = 16 * quarter + (it >> 6);
+            const int x = 8 * b, y = 8 * a + p;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                IO<T>::load4(fp + y * fsh + c * fsc + x, raw[u][0][c]);
+                IO<T>::load4(fp + y * fsh + c * fsc + x + 4, raw[u][0][c] + 4);
+                IO<T>::load4(rp + y * rsh + c * rsc + x, raw[u][1][c]);
+                IO<T>::load4(rp + y * rsh + c * rsc + x + 4, raw[u][1][c] + 4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NI; ++u) {
+            const int it = it0 + u * ctx.nthreads, b = it & 63, a = 16 * quarter + (it >> 6);
+            float z[2][8];  // [fake|real][q]
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (!quant) {
+                        float f = prm.lw[0] * raw[u][h][0][q];
+                        if constexpr (LUMA3) f = fmaf(prm.lw[2], raw[u][h][2][q], fmaf(prm.lw[1], raw[u][h][1][q], f));
+                        z[h][q] = f;
+                    } else if constexpr (LUMA3) {
+                        z[h][q] = (float)((19595 * IO<T>::quant(raw[u][h][0][q]) + 38470 * IO<T>::quant(raw[u][h][1][q]) +
+                                           7471 * IO<T>::quant(raw[u][h][2][q]) + 0x8000) >> 16);
+                    } else {
+                        z[h][q] = (float)IO<T>::quant(raw[u][h][0][q]);
+                    }
+                }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                dst[i][a * LD + b] = make_float2(z[0][2 * i], z[1][2 * i]);
+                dst[i][64 * LD + a * LD + b] = make_float2(z[0][2 * i + 1], z[1][2 * i + 1]);
+            }
+        }
+    }
+}
+
 // Forward passes of both work tiles on ONE copy of the 64-point core (callers keep the pass loop rolled, like
 // line_fft_pass): pass 0 = rows (one thread per row, in place), pass 1 = columns, written straight to the workspace
 // planes (coalesced across the column index).
@@ -265,6 +319,31 @@ TFC_HD void sub_inv_store_quad(const Ctx& ctx, const Params& prm, const TileCoor
         for (int c = 0; c < NC; ++c) {
             float v[4] = {go.w[c] * lo.x, go.w[c] * lo.y, go.w[c] * hi.x, go.w[c] * hi.y};
             grad_store4<T>(go, gp + y * sh + c * sc + x, v);
+        }
+    }
+}
+
+// D = 8 variant for a 4-CTA cluster (mirror of sub_fwd_load_oct): the CTA writes a QUARTER of the gradient rows of
+// row phase p with two 16-byte stores per pixel octet, taking pixels q = 2i, 2i+1 from CTA i's tile (src[i]).
+template <typename T, bool LUMA3, class Ctx>
+TFC_HD void sub_inv_store_oct(const Ctx& ctx, const Params& prm, const TileCoord& tc, int p, int quarter, const float2* const (&src)[4]) {
+    constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1, P = 512;
+    T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, P));
+    const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
+    const GradOut go = grad_out(prm);
+#pragma unroll 2
+    for (int it = ctx.tid; it < 1024; it += ctx.nthreads) {
+        const int b = it & 63, a = 16 * quarter + (it >> 6);
+        float2 g[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g[i] = src[i][a * LD + b];
+        const int x = 8 * b, y = 8 * a + p;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            float v0[4] = {go.w[c] * g[0].x, go.w[c] * g[0].y, go.w[c] * g[1].x, go.w[c] * g[1].y};
+            float v1[4] = {go.w[c] * g[2].x, go.w[c] * g[2].y, go.w[c] * g[3].x, go.w[c] * g[3].y};
+            grad_store4<T>(go, gp + y * sh + c * sc + x, v0);
+            grad_store4<T>(go, gp + y * sh + c * sc + x + 4, v1);
         }
     }
 }
@@ -420,6 +499,29 @@ QuadEval bin_eval_quad_call(const Params& prm, bool mse, bool phase, c2 zk0, c2 
     return r;
 }
 
+// four independent packed evaluations per call (A/B: -DTFC_EVAL_OCT)
+struct OctEval {
+    c2 g[4];
+    float2 a, p;
+};
+#ifdef __CUDA_ARCH__
+__device__ __noinline__
+#else
+inline
+#endif
+OctEval bin_eval_oct_call(const Params& prm, bool mse, bool phase, c2 zk0, c2 zm0, c2 zk1, c2 zm1, c2 zk2, c2 zm2, c2 zk3, c2 zm3) {
+    OctEval r;
+    const float2 z = make_float2(0.f, 0.f);
+    float2 a0 = z, p0 = z, a1 = z, p1 = z, a2 = z, p2 = z, a3 = z, p3 = z;
+    r.g[0] = bin_eval_pair(prm, mse, phase, zk0, zm0, a0, p0);
+    r.g[1] = bin_eval_pair(prm, mse, phase, zk1, zm1, a1, p1);
+    r.g[2] = bin_eval_pair(prm, mse, phase, zk2, zm2, a2, p2);
+    r.g[3] = bin_eval_pair(prm, mse, phase, zk3, zm3, a3, p3);
+    r.a = p_add(p_add(a0, a1), p_add(a2, a3));
+    r.p = p_add(p_add(p0, p1), p_add(p2, p3));
+    return r;
+}
+
 #ifdef __CUDA_ARCH__
 __device__ __noinline__
 #else
@@ -526,13 +628,18 @@ TFC_HD void combine_item(const Params& prm, float2* ws_tile, int item, float& ac
         float2 pA = make_float2(0.f, 0.f), pP = make_float2(0.f, 0.f);
         const float2 z0 = make_float2(0.f, 0.f);
         constexpr int NE = D * D / 2;  // packed evaluations: entry pairs (al, 2 bp), (al, 2 bp + 1)
+#ifdef TFC_EVAL_OCT
+        constexpr int EV = NE >= 4 ? 4 : 2;  // packed evaluations per out-of-line call
+#else
+        constexpr int EV = 2;
+#endif
 #pragma unroll
-        for (int e0 = 0; e0 < NE; e0 += 2) {
-            bool isM[2][2], both[2][2], live[2][2];
-            float2 k_[2][2], m_[2][2];
-            c2 zk[2], zm[2], g[2];
+        for (int e0 = 0; e0 < NE; e0 += EV) {
+            bool isM[EV][2], both[EV][2], live[EV][2];
+            float2 k_[EV][2], m_[EV][2];
+            c2 zk[EV], zm[EV], g[EV];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < EV; ++h) {
                 const int al = (e0 + h) / HD, bp = (e0 + h) % HD;
                 const int alB = kyA ? D - 1 - al : (D - al) % D;
 #pragma unroll
@@ -550,7 +657,13 @@ TFC_HD void combine_item(const Params& prm, float2* ws_tile, int item, float& ac
                 zk[h] = make_c2(make_float2(k_[h][0].x, k_[h][1].x), make_float2(k_[h][0].y, k_[h][1].y));
                 zm[h] = make_c2(make_float2(m_[h][0].x, m_[h][1].x), make_float2(m_[h][0].y, m_[h][1].y));
             }
-            {
+            if constexpr (EV == 4) {
+                const OctEval q = bin_eval_oct_call(prm, mse, phase, zk[0], zm[0], zk[1], zm[1], zk[2], zm[2], zk[3], zm[3]);
+#pragma unroll
+                for (int h = 0; h < 4; ++h) g[h] = q.g[h];
+                pA = p_add(pA, q.a);
+                pP = p_add(pP, q.p);
+            } else {
                 const QuadEval q = bin_eval_quad_call(prm, mse, phase, zk[0], zm[0], zk[1], zm[1]);
                 g[0] = q.g0;
                 g[1] = q.g1;
@@ -558,7 +671,7 @@ TFC_HD void combine_item(const Params& prm, float2* ws_tile, int item, float& ac
                 pP = p_add(pP, q.p);
             }
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < EV; ++h) {
                 const int al = (e0 + h) / HD, bp = (e0 + h) % HD;
                 c2 g2 = make_c2(z0, z0);
                 if (both[h][0] || both[h][1]) {  // self-conjugate columns only: evaluate the mirrored bin as well
@@ -639,7 +752,7 @@ TFC_HD void combine_item(const Params& prm, float2* ws_tile, int item, float& ac
 }
 
 TFC_HD bool sub_supported(const Params& prm) {
-    return (prm.p == 128 || prm.p == 256) && prm.spec_mode == 0 && !(prm.flags & (TFCFFT_FORCE_SPLIT | TFCFFT_FORCE_GENERIC));
+    return (prm.p == 128 || prm.p == 256 || prm.p == 512) && prm.spec_mode == 0 && !(prm.flags & (TFCFFT_FORCE_SPLIT | TFCFFT_FORCE_GENERIC));
 }
 
 }  // namespace tfcfft

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """GPU self-check of the sub-tile path's scheduling variants: tile-granular dependencies between the three launches
-(TFCFFT_FINE_DEPS=1), whole-grid waits (default) and the pipelined single kernel (TFCFFT_SUB_PIPE=1) must give the
+(TFCFFT_FINE_DEPS=1), whole-grid waits on one stream (TFCFFT_SUB_LANES=1), the two-lane chunk schedule (default) and
+the pipelined single kernel (TFCFFT_SUB_PIPE=1) must give the
 same loss / gradient BIT FOR BIT (same device functions, different scheduling).  Each variant runs in its own process
 (the switches are read once)."""
 import os
@@ -12,7 +13,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 CASES = [(1, 256, 1, "luma"), (2, 512, 5, "luma"), (1, 256, 3, "luma"), (1, 256, 64, "luma"), (2, 256, 37, "luma"), (2, 256, 256, "luma"), (1, 256, 20, "rgb"),
-         (4, 512, 9, "luma"), (2, 256, 600, "luma"), (1, 256, 130, "luma")]
+         (4, 512, 9, "luma"), (2, 256, 600, "luma"), (1, 256, 130, "luma"), (1, 256, 56, "luma"), (1, 256, 111, "luma"),
+         (1, 256, 300, "luma"), (2, 256, 223, "rgb")]
 
 
 def worker(path):
@@ -36,8 +38,9 @@ def main():
     if len(sys.argv) > 1:
         return worker(sys.argv[1])
     res = {}
-    for name, env in (("ring", {"TFCFFT_SUB_FWD_RING": "1"}), ("fine", {"TFCFFT_FINE_DEPS": "1"}),
-                      ("pipe", {"TFCFFT_SUB_PIPE": "1"}), ("three", {})):
+    one = {"TFCFFT_SUB_LANES": "1"}
+    for name, env in (("lanes", {}), ("lanes2w", {"TFCFFT_SUB_WAVES": "2"}), ("ring", {"TFCFFT_SUB_FWD_RING": "1", **one}),
+                      ("fine", {"TFCFFT_FINE_DEPS": "1"}), ("pipe", {"TFCFFT_SUB_PIPE": "1"}), ("three", one)):
         path = f"/tmp/pipe_check_{name}.pt"
         p = subprocess.run([sys.executable, __file__, path], env={**os.environ, **env}, timeout=100, stdout=subprocess.DEVNULL)
         if p.returncode != 0:
@@ -45,7 +48,7 @@ def main():
             sys.exit(1)
         res[name] = torch.load(path)
     ok = True
-    for name in ("ring", "fine", "pipe"):
+    for name in ("lanes", "lanes2w", "ring", "fine", "pipe"):
         for c, a, b in zip(CASES, res[name], res["three"]):
             same = all(torch.equal(x, y) for x, y in zip(a, b))
             ok &= same
