@@ -249,9 +249,10 @@ def hot_call(tfc, wl):
     cfg = tfc.SpectralConfig(grid=wl["grid"], channels=wl["channels"], weight=0.01, input_scale=255.0)
     if not wl.get("combined"):
         return lambda f, r: tfc.spectral_loss_and_grad(f, r, config=cfg)
-    # config 5: both grids per L2-sized chunk of the batch; the second call re-reads fake / real and adds into the
-    # gradient chunk while they are still L2-resident, so HBM sees ~3 tensor passes instead of 7
-    chunk = int(os.environ.get("TFCFFT_COMBINED_CHUNK", "8"))
+    # config 5: both grids on the whole batch, the second call adds into the first one's gradient (no add pass).
+    # Walking the batch in L2-sized chunks saves HBM bytes but runs every launch at a fraction of a wave: measured
+    # 57 k / 69 k / 84 k images/s at chunk 8 / 16 / 32 (profiles/r02_d8_ab.txt), so the whole batch is the default.
+    chunk = int(os.environ.get("TFCFFT_COMBINED_CHUNK", "0"))
     return lambda f, r: tfc.multi_grid_loss_and_grad(f, r, grids=(wl["grid"], 1), chunk=chunk, channels=wl["channels"],
                                                      weight=0.01, input_scale=255.0)
 

@@ -173,3 +173,33 @@ def test_triplet_on_spectra_variant():
     assert pha.item() == pytest.approx(p.item(), rel=1e-4)
     assert patch.item() == pytest.approx(t.item(), rel=1e-4)
     assert l2rel(fa.grad.cpu().numpy(), fo.grad.numpy()) <= 2e-3
+
+
+@pytest.mark.parametrize("chunk", [0, 3])
+def test_combined_patch16_plus_global_matches_oracle(chunk):
+    """BASELINE config 5: patch-16 + global FFT loss on the same 512 x 512 tensors through ``multi_grid_loss[_and_grad]``
+    (one summed gradient, the second grid adds into the first one's buffer; optional walk in chunks of the batch)
+    against the sum of the two fp64 oracle evaluations; the autograd entry gives the same loss and gradient."""
+    rs = np.random.RandomState(41)
+    fake = rs.uniform(-1, 1, (5, 3, 512, 512)).astype(np.float32)
+    real = rs.uniform(-1, 1, (5, 3, 512, 512)).astype(np.float32)
+    want_l, want_g, want_terms = 0.0, 0.0, []
+    for grid in (4, 1):
+        l, a, p, g = oracle.spectral_loss_and_grad_r1(fake, real, grid=grid, weight=0.01, input_scale=255.0)
+        want_l += l
+        want_g = want_g + g
+        want_terms.append((a, p))
+    f = torch.from_numpy(fake).cuda()
+    r = torch.from_numpy(real).cuda()
+    tfc.reset_launch_count()
+    loss, per_cfg, grad = tfc.multi_grid_loss_and_grad(f, r, grids=(4, 1), chunk=chunk, weight=0.01, input_scale=255.0)
+    torch.cuda.synchronize()
+    assert tfc.launch_count() > 0
+    assert loss.item() == pytest.approx(want_l, rel=1e-4)
+    np.testing.assert_allclose(per_cfg.cpu().numpy(), np.array(want_terms), rtol=1e-4)
+    assert np.linalg.norm(grad.cpu().numpy() - want_g) / np.linalg.norm(want_g) <= 1e-3
+    fa = f.clone().requires_grad_(True)
+    l2 = tfc.multi_grid_loss(fa, r, grids=(4, 1), chunk=chunk, weight=0.01, input_scale=255.0)
+    l2.backward()
+    assert l2.item() == pytest.approx(want_l, rel=1e-4)
+    assert np.linalg.norm(fa.grad.cpu().numpy() - want_g) / np.linalg.norm(want_g) <= 1e-3

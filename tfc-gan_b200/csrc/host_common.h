@@ -90,7 +90,8 @@ inline int validate_desc(const tfcfft_desc* d, Geometry* geo, bool allow_sub = t
         size_t z = 0;
         if (geo->split || geo->sub) {
             const size_t per_tile = (size_t)p * p * sizeof(float2);
-            long long ct = (long long)(kWsChunkBytes / per_tile);
+            static const long long ws_mb = getenv("TFCFFT_WS_CHUNK_MB") ? atoll(getenv("TFCFFT_WS_CHUNK_MB")) : 0;  // A/B switch
+            long long ct = (long long)((ws_mb > 0 ? (size_t)ws_mb << 20 : kWsChunkBytes) / per_tile);
             if (ct < 1) ct = 1;
             // (the launcher trims a chunk to whole waves of its launches from the device's occupancy: k_sub.cu)
             if (ct > kSchedMaxTiles) ct = kSchedMaxTiles;

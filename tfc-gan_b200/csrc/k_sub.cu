@@ -513,21 +513,26 @@ int launch_sub(Params prm, cudaStream_t st) {
         const int wave_tiles = wave_units / a;
         if (chunk >= wave_tiles) chunk = (chunk / wave_tiles) * wave_tiles;
     }
-    // Two lanes: when the batch is more than one wave of the forward launch, chunks of ONE wave alternate between the
-    // caller's stream and an auxiliary stream of this library (fork / join with events), each lane owning one half of
-    // the workspace.  Each launch is still bounded by the critical path of one CTA, but the ragged last wave of a lane
-    // (15 us of a 36 us forward launch at batch 64, where 85 % of the SMs idle) now runs under the other lane's
-    // combine / inverse launches instead of in front of them.
+    // Two lanes: when the batch is more than two waves of the forward launch, chunks of two waves alternate between
+    // the caller's stream and an auxiliary stream of this library (fork / join with events), each lane owning one half
+    // of the workspace: the ragged last wave and the load-only / store-only phases of one lane's launches run under
+    // the other lane's launches instead of in front of them.
     Lanes* lanes = nullptr;
     int lane_tiles = 0;
     {
-        static const int mode = getenv("TFCFFT_SUB_LANES") ? atoi(getenv("TFCFFT_SUB_LANES")) : 1;
-        static const int waves = getenv("TFCFFT_SUB_WAVES") ? atoi(getenv("TFCFFT_SUB_WAVES")) : 1;
+        // measured (profiles/r02_d8_ab.txt): +16 % at D = 8 (512^2 global b32), +4.6 % at D = 2 (4-patch b256,
+        // patch-16 at 512^2), -4 % at D = 4 (256^2 global rgb, and -9 % at b64 luma where the second lane is a short
+        // chain of three latency-bound launches): two lanes unless D = 4, chunks of two waves
+        static const int mode_env = getenv("TFCFFT_SUB_LANES") ? atoi(getenv("TFCFFT_SUB_LANES")) : 0;
+        static const int waves = getenv("TFCFFT_SUB_WAVES") ? atoi(getenv("TFCFFT_SUB_WAVES")) : 2;
+        const int mode = mode_env ? mode_env : (D == 4 ? 1 : 2);
         const int wave_tiles = (sms * per_sm_f / npp) * (waves < 1 ? 1 : waves);  // whole tiles that fit the wave(s)
         // every tile has its own workspace slot when the batch fits one workspace chunk; otherwise the lanes take
         // one half of the workspace each
         const int half = prm.tiles_total <= prm.chunk_tiles ? prm.tiles_total : prm.chunk_tiles / 2;
         if (mode >= 2 && !prm.fine_deps && wave_tiles >= 1 && prm.tiles_total > wave_tiles && half >= 1) {
+            // (trimming the lane's share to whole waves was measured too: 4-patch b256 in 222-tile chunks 1.02 M vs
+            // 1.04 M images/s in four even 256-tile chunks -- an extra ragged chunk costs more than ragged waves)
             lane_tiles = wave_tiles < half ? wave_tiles : half;
             lanes = lanes_get();
             if (lanes == nullptr) return (int)cudaErrorUnknown;
@@ -549,7 +554,7 @@ int launch_sub(Params prm, cudaStream_t st) {
             const int lane = nchunk & 1;
             st = lane ? lanes->aux : st0;
             prm.zws = zws0 + (long long)(ws_per_tile ? base : lane * (prm.chunk_tiles / 2)) * (D * D) * 4096;
-            if (lane && !forked) {  // fork: the auxiliary lane starts after everything already queued on the caller's stream
+            if (!forked) {  // fork BEFORE the first chunk is queued: the auxiliary lane waits only for earlier work
                 if (cudaError_t e = cudaEventRecord(lanes->fork, st0)) return (int)e;
                 if (cudaError_t e = cudaStreamWaitEvent(lanes->aux, lanes->fork, 0)) return (int)e;
                 forked = true;

@@ -175,52 +175,76 @@ def _resolve_grad_scale(grad_scale, dtype, dev, cfg=None, shape=None):
     return host, dev_t
 
 
-def _launch(fake, real, cfg: SpectralConfig, want_grad: bool, want_per_image: bool, *, gs_host: float = 1.0, gs_dev=None,
-            accumulate_into=None, real_quads=None, grad_buffer=None):
-    lib = _lib.load()
-    dev = fake.device
-    with torch.cuda.device(dev):
-        stream_ptr = torch.cuda.current_stream(dev).cuda_stream
-        out = torch.empty(8, dtype=torch.float32, device=dev)
-        per = torch.empty((fake.shape[0], 2), dtype=torch.float32, device=dev) if want_per_image else None
-        flags = cfg.flags()
-        if accumulate_into is not None:
-            if accumulate_into.shape != fake.shape or accumulate_into.dtype != fake.dtype or accumulate_into.device != dev \
-                    or not _acceptable(accumulate_into):
-                raise ValueError("accumulate_into must match fake in shape / dtype / device and have 16-byte friendly strides")
-            grad, flags = accumulate_into, flags | _lib.GRAD_ACCUMULATE
-        elif grad_buffer is not None:  # caller-owned destination, overwritten
-            if grad_buffer.shape != fake.shape or grad_buffer.dtype != fake.dtype or grad_buffer.device != dev \
-                    or not _acceptable(grad_buffer):
-                raise ValueError("grad_buffer must match fake in shape / dtype / device and have 16-byte friendly strides")
-            grad = grad_buffer
-        else:
-            grad = torch.empty(fake.shape, dtype=fake.dtype, device=dev) if want_grad else None
-        desc = _lib.make_desc(
-            _DTYPES[fake.dtype], cfg.grid, flags, fake.shape, fake.stride(), real.stride(),
-            grad.stride() if grad is not None else None, cfg.weight, cfg.input_scale,
-            grad_scale_host=gs_host, grad_scale_dev=gs_dev.data_ptr() if gs_dev is not None else None,
-        )
+_DESC_CACHE: dict = {}
+
+
+def _desc_for(lib, key):
+    """Filled descriptor + workspace size per distinct call signature (dtype, grid, flags, shape, strides, scalars): a
+    training loop repeats the same few signatures every step, and building the ctypes struct is ~12 us of host time
+    against a ~75 us GPU step."""
+    hit = _DESC_CACHE.get(key)
+    if hit is None:
+        dtype, grid, flags, shape, fst, rst, gst, weight, input_scale, gs_host, gs_ptr = key
+        desc = _lib.make_desc(dtype, grid, flags, shape, fst, rst, gst, weight, input_scale,
+                              grad_scale_host=gs_host, grad_scale_dev=gs_ptr)
         nbytes = lib.tfcfft_workspace_bytes(ctypes.byref(desc))
         if nbytes == 0:
             _lib.check(lib.tfcfft_validate(ctypes.byref(desc)), "tfcfft_validate")
-        ws = _workspace(dev, stream_ptr, nbytes)
-        if real_quads is None:
-            rc = lib.tfcfft_loss(
-                ctypes.byref(desc), fake.data_ptr(), real.data_ptr(), out.data_ptr(),
-                per.data_ptr() if want_per_image else None, grad.data_ptr() if grad is not None else None,
-                ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream_ptr),
-            )
-        else:
-            qp = (ctypes.c_void_p * 4)(*[q.data_ptr() for q in real_quads])
-            rc = lib.tfcfft_loss_quads(
-                ctypes.byref(desc), fake.data_ptr(), qp, out.data_ptr(),
-                per.data_ptr() if want_per_image else None, grad.data_ptr() if grad is not None else None,
-                ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream_ptr),
-            )
-        if rc > 0:  # a CUDA error may have left the ticket header dirty
-            _WORKSPACES.pop((dev.index, stream_ptr), None)
-        _lib.check(rc, "tfcfft_loss")
+        if len(_DESC_CACHE) >= 512:
+            _DESC_CACHE.clear()
+        hit = _DESC_CACHE[key] = (desc, ctypes.byref(desc), nbytes)
+    return hit
+
+
+def _launch(fake, real, cfg: SpectralConfig, want_grad: bool, want_per_image: bool, *, gs_host: float = 1.0, gs_dev=None,
+            accumulate_into=None, real_quads=None, grad_buffer=None):
+    dev = fake.device
+    if torch.cuda.current_device() == dev.index:  # the usual case: no device-guard round trip
+        return _launch_here(fake, real, cfg, want_grad, want_per_image, gs_host, gs_dev, accumulate_into, real_quads, grad_buffer)
+    with torch.cuda.device(dev):
+        return _launch_here(fake, real, cfg, want_grad, want_per_image, gs_host, gs_dev, accumulate_into, real_quads, grad_buffer)
+
+
+def _launch_here(fake, real, cfg, want_grad, want_per_image, gs_host, gs_dev, accumulate_into, real_quads, grad_buffer):
+    lib = _lib.load()
+    dev = fake.device
+    stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+    out = torch.empty(8, dtype=torch.float32, device=dev)
+    per = torch.empty((fake.shape[0], 2), dtype=torch.float32, device=dev) if want_per_image else None
+    flags = cfg.flags()
+    if accumulate_into is not None:
+        if accumulate_into.shape != fake.shape or accumulate_into.dtype != fake.dtype or accumulate_into.device != dev \
+                or not _acceptable(accumulate_into):
+            raise ValueError("accumulate_into must match fake in shape / dtype / device and have 16-byte friendly strides")
+        grad, flags = accumulate_into, flags | _lib.GRAD_ACCUMULATE
+    elif grad_buffer is not None:  # caller-owned destination, overwritten
+        if grad_buffer.shape != fake.shape or grad_buffer.dtype != fake.dtype or grad_buffer.device != dev \
+                or not _acceptable(grad_buffer):
+            raise ValueError("grad_buffer must match fake in shape / dtype / device and have 16-byte friendly strides")
+        grad = grad_buffer
+    else:
+        grad = torch.empty(fake.shape, dtype=fake.dtype, device=dev) if want_grad else None
+    key = (_DTYPES[fake.dtype], cfg.grid, flags, tuple(fake.shape), fake.stride(), real.stride(),
+           grad.stride() if grad is not None else None, cfg.weight, cfg.input_scale, gs_host,
+           gs_dev.data_ptr() if gs_dev is not None else None)
+    _, desc_ref, nbytes = _desc_for(lib, key)
+    ws = _workspace(dev, stream_ptr, nbytes)
+    if real_quads is None:
+        rc = lib.tfcfft_loss(
+            desc_ref, fake.data_ptr(), real.data_ptr(), out.data_ptr(),
+            per.data_ptr() if want_per_image else None, grad.data_ptr() if grad is not None else None,
+            ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream_ptr),
+        )
+    else:
+        qp = (ctypes.c_void_p * 4)(*[q.data_ptr() for q in real_quads])
+        rc = lib.tfcfft_loss_quads(
+            desc_ref, fake.data_ptr(), qp, out.data_ptr(),
+            per.data_ptr() if want_per_image else None, grad.data_ptr() if grad is not None else None,
+            ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream_ptr),
+        )
+    if rc > 0:  # a CUDA error may have left the ticket header dirty
+        _WORKSPACES.pop((dev.index, stream_ptr), None)
+    _lib.check(rc, "tfcfft_loss")
     return out, per, grad
 
 
@@ -345,12 +369,16 @@ def spectral_loss_and_grad(fake, real, *, config: SpectralConfig | None = None, 
 
 
 def _multi_launch(fake_p, real_p, cfgs, chunk, gs_host, gs_dev):
-    """Several loss configurations on the same tensors, one summed gradient: per L2-sized chunk of the batch the first
-    configuration writes the chunk's gradient and the others add into it (``TFCFFT_GRAD_ACCUMULATE``) while fake / real /
-    the gradient chunk are still L2-resident.  Chunk losses are means over their own images: weighted by chunk size."""
+    """Several loss configurations on the same tensors, one summed gradient: the first configuration writes the
+    gradient and the others add into it (``TFCFFT_GRAD_ACCUMULATE``: no add pass).  ``chunk`` (images; 0 / None = the
+    whole batch, the default) optionally walks the batch in L2-sized pieces so that the later configurations find fake /
+    real / the gradient piece in L2 -- fewer HBM bytes, but every launch then runs a fraction of a wave; measured on
+    B200 at 512 x 512, batch 32 (``profiles/r02_d8_ab.txt``): 57 k / 69 k / 84 k images/s at chunk 8 / 16 / whole batch.
+    Chunk losses are means over their own images: weighted by chunk size."""
     import dataclasses
 
     n = fake_p.shape[0]
+    chunk = n if not chunk or chunk <= 0 else min(int(chunk), n)
     grad = torch.empty(fake_p.shape, dtype=fake_p.dtype, device=fake_p.device)
     total, terms, out = None, [], None
     for lo in range(0, n, chunk):
@@ -393,21 +421,20 @@ def _grid_configs(grids, options):
     return tuple(SpectralConfig(grid=int(g), **options) for g in grids)
 
 
-def multi_grid_loss(fake, real, *, grids=(4, 1), chunk: int = 8, return_terms: bool = False, grad_scale=None, **options):
+def multi_grid_loss(fake, real, *, grids=(4, 1), chunk: int = 0, return_terms: bool = False, grad_scale=None, **options):
     """Sum of the FFT losses of several grids on the SAME tensors -- BASELINE config 5's "patch-FFT-16 + global-FFT
     combined loss" -- with ONE gradient tensor.  Differentiable w.r.t. ``fake``; ``options`` as for
-    :func:`spectral_loss` (each grid's loss carries ``weight``).  ``chunk`` images are processed per step so that the
-    second grid finds fake / real / the gradient chunk in L2 (8 images of 512 x 512 = 75 MB of the 126 MB L2)."""
-    total, per_cfg = _MultiGridLossFn.apply(fake, real, _grid_configs(grids, options), int(chunk), grad_scale)
+    :func:`spectral_loss` (each grid's loss carries ``weight``).  ``chunk``: see :func:`_multi_launch` (0 = whole batch)."""
+    total, per_cfg = _MultiGridLossFn.apply(fake, real, _grid_configs(grids, options), int(chunk or 0), grad_scale)
     return (total, per_cfg) if return_terms else total
 
 
 @torch.no_grad()
-def multi_grid_loss_and_grad(fake, real, *, grids=(4, 1), chunk: int = 8, grad_scale=None, **options):
+def multi_grid_loss_and_grad(fake, real, *, grids=(4, 1), chunk: int = 0, grad_scale=None, **options):
     """The fused hot path of :func:`multi_grid_loss` without autograd: ``(loss, per-grid (amp, pha), d loss / d fake)``."""
     fake_p, real_p = _prep(fake, real)
     gs_host, gs_dev = (1.0, None) if grad_scale is None else _resolve_grad_scale(grad_scale, fake_p.dtype, fake_p.device)
-    total, per_cfg, grad, _ = _multi_launch(fake_p, real_p, _grid_configs(grids, options), int(chunk), gs_host, gs_dev)
+    total, per_cfg, grad, _ = _multi_launch(fake_p, real_p, _grid_configs(grids, options), int(chunk or 0), gs_host, gs_dev)
     return total, per_cfg, grad
 
 

@@ -6,7 +6,7 @@ timeout 300 python tools/pipe_check.py > $OUT/pipecheck_lanes.log 2>&1; echo "pi
 grep -E "MISMATCH|PASS|FAIL" $OUT/pipecheck_lanes.log | head -20
 STEPS=${1:-300}
 for WL in global-fft-256-b64 global-fft-256-b64-rgb patch4-fft-256-b256 patch16-fft-512-b64 global-fft-512-b32; do
-  for V in "" "TFCFFT_SUB_LANES=1" "TFCFFT_SUB_WAVES=2"; do
+  for V in "" "TFCFFT_SUB_LANES=2" "TFCFFT_SUB_LANES=2 TFCFFT_SUB_WAVES=2"; do
     F=$OUT/bench_${WL}_lanes_$(echo "$V" | tr -c 'A-Za-z0-9' '_').json
     env $V timeout 300 python bench.py --workload $WL --steps $STEPS --warmup 20 --no-variants --no-cpu-baseline > $F 2>> $OUT/bench_lanes.err
     python - "$F" "$WL" "$V" <<'PY'

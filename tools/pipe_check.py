@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 CASES = [(1, 256, 1, "luma"), (2, 512, 5, "luma"), (1, 256, 3, "luma"), (1, 256, 64, "luma"), (2, 256, 37, "luma"), (2, 256, 256, "luma"), (1, 256, 20, "rgb"),
          (4, 512, 9, "luma"), (2, 256, 600, "luma"), (1, 256, 130, "luma"), (1, 256, 56, "luma"), (1, 256, 111, "luma"),
-         (1, 256, 300, "luma"), (2, 256, 223, "rgb")]
+         (1, 256, 300, "luma"), (2, 256, 223, "rgb"), (1, 512, 32, "luma"), (1, 512, 40, "luma"), (1, 512, 11, "rgb")]
 
 
 def worker(path):
@@ -38,8 +38,9 @@ def main():
     if len(sys.argv) > 1:
         return worker(sys.argv[1])
     res = {}
-    one = {"TFCFFT_SUB_LANES": "1"}
-    for name, env in (("lanes", {}), ("lanes2w", {"TFCFFT_SUB_WAVES": "2"}), ("ring", {"TFCFFT_SUB_FWD_RING": "1", **one}),
+    one = {"TFCFFT_SUB_LANES": "1"}  # the reference schedule: one stream
+    two = {"TFCFFT_SUB_LANES": "2"}
+    for name, env in (("lanes", two), ("lanes2w", {"TFCFFT_SUB_WAVES": "2", **two}), ("ring", {"TFCFFT_SUB_FWD_RING": "1", **one}),
                       ("fine", {"TFCFFT_FINE_DEPS": "1"}), ("pipe", {"TFCFFT_SUB_PIPE": "1"}), ("three", one)):
         path = f"/tmp/pipe_check_{name}.pt"
         p = subprocess.run([sys.executable, __file__, path], env={**os.environ, **env}, timeout=100, stdout=subprocess.DEVNULL)
