@@ -106,8 +106,9 @@ size_t tfcfft_workspace_bytes(const tfcfft_desc* d);
 size_t tfcfft_spectra_workspace_bytes(const tfcfft_desc* d);
 
 /* Zeroes the workspace header.  Call once after allocating a workspace (and after any call that
- * returned a CUDA error); calls leave the header zeroed for the next call.  A workspace must not be
- * shared by calls that may run concurrently on different streams. */
+ * returned a CUDA error); calls leave the tickets / counters of the header zeroed for the next call (its
+ * scratch areas are rewritten before they are read).  A workspace must not be shared by calls that may run
+ * concurrently on different streams. */
 int tfcfft_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 
 /* Loss (and, when grad_fake != NULL, d loss / d fake) in one pass over the inputs.

@@ -135,19 +135,39 @@ def test_temperature_accumulate_into_is_validated():
     assert out_a[0].item() == out_b[0].item()
 
 
-def test_fake_equals_real_gives_exact_zero():
+@pytest.mark.parametrize("side,grid,channels", [(256, 4, "luma"), (256, 2, "luma"), (256, 1, "luma"), (256, 1, "rgb"),
+                                                (256, 2, "rgb"), (512, 1, "luma"), (512, 4, "luma")])
+def test_fake_equals_real_gives_exact_zero(side, grid, channels):
     """Known answer: identical inputs -> loss 0 and gradient EXACTLY 0 (sign(0) = 0 in the reference's
-    L1Loss); the 64 x 64 engine detects the tile-level equality while it folds the pixels to luma."""
-    f, _ = _pair(9, seed=51)
-    loss, terms, grad = tfc.spectral_loss_and_grad(f, f.clone(), grid=4, weight=0.01, input_scale=255.0)
+    L1Loss).  The 64 x 64 engine detects the tile-level equality while it folds the pixels to luma; the sub-tile engine
+    (128 / 256 / 512 tiles) has its forward launch leave one flag per load unit and the combine launch zero-fills the
+    planes of a tile whose units are all flagged."""
+    n = 9 if side == 256 else 3
+    g = torch.Generator(device="cuda").manual_seed(51)
+    f = torch.empty(n, 3, side, side, device="cuda").uniform_(-1, 1, generator=g)
+    kw = dict(grid=grid, channels=channels, weight=0.01, input_scale=255.0)
+    loss, terms, grad = tfc.spectral_loss_and_grad(f, f.clone(), **kw)
     assert loss.item() == 0.0 and float(terms.abs().max()) == 0.0
     assert float(grad.abs().max()) == 0.0
-    # mixed batch: only the identical images get the exact zero
+    # mixed batch: only the identical images get the exact zero, the others the value they have on their own
     r = f.clone()
     r[::2] = torch.rand_like(r[::2])
-    loss, _, grad = tfc.spectral_loss_and_grad(f, r, grid=4, weight=0.01, input_scale=255.0)
+    loss, _, grad = tfc.spectral_loss_and_grad(f, r, **kw)
     assert loss.item() > 0
     assert float(grad[1::2].abs().max()) == 0.0 and float(grad[::2].abs().max()) > 0.0
+    alone, _, g_alone = tfc.spectral_loss_and_grad(f[::2].contiguous(), r[::2].contiguous(), **kw)
+    k = f[::2].shape[0]
+    assert loss.item() == pytest.approx(alone.item() * k / n, rel=1e-5)
+    assert torch.allclose(grad[::2] * (n / k), g_alone, rtol=1e-4, atol=1e-5 * float(g_alone.abs().max()))
+    # one differing pixel in one tile is enough to switch the whole tile back to the normal path
+    r2 = f.clone()
+    r2[0, 1, side - 1, side - 1] += 0.25
+    loss, _, grad = tfc.spectral_loss_and_grad(f, r2, **kw)
+    assert loss.item() > 0 and float(grad[0].abs().max()) > 0.0 and float(grad[1:].abs().max()) == 0.0
+    # accumulate mode: an identical batch adds exactly nothing
+    acc = torch.full_like(f, 0.5)
+    tfc.spectral_loss_and_grad(f, f.clone(), accumulate_into=acc, **kw)
+    assert bool((acc == 0.5).all())
 
 
 def test_triplet_on_spectra_variant():

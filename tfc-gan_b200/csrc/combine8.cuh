@@ -76,10 +76,25 @@ TFC_HD c2 tw2(const float2* tw, int ia, int ib) {
 }
 
 template <class Ctx>
-TFC_HD void combine8_rows(const Ctx& ctx, const Params& prm, float2* ws_tile, int row, float2* sm, float& accA, float& accP) {
+TFC_HD void combine8_rows(const Ctx& ctx, const Params& prm, float2* ws_tile, int row, float2* sm, float& accA, float& accP,
+                          bool same = false) {
     constexpr int D = 8, P = 512, NS = Combine8Cfg::NSLOT, NP = Combine8Cfg::NPAIR;
     const int npair = row <= 32 ? NP : NP - 2;
     const bool want_grad = prm.grad != nullptr;
+    if (same) {  // fake == real on the whole tile: zero loss terms, zero-filled packed planes (see combine_item)
+        if (want_grad) {
+            for (int t = ctx.tid; t < 4 * NS; t += ctx.nthreads) {
+                const int pg = t / NS;
+                const Pos8 ps = pos8(row, t % NS, npair);
+                if (ps.ok) {
+                    float2* dst = ws_tile + (pg * 8) * 4096 + ps.off;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i * 4096] = make_float2(0.f, 0.f);
+                }
+            }
+        }
+        return;
+    }
     // W_512^k table: the butterflies' twiddles W^{q kx'} / W^{p ky'} are looked up instead of being chained products
     float2* tw = sm + 64 * NS;
     for (int k = ctx.tid; k < P; k += ctx.nthreads) tw[k] = cis_neg((float)k / (float)P);

@@ -15,8 +15,12 @@ namespace tfcfft {
 //   [0]    finalise ticket          [64..95] scratch outputs of the spectra entry points     [128] rescale ticket
 //   [256]  scheduler of the pipelined sub-tile kernel: 3 queue heads + exit ticket (kSchedHeads)
 //   [512]  forward-done counters, one per chunk tile (kSchedMaxTiles)     [512 + 4096] combine-done counters
-constexpr size_t kWsHeader = 512 + 2 * 4096;
-constexpr size_t kSchedHeads = 256, kSchedFwdDone = 512, kSchedCmbDone = 512 + 4096;
+//   [512 + 8192]  sub-tile path: one byte per forward load unit of the chunk (D*D/2 per tile), 1 = every fake pixel of
+//                 the unit equals its real pixel after the luma fold; REWRITTEN by every forward launch before the
+//                 combine launch of the same chunk reads it (never relied upon to be zero)
+constexpr size_t kWsHeader = 512 + 3 * 4096;
+constexpr size_t kSchedHeads = 256, kSchedFwdDone = 512, kSchedCmbDone = 512 + 4096, kEqFlags = 512 + 2 * 4096;
+constexpr int kEqFlagBytes = 4096;
 constexpr int kSchedMaxTiles = 1024;
 constexpr size_t kWsChunkBytes = (size_t)64 << 20;  // spectrum workspace per chunk: stays L2-resident (126 MB L2, pixel streams are evict-first)
 
@@ -166,6 +170,7 @@ inline Params make_params(const tfcfft_desc* d, const Geometry& g, const void* f
     p.per_image = per_image;
     p.zws = (g.split || g.sub) ? reinterpret_cast<float2*>(w + kWsHeader + g.partial_bytes) : nullptr;
     p.sched = reinterpret_cast<unsigned*>(w + kSchedHeads);
+    p.eq = reinterpret_cast<unsigned char*>(w + kEqFlags);
     p.sub_d = g.sub ? g.p / 64 : 0;
     p.tile_base = 0;
     p.chunk_tiles = (int)g.chunk_tiles;

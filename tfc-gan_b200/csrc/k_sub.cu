@@ -79,7 +79,11 @@ __global__ void __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd_kernel(const __grid
     int iter = 0;
     for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++iter) {
         ctx.trace = (prm.trace != nullptr && iter < 6) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
-        sub_fwd_process<T, LUMA3>(ctx, prm, u, s);
+        const bool same = sub_fwd_process<T, LUMA3>(ctx, prm, u, s);
+        if (prm.eq != nullptr) {  // one "fake == real" byte per unit, rewritten by every launch
+            const int all_same = __syncthreads_and(same);
+            if (threadIdx.x == 0) prm.eq[u] = (unsigned char)all_same;
+        }
         if (ctx.trace != nullptr && threadIdx.x == 0) ctx.trace[15] = 1;
         if (prm.fine_deps) sched_signal(sched_fwd_done(prm) + u / npp);
     }
@@ -109,7 +113,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
         su.p = w & 3;
         su.i = rank;
         su.plane = su.p * 2 + rank;
-        sub_fwd_load_quad<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, dst01, dst23);
+        const bool same = sub_fwd_load_quad<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, dst01, dst23);
+        if (prm.eq != nullptr) {  // "fake == real" on the half of the row phase this CTA loaded
+            const int all_same = __syncthreads_and(same);
+            if (threadIdx.x == 0) prm.eq[w * 2 + rank] = (unsigned char)all_same;
+        }
         cl.sync();
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the 64-point core
@@ -143,7 +151,11 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
         su.p = w & 7;
         su.i = rank;
         su.plane = su.p * 4 + rank;
-        sub_fwd_load_oct<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, dst);
+        const bool same = sub_fwd_load_oct<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, dst);
+        if (prm.eq != nullptr) {  // "fake == real" on the quarter of the row phase this CTA loaded
+            const int all_same = __syncthreads_and(same);
+            if (threadIdx.x == 0) prm.eq[w * 4 + rank] = (unsigned char)all_same;
+        }
         cl.sync();
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the 64-point core
@@ -259,10 +271,11 @@ __global__ void __launch_bounds__(kCombineThreads, 512 / kCombineThreads) combin
     }
     float a = 0.f, p = 0.f;
     float2* ws_tile = sub_plane(prm, lt, 0);
+    const bool same = sub_tile_same(prm, lt);  // fake == real on this tile (flags of the forward launch)
 #pragma unroll 1
     for (int rep = 0; rep < kCombineRep; ++rep) {
         const int item = part * kCombineItemsPerPart + rep * kCombineThreads + (int)threadIdx.x;
-        if (item < kCombineItems) combine_item<D>(prm, ws_tile, item, a, p);
+        if (item < kCombineItems) combine_item<D>(prm, ws_tile, item, a, p, same);
     }
     block_sum2(a, p);
     if (threadIdx.x == 0) {
@@ -291,7 +304,7 @@ __global__ void __launch_bounds__(Combine8Cfg::NT, TFC_C8_MINB) combine8_kernel(
     pdl_wait();
     float a = 0.f, p = 0.f;
     const BlockCtx ctx{(int)threadIdx.x, Combine8Cfg::NT};
-    combine8_rows(ctx, prm, sub_plane(prm, lt, 0), row, sm, a, p);
+    combine8_rows(ctx, prm, sub_plane(prm, lt, 0), row, sm, a, p, sub_tile_same(prm, lt));
     pdl_release();
     block_sum2(a, p);
     if (threadIdx.x == 0) {
@@ -395,7 +408,7 @@ __global__ void __launch_bounds__(PipeCfg::NT, 3) sub_pipe_kernel(const __grid_c
         if (type == 0) continue;
         if (type == 1) {
             const BlockCtxT<PipeCfg::NT> ctx{tid, nullptr};
-            sub_fwd_process<T, LUMA3>(ctx, prm, idx, s);  // ends with a block barrier
+            (void)sub_fwd_process<T, LUMA3>(ctx, prm, idx, s);  // ends with a block barrier
             __threadfence();
             __syncthreads();
             if (tid == 0) red_release_add(fwd_done + idx / npp, 1u);
@@ -481,6 +494,9 @@ int launch_sub(Params prm, cudaStream_t st) {
     // inverse code of both decimations thrashes the instruction cache, runs the combine at 12 instead of 16 warps per
     // SM and loses the 2-CTA cluster loads -- so it is opt-in (TFCFFT_SUB_PIPE=1) and the three launches stay.
     static const bool pipe = getenv("TFCFFT_SUB_PIPE") != nullptr;
+    static const bool no_eq = getenv("TFCFFT_NO_EQ") != nullptr;  // A/B: identical-tile tracking off
+    unsigned char* const eq0 = (!no_eq && (long long)prm.chunk_tiles * npp <= kEqFlagBytes) ? prm.eq : nullptr;
+    prm.eq = nullptr;  // only the three-launch product path below tracks identical tiles
     if (pipe && D != 8) {
         auto kp = sub_pipe_kernel<T, LUMA3>;
         static KernelFacts fp;
@@ -525,8 +541,10 @@ int launch_sub(Params prm, cudaStream_t st) {
         // chain of three latency-bound launches): two lanes unless D = 4, chunks of two waves
         static const int mode_env = getenv("TFCFFT_SUB_LANES") ? atoi(getenv("TFCFFT_SUB_LANES")) : 0;
         static const int waves = getenv("TFCFFT_SUB_WAVES") ? atoi(getenv("TFCFFT_SUB_WAVES")) : 2;
+        static const int lane_tiles_env = getenv("TFCFFT_SUB_LANE_TILES") ? atoi(getenv("TFCFFT_SUB_LANE_TILES")) : 0;  // A/B: even splits
         const int mode = mode_env ? mode_env : (D == 4 ? 1 : 2);
-        const int wave_tiles = (sms * per_sm_f / npp) * (waves < 1 ? 1 : waves);  // whole tiles that fit the wave(s)
+        const int wave_tiles = lane_tiles_env > 0 ? lane_tiles_env
+                                                  : (sms * per_sm_f / npp) * (waves < 1 ? 1 : waves);  // whole tiles that fit the wave(s)
         // every tile has its own workspace slot when the batch fits one workspace chunk; otherwise the lanes take
         // one half of the workspace each
         const int half = prm.tiles_total <= prm.chunk_tiles ? prm.tiles_total : prm.chunk_tiles / 2;
@@ -554,6 +572,7 @@ int launch_sub(Params prm, cudaStream_t st) {
             const int lane = nchunk & 1;
             st = lane ? lanes->aux : st0;
             prm.zws = zws0 + (long long)(ws_per_tile ? base : lane * (prm.chunk_tiles / 2)) * (D * D) * 4096;
+            prm.eq = eq0 != nullptr ? eq0 + (long long)(ws_per_tile ? base : lane * (prm.chunk_tiles / 2)) * npp : nullptr;
             if (!forked) {  // fork BEFORE the first chunk is queued: the auxiliary lane waits only for earlier work
                 if (cudaError_t e = cudaEventRecord(lanes->fork, st0)) return (int)e;
                 if (cudaError_t e = cudaStreamWaitEvent(lanes->aux, lanes->fork, 0)) return (int)e;
@@ -568,6 +587,8 @@ int launch_sub(Params prm, cudaStream_t st) {
         // slower (77.0 vs 74.1 us; rgb 190 vs 153 us) -- its 207 KB CTA cannot become resident while the previous
         // call's inverse CTAs drain, and 72 KB of ring is not enough bytes in flight per SM -- so it is opt-in
         static const bool use_ring = getenv("TFCFFT_SUB_FWD_RING") != nullptr;
+        if (lanes == nullptr) prm.eq = eq0;
+        if (prm.fine_deps || (D == 4 && use_ring)) prm.eq = nullptr;  // the opt-in schedules do not write the flags
         int ring_rc = TFCFFT_ERR_STRIDE;
         if (D == 4 && use_ring && !prm.fine_deps && ring_addressable<T>(prm)) ring_rc = launch_sub_fwd_ring<T, LUMA3>(prm, st);
         if (ring_rc == 0) {

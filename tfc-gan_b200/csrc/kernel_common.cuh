@@ -102,6 +102,21 @@ cudaError_t launch_pdl(K kernel, int grid, int block, size_t smem, cudaStream_t 
     cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kernel, prm);
 }
+// the same for kernels with a plain argument list (no cluster)
+template <class... KA, class... A>
+cudaError_t launch_pdl_args(void (*kernel)(KA...), int grid, int block, cudaStream_t st, A... args) {
+    static const bool off = getenv("TFCFFT_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
+}
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------------------------

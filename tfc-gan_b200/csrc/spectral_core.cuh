@@ -40,6 +40,7 @@ struct Params {
     unsigned* counter;     // self-resetting ticket for the last-block finalise
     int fine_deps;         // sub-tile launches: tile-granular dependencies through `sched` instead of whole-grid waits
     unsigned* sched;       // pipelined sub-tile kernel: queue heads, exit ticket, per-tile done counters (workspace header)
+    unsigned char* eq;     // sub-tile path: "fake == real" flag per forward load unit of the chunk (nullptr: not tracked)
     float* out;            // [8]: loss, amp, pha, non-finite flag, gradient scale applied, 3 reserved
     float* per_image;      // [N][2] or nullptr
     float2* zws;           // split path: spectrum workspace [chunk_tiles][P][P]

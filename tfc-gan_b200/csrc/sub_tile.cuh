@@ -57,14 +57,17 @@ TFC_HD float2 ws_load(const float2* p) {
 }
 
 // ---- forward launch: sub-image pair (columns q = 2i, 2i+1 of row phase p) -> two complex work tiles ------
+// The three loaders return whether every luma value of `fake` this THREAD folded equals the `real` one (the kernels
+// reduce that over the tile: identical tiles get loss 0 and an exactly zero gradient, like the reference's L1Loss).
 template <typename T, bool LUMA3, class Ctx>
-TFC_HD void sub_fwd_load(const Ctx& ctx, const Params& prm, const TileCoord& tc, const SubUnit& su, float2* s) {
+TFC_HD bool sub_fwd_load(const Ctx& ctx, const Params& prm, const TileCoord& tc, const SubUnit& su, float2* s) {
     constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1, NI = SubCfg::LOAD_NI;
     const int D = prm.sub_d, P = 64 * D;
     const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, P);
     const T* rp = real_tile_ptr<T>(prm, tc, P);
     const int fsh = (int)prm.fs[2], fsc = (int)prm.fs[1], rsh = (int)prm.rs[2], rsc = (int)prm.rs[1];
     const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
+    bool same = true;
     // one sub-image column b per lane (consecutive lanes -> consecutive 8-byte pixel pairs of the source row),
     // NI rows per thread in flight
 #pragma unroll 1
@@ -101,20 +104,23 @@ TFC_HD void sub_fwd_load(const Ctx& ctx, const Params& prm, const TileCoord& tc,
                 }
             s[a * LD + b] = make_float2(z[0][0], z[1][0]);
             s[64 * LD + a * LD + b] = make_float2(z[0][1], z[1][1]);
+            same = same && z[0][0] == z[1][0] && z[0][1] == z[1][1];
         }
     }
+    return same;
 }
 // D = 4 variant for a 2-CTA cluster (one cluster = one row phase p of a tile = the two column pairs i = 0, 1): each
 // CTA reads HALF of the rows with full 16-byte loads (all four column phases q: every 32-byte sector is fetched
 // once instead of twice) and distributes the luma values: q = 0, 1 -> the work tiles of the i = 0 CTA (dst01),
 // q = 2, 3 -> those of the i = 1 CTA (dst23); one of the two destinations is the peer CTA's shared memory.
 template <typename T, bool LUMA3, class Ctx>
-TFC_HD void sub_fwd_load_quad(const Ctx& ctx, const Params& prm, const TileCoord& tc, int p, int half, float2* dst01, float2* dst23) {
+TFC_HD bool sub_fwd_load_quad(const Ctx& ctx, const Params& prm, const TileCoord& tc, int p, int half, float2* dst01, float2* dst23) {
     constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1, NI = SubCfg::LOAD_NI, P = 256;
     const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, P);
     const T* rp = real_tile_ptr<T>(prm, tc, P);
     const int fsh = (int)prm.fs[2], fsc = (int)prm.fs[1], rsh = (int)prm.rs[2], rsc = (int)prm.rs[1];
     const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
+    bool same = true;
 #pragma unroll 1
     for (int it0 = ctx.tid; it0 < 2048; it0 += NI * ctx.nthreads) {
         float raw[NI][2][NC][4];  // [item][fake|real][channel][q]
@@ -151,8 +157,10 @@ TFC_HD void sub_fwd_load_quad(const Ctx& ctx, const Params& prm, const TileCoord
             dst01[64 * LD + a * LD + b] = make_float2(z[0][1], z[1][1]);
             dst23[a * LD + b] = make_float2(z[0][2], z[1][2]);
             dst23[64 * LD + a * LD + b] = make_float2(z[0][3], z[1][3]);
+            same = same && z[0][0] == z[1][0] && z[0][1] == z[1][1] && z[0][2] == z[1][2] && z[0][3] == z[1][3];
         }
     }
+    return same;
 }
 
 // D = 8 variant for a 4-CTA cluster (one cluster = one row phase p of a 512 x 512 tile = the four column pairs
@@ -160,12 +168,13 @@ TFC_HD void sub_fwd_load_quad(const Ctx& ctx, const Params& prm, const TileCoord
 // every 32-byte sector is fetched once instead of four times) and distributes the luma values: q = 2i, 2i+1 -> the
 // work tiles of CTA i (dst[i]); three of the four destinations are peer CTAs' shared memory.
 template <typename T, bool LUMA3, class Ctx>
-TFC_HD void sub_fwd_load_oct(const Ctx& ctx, const Params& prm, const TileCoord& tc, int p, int quarter, float2* const (&dst)[4]) {
+TFC_HD bool sub_fwd_load_oct(const Ctx& ctx, const Params& prm, const TileCoord& tc, int p, int quarter, float2* const (&dst)[4]) {
     constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1, NI = 2, P = 512;
     const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, P);
     const T* rp = real_tile_ptr<T>(prm, tc, P);
     const int fsh = (int)prm.fs[2], fsc = (int)prm.fs[1], rsh = (int)prm.rs[2], rsc = (int)prm.rs[1];
     const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
+    bool same = true;
 #pragma unroll 1
     for (int it0 = ctx.tid; it0 < 1024; it0 += NI * ctx.nthreads) {
         float raw[NI][2][NC][8];  // [item][fake|real][channel][q]
@@ -205,8 +214,11 @@ TFC_HD void sub_fwd_load_oct(const Ctx& ctx, const Params& prm, const TileCoord&
                 dst[i][a * LD + b] = make_float2(z[0][2 * i], z[1][2 * i]);
                 dst[i][64 * LD + a * LD + b] = make_float2(z[0][2 * i + 1], z[1][2 * i + 1]);
             }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) same = same && z[0][q] == z[1][q];
         }
     }
+    return same;
 }
 
 // Forward passes of both work tiles on ONE copy of the 64-point core (callers keep the pass loop rolled, like
@@ -349,10 +361,10 @@ TFC_HD void sub_inv_store_oct(const Ctx& ctx, const Params& prm, const TileCoord
 }
 
 template <typename T, bool LUMA3, class Ctx>
-TFC_HD void sub_fwd_process(const Ctx& ctx, const Params& prm, int u, float2* s) {
+TFC_HD bool sub_fwd_process(const Ctx& ctx, const Params& prm, int u, float2* s) {
     const SubUnit su = sub_unit(u, prm.sub_d);
     ctx.mark(0);
-    sub_fwd_load<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
+    const bool same = sub_fwd_load<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
     ctx.sync();
     ctx.mark(1);
 #pragma unroll 1
@@ -361,6 +373,7 @@ TFC_HD void sub_fwd_process(const Ctx& ctx, const Params& prm, int u, float2* s)
         ctx.sync();
         ctx.mark(2 + pass);
     }
+    return same;
 }
 template <typename T, bool LUMA3, class Ctx>
 TFC_HD void sub_inv_process(const Ctx& ctx, const Params& prm, int u, float2* s) {
@@ -531,10 +544,29 @@ float2 bin_eval_call(const Params& prm, float2 zk, float2 zm, float mult, float&
     return bin_eval(prm, zk, zm, mult, accA, accP);
 }
 
+// `fake == real` on the whole tile?  The forward launch of this chunk left one byte per load unit (D*D/2 per tile).
+TFC_HD bool sub_tile_same(const Params& prm, int tile_local) {
+    if (prm.eq == nullptr) return false;
+    const int n = prm.sub_d * prm.sub_d / 2;  // 2, 8 or 32: naturally aligned groups
+    const unsigned char* f = prm.eq + (long long)tile_local * n;
+#ifdef __CUDA_ARCH__
+    if (n == 2) return __ldcg(reinterpret_cast<const unsigned short*>(f)) == 0x0101u;
+    bool same = true;
+    for (int i = 0; i < n / 8; ++i) same = same && __ldcg(reinterpret_cast<const unsigned long long*>(f) + i) == 0x0101010101010101ull;
+    return same;
+#else
+    bool same = true;
+    for (int i = 0; i < n; ++i) same = same && f[i] == 1;
+    return same;
+#endif
+}
+
 // One position pair of one tile: load the D^2 sub-spectra at both positions, combine, evaluate every
-// full-size half-plane bin they contain, un-combine the spectral gradient, store back.
+// full-size half-plane bin they contain, un-combine the spectral gradient, store back.  `same`: the tile's fake and
+// real pixels are identical -- every loss term and its gradient vanish exactly (sign(0) = 0 in the reference's
+// L1Loss), so the packed planes of the inverse launch are zero-filled instead.
 template <int D>
-TFC_HD void combine_item(const Params& prm, float2* ws_tile, int item, float& accA, float& accP) {
+TFC_HD void combine_item(const Params& prm, float2* ws_tile, int item, float& accA, float& accP, bool same = false) {
     constexpr int P = 64 * D, HD = D / 2;
     int kyA, kxA;
     if (item < 64 * 32) {
@@ -549,6 +581,17 @@ TFC_HD void combine_item(const Params& prm, float2* ws_tile, int item, float& ac
     const int kyB = (64 - kyA) & 63, kxB = (64 - kxA) & 63;
     const bool self = (kyA == kyB) && (kxA == kxB);
     const int offA = kyA * 64 + kxA, offB = kyB * 64 + kxB;
+    if (same) {
+        if (prm.grad != nullptr) {
+            const float2 z0 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int pl = 0; pl < D * HD; ++pl) {
+                ws_tile[pl * 4096 + offA] = z0;
+                if (!self) ws_tile[pl * 4096 + offB] = z0;
+            }
+        }
+        return;
+    }
     float2 za[D][D], zb[D][D];
 #pragma unroll
     for (int p = 0; p < D; ++p)

@@ -312,6 +312,7 @@ class _SpectralLossFn(torch.autograd.Function):
         out, _, grad = _launch(fake_p, real_p, cfg, want_grad, False, gs_host=gs_host, gs_dev=gs_dev, real_quads=qs)
         ctx.has_grad = want_grad
         ctx.in_dtype = fake.dtype
+        ctx.set_materialize_grads(False)  # no zero-fill launch for the non-differentiable `terms` output in backward
         if want_grad:
             ctx.buf, ctx.out = grad, out
             ctx.regen = (fake_p, real_p, cfg, gs_host, gs_dev, qs)
@@ -322,7 +323,7 @@ class _SpectralLossFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_loss, _grad_terms):
-        if not ctx.has_grad:
+        if not ctx.has_grad or grad_loss is None:
             return None, None, None, None, None
         buf = ctx.buf
         if buf is None:  # a second backward through a retained graph: the buffer was handed out, produce it again
@@ -403,12 +404,15 @@ class _MultiGridLossFn(torch.autograd.Function):
         total, per_cfg, grad, out = _multi_launch(fake_p, real_p, cfgs, chunk, gs_host, gs_dev)
         ctx.buf, ctx.out, ctx.in_dtype = grad, out, fake.dtype
         ctx.regen = (fake_p, real_p, cfgs, chunk, gs_host, gs_dev)
+        ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(per_cfg)
         return total, per_cfg
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_loss, _g):
+        if grad_loss is None:
+            return None, None, None, None, None
         buf = ctx.buf
         if buf is None:
             _, _, buf, ctx.out = _multi_launch(*ctx.regen)
