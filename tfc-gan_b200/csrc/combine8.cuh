@@ -77,23 +77,21 @@ TFC_HD c2 tw2(const float2* tw, int ia, int ib) {
 
 template <class Ctx>
 TFC_HD void combine8_rows(const Ctx& ctx, const Params& prm, float2* ws_tile, int row, float2* sm, float& accA, float& accP,
-                          bool same = false) {
+                          const unsigned char* eqf = nullptr) {
     constexpr int D = 8, P = 512, NS = Combine8Cfg::NSLOT, NP = Combine8Cfg::NPAIR;
     const int npair = row <= 32 ? NP : NP - 2;
     const bool want_grad = prm.grad != nullptr;
-    if (same) {  // fake == real on the whole tile: zero loss terms, zero-filled packed planes (see combine_item)
-        if (want_grad) {
-            for (int t = ctx.tid; t < 4 * NS; t += ctx.nthreads) {
-                const int pg = t / NS;
-                const Pos8 ps = pos8(row, t % NS, npair);
-                if (ps.ok) {
-                    float2* dst = ws_tile + (pg * 8) * 4096 + ps.off;
+    // the tile's 32 "fake == real" flag bytes (forward launch): loaded here, tested after the staging loads below
+    unsigned long long fl[4] = {0ull, 0ull, 0ull, 0ull};
+    if (eqf != nullptr) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dst[i * 4096] = make_float2(0.f, 0.f);
-                }
-            }
+        for (int i = 0; i < 4; ++i) {
+#ifdef __CUDA_ARCH__
+            fl[i] = __ldcg(reinterpret_cast<const unsigned long long*>(eqf) + i);
+#else
+            for (int b = 0; b < 8; ++b) fl[i] |= (unsigned long long)eqf[8 * i + b] << (8 * b);
+#endif
         }
-        return;
     }
     // W_512^k table: the butterflies' twiddles W^{q kx'} / W^{p ky'} are looked up instead of being chained products
     float2* tw = sm + 64 * NS;
@@ -113,6 +111,22 @@ TFC_HD void combine8_rows(const Ctx& ctx, const Params& prm, float2* ws_tile, in
         }
     }
     ctx.sync();
+    if ((fl[0] & fl[1] & fl[2] & fl[3]) == 0x0101010101010101ull) {
+        // fake == real on the whole tile (uniform over the CTA): zero loss terms, zero-filled packed planes (see combine_item)
+        if (want_grad) {
+            for (int t = ctx.tid; t < 4 * NS; t += ctx.nthreads) {
+                const int pg = t / NS;
+                const Pos8 ps = pos8(row, t % NS, npair);
+                if (ps.ok) {
+                    float2* dst = ws_tile + (pg * 8) * 4096 + ps.off;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i * 4096] = make_float2(0.f, 0.f);
+                }
+            }
+        }
+        ctx.sync();
+        return;
+    }
     // ---- phase a: (p, pair): along q ----
     for (int it = ctx.tid; it < D * npair; it += ctx.nthreads) {
         const int p = it / npair, j = it % npair;

@@ -114,10 +114,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
         su.i = rank;
         su.plane = su.p * 2 + rank;
         const bool same = sub_fwd_load_quad<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, dst01, dst23);
-        if (prm.eq != nullptr) {  // "fake == real" on the half of the row phase this CTA loaded
-            const int all_same = __syncthreads_and(same);
-            if (threadIdx.x == 0) prm.eq[w * 2 + rank] = (unsigned char)all_same;
-        }
+        // "fake == real" on the half of the row phase this CTA loaded.  The flag byte is stored AFTER the last cluster
+        // barrier of the item: a global store in front of a cluster barrier (release semantics) makes every thread
+        // wait for its L2 round trip (measured: 2 us per step)
+        const int all_same = prm.eq != nullptr ? __syncthreads_and(same) : 0;
         cl.sync();
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the 64-point core
@@ -126,6 +126,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
         }
         if (prm.fine_deps) sched_signal(sched_fwd_done(prm) + su.tile_local);  // this CTA's two planes are out
         cl.sync();  // the peer may refill my tiles only after my column pass has read them
+        if (prm.eq != nullptr && threadIdx.x == 0) prm.eq[w * 2 + rank] = (unsigned char)all_same;
     }
     if (!prm.fine_deps) pdl_release();
 }
@@ -152,10 +153,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
         su.i = rank;
         su.plane = su.p * 4 + rank;
         const bool same = sub_fwd_load_oct<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, dst);
-        if (prm.eq != nullptr) {  // "fake == real" on the quarter of the row phase this CTA loaded
-            const int all_same = __syncthreads_and(same);
-            if (threadIdx.x == 0) prm.eq[w * 4 + rank] = (unsigned char)all_same;
-        }
+        // "fake == real" on the quarter of the row phase this CTA loaded (stored after the item's last cluster barrier)
+        const int all_same = prm.eq != nullptr ? __syncthreads_and(same) : 0;
         cl.sync();
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the 64-point core
@@ -163,6 +162,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
             if (pass == 0) ctx.sync();
         }
         cl.sync();  // the peers may refill my tiles only after my column pass has read them
+        if (prm.eq != nullptr && threadIdx.x == 0) prm.eq[w * 4 + rank] = (unsigned char)all_same;
     }
     pdl_release();
 }
@@ -271,11 +271,12 @@ __global__ void __launch_bounds__(kCombineThreads, 512 / kCombineThreads) combin
     }
     float a = 0.f, p = 0.f;
     float2* ws_tile = sub_plane(prm, lt, 0);
-    const bool same = sub_tile_same(prm, lt);  // fake == real on this tile (flags of the forward launch)
+    // "fake == real on this tile" flags of the forward launch
+    const unsigned char* eqf = prm.eq != nullptr ? prm.eq + (long long)lt * (D * D / 2) : nullptr;
 #pragma unroll 1
     for (int rep = 0; rep < kCombineRep; ++rep) {
         const int item = part * kCombineItemsPerPart + rep * kCombineThreads + (int)threadIdx.x;
-        if (item < kCombineItems) combine_item<D>(prm, ws_tile, item, a, p, same);
+        if (item < kCombineItems) combine_item<D>(prm, ws_tile, item, a, p, eqf);
     }
     block_sum2(a, p);
     if (threadIdx.x == 0) {
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(Combine8Cfg::NT, TFC_C8_MINB) combine8_kernel(
     pdl_wait();
     float a = 0.f, p = 0.f;
     const BlockCtx ctx{(int)threadIdx.x, Combine8Cfg::NT};
-    combine8_rows(ctx, prm, sub_plane(prm, lt, 0), row, sm, a, p, sub_tile_same(prm, lt));
+    combine8_rows(ctx, prm, sub_plane(prm, lt, 0), row, sm, a, p, prm.eq != nullptr ? prm.eq + (long long)lt * 32 : nullptr);
     pdl_release();
     block_sum2(a, p);
     if (threadIdx.x == 0) {

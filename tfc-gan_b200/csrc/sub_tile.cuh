@@ -544,29 +544,13 @@ float2 bin_eval_call(const Params& prm, float2 zk, float2 zm, float mult, float&
     return bin_eval(prm, zk, zm, mult, accA, accP);
 }
 
-// `fake == real` on the whole tile?  The forward launch of this chunk left one byte per load unit (D*D/2 per tile).
-TFC_HD bool sub_tile_same(const Params& prm, int tile_local) {
-    if (prm.eq == nullptr) return false;
-    const int n = prm.sub_d * prm.sub_d / 2;  // 2, 8 or 32: naturally aligned groups
-    const unsigned char* f = prm.eq + (long long)tile_local * n;
-#ifdef __CUDA_ARCH__
-    if (n == 2) return __ldcg(reinterpret_cast<const unsigned short*>(f)) == 0x0101u;
-    bool same = true;
-    for (int i = 0; i < n / 8; ++i) same = same && __ldcg(reinterpret_cast<const unsigned long long*>(f) + i) == 0x0101010101010101ull;
-    return same;
-#else
-    bool same = true;
-    for (int i = 0; i < n; ++i) same = same && f[i] == 1;
-    return same;
-#endif
-}
-
 // One position pair of one tile: load the D^2 sub-spectra at both positions, combine, evaluate every
 // full-size half-plane bin they contain, un-combine the spectral gradient, store back.  `same`: the tile's fake and
 // real pixels are identical -- every loss term and its gradient vanish exactly (sign(0) = 0 in the reference's
 // L1Loss), so the packed planes of the inverse launch are zero-filled instead.
+// `eqf`: the tile's flag bytes (nullptr: not tracked), D*D/2 of them, naturally aligned
 template <int D>
-TFC_HD void combine_item(const Params& prm, float2* ws_tile, int item, float& accA, float& accP, bool same = false) {
+TFC_HD void combine_item(const Params& prm, float2* ws_tile, int item, float& accA, float& accP, const unsigned char* eqf = nullptr) {
     constexpr int P = 64 * D, HD = D / 2;
     int kyA, kxA;
     if (item < 64 * 32) {
@@ -581,6 +565,26 @@ TFC_HD void combine_item(const Params& prm, float2* ws_tile, int item, float& ac
     const int kyB = (64 - kyA) & 63, kxB = (64 - kxA) & 63;
     const bool self = (kyA == kyB) && (kxA == kxB);
     const int offA = kyA * 64 + kxA, offB = kyB * 64 + kxB;
+    // the flag word is loaded first and tested AFTER the sub-spectra loads are in flight: its latency hides under them
+    static_assert(D == 2 || D == 4, "D = 8 runs combine8_rows");
+    unsigned long long flags = 0ull;
+    if (eqf != nullptr) {
+#ifdef __CUDA_ARCH__
+        if constexpr (D == 2) flags = __ldcg(reinterpret_cast<const unsigned short*>(eqf));
+        else flags = __ldcg(reinterpret_cast<const unsigned long long*>(eqf));
+#else
+        for (int i = 0; i < D * D / 2; ++i) flags |= (unsigned long long)eqf[i] << (8 * i);
+#endif
+    }
+    float2 za[D][D], zb[D][D];
+#pragma unroll
+    for (int p = 0; p < D; ++p)
+#pragma unroll
+        for (int q = 0; q < D; ++q) {
+            za[p][q] = ws_load(ws_tile + (p * D + q) * 4096 + offA);
+            zb[p][q] = ws_load(ws_tile + (p * D + q) * 4096 + offB);
+        }
+    const bool same = flags == (D == 2 ? 0x0101ull : 0x0101010101010101ull);
     if (same) {
         if (prm.grad != nullptr) {
             const float2 z0 = make_float2(0.f, 0.f);
@@ -592,14 +596,6 @@ TFC_HD void combine_item(const Params& prm, float2* ws_tile, int item, float& ac
         }
         return;
     }
-    float2 za[D][D], zb[D][D];
-#pragma unroll
-    for (int p = 0; p < D; ++p)
-#pragma unroll
-        for (int q = 0; q < D; ++q) {
-            za[p][q] = ws_load(ws_tile + (p * D + q) * 4096 + offA);
-            zb[p][q] = ws_load(ws_tile + (p * D + q) * 4096 + offB);
-        }
     {
         c2 z2[D][D];
 #pragma unroll
