@@ -223,3 +223,41 @@ def test_combined_patch16_plus_global_matches_oracle(chunk):
     l2.backward()
     assert l2.item() == pytest.approx(want_l, rel=1e-4)
     assert np.linalg.norm(fa.grad.cpu().numpy() - want_g) / np.linalg.norm(want_g) <= 1e-3
+
+
+_QUAD_SCRIPT = r"""
+import sys
+import numpy as np, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import oracle
+import tfc_gan_b200 as tfc
+from util import l2rel
+g = torch.Generator(device="cuda").manual_seed(77)
+for ch, n in (("luma", 5), ("rgb", 2)):
+    f = torch.empty(n, 3, 256, 256, device="cuda").uniform_(-1, 1, generator=g)
+    r = torch.empty(n, 3, 256, 256, device="cuda").uniform_(-1, 1, generator=g)
+    r[1] = f[1]                                   # one identical image: exact zeros
+    tfc.reset_launch_count()
+    loss, terms, grad = tfc.spectral_loss_and_grad(f, r, grid=1, channels=ch, weight=0.01, input_scale=255.0)
+    fwd = tfc.spectral_loss(f, r, grid=1, channels=ch, weight=0.01, input_scale=255.0)
+    l, a, p, go = oracle.spectral_loss_and_grad_r1(f.cpu().numpy(), r.cpu().numpy(), grid=1, weight=0.01, input_scale=255.0, channels=ch)
+    assert abs(loss.item() - l) <= 1e-4 * abs(l), (ch, loss.item(), l)
+    assert abs(fwd.item() - l) <= 1e-4 * abs(l), (ch, fwd.item(), l)
+    assert l2rel(grad.cpu().numpy(), go) <= 1e-3, (ch, l2rel(grad.cpu().numpy(), go))
+    assert float(grad[1].abs().max()) == 0.0
+print("quad ok")
+"""
+
+
+def test_quad_combine_opt_in_matches_oracle():
+    """The opt-in quad combine launch of 256 x 256 tiles (``TFCFFT_COMBINE_QUAD=1``, read once per process: run in a
+    subprocess) against the fp64 oracle, luma and per-channel, with an identical image in the batch."""
+    import os
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    env = dict(os.environ, TFCFFT_COMBINE_QUAD="1")
+    p = subprocess.run([sys.executable, "-c", _QUAD_SCRIPT.format(root=root, tests=here)], env=env, capture_output=True, text=True, timeout=280)
+    assert p.returncode == 0 and "quad ok" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]

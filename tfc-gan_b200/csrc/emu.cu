@@ -6,6 +6,7 @@
 // to get subtly wrong -- can be checked against the oracle by the `-m "not gpu"` tests in a
 // container without a GPU.  It runs the same __host__ __device__ templates the sm_100a kernels
 // instantiate, with one serial "thread" (SerialCtx) instead of a thread block.
+#define TFCFFT_EMU_BUILD 1  // serial emulation: the one-thread combine item (9 partial sums per 256 x 256 tile)
 #include <cstdlib>
 #include <vector>
 

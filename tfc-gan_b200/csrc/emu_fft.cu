@@ -1,5 +1,6 @@
 // emu_fft.cu -- serial CPU execution of the FFT-loss kernels' arithmetic for ONE element type (-DTFC_DT=0..3); part of
 // libtfcfft_emu.so (TEST INFRASTRUCTURE, see emu.cu).  Split per dtype so that the host compile parallelises.
+#define TFCFFT_EMU_BUILD 1  // serial emulation: the one-thread combine item (9 partial sums per 256 x 256 tile)
 #include <cstdlib>
 #include <vector>
 

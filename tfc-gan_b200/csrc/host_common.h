@@ -46,6 +46,21 @@ struct Geometry {
     size_t partial_bytes, ws_bytes;
 };
 
+// 256 x 256 tiles: one position pair per thread QUAD (combine_quad.cuh) instead of per thread.  Opt-in
+// (TFCFFT_COMBINE_QUAD=1): measured at parity with the one-thread item (profiles/r02_final_ab.txt: -3.5 % on luma, +1.5 %
+// on per-channel RGB), so the one-thread item stays the product path.  Never with a generic-evaluation flag or one of the
+// opt-in schedules that are built on the one-thread item.
+inline bool combine_quad_enabled(long long p, unsigned flags) {
+#ifdef TFCFFT_EMU_BUILD
+    (void)p;
+    (void)flags;
+    return false;
+#else
+    static const bool on = getenv("TFCFFT_COMBINE_QUAD") != nullptr && getenv("TFCFFT_SUB_PIPE") == nullptr &&
+                           !(getenv("TFCFFT_FINE_DEPS") != nullptr && getenv("TFCFFT_NO_PDL") == nullptr);
+    return on && p == 256 && !(flags & (TFCFFT_LOG_MAGNITUDE | TFCFFT_FULL_SPECTRUM));
+#endif
+}
 inline int split_parts(int p) {
     switch (p) {
         case 64: return Split<64>::PARTS;
@@ -87,7 +102,8 @@ inline int validate_desc(const tfcfft_desc* d, Geometry* geo, bool allow_sub = t
         static const bool no_d8 = getenv("TFCFFT_NO_D8") != nullptr;  // A/B switch: 512 x 512 tiles back on the split kernels
         geo->sub = allow_sub && (p == 128 || p == 256 || (p == 512 && !no_d8)) && !(d->flags & (TFCFFT_FORCE_SPLIT | TFCFFT_FORCE_GENERIC));
         geo->split = !geo->sub && ((p >= 256) || (d->flags & TFCFFT_FORCE_SPLIT));
-        geo->parts = geo->sub ? (p == 512 ? kCombine8Parts : kCombineParts) : geo->split ? split_parts((int)p) : 1;
+        geo->parts = geo->sub ? (p == 512 ? kCombine8Parts : combine_quad_enabled(p, d->flags) ? kCombineQParts : kCombineParts)
+                              : geo->split ? split_parts((int)p) : 1;
         geo->tiles_total = (long long)d->n * geo->cprime * d->grid * d->grid;
         geo->partial_bytes = align_up((size_t)geo->tiles_total * geo->parts * 2 * sizeof(float), 256);
         geo->chunk_tiles = 0;

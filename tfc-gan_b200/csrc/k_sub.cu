@@ -7,6 +7,7 @@
 #include "launchers.h"
 #include "sub_tile.cuh"
 #include "combine8.cuh"
+#include "combine_quad.cuh"
 #include "sub_ring.cuh"
 
 namespace tfcfft {
@@ -293,6 +294,54 @@ __global__ void __launch_bounds__(kCombineThreads, 512 / kCombineThreads) combin
         finish(prm, (unsigned)prm.tiles_total * PARTS);
     }
 }
+// Launch 2 for 256 x 256 tiles, one position pair per thread quad (combine_quad.cuh).  The first `chunk_now` CTAs run the 66
+// pairs of the self-conjugate columns of one tile each on the one-thread item (first in the grid: their threads have the
+// longest instruction stream), the others kCombineQRows rows of the position grid of one tile each.
+#ifndef TFC_CQ_MINB
+#define TFC_CQ_MINB 5
+#endif
+__global__ void __launch_bounds__(CombineQCfg::NT, TFC_CQ_MINB) combine_quad_kernel(const __grid_constant__ Params prm) {
+    constexpr int PARTS = CombineQCfg::PARTS;
+    __shared__ float4 xbuf[(CombineQCfg::NT / 32) * CombineQCfg::XWARP];
+    const int bx = (int)blockIdx.x, nt = prm.chunk_now;
+    const int lt = bx < nt ? bx : (bx - nt) / CombineQCfg::GROUPS, part = bx < nt ? 0 : 1 + (bx - nt) % CombineQCfg::GROUPS;
+    pdl_wait();
+    float a = 0.f, p = 0.f;
+    float2* ws_tile = sub_plane(prm, lt, 0);
+    const unsigned char* eqf = prm.eq != nullptr ? prm.eq + (long long)lt * 8 : nullptr;
+    if (part == 0) {
+        const int item = 64 * 32 + (int)threadIdx.x;
+        if (item < kCombineItems) combine_item<4>(prm, ws_tile, item, a, p, eqf);
+    } else {
+        const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+        const int kx0 = warp * 8 + (lane >> 2), kx = kx0 ? kx0 : 1;
+        const int row0 = (part - 1) * CombineQCfg::RPC;
+        unsigned long long flags = 0ull;
+        if (eqf != nullptr) flags = __ldcg(reinterpret_cast<const unsigned long long*>(eqf));
+        float2 sa[4], sb[4];
+        combine_quad_load(ws_tile, row0, kx, sa, sb);
+        const c2 wx = quad_twiddle(kx);
+#pragma unroll 1
+        for (int i = 0; i < CombineQCfg::RPC; ++i) {
+            float2 na[4], nb[4];  // the next row's sub-spectra travel while this row is processed (last row: reloads itself)
+            combine_quad_load(ws_tile, row0 + (i + 1 < CombineQCfg::RPC ? i + 1 : i), kx, na, nb);
+            combine_quad_item(prm, ws_tile, row0 + i, kx, kx0 != 0, wx, flags, sa, sb, xbuf + warp * CombineQCfg::XWARP, a, p);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                sa[q] = na[q];
+                sb[q] = nb[q];
+            }
+        }
+    }
+    pdl_release();
+    block_sum2(a, p);
+    if (threadIdx.x == 0) {
+        const long long slot = (long long)(prm.tile_base + lt) * PARTS + part;
+        prm.partials[2 * slot] = a;
+        prm.partials[2 * slot + 1] = p;
+    }
+    finish(prm, (unsigned)prm.tiles_total * PARTS);
+}
 #ifndef TFC_C8_MINB
 #define TFC_C8_MINB 2
 #endif
@@ -335,6 +384,7 @@ Lanes* lanes_get() {
 }
 cudaError_t launch_combine(int d, int grid, const Params& prm, cudaStream_t st) {
     if (d == 8) return launch_pdl(combine8_kernel, grid, Combine8Cfg::NT, Combine8Cfg::SMEM, st, prm);
+    if (d == 4 && combine_quad_enabled(256, prm.flags)) return launch_pdl(combine_quad_kernel, grid, CombineQCfg::NT, 0, st, prm);
     return d == 2 ? launch_pdl(combine_kernel<2>, grid, kCombineThreads, 0, st, prm)
                   : launch_pdl(combine_kernel<4>, grid, kCombineThreads, 0, st, prm);
 }
@@ -606,7 +656,7 @@ int launch_sub(Params prm, cudaStream_t st) {
         }
         if (e != cudaSuccess) return (int)e;
         g_launches++;
-        e = launch_combine(D, prm.chunk_now * (D == 8 ? kCombine8Parts : kCombineParts), prm, st);
+        e = launch_combine(D, prm.chunk_now * prm.parts, prm, st);
         if (e != cudaSuccess) return (int)e;
         g_launches++;
         if (prm.grad) {

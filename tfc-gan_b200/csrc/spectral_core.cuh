@@ -78,6 +78,13 @@ constexpr int kCombineThreads = TFCFFT_COMBINE_THREADS;
 constexpr int kCombineRep = TFCFFT_COMBINE_REP;  // items per thread (a rolled loop)
 constexpr int kCombineItemsPerPart = kCombineThreads * kCombineRep;
 constexpr int kCombineParts = (kCombineItems + kCombineItemsPerPart - 1) / kCombineItemsPerPart;  // CTAs (= partial sums) per tile
+// 256 x 256 tiles on the quad combine (combine_quad.cuh): a CTA walks kCombineQRows rows of the 64 x 64 position grid;
+// one more CTA per tile runs the self-conjugate columns
+#ifndef TFC_CQ_RPC
+#define TFC_CQ_RPC 4
+#endif
+constexpr int kCombineQRows = TFC_CQ_RPC;
+constexpr int kCombineQParts = 64 / kCombineQRows + 1;
 constexpr int kCombine8Parts = 64;  // 512 x 512 tiles (combine8.cuh): one CTA per row of the 64 x 64 position grid
 
 template <typename T> struct IO;

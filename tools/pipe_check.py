@@ -38,10 +38,13 @@ def main():
     if len(sys.argv) > 1:
         return worker(sys.argv[1])
     res = {}
-    one = {"TFCFFT_SUB_LANES": "1"}  # the reference schedule: one stream
-    two = {"TFCFFT_SUB_LANES": "2"}
+    # the scheduling variants share the one-thread combine item; the opt-in quad combine (256 x 256 tiles,
+    # TFCFFT_COMBINE_QUAD=1) is compared with it to a tolerance below
+    v1 = {}
+    one = {"TFCFFT_SUB_LANES": "1", **v1}  # the reference schedule: one stream
+    two = {"TFCFFT_SUB_LANES": "2", **v1}
     for name, env in (("lanes", two), ("lanes2w", {"TFCFFT_SUB_WAVES": "2", **two}), ("ring", {"TFCFFT_SUB_FWD_RING": "1", **one}),
-                      ("fine", {"TFCFFT_FINE_DEPS": "1"}), ("pipe", {"TFCFFT_SUB_PIPE": "1"}), ("three", one)):
+                      ("fine", {"TFCFFT_FINE_DEPS": "1"}), ("pipe", {"TFCFFT_SUB_PIPE": "1"}), ("three", one), ("quad", {"TFCFFT_COMBINE_QUAD": "1", "TFCFFT_SUB_LANES": "1"})):
         path = f"/tmp/pipe_check_{name}.pt"
         p = subprocess.run([sys.executable, __file__, path], env={**os.environ, **env}, timeout=100, stdout=subprocess.DEVNULL)
         if p.returncode != 0:
@@ -54,6 +57,14 @@ def main():
             same = all(torch.equal(x, y) for x, y in zip(a, b))
             ok &= same
             print(name, c, "bit-identical" if same else f"MISMATCH loss {float(a[0])} vs {float(b[0])} grad rel {float((a[2] - b[2]).norm() / b[2].norm()):.2e}")
+    # quad combine against the one-thread item: same arithmetic in the same order (bit-identical so far), twiddles of
+    # the partner position derived by symmetry and a different grouping of the loss sums -> equal at least to rounding
+    for c, a, b in zip(CASES, res["quad"], res["three"]):
+        dl = abs(float(a[0]) - float(b[0])) / max(abs(float(b[0])), 1e-30)
+        dg = float((a[2] - b[2]).norm() / b[2].norm())
+        good = dl <= 2e-6 and dg <= 2e-4
+        ok &= good
+        print("quad", c, f"loss rel {dl:.2e} grad rel {dg:.2e}", "ok" if good else "MISMATCH")
     print("pipe_check", "PASS" if ok else "FAIL")
     sys.exit(0 if ok else 1)
 
