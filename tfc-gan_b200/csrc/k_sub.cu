@@ -67,20 +67,68 @@ __device__ __forceinline__ void sched_finish(const Params& prm, bool reduce) {
     if (threadIdx.x == 0) prm.sched[3] = 0u;
 }
 
+
+// ---- L2 look-ahead of the forward launches ----------------------------------------------------------------------------
+// A forward CTA alternates between a load phase (DRAM-bound) and two transform passes (DRAM idle); at batch 64 the second
+// round of the 256 x 256 launch (34 of 256 row phases on 222 cluster slots) is a lone CTA streaming its rows at DRAM
+// latency.  Once a CTA's own loads have landed it asks L2 for the rows of its NEXT unit (one bulk prefetch per pixel row
+// and channel; plain line prefetches when a row is not 16-byte aligned), so they arrive while it transforms; the first
+// unit is requested before the whole-grid wait (the inputs are not written by this library's earlier launches, and a
+// prefetch cannot change results either way).  Rows [a0, a0 + na) of row phase p of the tile.
+// NEGATIVE RESULT, opt-in (TFCFFT_SUB_LOOKAHEAD=1|2|3): see launch_sub.
+__device__ __forceinline__ void l2_prefetch_row(const void* q, unsigned bytes) {
+    const unsigned long long a = (unsigned long long)q;
+    if (((a | bytes) & 15ull) == 0ull) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q), "r"(bytes) : "memory");
+    } else {
+        for (unsigned long long l = a & ~127ull; l < a + bytes; l += 128ull) asm volatile("prefetch.global.L2 [%0];" ::"l"(l));
+    }
+}
+template <typename T, bool LUMA3>
+__device__ __forceinline__ void sub_fwd_lookahead(const Params& prm, int tile, int p, int a0, int na) {
+    constexpr int NC = LUMA3 ? 3 : 1;
+    const int D = prm.sub_d, P = 64 * D;
+    const TileCoord tc = decode_tile(prm, tile);
+    const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, P);
+    const T* rp = real_tile_ptr<T>(prm, tc, P);
+    const unsigned bytes = (unsigned)(P * sizeof(T));
+    for (int it = (int)threadIdx.x; it < na * NC * 2; it += (int)blockDim.x) {
+        const int h = it & 1, c = (it >> 1) % NC, y = D * (a0 + (it >> 1) / NC) + p;
+        l2_prefetch_row(h ? rp + y * prm.rs[2] + c * prm.rs[1] : fp + y * prm.fs[2] + c * prm.fs[1], bytes);
+    }
+}
+
 // Forward: one CTA = one sub-image PAIR (adjacent pixel columns, so the source rows are read as
 // 8-byte pairs), two 64-thread groups with a work tile each.  Inverse: one 64-thread CTA = one packed plane.
 template <typename T, bool LUMA3>
 __global__ void __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd_kernel(const __grid_constant__ Params prm) {
+    const int npp = prm.sub_d * prm.sub_d / 2, nunits = prm.chunk_now * npp, hd = prm.sub_d / 2;
+    // look-ahead: a unit reads all 64 rows of its row phase (the column pairs of one row phase share them)
+    if ((prm.lookahead & 2) && (int)blockIdx.x < nunits)
+        sub_fwd_lookahead<T, LUMA3>(prm, prm.tile_base + (int)blockIdx.x / npp, ((int)blockIdx.x % npp) / hd, 0, 64);
     pdl_wait();  // whole previous grid: this launch overwrites the workspace planes
     if (prm.fine_deps) pdl_release();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
     BlockCtxT<SubCfg::NT_FWD> ctx{(int)threadIdx.x, nullptr};
-    const int npp = prm.sub_d * prm.sub_d / 2, nunits = prm.chunk_now * npp;
     int iter = 0;
     for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++iter) {
         ctx.trace = (prm.trace != nullptr && iter < 6) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
-        const bool same = sub_fwd_process<T, LUMA3>(ctx, prm, u, s);
+        const SubUnit su = sub_unit(u, prm.sub_d);
+        ctx.mark(0);
+        const bool same = sub_fwd_load<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
+        if ((prm.lookahead & 1) && u + (int)gridDim.x < nunits) {
+            const int un = u + (int)gridDim.x;
+            sub_fwd_lookahead<T, LUMA3>(prm, prm.tile_base + un / npp, (un % npp) / hd, 0, 64);
+        }
+        ctx.sync();
+        ctx.mark(1);
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the 64-point core
+            sub_fwd_pass(ctx, prm, su, s, pass);
+            ctx.sync();
+            ctx.mark(2 + pass);
+        }
         if (prm.eq != nullptr) {  // one "fake == real" byte per unit, rewritten by every launch
             const int all_same = __syncthreads_and(same);
             if (threadIdx.x == 0) prm.eq[u] = (unsigned char)all_same;
@@ -96,12 +144,15 @@ __global__ void __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd_kernel(const __grid
 template <typename T, bool LUMA3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd4_kernel(const __grid_constant__ Params prm) {
     namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    // look-ahead: this CTA reads rows [32 rank, 32 rank + 32) of row phase w & 3 of tile w >> 2
+    if ((prm.lookahead & 2) && (int)(blockIdx.x >> 1) < prm.chunk_now * 4)
+        sub_fwd_lookahead<T, LUMA3>(prm, prm.tile_base + (int)(blockIdx.x >> 3), (int)(blockIdx.x >> 1) & 3, 32 * rank, 32);
     pdl_wait();  // whole previous grid: this launch overwrites the workspace planes
     if (prm.fine_deps) pdl_release();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
-    cg::cluster_group cl = cg::this_cluster();
-    const int rank = (int)cl.block_rank();
     float2* peer = cl.map_shared_rank(s, rank ^ 1);
     float2* dst01 = rank == 0 ? s : peer;
     float2* dst23 = rank == 0 ? peer : s;
@@ -115,6 +166,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
         su.i = rank;
         su.plane = su.p * 2 + rank;
         const bool same = sub_fwd_load_quad<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, dst01, dst23);
+        if ((prm.lookahead & 1) && w + (int)(gridDim.x >> 1) < npairs) {
+            const int wn = w + (int)(gridDim.x >> 1);
+            sub_fwd_lookahead<T, LUMA3>(prm, prm.tile_base + (wn >> 2), wn & 3, 32 * rank, 32);
+        }
         // "fake == real" on the half of the row phase this CTA loaded.  The flag byte is stored AFTER the last cluster
         // barrier of the item: a global store in front of a cluster barrier (release semantics) makes every thread
         // wait for its L2 round trip (measured: 2 us per step)
@@ -138,11 +193,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
 template <typename T, bool LUMA3>
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd8_kernel(const __grid_constant__ Params prm) {
     namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    // look-ahead: this CTA reads rows [16 rank, 16 rank + 16) of row phase w & 7 of tile w >> 3
+    if ((prm.lookahead & 2) && (int)(blockIdx.x >> 2) < prm.chunk_now * 8)
+        sub_fwd_lookahead<T, LUMA3>(prm, prm.tile_base + (int)(blockIdx.x >> 5), (int)(blockIdx.x >> 2) & 7, 16 * rank, 16);
     pdl_wait();  // whole previous grid: this launch overwrites the workspace planes
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
-    cg::cluster_group cl = cg::this_cluster();
-    const int rank = (int)cl.block_rank();
     float2* const dst[4] = {cl.map_shared_rank(s, 0), cl.map_shared_rank(s, 1), cl.map_shared_rank(s, 2), cl.map_shared_rank(s, 3)};
     BlockCtxT<SubCfg::NT_FWD> ctx{(int)threadIdx.x, nullptr};
     const int nrows = prm.chunk_now * 8;  // (tile, row phase)
@@ -154,6 +212,10 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
         su.i = rank;
         su.plane = su.p * 4 + rank;
         const bool same = sub_fwd_load_oct<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, dst);
+        if ((prm.lookahead & 1) && w + (int)(gridDim.x >> 2) < nrows) {
+            const int wn = w + (int)(gridDim.x >> 2);
+            sub_fwd_lookahead<T, LUMA3>(prm, prm.tile_base + (wn >> 3), wn & 7, 16 * rank, 16);
+        }
         // "fake == real" on the quarter of the row phase this CTA loaded (stored after the item's last cluster barrier)
         const int all_same = prm.eq != nullptr ? __syncthreads_and(same) : 0;
         cl.sync();
@@ -569,6 +631,10 @@ int launch_sub(Params prm, cudaStream_t st) {
     // counter next to the CTAs that do the work -- so they are opt-in (TFCFFT_FINE_DEPS=1)
     static const bool fine = getenv("TFCFFT_FINE_DEPS") != nullptr && getenv("TFCFFT_NO_PDL") == nullptr;
     prm.fine_deps = (fine && D != 8) ? 1 : 0;
+    // measured (profiles/r02_final_ab.txt): next-unit look-ahead +-0.5 % on every sub-tile workload (the second round of a
+    // launch is bound by the lone CTA's transforms, not by its loads), look-ahead before the wait -4 ... -8 %: off
+    static const int lookahead = getenv("TFCFFT_SUB_LOOKAHEAD") ? atoi(getenv("TFCFFT_SUB_LOOKAHEAD")) : 0;
+    prm.lookahead = lookahead;
     const int sms = device_sms();
     // trim the workspace chunk to a whole number of waves of the forward launch on THIS device (smallest tile count
     // whose units fill whole waves: 222 tiles of 128 x 128 / 111 tiles of 256 x 256 on a 148-SM part at 3 CTAs per SM)

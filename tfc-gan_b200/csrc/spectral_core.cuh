@@ -39,6 +39,8 @@ struct Params {
     int parts;             // partial sums per tile (1 resident, #column-group pairs split)
     unsigned* counter;     // self-resetting ticket for the last-block finalise
     int fine_deps;         // sub-tile launches: tile-granular dependencies through `sched` instead of whole-grid waits
+    int lookahead;         // sub-tile forward launches: L2 look-ahead bits (1: the CTA's next unit once its own loads have
+                           // landed, 2: its first unit before the whole-grid wait)
     unsigned* sched;       // pipelined sub-tile kernel: queue heads, exit ticket, per-tile done counters (workspace header)
     unsigned char* eq;     // sub-tile path: "fake == real" flag per forward load unit of the chunk (nullptr: not tracked)
     float* out;            // [8]: loss, amp, pha, non-finite flag, gradient scale applied, 3 reserved
