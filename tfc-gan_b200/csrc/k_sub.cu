@@ -68,6 +68,19 @@ __device__ __forceinline__ void sched_finish(const Params& prm, bool reduce) {
 }
 
 
+// Execution-only cluster barrier for the write-after-read hand-backs ("the peer has finished READING my tile", so I may
+// overwrite it / exit): cg::cluster_group::sync() arrives with release semantics, and a release in front of which the
+// CTA has global stores in flight (workspace planes, gradient rows) makes every thread wait for their L2 round trip
+// (ncu: MEMBAR stall, 3-6 % of the forward / inverse launches).  The peer's reads completed before it issued its
+// dependent stores, so no memory ordering is needed here.  TFCFFT_NO_RELAXED_BAR builds fall back to sync().
+__device__ __forceinline__ void cluster_sync_exec() {
+#ifdef TFCFFT_NO_RELAXED_BAR
+    cooperative_groups::this_cluster().sync();
+#else
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+#endif
+}
+
 // ---- L2 look-ahead of the forward launches ----------------------------------------------------------------------------
 // A forward CTA alternates between a load phase (DRAM-bound) and two transform passes (DRAM idle); at batch 64 the second
 // round of the 256 x 256 launch (34 of 256 row phases on 222 cluster slots) is a lone CTA streaming its rows at DRAM
@@ -181,7 +194,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
             if (pass == 0) ctx.sync();
         }
         if (prm.fine_deps) sched_signal(sched_fwd_done(prm) + su.tile_local);  // this CTA's two planes are out
-        cl.sync();  // the peer may refill my tiles only after my column pass has read them
+        cluster_sync_exec();  // the peer may refill my tiles only after my column pass has read them
         if (prm.eq != nullptr && threadIdx.x == 0) prm.eq[w * 2 + rank] = (unsigned char)all_same;
     }
     if (!prm.fine_deps) pdl_release();
@@ -224,7 +237,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
             sub_fwd_pass(ctx, prm, su, s, pass);
             if (pass == 0) ctx.sync();
         }
-        cl.sync();  // the peers may refill my tiles only after my column pass has read them
+        cluster_sync_exec();  // the peers may refill my tiles only after my column pass has read them
         if (prm.eq != nullptr && threadIdx.x == 0) prm.eq[w * 4 + rank] = (unsigned char)all_same;
     }
     pdl_release();
@@ -281,7 +294,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) s
         }
         cl.sync();  // both column pairs are ready
         sub_inv_store_quad<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, s01, s23);
-        cl.sync();  // the peer has read my tile
+        cluster_sync_exec();  // the peer has read my tile
     }
     if (prm.fine_deps) sched_finish(prm, true);
     else pdl_release();
@@ -315,7 +328,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) s
         }
         cl.sync();  // all four column pairs are ready
         sub_inv_store_oct<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, src);
-        cl.sync();  // the peers have read my tile
+        cluster_sync_exec();  // the peers have read my tile
     }
     pdl_release();
 }

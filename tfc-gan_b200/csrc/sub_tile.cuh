@@ -25,6 +25,10 @@ struct SubCfg {
     static constexpr int NT_FWD = 128;  // two 64-thread groups, one sub-image of the pair each
     static constexpr int NT_INV = 64;
     static constexpr int LOAD_NI = 4;  // rows in flight per thread in the forward load (8 measured the same)
+#ifndef TFC_STORE_NB
+#define TFC_STORE_NB 8
+#endif
+    static constexpr int STORE_NB = TFC_STORE_NB;  // cluster inverse store: items whose tile reads are batched in front of their stores
     static constexpr size_t SMEM_FWD = (size_t)2 * 64 * LD * sizeof(float2);
     static constexpr size_t SMEM_INV = (size_t)64 * LD * sizeof(float2);
 };
@@ -322,15 +326,29 @@ TFC_HD void sub_inv_store_quad(const Ctx& ctx, const Params& prm, const TileCoor
     T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, P));
     const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
     const GradOut go = grad_out(prm);
-#pragma unroll 4
-    for (int it = ctx.tid; it < 2048; it += ctx.nthreads) {
-        const int b = it & 63, a = 32 * half + (it >> 6);
-        const float2 lo = s01[a * LD + b], hi = s23[a * LD + b];
-        const int x = 4 * b, y = 4 * a + p;
+    // The two tiles are read through generic pointers (one of them is the peer CTA's shared memory), which the compiler
+    // cannot reorder across the global stores: a plainly unrolled loop waits for one distributed-shared-memory round
+    // trip PER ITEM (ncu: 56 % of the launch's stall samples on the first use of these loads).  So the loads of NB
+    // items are issued as one batch in front of their stores.
+    constexpr int NB = SubCfg::STORE_NB;
+#pragma unroll 1
+    for (int it0 = ctx.tid; it0 < 2048; it0 += NB * ctx.nthreads) {
+        float2 lo[NB], hi[NB];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            float v[4] = {go.w[c] * lo.x, go.w[c] * lo.y, go.w[c] * hi.x, go.w[c] * hi.y};
-            grad_store4<T>(go, gp + y * sh + c * sc + x, v);
+        for (int u = 0; u < NB; ++u) {
+            const int it = it0 + u * ctx.nthreads, b = it & 63, a = 32 * half + (it >> 6);
+            lo[u] = s01[a * LD + b];
+            hi[u] = s23[a * LD + b];
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int it = it0 + u * ctx.nthreads, b = it & 63, a = 32 * half + (it >> 6);
+            const int x = 4 * b, y = 4 * a + p;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                float v[4] = {go.w[c] * lo[u].x, go.w[c] * lo[u].y, go.w[c] * hi[u].x, go.w[c] * hi[u].y};
+                grad_store4<T>(go, gp + y * sh + c * sc + x, v);
+            }
         }
     }
 }
@@ -343,19 +361,28 @@ TFC_HD void sub_inv_store_oct(const Ctx& ctx, const Params& prm, const TileCoord
     T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, P));
     const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
     const GradOut go = grad_out(prm);
-#pragma unroll 2
-    for (int it = ctx.tid; it < 1024; it += ctx.nthreads) {
-        const int b = it & 63, a = 16 * quarter + (it >> 6);
-        float2 g[4];
+    // loads of NB items in one batch in front of their stores (see sub_inv_store_quad)
+    constexpr int NB = SubCfg::STORE_NB >= 2 ? SubCfg::STORE_NB / 2 : 1;
+#pragma unroll 1
+    for (int it0 = ctx.tid; it0 < 1024; it0 += NB * ctx.nthreads) {
+        float2 g[NB][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) g[i] = src[i][a * LD + b];
-        const int x = 8 * b, y = 8 * a + p;
+        for (int u = 0; u < NB; ++u) {
+            const int it = it0 + u * ctx.nthreads, b = it & 63, a = 16 * quarter + (it >> 6);
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            float v0[4] = {go.w[c] * g[0].x, go.w[c] * g[0].y, go.w[c] * g[1].x, go.w[c] * g[1].y};
-            float v1[4] = {go.w[c] * g[2].x, go.w[c] * g[2].y, go.w[c] * g[3].x, go.w[c] * g[3].y};
-            grad_store4<T>(go, gp + y * sh + c * sc + x, v0);
-            grad_store4<T>(go, gp + y * sh + c * sc + x + 4, v1);
+            for (int i = 0; i < 4; ++i) g[u][i] = src[i][a * LD + b];
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int it = it0 + u * ctx.nthreads, b = it & 63, a = 16 * quarter + (it >> 6);
+            const int x = 8 * b, y = 8 * a + p;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                float v0[4] = {go.w[c] * g[u][0].x, go.w[c] * g[u][0].y, go.w[c] * g[u][1].x, go.w[c] * g[u][1].y};
+                float v1[4] = {go.w[c] * g[u][2].x, go.w[c] * g[u][2].y, go.w[c] * g[u][3].x, go.w[c] * g[u][3].y};
+                grad_store4<T>(go, gp + y * sh + c * sc + x, v0);
+                grad_store4<T>(go, gp + y * sh + c * sc + x + 4, v1);
+            }
         }
     }
 }
