@@ -275,8 +275,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) s
     cg::cluster_group cl = cg::this_cluster();
     const int rank = (int)cl.block_rank();
     const float2* peer = cl.map_shared_rank(s, rank ^ 1);
-    const float2* s01 = rank == 0 ? s : peer;
-    const float2* s23 = rank == 0 ? peer : s;
     BlockCtxT<SubCfg::NT_INV> ctx{(int)threadIdx.x, nullptr};
     const int npairs = prm.chunk_now * 4;
     cl.sync();
@@ -293,7 +291,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) s
             if (pass == 0) ctx.sync();
         }
         cl.sync();  // both column pairs are ready
-        sub_inv_store_quad<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, s01, s23);
+        sub_inv_store_quad<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, rank, s, peer);
         cluster_sync_exec();  // the peer has read my tile
     }
     if (prm.fine_deps) sched_finish(prm, true);

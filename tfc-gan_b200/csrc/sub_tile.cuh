@@ -320,33 +320,31 @@ TFC_HD void sub_inv_store(const Ctx& ctx, const Params& prm, const TileCoord& tc
 // phase p with full 16-byte stores, taking pixels q = 0, 1 from the i = 0 CTA's tile (s01) and q = 2, 3 from the
 // i = 1 CTA's (s23); one of the two is the peer CTA's shared memory.
 template <typename T, bool LUMA3, class Ctx>
-TFC_HD void sub_inv_store_quad(const Ctx& ctx, const Params& prm, const TileCoord& tc, int p, int half, const float2* s01,
-                               const float2* s23) {
+TFC_HD void sub_inv_store_quad(const Ctx& ctx, const Params& prm, const TileCoord& tc, int p, int half, const float2* own,
+                               const float2* peer) {
     constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1, P = 256;
     T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, P));
     const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
     const GradOut go = grad_out(prm);
-    // The two tiles are read through generic pointers (one of them is the peer CTA's shared memory), which the compiler
-    // cannot reorder across the global stores: a plainly unrolled loop waits for one distributed-shared-memory round
-    // trip PER ITEM (ncu: 56 % of the launch's stall samples on the first use of these loads).  So the loads of NB
-    // items are issued as one batch in front of their stores.
+    // `peer` is the other CTA's tile, read through a generic pointer; the compiler cannot move such loads across the
+    // global stores, so a plainly unrolled loop waits for one distributed-shared-memory round trip PER ITEM (ncu: 56 % of
+    // the launch's stall samples on the first use of these loads).  All peer values of a batch of NB items are
+    // requested in front of the batch's stores; the CTA's own tile is read as plain shared memory next to them.
     constexpr int NB = SubCfg::STORE_NB;
 #pragma unroll 1
     for (int it0 = ctx.tid; it0 < 2048; it0 += NB * ctx.nthreads) {
-        float2 lo[NB], hi[NB];
+        float2 rem[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) rem[u] = peer[(32 * half + ((it0 + u * ctx.nthreads) >> 6)) * LD + ((it0 + u * ctx.nthreads) & 63)];
 #pragma unroll
         for (int u = 0; u < NB; ++u) {
-            const int it = it0 + u * ctx.nthreads, b = it & 63, a = 32 * half + (it >> 6);
-            lo[u] = s01[a * LD + b];
-            hi[u] = s23[a * LD + b];
-        }
-#pragma unroll
-        for (int u = 0; u < NB; ++u) {
-            const int it = it0 + u * ctx.nthreads, b = it & 63, a = 32 * half + (it >> 6);
-            const int x = 4 * b, y = 4 * a + p;
+            const int it = it0 + u * ctx.nthreads, bb = it & 63, a = 32 * half + (it >> 6);
+            const float2 loc = own[a * LD + bb];
+            const float2 lo = half == 0 ? loc : rem[u], hi = half == 0 ? rem[u] : loc;
+            const int x = 4 * bb, y = 4 * a + p;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                float v[4] = {go.w[c] * lo[u].x, go.w[c] * lo[u].y, go.w[c] * hi[u].x, go.w[c] * hi[u].y};
+                float v[4] = {go.w[c] * lo.x, go.w[c] * lo.y, go.w[c] * hi.x, go.w[c] * hi.y};
                 grad_store4<T>(go, gp + y * sh + c * sc + x, v);
             }
         }
@@ -362,7 +360,7 @@ TFC_HD void sub_inv_store_oct(const Ctx& ctx, const Params& prm, const TileCoord
     const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
     const GradOut go = grad_out(prm);
     // loads of NB items in one batch in front of their stores (see sub_inv_store_quad)
-    constexpr int NB = SubCfg::STORE_NB >= 2 ? SubCfg::STORE_NB / 2 : 1;
+    constexpr int NB = SubCfg::STORE_NB >= 8 ? 4 : 1;
 #pragma unroll 1
     for (int it0 = ctx.tid; it0 < 1024; it0 += NB * ctx.nthreads) {
         float2 g[NB][4];
