@@ -11,7 +11,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-# TFCFFT_LIB selects another build of the SAME library (A/B runs of kernel variants, tools/gpu_ab.sh)
+# TFCFFT_LIB selects another build of the SAME library (A/B runs of kernel variants, tools/sessions/gpu_ab.sh)
 LIB_PATH = os.environ.get("TFCFFT_LIB") or os.path.join(HERE, "libtfcfft.so")
 
 # enum tfcfft_dtype

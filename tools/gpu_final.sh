@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# GPU session (final records of round 2): suite, smoke, A/B of the opt-in quad combine, default bench line, reference arm,
+# GPU session (final records of round 2): suite, smoke, three short bench lines, default bench line, reference arm,
 # ncu launch lists, one --set full capture of the three global-256 launches.
 set -u
 OUT=gpurun_out; mkdir -p $OUT
@@ -25,12 +25,9 @@ except Exception as e:
     print(wl, v, "failed", e)
 PY
 }
-run global-fft-256-b64 ""
-run global-fft-256-b64 "TFCFFT_COMBINE_QUAD=1"
-run global-fft-256-b64 ""
-run global-fft-256-b64 "TFCFFT_COMBINE_QUAD=1"
-run global-fft-256-b64-rgb ""
-run global-fft-256-b64-rgb "TFCFFT_COMBINE_QUAD=1"
+run global-fft-256-b64 "X=1"
+run global-fft-256-b64-rgb "X=1"
+run patch16-fft-256-b256 "X=1"
 timeout 900 python bench.py > $OUT/bench_default_$TAG.json 2> $OUT/bench_default_$TAG.err; echo "default bench exit $?"
 cut -c1-400 $OUT/bench_default_$TAG.json
 timeout 300 python bench.py --impl reference --steps 50 --warmup 3 > $OUT/bench_ref_$TAG.json 2>> $OUT/bench_default_$TAG.err; echo "ref bench exit $?"
