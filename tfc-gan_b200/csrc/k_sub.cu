@@ -111,6 +111,28 @@ __device__ __forceinline__ void sub_fwd_lookahead(const Params& prm, int tile, i
     }
 }
 
+// ---- deferred final reduction ------------------------------------------------------------------------------------------
+// finish() at the end of every combine CTA is a serial chain -- barrier, fence, ticket atomic and its round trip, barrier --
+// during which the CTA holds its slot (ncu per-instruction page: 13 % of the warp time of combine_kernel<4> at one wave, 30 %
+// of combine_kernel<2> at four waves).  With a gradient the combine launches are always followed by an inverse launch, so
+// they only store their partial sums and the sum is taken behind a kernel boundary instead: by `fin_ctas` CTAs appended to
+// the last inverse launch (one cluster's worth; the first one works, after the whole-grid wait, next to the workers), or
+// -- two-lane schedule, where the last inverse launch is not ordered behind the other lane's combine launches -- by a
+// one-CTA launch after the join.  TFCFFT_NO_DEFER=1 restores the ticket.
+__device__ __forceinline__ bool fin_cta(const Params& prm) {  // true: this CTA is not a worker
+    if ((int)blockIdx.x < (int)gridDim.x - prm.fin_ctas) return false;
+    if ((int)blockIdx.x == (int)gridDim.x - prm.fin_ctas) {
+        pdl_wait();
+        finalize_sums(prm);
+    }
+    return true;
+}
+template <int DT>  // one instance per translation unit (k_sub.cu is compiled once per element type)
+__global__ void __launch_bounds__(128) sub_finalize_kernel(const __grid_constant__ Params prm) {
+    pdl_wait();
+    finalize_sums(prm);
+}
+
 // Forward: one CTA = one sub-image PAIR (adjacent pixel columns, so the source rows are read as
 // 8-byte pairs), two 64-thread groups with a work tile each.  Inverse: one 64-thread CTA = one packed plane.
 template <typename T, bool LUMA3>
@@ -245,6 +267,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
 
 template <typename T, bool LUMA3>
 __global__ void __launch_bounds__(SubCfg::NT_INV, 6) sub_inv_kernel(const __grid_constant__ Params prm) {
+    if (prm.fin_ctas && fin_cta(prm)) return;
+    const int nworkers = (int)gridDim.x - prm.fin_ctas;
     if (prm.fine_deps) pdl_release();
     else pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -252,7 +276,7 @@ __global__ void __launch_bounds__(SubCfg::NT_INV, 6) sub_inv_kernel(const __grid
     BlockCtxT<SubCfg::NT_INV> ctx{(int)threadIdx.x, nullptr};
     const int npp = prm.sub_d * prm.sub_d / 2, nunits = prm.chunk_now * npp;
     int iter = 0;
-    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++iter) {
+    for (int u = blockIdx.x; u < nunits; u += nworkers, ++iter) {
         ctx.trace = (prm.trace != nullptr && iter < 6) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
         if (prm.fine_deps) sched_wait(sched_cmb_done(prm) + u / npp, (unsigned)kCombineParts);
         sub_inv_process<T, LUMA3>(ctx, prm, u, s);
@@ -268,6 +292,8 @@ __global__ void __launch_bounds__(SubCfg::NT_INV, 6) sub_inv_kernel(const __grid
 template <typename T, bool LUMA3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) sub_inv4_kernel(const __grid_constant__ Params prm) {
     namespace cg = cooperative_groups;
+    if (prm.fin_ctas && fin_cta(prm)) return;  // a whole cluster: none of its CTAs reaches a cluster barrier
+    const int nworkers = (int)gridDim.x - prm.fin_ctas;
     if (prm.fine_deps) pdl_release();
     else pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -278,7 +304,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) s
     BlockCtxT<SubCfg::NT_INV> ctx{(int)threadIdx.x, nullptr};
     const int npairs = prm.chunk_now * 4;
     cl.sync();
-    for (int w = blockIdx.x >> 1; w < npairs; w += gridDim.x >> 1) {
+    for (int w = blockIdx.x >> 1; w < npairs; w += nworkers >> 1) {
         SubUnit su;
         su.tile_local = w >> 2;
         su.p = w & 3;
@@ -304,6 +330,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) s
 template <typename T, bool LUMA3>
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) sub_inv8_kernel(const __grid_constant__ Params prm) {
     namespace cg = cooperative_groups;
+    if (prm.fin_ctas && fin_cta(prm)) return;  // a whole cluster: none of its CTAs reaches a cluster barrier
+    const int nworkers = (int)gridDim.x - prm.fin_ctas;
     pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
@@ -313,7 +341,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) s
     BlockCtxT<SubCfg::NT_INV> ctx{(int)threadIdx.x, nullptr};
     const int nrows = prm.chunk_now * 8;
     cl.sync();
-    for (int w = blockIdx.x >> 2; w < nrows; w += gridDim.x >> 2) {
+    for (int w = blockIdx.x >> 2; w < nrows; w += nworkers >> 2) {
         SubUnit su;
         su.tile_local = w >> 3;
         su.p = w & 7;
@@ -364,7 +392,7 @@ __global__ void __launch_bounds__(kCombineThreads, 512 / kCombineThreads) combin
         if (prm.grad == nullptr) sched_finish(prm, true);
     } else {
         pdl_release();
-        finish(prm, (unsigned)prm.tiles_total * PARTS);
+        if (!prm.defer_finish) finish(prm, (unsigned)prm.tiles_total * PARTS);
     }
 }
 // Launch 2 for 256 x 256 tiles, one position pair per thread quad (combine_quad.cuh).  The first `chunk_now` CTAs run the 66
@@ -413,7 +441,7 @@ __global__ void __launch_bounds__(CombineQCfg::NT, TFC_CQ_MINB) combine_quad_ker
         prm.partials[2 * slot] = a;
         prm.partials[2 * slot + 1] = p;
     }
-    finish(prm, (unsigned)prm.tiles_total * PARTS);
+    if (!prm.defer_finish) finish(prm, (unsigned)prm.tiles_total * PARTS);
 }
 #ifndef TFC_C8_MINB
 #define TFC_C8_MINB 2
@@ -435,7 +463,7 @@ __global__ void __launch_bounds__(Combine8Cfg::NT, TFC_C8_MINB) combine8_kernel(
         prm.partials[2 * slot] = a;
         prm.partials[2 * slot + 1] = p;
     }
-    finish(prm, (unsigned)prm.tiles_total * PARTS);
+    if (!prm.defer_finish) finish(prm, (unsigned)prm.tiles_total * PARTS);
 }
 // auxiliary stream + fork / join events of the two-lane schedule (launch_sub), one set per device, created on first use
 Lanes* lanes_get() {
@@ -646,6 +674,11 @@ int launch_sub(Params prm, cudaStream_t st) {
     // launch is bound by the lone CTA's transforms, not by its loads), look-ahead before the wait -4 ... -8 %: off
     static const int lookahead = getenv("TFCFFT_SUB_LOOKAHEAD") ? atoi(getenv("TFCFFT_SUB_LOOKAHEAD")) : 0;
     prm.lookahead = lookahead;
+    static const bool no_defer = getenv("TFCFFT_NO_DEFER") != nullptr;
+    // measured (profiles/r02_final_ab.txt): +5.6 % global 256^2 b64, +4 % per-channel RGB, +6.8 % 4-patch b256, +4.8 % patch-16
+    // at 512^2; -0.6 % at D = 8 (few large combine CTAs, and the extra launch after the join): not for D = 8
+    prm.defer_finish = (prm.grad != nullptr && !prm.fine_deps && !no_defer && D != 8) ? 1 : 0;
+    prm.fin_ctas = 0;
     const int sms = device_sms();
     // trim the workspace chunk to a whole number of waves of the forward launch on THIS device (smallest tile count
     // whose units fill whole waves: 222 tiles of 128 x 128 / 111 tiles of 256 x 256 on a 148-SM part at 3 CTAs per SM)
@@ -737,13 +770,19 @@ int launch_sub(Params prm, cudaStream_t st) {
         if (e != cudaSuccess) return (int)e;
         g_launches++;
         if (prm.grad) {
+            // one launch order (no lanes): the last inverse launch follows every combine launch -> it carries the
+            // CTAs (one cluster's worth) that sum the partial sums
+            const bool last = prm.tile_base + prm.chunk_now >= prm.tiles_total;
+            const int fin = (prm.defer_finish && lanes == nullptr && last) ? (cluster8 ? 4 : cluster ? 2 : 1) : 0;
+            prm.fin_ctas = fin;
             if (cluster8) {
-                e = launch_pdl(ki8, grid_i & ~3, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
+                e = launch_pdl(ki8, (grid_i & ~3) + fin, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
             } else if (cluster) {
-                e = launch_pdl(ki4, grid_i & ~1, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
+                e = launch_pdl(ki4, (grid_i & ~1) + fin, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
             } else {
-                e = launch_pdl(ki, grid_i, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
+                e = launch_pdl(ki, grid_i + fin, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
             }
+            prm.fin_ctas = 0;
             if (e != cudaSuccess) return (int)e;
             g_launches++;
         }
@@ -751,6 +790,12 @@ int launch_sub(Params prm, cudaStream_t st) {
     if (forked) {  // join: the caller's stream continues after the auxiliary lane
         if (cudaError_t e = cudaEventRecord(lanes->join, lanes->aux)) return (int)e;
         if (cudaError_t e = cudaStreamWaitEvent(st0, lanes->join, 0)) return (int)e;
+    }
+    if (prm.defer_finish && lanes != nullptr) {  // both lanes are behind the caller's stream here
+        // a plain launch: ordered behind everything the join put in front of it
+        sub_finalize_kernel<TFC_DT><<<1, 128, 0, st0>>>(prm);
+        if (cudaError_t e = cudaGetLastError()) return (int)e;
+        g_launches++;
     }
     return 0;
 }

@@ -39,6 +39,10 @@ struct Params {
     int parts;             // partial sums per tile (1 resident, #column-group pairs split)
     unsigned* counter;     // self-resetting ticket for the last-block finalise
     int fine_deps;         // sub-tile launches: tile-granular dependencies through `sched` instead of whole-grid waits
+    int defer_finish;      // sub-tile path with a gradient: the combine launches only store their partial sums; they are
+                           // summed by the CTAs appended to the last inverse launch (`fin_ctas` of them, the first one
+                           // works) or, on the two-lane schedule, by a one-CTA launch after the join
+    int fin_ctas;
     int lookahead;         // sub-tile forward launches: L2 look-ahead bits (1: the CTA's next unit once its own loads have
                            // landed, 2: its first unit before the whole-grid wait)
     unsigned* sched;       // pipelined sub-tile kernel: queue heads, exit ticket, per-tile done counters (workspace header)
