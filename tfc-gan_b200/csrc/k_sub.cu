@@ -73,6 +73,15 @@ __device__ __forceinline__ void sched_finish(const Params& prm, bool reduce) {
 // CTA has global stores in flight (workspace planes, gradient rows) makes every thread wait for their L2 round trip
 // (ncu: MEMBAR stall, 3-6 % of the forward / inverse launches).  The peer's reads completed before it issued its
 // dependent stores, so no memory ordering is needed here.  TFCFFT_NO_RELAXED_BAR builds fall back to sync().
+// split form: arrive as soon as the CTA runs, wait right before the first access to a peer's shared memory ("the peer has
+// started"), so the barrier's latency hides behind the whole-grid wait
+#ifdef TFCFFT_NO_SPLIT_BAR  // A/B builds: one full barrier where the wait is
+__device__ __forceinline__ void cluster_arrive_exec() {}
+__device__ __forceinline__ void cluster_wait_exec() { cooperative_groups::this_cluster().sync(); }
+#else
+__device__ __forceinline__ void cluster_arrive_exec() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_exec() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
+#endif
 __device__ __forceinline__ void cluster_sync_exec() {
 #ifdef TFCFFT_NO_RELAXED_BAR
     cooperative_groups::this_cluster().sync();
@@ -181,6 +190,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
     namespace cg = cooperative_groups;
     cg::cluster_group cl = cg::this_cluster();
     const int rank = (int)cl.block_rank();
+    cluster_arrive_exec();
     // look-ahead: this CTA reads rows [32 rank, 32 rank + 32) of row phase w & 3 of tile w >> 2
     if ((prm.lookahead & 2) && (int)(blockIdx.x >> 1) < prm.chunk_now * 4)
         sub_fwd_lookahead<T, LUMA3>(prm, prm.tile_base + (int)(blockIdx.x >> 3), (int)(blockIdx.x >> 1) & 3, 32 * rank, 32);
@@ -193,7 +203,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
     float2* dst23 = rank == 0 ? peer : s;
     BlockCtxT<SubCfg::NT_FWD> ctx{(int)threadIdx.x, nullptr};
     const int npairs = prm.chunk_now * 4;  // (tile, row phase)
-    cl.sync();                             // the peer's shared memory exists from here on
+    cluster_wait_exec();                   // the peer's shared memory exists from here on
     for (int w = blockIdx.x >> 1; w < npairs; w += gridDim.x >> 1) {
         SubUnit su;
         su.tile_local = w >> 2;
@@ -230,6 +240,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
     namespace cg = cooperative_groups;
     cg::cluster_group cl = cg::this_cluster();
     const int rank = (int)cl.block_rank();
+    cluster_arrive_exec();
     // look-ahead: this CTA reads rows [16 rank, 16 rank + 16) of row phase w & 7 of tile w >> 3
     if ((prm.lookahead & 2) && (int)(blockIdx.x >> 2) < prm.chunk_now * 8)
         sub_fwd_lookahead<T, LUMA3>(prm, prm.tile_base + (int)(blockIdx.x >> 5), (int)(blockIdx.x >> 2) & 7, 16 * rank, 16);
@@ -239,7 +250,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SubCfg::NT_FWD, 3) s
     float2* const dst[4] = {cl.map_shared_rank(s, 0), cl.map_shared_rank(s, 1), cl.map_shared_rank(s, 2), cl.map_shared_rank(s, 3)};
     BlockCtxT<SubCfg::NT_FWD> ctx{(int)threadIdx.x, nullptr};
     const int nrows = prm.chunk_now * 8;  // (tile, row phase)
-    cl.sync();                            // the peers' shared memory exists from here on
+    cluster_wait_exec();                  // the peers' shared memory exists from here on
     for (int w = blockIdx.x >> 2; w < nrows; w += gridDim.x >> 2) {
         SubUnit su;
         su.tile_local = w >> 3;
@@ -303,7 +314,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) s
     const float2* peer = cl.map_shared_rank(s, rank ^ 1);
     BlockCtxT<SubCfg::NT_INV> ctx{(int)threadIdx.x, nullptr};
     const int npairs = prm.chunk_now * 4;
-    cl.sync();
+    // no barrier here: the first access to the peer's tile is behind the cluster barrier of the first item
     for (int w = blockIdx.x >> 1; w < npairs; w += nworkers >> 1) {
         SubUnit su;
         su.tile_local = w >> 2;
@@ -340,7 +351,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) s
     const float2* const src[4] = {cl.map_shared_rank(s, 0), cl.map_shared_rank(s, 1), cl.map_shared_rank(s, 2), cl.map_shared_rank(s, 3)};
     BlockCtxT<SubCfg::NT_INV> ctx{(int)threadIdx.x, nullptr};
     const int nrows = prm.chunk_now * 8;
-    cl.sync();
+    // no barrier here: the first access to the peers' tiles is behind the cluster barrier of the first item
     for (int w = blockIdx.x >> 2; w < nrows; w += nworkers >> 2) {
         SubUnit su;
         su.tile_local = w >> 3;
