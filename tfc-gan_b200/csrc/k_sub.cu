@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(SubCfg::NT_FWD, 3) sub_fwd_kernel(const __grid
         ctx.trace = (prm.trace != nullptr && iter < 6) ? prm.trace + ((long long)blockIdx.x * 6 + iter) * 16 : nullptr;
         const SubUnit su = sub_unit(u, prm.sub_d);
         ctx.mark(0);
-        const bool same = sub_fwd_load<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
+        const TileCoord tc = decode_tile(prm, prm.tile_base + su.tile_local);
+        const bool same = sub_d2_quads(prm) ? sub_fwd_load_d2<T, LUMA3>(ctx, prm, tc, su, s) : sub_fwd_load<T, LUMA3>(ctx, prm, tc, su, s);
         if ((prm.lookahead & 1) && u + (int)gridDim.x < nunits) {
             const int un = u + (int)gridDim.x;
             sub_fwd_lookahead<T, LUMA3>(prm, prm.tile_base + un / npp, (un % npp) / hd, 0, 64);

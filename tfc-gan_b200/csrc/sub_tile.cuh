@@ -113,6 +113,67 @@ TFC_HD bool sub_fwd_load(const Ctx& ctx, const Params& prm, const TileCoord& tc,
     }
     return same;
 }
+// A/B builds (-DTFCFFT_D2_PAIR8): D = 2 on the generic 8-byte forms
+TFC_HD bool sub_d2_quads(const Params& prm) {
+#ifdef TFCFFT_D2_PAIR8
+    (void)prm;
+    return false;
+#else
+    return prm.sub_d == 2;
+#endif
+}
+// D = 2 variant (one unit = one row phase: both column phases of every second row): 16-byte loads -- two pixel pairs
+// (A_b, B_b, A_b+1, B_b+1) per lane, half the load instructions of the 8-byte form (ncu: 17 % of the launch was load issue)
+template <typename T, bool LUMA3, class Ctx>
+TFC_HD bool sub_fwd_load_d2(const Ctx& ctx, const Params& prm, const TileCoord& tc, const SubUnit& su, float2* s) {
+    constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1, NI = SubCfg::LOAD_NI, P = 128;
+    const T* fp = tile_ptr<T>(prm.fake, prm.fs, tc, P);
+    const T* rp = real_tile_ptr<T>(prm, tc, P);
+    const int fsh = (int)prm.fs[2], fsc = (int)prm.fs[1], rsh = (int)prm.rs[2], rsc = (int)prm.rs[1];
+    const bool quant = (prm.flags & TFCFFT_QUANTIZE_U8) != 0;
+    bool same = true;
+#pragma unroll 1
+    for (int it0 = ctx.tid; it0 < 2048; it0 += NI * ctx.nthreads) {
+        float raw[NI][2][NC][4];  // [item][fake|real][channel][A_b, B_b, A_b+1, B_b+1]
+#pragma unroll
+        for (int u = 0; u < NI; ++u) {
+            const int it = it0 + u * ctx.nthreads, bp = it & 31, a = it >> 5;
+            const int x = 4 * bp, y = 2 * a + su.p;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                IO<T>::load4(fp + y * fsh + c * fsc + x, raw[u][0][c]);
+                IO<T>::load4(rp + y * rsh + c * rsc + x, raw[u][1][c]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NI; ++u) {
+            const int it = it0 + u * ctx.nthreads, bp = it & 31, a = it >> 5;
+            float z[2][4];  // [fake|real][A_b, B_b, A_b+1, B_b+1]
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    if (!quant) {
+                        float f = prm.lw[0] * raw[u][h][0][l];
+                        if constexpr (LUMA3) f = fmaf(prm.lw[2], raw[u][h][2][l], fmaf(prm.lw[1], raw[u][h][1][l], f));
+                        z[h][l] = f;
+                    } else if constexpr (LUMA3) {
+                        z[h][l] = (float)((19595 * IO<T>::quant(raw[u][h][0][l]) + 38470 * IO<T>::quant(raw[u][h][1][l]) +
+                                           7471 * IO<T>::quant(raw[u][h][2][l]) + 0x8000) >> 16);
+                    } else {
+                        z[h][l] = (float)IO<T>::quant(raw[u][h][0][l]);
+                    }
+                }
+            float2* d = s + a * LD + 2 * bp;
+            d[0] = make_float2(z[0][0], z[1][0]);
+            d[1] = make_float2(z[0][2], z[1][2]);
+            d[64 * LD] = make_float2(z[0][1], z[1][1]);
+            d[64 * LD + 1] = make_float2(z[0][3], z[1][3]);
+            same = same && z[0][0] == z[1][0] && z[0][1] == z[1][1] && z[0][2] == z[1][2] && z[0][3] == z[1][3];
+        }
+    }
+    return same;
+}
 // D = 4 variant for a 2-CTA cluster (one cluster = one row phase p of a tile = the two column pairs i = 0, 1): each
 // CTA reads HALF of the rows with full 16-byte loads (all four column phases q: every 32-byte sector is fetched
 // once instead of twice) and distributes the luma values: q = 0, 1 -> the work tiles of the i = 0 CTA (dst01),
@@ -316,6 +377,27 @@ TFC_HD void sub_inv_store(const Ctx& ctx, const Params& prm, const TileCoord& tc
     }
 }
 
+// D = 2 variant: 16-byte stores -- the gradients of two adjacent pixel pairs per lane (half the store instructions and
+// address arithmetic of the 8-byte form; ncu: the store loop was 53 % of the launch, issue-bound)
+template <typename T, bool LUMA3, class Ctx>
+TFC_HD void sub_inv_store_d2(const Ctx& ctx, const Params& prm, const TileCoord& tc, const SubUnit& su, const float2* s) {
+    constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1, P = 128;
+    T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, P));
+    const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
+    const GradOut go = grad_out(prm);
+#pragma unroll 4
+    for (int it = ctx.tid; it < 2048; it += ctx.nthreads) {
+        const int bp = it & 31, a = it >> 5;  // consecutive lanes: consecutive 16-byte quads of the gradient row
+        const int x = 4 * bp, y = 2 * a + su.p;
+        const float2 g0 = s[a * LD + 2 * bp], g1 = s[a * LD + 2 * bp + 1];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            float v[4] = {go.w[c] * g0.x, go.w[c] * g0.y, go.w[c] * g1.x, go.w[c] * g1.y};
+            grad_store4<T>(go, gp + y * sh + c * sc + x, v);
+        }
+    }
+}
+
 // D = 4 variant for a 2-CTA cluster (mirror of sub_fwd_load_quad): the CTA writes HALF of the gradient rows of row
 // phase p with full 16-byte stores, taking pixels q = 0, 1 from the i = 0 CTA's tile (s01) and q = 2, 3 from the
 // i = 1 CTA's (s23); one of the two is the peer CTA's shared memory.
@@ -389,7 +471,8 @@ template <typename T, bool LUMA3, class Ctx>
 TFC_HD bool sub_fwd_process(const Ctx& ctx, const Params& prm, int u, float2* s) {
     const SubUnit su = sub_unit(u, prm.sub_d);
     ctx.mark(0);
-    const bool same = sub_fwd_load<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
+    const TileCoord tc = decode_tile(prm, prm.tile_base + su.tile_local);
+    const bool same = sub_d2_quads(prm) ? sub_fwd_load_d2<T, LUMA3>(ctx, prm, tc, su, s) : sub_fwd_load<T, LUMA3>(ctx, prm, tc, su, s);
     ctx.sync();
     ctx.mark(1);
 #pragma unroll 1
@@ -410,7 +493,9 @@ TFC_HD void sub_inv_process(const Ctx& ctx, const Params& prm, int u, float2* s)
         ctx.sync();
         ctx.mark(1 + pass);
     }
-    sub_inv_store<T, LUMA3>(ctx, prm, decode_tile(prm, prm.tile_base + su.tile_local), su, s);
+    const TileCoord tc = decode_tile(prm, prm.tile_base + su.tile_local);
+    if (sub_d2_quads(prm)) sub_inv_store_d2<T, LUMA3>(ctx, prm, tc, su, s);
+    else sub_inv_store<T, LUMA3>(ctx, prm, tc, su, s);
     ctx.sync();
     ctx.mark(3);
 }
