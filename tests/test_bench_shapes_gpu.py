@@ -105,3 +105,30 @@ def test_bench_shape_f16_storage():
     # none of it lives in the subnormal range (the advisor's finding for the unscaled fp16 gradient)
     nz = np.abs(got[got != 0])
     assert np.median(nz) > 6.2e-5
+
+
+# The loss value is summed two ways on the sub-tile engine: forward-only calls keep the per-CTA ticket (the last combine
+# CTA sums the partial sums), calls with a gradient sum them behind the kernel boundary (CTAs appended to the last
+# inverse launch, or a one-CTA launch after the join of the two-lane schedule).  Same partial sums,
+# same fixed-order double-precision sum: the two must agree BIT FOR BIT, at one chunk and at several, one lane and two.
+REDUCTION_SHAPES = [
+    (1, 256, 64, "luma"),   # D = 4, one chunk: extra cluster in the only inverse launch
+    (1, 256, 64, "rgb"),    # D = 4, two chunks on one lane: extra cluster in the last inverse launch
+    (1, 256, 7, "luma"),    # D = 4, ragged
+    (2, 256, 32, "luma"),   # D = 2, one chunk
+    (2, 256, 256, "luma"),  # D = 2, two lanes: one-CTA launch after the join
+    (4, 512, 16, "luma"),   # D = 2 inside 512 x 512 images
+]
+
+
+@pytest.mark.parametrize("grid,side,batch,channels", REDUCTION_SHAPES)
+def test_deferred_reduction_equals_ticket(grid, side, batch, channels):
+    fake, real = _inputs(batch, side, 777 + batch + grid)
+    f, r = fake.cuda(), real.cuda()
+    kw = dict(grid=grid, channels=channels, weight=0.01, input_scale=255.0)
+    for _ in range(2):  # twice: nothing may be left behind in the workspace header
+        loss_g, terms_g, grad = tfc.spectral_loss_and_grad(f, r, **kw)
+        with torch.no_grad():
+            loss_f = tfc.spectral_loss(f, r, **kw)
+        assert torch.equal(loss_g.reshape(()).cpu(), loss_f.detach().reshape(()).cpu())
+    assert torch.isfinite(grad).all()
