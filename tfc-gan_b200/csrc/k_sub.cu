@@ -336,6 +336,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SubCfg::NT_INV, 6) s
     else pdl_release();
 }
 
+// D = 4 inverse launch WITHOUT clusters (the product path): one 128-thread CTA = one (tile, row phase) = both packed planes,
+// one 64-thread group per plane (group-local barrier between the two passes), then all 128 threads store the 64
+// gradient rows of the row phase with full 16-byte stores from local shared memory (sub_inv_store_rows4).  The 2-CTA
+// cluster form above pulled the other column pair out of the peer's shared memory: ncu showed a third of that launch's
+// warp time waiting on those reads (8 exposed round trips per CTA at ~5 B / clk / SM of distributed-shared-memory
+// bandwidth).  Same threads per SM (256 CTAs x 128 instead of 512 x 64), same arithmetic, bit-identical gradient.
+template <typename T, bool LUMA3>
+__global__ void __launch_bounds__(SubCfg::NT_FWD, 3) sub_inv4w_kernel(const __grid_constant__ Params prm) {
+    if (prm.fin_ctas && fin_cta(prm)) return;
+    const int nworkers = (int)gridDim.x - prm.fin_ctas;
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    const int g = (int)threadIdx.x >> 6;
+    float2* sg = s + g * 64 * SubCfg::LD;
+    BlockCtxT<64> cg{(int)threadIdx.x & 63, nullptr};
+    BlockCtxT<SubCfg::NT_FWD> cb{(int)threadIdx.x, nullptr};
+    const int npairs = prm.chunk_now * 4;
+    for (int w = blockIdx.x; w < npairs; w += nworkers) {
+        SubUnit su;
+        su.tile_local = w >> 2;
+        su.p = w & 3;
+        su.i = g;
+        su.plane = su.p * 2 + g;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the 64-point core
+            sub_inv_pass(cg, prm, su, sg, pass);
+            if (pass == 0) bar_sync(1 + g, 64);
+        }
+        __syncthreads();  // both planes are ready
+        sub_inv_store_rows4<T, LUMA3>(cb, prm, decode_tile(prm, prm.tile_base + su.tile_local), su.p, s, s + 64 * SubCfg::LD);
+        __syncthreads();  // before the next item's column pass overwrites the tiles
+    }
+    pdl_release();
+}
+
 // D = 8 inverse launch as 4-CTA clusters (the four packed planes i = 0..3 of one (tile, row phase)): transforms as
 // in sub_inv_kernel, then each CTA stores a quarter of the rows with full-sector stores, reading the other column
 // pairs from the peers' shared memory (sub_inv_store_oct).
@@ -637,7 +673,8 @@ int launch_sub(Params prm, cudaStream_t st) {
     auto ki4 = sub_inv4_kernel<T, LUMA3>;
     auto kf8 = sub_fwd8_kernel<T, LUMA3>;
     auto ki8 = sub_inv8_kernel<T, LUMA3>;
-    static KernelFacts ff, fi, ff4, fi4, ff8, fi8;
+    auto ki4w = sub_inv4w_kernel<T, LUMA3>;
+    static KernelFacts ff, fi, ff4, fi4, ff8, fi8, fi4w;
     int per_sm_f = 1, per_sm_i = 1;
     if (int rc = ff.get(kf, SubCfg::NT_FWD, SubCfg::SMEM_FWD, &per_sm_f)) return rc;
     if (int rc = fi.get(ki, SubCfg::NT_INV, SubCfg::SMEM_INV, &per_sm_i)) return rc;
@@ -649,9 +686,11 @@ int launch_sub(Params prm, cudaStream_t st) {
         if (int rc = ff8.get(kf8, SubCfg::NT_FWD, SubCfg::SMEM_FWD, nullptr)) return rc;
         if (int rc = fi8.get(ki8, SubCfg::NT_INV, SubCfg::SMEM_INV, nullptr)) return rc;
     }
+    int per_sm_i4w = 1;
     if (cluster) {
         if (int rc = ff4.get(kf4, SubCfg::NT_FWD, SubCfg::SMEM_FWD, nullptr)) return rc;
         if (int rc = fi4.get(ki4, SubCfg::NT_INV, SubCfg::SMEM_INV, nullptr)) return rc;
+        if (int rc = fi4w.get(ki4w, SubCfg::NT_FWD, SubCfg::SMEM_FWD, &per_sm_i4w)) return rc;
     }
     // measured (profiles/r02_sub_pipe_ab.txt): the pipelined kernel is bit-identical but SLOWER than the three launches
     // (global 256^2 b64: 118 vs 73 us; 4-patch b256: 372 vs 248 us) -- one kernel that holds the forward, combine and
@@ -785,9 +824,16 @@ int launch_sub(Params prm, cudaStream_t st) {
             // one launch order (no lanes): the last inverse launch follows every combine launch -> it carries the
             // CTAs (one cluster's worth) that sum the partial sums
             const bool last = prm.tile_base + prm.chunk_now >= prm.tiles_total;
-            const int fin = (prm.defer_finish && lanes == nullptr && last) ? (cluster8 ? 4 : cluster ? 2 : 1) : 0;
+            // D = 4: one CTA per (tile, row phase) without clusters (measured: profiles/r02_final_ab.txt); the 2-CTA cluster
+            // form stays for the tile-granular-dependency schedule and behind TFCFFT_INV4_CLUSTER=1
+            static const bool inv4_cluster = getenv("TFCFFT_INV4_CLUSTER") != nullptr;
+            const bool wide = cluster && !prm.fine_deps && !inv4_cluster;
+            const int fin = (prm.defer_finish && lanes == nullptr && last) ? (cluster8 ? 4 : (cluster && !wide) ? 2 : 1) : 0;
             prm.fin_ctas = fin;
-            if (cluster8) {
+            if (wide) {
+                const int rows = prm.chunk_now * 4, cap = sms * per_sm_i4w;
+                e = launch_pdl(ki4w, (rows < cap ? rows : cap) + fin, SubCfg::NT_FWD, SubCfg::SMEM_FWD, st, prm);
+            } else if (cluster8) {
                 e = launch_pdl(ki8, (grid_i & ~3) + fin, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);
             } else if (cluster) {
                 e = launch_pdl(ki4, (grid_i & ~1) + fin, SubCfg::NT_INV, SubCfg::SMEM_INV, st, prm);

@@ -433,6 +433,28 @@ TFC_HD void sub_inv_store_quad(const Ctx& ctx, const Params& prm, const TileCoor
     }
 }
 
+// D = 4 without clusters: one CTA holds BOTH packed planes of a row phase (s01: pixels q = 0, 1; s23: q = 2, 3; thanks
+// to the Hermitian packing that is 66 KB, the size of one forward work-tile pair), so all four column phases are
+// local: full 16-byte stores straight from plain shared memory, no distributed-shared-memory traffic at all.
+template <typename T, bool LUMA3, class Ctx>
+TFC_HD void sub_inv_store_rows4(const Ctx& ctx, const Params& prm, const TileCoord& tc, int p, const float2* s01, const float2* s23) {
+    constexpr int LD = SubCfg::LD, NC = LUMA3 ? 3 : 1, P = 256;
+    T* gp = const_cast<T*>(tile_ptr<T>(prm.grad, prm.gs, tc, P));
+    const int sh = (int)prm.gs[2], sc = (int)prm.gs[1];
+    const GradOut go = grad_out(prm);
+#pragma unroll 4
+    for (int it = ctx.tid; it < 4096; it += ctx.nthreads) {
+        const int b = it & 63, a = it >> 6;
+        const float2 lo = s01[a * LD + b], hi = s23[a * LD + b];
+        const int x = 4 * b, y = 4 * a + p;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            float v[4] = {go.w[c] * lo.x, go.w[c] * lo.y, go.w[c] * hi.x, go.w[c] * hi.y};
+            grad_store4<T>(go, gp + y * sh + c * sc + x, v);
+        }
+    }
+}
+
 // D = 8 variant for a 4-CTA cluster (mirror of sub_fwd_load_oct): the CTA writes a QUARTER of the gradient rows of
 // row phase p with two 16-byte stores per pixel octet, taking pixels q = 2i, 2i+1 from CTA i's tile (src[i]).
 template <typename T, bool LUMA3, class Ctx>

@@ -5,7 +5,7 @@ set -u
 OUT=gpurun_out; mkdir -p $OUT
 TAG=${1:-envab}; ALT=${ALT:-TFCFFT_NO_DEFER=1}
 export TFC_SAMPLES_DIR=$PWD/tests/_local_samples
-timeout 400 python tools/pipe_check.py > $OUT/pipecheck_$TAG.log 2>&1; echo "pipe_check exit $?"; grep -E "MISMATCH|PASS|FAIL" $OUT/pipecheck_$TAG.log | head -5
+if [ "${PIPE:-1}" = "1" ]; then timeout 400 python tools/pipe_check.py > $OUT/pipecheck_$TAG.log 2>&1; echo "pipe_check exit $?"; grep -E "MISMATCH|PASS|FAIL" $OUT/pipecheck_$TAG.log | head -5; fi
 timeout 1200 python -m pytest ${PYT:-tests} -m gpu -q --timeout 300 -p no:cacheprovider -x > $OUT/pytest_$TAG.log 2>&1
 echo "pytest exit $?"; grep -E "^(FAILED|ERROR)|passed|failed" $OUT/pytest_$TAG.log | head -20
 run() {
