@@ -141,10 +141,14 @@ void run_sub(Params prm) {
                     sub_inv_rows(ctx, t);
                 }
                 const TileCoord tc = decode_tile(prm, base + (w >> 2));
-                for (int half = 0; half < 2; ++half)  // (own tile, peer tile) of the CTA with this rank (2-CTA cluster form)
-                    sub_inv_store_quad<T, LUMA3>(ctx, prm, tc, w & 3, half, half == 0 ? t0.data() : t1.data(), half == 0 ? t1.data() : t0.data());
-                if (!(prm.flags & TFCFFT_GRAD_ACCUMULATE))  // the product form (one CTA, both planes) writes the same values again
+                // both store forms get checked against the oracle: odd tiles take the product form (one CTA, both planes),
+                // even tiles the 2-CTA cluster form ((own tile, peer tile) of the CTA with each rank)
+                if ((w >> 2) & 1) {
                     sub_inv_store_rows4<T, LUMA3>(ctx, prm, tc, w & 3, t0.data(), t1.data());
+                } else {
+                    for (int half = 0; half < 2; ++half)
+                        sub_inv_store_quad<T, LUMA3>(ctx, prm, tc, w & 3, half, half == 0 ? t0.data() : t1.data(), half == 0 ? t1.data() : t0.data());
+                }
             }
         } else if (prm.grad && D == 8) {  // the 4-CTA cluster variant's store (sub_inv_store_oct)
             std::vector<float2> tb[4];
